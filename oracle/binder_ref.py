@@ -149,6 +149,9 @@ class TreeNode(object):
     """lib/zk.js:78-119."""
 
     def __init__(self, cache, p_domain, name):
+        # strings are handled as the latin-1 view of their UTF-8 bytes, so that they compare
+        # byte-for-byte with the latin-1 view of wire names
+        name = name.encode('utf-8', 'surrogatepass').decode('latin-1')
         self.tn_name = name
         dom = name
         if len(p_domain) > 0:
@@ -185,10 +188,12 @@ class TreeNode(object):
             addr = _get(record, 'address')
             if self.tn_ip:
                 self.tn_cache.ca_revLookup.pop(self.tn_ip, None)
-            self.tn_ip = addr if addr is not _UNDEF else None
+            self.tn_ip = None
             # contract: only string addresses index the reverse map
             if isinstance(addr, str) and addr:
-                self.tn_cache.ca_revLookup[addr] = self
+                key = addr.encode('utf-8', 'surrogatepass').decode('latin-1')
+                self.tn_ip = key
+                self.tn_cache.ca_revLookup[key] = self
 
 
 def _no_constants(name):
@@ -299,7 +304,7 @@ def encodable(name):
     """Every '.'-separated label fits the wire format (1..63 bytes, <= 255 total)."""
     if name == '':
         return True
-    labs = name.encode('utf-8').split(b'.')
+    labs = name.encode('latin-1').split(b'.')
     if any(len(l) < 1 or len(l) > 63 for l in labs):
         return False
     return sum(len(l) + 1 for l in labs) + 1 <= 255

@@ -29,8 +29,8 @@ def split_query(pkt):
 
 
 def _name(n):
-    t = n.to_text(omit_final_dot=True)
-    return '' if t == '@' or t == '.' else t
+    """dns.name.Name -> latin-1 view of the raw labels joined by '.' (no escaping)."""
+    return '.'.join(l.decode('latin-1') for l in n.labels if l)
 
 
 def decode_semantic(wire):
