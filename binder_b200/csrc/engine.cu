@@ -1,0 +1,851 @@
+// binder_b200 engine: the CUDA resolve kernel for sm_100a and the host side of the C ABI.
+//
+// One kernel does the whole of binder's per-query path for a batch of raw DNS packets:
+//   mname decode                      -> decode()                 (call site lib/server.js:443-446,471)
+//   onQuery type dispatch             -> resolve_query()          (lib/server.js:491-506)
+//   resolve / resolvePtr              -> resolve_forward/_ptr()   (lib/server.js:67-134,136-429)
+//   zkCache.lookup / reverseLookup    -> probe()                  (lib/zk.js:62-67)
+//   shuffle                           -> make_perm()/perm_at()    (lib/server.js:40-53)
+//   mname encode + respond            -> emit_response()          (lib/server.js:130,286,299,310,398-402,413-414,427)
+//   miss hand-off to recursion        -> compacted miss_idx[]     (lib/server.js:110-113,222-225)
+//
+// Data movement (HBM-bound integer/byte work, no tensor cores):
+//   * a CTA owns a tile of 128 consecutive queries; their packed bytes are one contiguous
+//     range of the input, staged into shared memory with coalesced 16-byte loads;
+//   * each thread parses its packet from shared memory, hashes the normalised name and
+//     probes the zone table in HBM (one 64-byte slot = two sectors per host record);
+//   * response sizes are scanned in the CTA, tile bases come from a single-pass decoupled
+//     look-back across CTAs (so output is packed, in query order, in ONE kernel);
+//   * responses are assembled in shared memory and flushed with 16-byte coalesced stores.
+#include "zone_image.h"
+#include "../../include/binder_b200.h"
+
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
+
+namespace bbk {
+using namespace bb;
+
+constexpr int T = 128;                    // queries (= threads) per tile
+constexpr int S_IN = 8192;                // staged input bytes per tile
+constexpr int CAPW = 12288;               // output staging window per flush round
+constexpr int MAXRESP = 1232;             // >= the largest response (1200)
+constexpr int S_OUT = CAPW + MAXRESP + 32;
+constexpr uint32_t NONE16 = 0xFFFF;
+
+constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
+constexpr int D_MISS_SHIFT = 40;
+
+enum { ST_ANSWERED = 0, ST_MISS = 1, ST_DROPPED = 2 };
+enum { RC_NOERROR = 0, RC_SERVFAIL = 2, RC_NXDOMAIN = 3, RC_NOTIMP = 4, RC_REFUSED = 5 };
+enum { QT_A = 1, QT_SOA = 6, QT_PTR = 12, QT_SRV = 33, QT_OPT = 41 };
+enum { RK_NONE = 0, RK_HEADER = 1, RK_A1 = 2, RK_PTR = 3, RK_SOA = 4, RK_SVC_A = 5, RK_SVC_SRV = 6 };
+
+struct Params {
+    const uint8_t* pkts; const uint32_t* pkt_off; uint32_t n;
+    uint64_t seed; uint32_t qidx_base;
+    uint8_t* out; uint32_t out_cap; uint32_t* out_off; uint8_t* status; uint32_t* miss_idx; uint32_t* totals;
+    const Slot* table; uint32_t mask; const uint8_t* arena; int ready;
+    const EngineConst* eng;
+    unsigned long long* desc; uint32_t* counter; uint32_t ntiles;
+};
+
+// per-thread state carried from the sizing pass to the emit pass
+struct Res {
+    const uint8_t* p;        // packet bytes (shared memory, or global when the tile did not fit)
+    uint32_t qn_len;         // QNAME wire length incl. terminator
+    uint32_t ttl, val;
+    uint64_t perm;           // shuffled child order, 4 bits each (nk <= 16)
+    uint16_t rlen, maxsz, qtype, adv;
+    uint16_t d_off, d_end;   // domain part [d_off, d_end) in QNAME wire coordinates
+    uint16_t ptr_tgt;        // label boundary the owner's compression pointer targets, or NONE16
+    uint16_t lastlen;        // position of the domain's last length byte
+    uint16_t keep_ans, keep_add, n_walk, nk;
+    uint8_t status, rk, rcode, tc, opcode, rd, edns, trunc;
+};
+
+__device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
+__device__ __forceinline__ uint32_t be16(const uint8_t* p) { return (uint32_t)p[0] << 8 | p[1]; }
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }    // 4-byte aligned
+__device__ __forceinline__ uint32_t ld16a(const uint8_t* p) { return *(const uint16_t*)p; }   // 2-byte aligned
+
+// byte-fed murmur (same result as bb::hash_key over the materialised key)
+struct KeyHash {
+    uint32_t h, acc, n;
+    __device__ void init(uint32_t ns) { h = hash_init(ns); acc = 0; n = 0; }
+    __device__ void feed(uint32_t c) {
+        acc |= c << (8 * (n & 3)); ++n;
+        if ((n & 3) == 0) { h = hash_word(h, acc); acc = 0; }
+    }
+    __device__ uint32_t finish() { if (n & 3) h = hash_word(h, acc); return hash_finish(h, n); }
+};
+
+// ---- mname decode (DESIGN.md "Wire spec: decode") ---------------------------------------
+__device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
+    if (len < 12) return false;
+    if (p[2] & 0x80) return false;
+    r.opcode = (p[2] >> 3) & 0xF; r.rd = p[2] & 1;
+    uint32_t qd = be16(p + 4), an = be16(p + 6), ns = be16(p + 8), ar = be16(p + 10);
+    if (qd != 1 || an != 0 || ns != 0 || ar > 1) return false;
+    uint32_t pos = 12;
+    for (;;) {
+        if (pos >= len) return false;
+        uint32_t c = p[pos];
+        if (c == 0) { ++pos; break; }
+        if (c > 63 || pos + 1 + c > len) return false;
+        pos += 1 + c;
+        if (pos - 12 + 1 > 255) return false;
+    }
+    r.qn_len = pos - 12;
+    if (pos + 4 > len) return false;
+    r.qtype = (uint16_t)be16(p + pos);
+    if (be16(p + pos + 2) != 1) return false;
+    pos += 4;
+    r.edns = 0; r.adv = 0;
+    if (ar == 1) {
+        if (pos + 11 > len || p[pos] != 0 || be16(p + pos + 1) != QT_OPT) return false;
+        r.adv = (uint16_t)be16(p + pos + 3);
+        if (pos + 11 + be16(p + pos + 9) > len) return false;
+        r.edns = 1;
+    }
+    return true;
+}
+
+// ---- zkCache.lookup / reverseLookup ------------------------------------------------------
+// The key is produced twice (hash, then compare) by the same generator so that nothing is
+// materialised.  Forward keys: the domain part in dotted lower case.  Reverse keys: the
+// labels before "in-addr.arpa", reversed, joined by '.'.
+struct FwdKey {
+    const uint8_t* nm; uint32_t d_off, d_end;
+    uint32_t pos, nlp;
+    __device__ uint32_t length() const { return d_end - d_off - 1; }
+    __device__ void start() { pos = d_off + 1; nlp = d_off + 1 + nm[d_off]; }
+    __device__ uint32_t next() {
+        uint32_t c;
+        if (pos == nlp) { c = '.'; nlp = pos + 1 + nm[pos]; } else c = lower8(nm[pos]);
+        ++pos; return c;
+    }
+};
+struct RevKey {
+    const uint8_t* nm; uint32_t nlab;       // labels before in-addr.arpa
+    uint32_t len_;
+    int k; uint32_t pos, rem; bool dot;
+    __device__ uint32_t label_pos(int idx) const { uint32_t q = 0; for (int i = 0; i < idx; i++) q += 1 + nm[q]; return q; }
+    __device__ void measure() { len_ = 0; uint32_t q = 0; for (uint32_t i = 0; i < nlab; i++) { len_ += nm[q] + (i ? 1 : 0); q += 1 + nm[q]; } }
+    __device__ uint32_t length() const { return len_; }
+    __device__ void start() { k = (int)nlab - 1; dot = false; if (k >= 0) { pos = label_pos(k); rem = nm[pos]; ++pos; } }
+    __device__ uint32_t next() {
+        if (dot) { dot = false; return '.'; }
+        uint32_t c = nm[pos++]; --rem;
+        if (rem == 0 && k > 0) { --k; pos = label_pos(k); rem = nm[pos]; ++pos; dot = true; }
+        return c;
+    }
+};
+
+template <class KG>
+__device__ bool probe(const Params& P, uint32_t ns, KG& kg, uint32_t& kind, uint32_t& ttl, uint32_t& val) {
+    uint32_t klen = kg.length();
+    KeyHash kh; kh.init(ns);
+    kg.start();
+    for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
+    uint32_t h = kh.finish();
+    uint32_t i = h & P.mask;
+    for (;;) {
+        const Slot* s = P.table + i;
+        uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,pad | ttl | val
+        uint32_t sk = (hd.y >> 8) & 0xFF;
+        if (sk == K_EMPTY) return false;
+        if (hd.x == h && ((hd.y >> 16) & 0xFF) == ns) {
+            uint32_t sl = hd.y & 0xFF;
+            const uint8_t* kb = nullptr;
+            if (sl == KLEN_OVERFLOW) {
+                uint32_t off = __ldg((const uint32_t*)s->key), l = __ldg((const uint32_t*)(s->key + 4));
+                if (l == klen) kb = P.arena + off;
+            } else if (sl == klen) kb = s->key;
+            if (kb) {
+                kg.start();
+                bool eq = true;
+                for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
+                if (eq) { kind = sk; ttl = hd.z; val = hd.w; return true; }
+            }
+        }
+        i = (i + 1) & P.mask;
+    }
+}
+
+// ---- shuffle (lib/server.js:40-53) --------------------------------------------------------
+__device__ uint64_t make_perm(uint32_t n, uint64_t seed, uint32_t qidx) {     // n <= 16
+    uint64_t perm = 0xFEDCBA9876543210ull;
+    for (uint32_t i = n; i-- > 1;) {
+        uint32_t j = shuffle_rand(seed, qidx, i);
+        uint64_t x = ((perm >> (4 * i)) ^ (perm >> (4 * j))) & 15;
+        perm ^= (x << (4 * i)) | (x << (4 * j));
+    }
+    return perm;
+}
+// element that ends up at position `p`, for any n: undo the swaps in reverse order
+__device__ uint32_t perm_at_slow(uint32_t p, uint32_t n, uint64_t seed, uint32_t qidx) {
+    uint32_t pos = p;
+    for (uint32_t i = 1; i < n; i++) {
+        uint32_t j = shuffle_rand(seed, qidx, i);
+        if (pos == i) pos = j; else if (pos == j) pos = i;
+    }
+    return pos;
+}
+__device__ __forceinline__ uint32_t perm_at(const Res& r, uint32_t t, uint64_t seed, uint32_t qidx) {
+    return r.nk <= 16 ? (uint32_t)(r.perm >> (4 * t)) & 15 : perm_at_slow(t, r.nk, seed, qidx);
+}
+
+struct SvcView {
+    const uint8_t* base; const uint8_t* arena; const uint32_t* kid_off;
+    __device__ void open(const uint8_t* arena_, uint32_t off) {
+        arena = arena_; base = arena_ + off;
+        const SvcHdr* h = (const SvcHdr*)base;
+        uint32_t sl = h->srvce_len == 0xFF ? 0 : h->srvce_len, pl = h->proto_len == 0xFF ? 0 : h->proto_len;
+        kid_off = (const uint32_t*)(base + ((sizeof(SvcHdr) + sl + pl + 3) & ~3u));
+    }
+    __device__ const SvcHdr* hdr() const { return (const SvcHdr*)base; }
+    __device__ const KidRec* kid(uint32_t i) const { return (const KidRec*)(arena + kid_off[i]); }
+};
+
+// owner-name sizes for this query's domain part (DESIGN.md "Wire spec: compression")
+__device__ __forceinline__ uint32_t dom_owner_len(const Res& r) {
+    return r.ptr_tgt != NONE16 ? (uint32_t)(r.ptr_tgt - r.d_off) + 2 : (uint32_t)(r.d_end - r.d_off) + 1;
+}
+__device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_t)(r.d_end - r.d_off) + 1; }
+
+// Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
+__device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
+    SvcView sv; sv.open(P.arena, r.val);
+    uint32_t nk = sv.hdr()->nkids;
+    r.nk = (uint16_t)nk;
+    r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
+    const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
+    uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
+    const uint8_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
+    for (uint32_t t = 0; t < nk; t++) {
+        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+        uint32_t fl = k->flags;
+        if (fl & badbit) { r.rcode = RC_SERVFAIL; n_walk = t; break; }       // :366-376
+        if (fl & KID_ADDR_NULL) continue;                                     // :378-381
+        if (srv) {
+            ans_b += (uint32_t)k->nports * (18 + k->wire_len + dwl); n_ans += k->nports;
+            add_b += k->wire_len + dol + 14; n_add++;
+        } else { ans_b += dol + 14; n_ans++; }
+    }
+    r.n_walk = (uint16_t)n_walk;
+    if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = (uint16_t)n_ans; r.keep_add = (uint16_t)n_add; r.rlen = (uint16_t)(fixed + ans_b + add_b); return; }
+    // truncation: keep the longest prefix of [answers..., additionals...] that fits
+    r.tc = 1;
+    uint32_t total = fixed, ka = 0, kd = 0; bool full = false;
+    for (uint32_t t = 0; t < n_walk && !full; t++) {
+        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+        if (k->flags & KID_ADDR_NULL) continue;
+        uint32_t each = srv ? 18 + k->wire_len + dwl : dol + 14, cnt = srv ? k->nports : 1;
+        for (uint32_t c = 0; c < cnt; c++) { if (total + each > r.maxsz) { full = true; break; } total += each; ++ka; }
+    }
+    if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {
+        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+        if (k->flags & KID_ADDR_NULL) continue;
+        uint32_t each = k->wire_len + dol + 14;
+        if (total + each > r.maxsz) break;
+        total += each; ++kd;
+    }
+    r.keep_ans = (uint16_t)ka; r.keep_add = (uint16_t)kd; r.rlen = (uint16_t)total;
+}
+
+// one RR that either fits or is dropped (TC)
+__device__ __forceinline__ void size_single(Res& r, uint32_t fixed, uint32_t rr) {
+    if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
+    else { r.rlen = (uint16_t)fixed; r.keep_ans = 0; r.tc = 1; }
+}
+
+// ---- resolve (lib/server.js:136-429) -------------------------------------------------------
+__device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed) {
+    const uint8_t* nm = r.p + 12;
+    const EngineConst* E = P.eng;
+    const bool srv = r.qtype == QT_SRV;
+    uint32_t d_off = 0, d_end = r.qn_len - 1;
+    uint32_t l0 = 0, l1 = 0;
+    r.trunc = 0;
+    if (srv) {
+        // /^(_[^_.]*)[.](_[^_.]*)[.](.*)/ on query.name() (:141-154); labels hold no '.' here
+        l0 = nm[0];
+        if (l0 == 0 || nm[1] != '_') { r.rcode = RC_REFUSED; return; }
+        for (uint32_t i = 2; i <= l0; i++) if (nm[i] == '_') { r.rcode = RC_REFUSED; return; }
+        uint32_t p1 = 1 + l0; l1 = nm[p1];
+        if (l1 == 0 || nm[p1 + 1] != '_') { r.rcode = RC_REFUSED; return; }
+        for (uint32_t i = 2; i <= l1; i++) if (nm[p1 + i] == '_') { r.rcode = RC_REFUSED; return; }
+        d_off = p1 + 1 + l1;
+        if (nm[d_off] == 0) { r.rcode = RC_REFUSED; return; }                 // no third part
+        // group 3 stops at the first \n or \r (JS '.' excludes line terminators, no '$')
+        uint32_t nlp = d_off;
+        for (uint32_t pos = d_off; pos < d_end; pos++) {
+            if (pos == nlp) { nlp = pos + 1 + nm[pos]; continue; }
+            if (nm[pos] == '\n' || nm[pos] == '\r') { d_end = pos; r.trunc = 1; break; }
+        }
+        if (d_end - d_off - 1 < 1 || d_end <= d_off + 1) { r.rcode = RC_REFUSED; return; }   // :144
+    }
+    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end;
+    if (d_end <= d_off + 1 && !srv) {                                         // root name: ''
+        // isSuffix('.dom', '') is false -> refused; with no dnsDomain: length < 1 -> refused (:198)
+        r.rcode = P.ready || E->suffix_len ? RC_REFUSED : RC_SERVFAIL; return;
+    }
+    // one pass over the domain in dotted view: suffix gate (:157-166, case-sensitive), charset
+    // after toLowerCase (:207-215), and where an owner-name pointer may land
+    const uint32_t dl = d_end - d_off - 1;
+    const uint32_t sl = E->suffix_len;
+    bool suffix_ok = sl == 0 || dl >= sl, charset_ok = true, need_b = false;
+    uint32_t pos0 = d_end - sl, ptr_tgt = d_off, lastlen = d_off;
+    {
+        uint32_t nlp = d_off + 1 + nm[d_off];
+        for (uint32_t pos = d_off + 1; pos < d_end; pos++) {
+            uint32_t c, raw;
+            if (pos == nlp) { raw = c = '.'; nlp = pos + 1 + nm[pos]; lastlen = pos; if (need_b) { ptr_tgt = pos; need_b = false; } }
+            else {
+                raw = nm[pos]; c = lower8(raw);
+                if (raw != c) need_b = true;
+                if (!((c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-')) charset_ok = false;
+            }
+            if (suffix_ok && sl && pos >= pos0 && raw != E->suffix[pos - pos0]) suffix_ok = false;
+        }
+    }
+    if (!suffix_ok) { r.rcode = RC_REFUSED; return; }
+    if (!P.ready) { r.rcode = RC_SERVFAIL; return; }                         // :186-192
+    if (!charset_ok) { r.rcode = RC_REFUSED; return; }
+    r.ptr_tgt = (need_b || r.trunc) ? (uint16_t)NONE16 : (uint16_t)ptr_tgt;
+    r.lastlen = (uint16_t)lastlen;
+
+    FwdKey kg; kg.nm = nm; kg.d_off = d_off; kg.d_end = d_end;
+    uint32_t kind, ttl, val;
+    if (!probe(P, NS_FORWARD, kg, kind, ttl, val)) {                          // :219-247
+        if (E->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        r.rcode = RC_REFUSED; return;
+    }
+    r.ttl = ttl; r.val = val;
+    if (kind == K_INVALID) { r.rcode = RC_SERVFAIL; return; }                 // :251-260
+    if (srv && kind != K_SERVICE) {                                           // :276-292 NODATA + SOA
+        r.rcode = RC_NOERROR; r.rk = RK_SOA;
+        uint32_t rr = dom_owner_len(r) + 10 + E->soa_len + 20;
+        if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
+        else { r.keep_ans = 0; r.tc = 1; }
+        return;
+    }
+    if (kind == K_ADDR) { r.rcode = RC_NOERROR; r.rk = RK_A1; size_single(r, fixed, dom_owner_len(r) + 14); return; }
+    if (kind == K_ADDR_BAD) { r.rcode = RC_SERVFAIL; return; }                // contract
+    if (kind == K_UNKNOWN) { r.rcode = RC_NOTIMP; return; }                   // :419-424 + :346-350
+    // K_SERVICE (:313-417)
+    SvcView sv; sv.open(P.arena, val);
+    const SvcHdr* h = sv.hdr();
+    r.ttl = h->ttl;
+    if (srv) {
+        const uint8_t* sb = sv.base + sizeof(SvcHdr);
+        bool match = h->srvce_len == l0 && h->proto_len == l1;
+        for (uint32_t i = 0; match && i < l0; i++) if (sb[i] != nm[1 + i]) match = false;
+        for (uint32_t i = 0; match && i < l1; i++) if (sb[l0 + i] != nm[2 + l0 + i]) match = false;
+        if (!match) { r.rcode = RC_NXDOMAIN; return; }                        // :334-345
+    }
+    r.rcode = RC_NOERROR;                                                     // :351
+    r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
+    size_service(P, r, qidx, srv, fixed);
+}
+
+// ---- resolvePtr (lib/server.js:67-134) -----------------------------------------------------
+__device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
+    const uint8_t* nm = r.p + 12;
+    uint32_t nlab = 0, last = 0, prev = 0;
+    for (uint32_t q = 0; nm[q]; q += 1 + nm[q]) { prev = last; last = q; ++nlab; }
+    // parts.reverse(): [0] must be 'arpa', [1] 'in-addr' — case-sensitive (:71-78)
+    bool ok = nlab >= 2 && nm[last] == 4 && nm[last + 1] == 'a' && nm[last + 2] == 'r' && nm[last + 3] == 'p' && nm[last + 4] == 'a' &&
+              nm[prev] == 7 && nm[prev + 1] == 'i' && nm[prev + 2] == 'n' && nm[prev + 3] == '-' && nm[prev + 4] == 'a' &&
+              nm[prev + 5] == 'd' && nm[prev + 6] == 'd' && nm[prev + 7] == 'r';
+    if (!ok) { r.rcode = RC_REFUSED; return; }
+    if (!P.ready) { r.rcode = RC_SERVFAIL; return; }                          // :86-92
+    RevKey kg; kg.nm = nm; kg.nlab = nlab - 2; kg.measure();
+    uint32_t kind = 0, ttl = 0, val = 0;
+    bool hit = kg.length() > 0 && probe(P, NS_REVERSE, kg, kind, ttl, val);
+    if (!hit) {                                                               // :107-121
+        if (P.eng->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        r.rcode = RC_REFUSED; return;
+    }
+    if (kind != K_PTR) { r.rcode = RC_SERVFAIL; return; }                     // contract
+    r.ttl = ttl; r.val = val; r.rcode = RC_NOERROR; r.rk = RK_PTR;
+    size_single(r, fixed, 2 + 10 + P.arena[val]);
+}
+
+// onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
+__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx) {
+    r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
+    r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
+    if (!decode(r.p, len, r)) { r.status = ST_DROPPED; return; }
+    r.maxsz = r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
+    const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
+    r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
+    const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
+    if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
+    const uint8_t* nm = r.p + 12;
+    for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
+        uint32_t l = nm[q];
+        for (uint32_t i = 1; i <= l; i++) if (nm[q + i] == '.') { r.rcode = RC_REFUSED; return; }
+        q += 1 + l;
+    }
+    if (r.qtype == QT_PTR) resolve_ptr(P, r, fixed);
+    else resolve_forward(P, r, qidx, fixed);
+}
+
+// ---- mname encode (DESIGN.md "Wire spec: encode") ------------------------------------------
+// OPT echoed when the query carried one: root owner, type 41, udp size 1200, ttl 0, rdlen 0
+__constant__ uint8_t c_opt_rr[11] = { 0, 0, QT_OPT, 0x04, 0xB0, 0, 0, 0, 0, 0, 0 };
+struct Out {
+    uint8_t* o;
+    __device__ void u8(uint32_t v) { *o++ = (uint8_t)v; }
+    __device__ void u16(uint32_t v) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)v; o += 2; }
+    __device__ void u32(uint32_t v) { o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v; o += 4; }
+    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) o[i] = s[i]; o += n; }
+};
+// the domain part, lower-cased, as wire labels up to `stop` (no terminator)
+__device__ void put_dom_labels(Out& w, const Res& r, uint32_t stop) {
+    const uint8_t* nm = r.p + 12;
+    uint8_t* start = w.o;
+    for (uint32_t pos = r.d_off; pos < stop; pos++) w.u8(lower8(nm[pos]));    // length bytes (<64) are unaffected
+    if (r.trunc && stop > r.lastlen) start[r.lastlen - r.d_off] = (uint8_t)(r.d_end - r.lastlen - 1);
+}
+__device__ void put_dom_owner(Out& w, const Res& r) {
+    if (r.ptr_tgt != NONE16) { put_dom_labels(w, r, r.ptr_tgt); w.u16(0xC000 | (12 + r.ptr_tgt)); }
+    else { put_dom_labels(w, r, r.d_end); w.u8(0); }
+}
+__device__ void put_rr_head(Out& w, uint32_t type, uint32_t ttl, uint32_t rdlen) { w.u16(type); w.u16(1); w.u32(ttl); w.u16(rdlen); }
+
+__device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint32_t qidx) {
+    Out w; w.o = dst;
+    const uint8_t* p = r.p;
+    uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
+    switch (r.rk) {
+    case RK_A1: case RK_PTR: an = r.keep_ans; break;
+    case RK_SOA: ns = r.keep_ans; break;
+    case RK_SVC_A: case RK_SVC_SRV: an = r.keep_ans; ar += r.keep_add; break;
+    }
+    w.u8(p[0]); w.u8(p[1]);
+    w.u8(0x80 | (r.opcode << 3) | 0x04 | (r.tc ? 0x02 : 0) | r.rd);          // QR AA TC RD
+    w.u8(r.rcode);                                                            // RA=0 Z=0
+    w.u16(1); w.u16(an); w.u16(ns); w.u16(ar);
+    w.copy(p + 12, r.qn_len + 4);                                             // question, verbatim
+    const uint8_t* opt = c_opt_rr;
+    bool opt_done = !r.edns;
+    if (r.rk == RK_A1 && r.keep_ans) {                                        // :299,310
+        put_dom_owner(w, r); put_rr_head(w, QT_A, r.ttl, 4); w.u32(r.val);
+    } else if (r.rk == RK_PTR && r.keep_ans) {                                // :130
+        w.u16(0xC00C); uint32_t tl = P.arena[r.val]; put_rr_head(w, QT_PTR, r.ttl, tl); w.copy(P.arena + r.val + 1, tl);
+    } else if (r.rk == RK_SOA && r.keep_ans) {                                // :286-287
+        const EngineConst* E = P.eng;
+        put_dom_owner(w, r); put_rr_head(w, QT_SOA, r.ttl, E->soa_len + 20);
+        w.copy(E->soa, E->soa_len); w.u32(0); w.u32(10); w.u32(10); w.u32(10); w.u32(r.ttl);
+    } else if (r.rk == RK_SVC_A || r.rk == RK_SVC_SRV) {
+        const bool srv = r.rk == RK_SVC_SRV;
+        SvcView sv; sv.open(P.arena, r.val);
+        uint32_t left = r.keep_ans;
+        for (uint32_t t = 0; t < r.n_walk && left; t++) {
+            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+            if (k->flags & KID_ADDR_NULL) continue;
+            if (srv) {                                                        // :396-400
+                const uint8_t* ports = (const uint8_t*)(k + 1);
+                const uint8_t* kw = ports + 2 * k->nports;
+                for (uint32_t c = 0; c < k->nports && left; c++, left--) {
+                    w.u16(0xC00C); put_rr_head(w, QT_SRV, r.ttl, 6 + k->wire_len + dom_wire_len(r));
+                    w.u16(0); w.u16(10); w.u16(ld16a(ports + 2 * c));
+                    w.copy(kw, k->wire_len); put_dom_labels(w, r, r.d_end); w.u8(0);
+                }
+            } else {                                                          // :411-414
+                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                if (r.ttl < rttl) rttl = r.ttl;
+                put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
+            }
+        }
+        if (srv) {
+            if (!opt_done) { w.copy(opt, 11); opt_done = true; }
+            left = r.keep_add;
+            for (uint32_t t = 0; t < r.n_walk && left; t++) {                 // :401-402
+                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+                if (k->flags & KID_ADDR_NULL) continue;
+                const uint8_t* kw = (const uint8_t*)(k + 1) + 2 * k->nports;
+                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                w.copy(kw, k->wire_len); put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
+            }
+        }
+    }
+    if (!opt_done) w.copy(opt, 11);
+}
+
+// ---- the kernel ------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
+    __shared__ __align__(16) uint8_t s_in[S_IN + 32];
+    __shared__ __align__(16) uint8_t s_out[S_OUT];
+    __shared__ uint32_t s_off[T + 1];
+    __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
+    __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_tile;
+    __shared__ unsigned long long s_prefix;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    if (tid == 0) s_tile = atomicAdd(P.counter, 1u);                          // ticket = look-back order
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= P.ntiles) return;
+    const uint32_t q0 = tile * T;
+    const uint32_t nq = min((uint32_t)T, P.n - q0);
+
+    // ---- stage this tile's packets ---------------------------------------------------------
+    for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
+    __syncthreads();
+    const uint32_t b0 = s_off[0], b1 = s_off[nq];
+    const uint32_t a0 = b0 & ~15u;
+    const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
+    if (staged) {
+        const uint4* src = (const uint4*)(P.pkts + a0);
+        uint4* dst = (uint4*)s_in;
+        const uint32_t nv = (b1 - a0 + 15) >> 4;
+        for (uint32_t i = tid; i < nv; i += T) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+
+    // ---- parse + lookup + size ----------------------------------------------------------------
+    Res r;
+    r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
+    const uint32_t qidx = P.qidx_base + q0 + tid;
+    if (tid < (int)nq) {
+        const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
+        if (o1 >= o0 && o1 - o0 <= 65535u) {
+            r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
+            resolve_query(P, r, o1 - o0, qidx);
+        }
+    }
+    const uint32_t my_len = r.rlen;
+    const uint32_t my_miss = (tid < (int)nq && r.status == ST_MISS) ? 1u : 0u;
+
+    // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
+    uint32_t v = my_len | (my_miss << 24);     // 128 x 1232 < 2^24
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+    for (int w = 0; w < T / 32; w++) { uint32_t x = s_wsum[w]; if (w < warp) wbase += x; tot += x; }
+    const uint32_t excl = wbase + inc - v;
+    const uint32_t my_o = excl & 0xFFFFFF, my_mrank = excl >> 24;
+    const uint32_t tile_bytes = tot & 0xFFFFFF, tile_miss = tot >> 24;
+    s_scan[tid] = my_o;
+    if (tid == 0) s_scan[T] = tile_bytes;
+
+    // ---- decoupled look-back: exclusive (bytes, misses) over all earlier tiles ---------------
+    if (warp == 0) {
+        volatile unsigned long long* D = P.desc;
+        const uint64_t agg = (uint64_t)tile_bytes | ((uint64_t)tile_miss << D_MISS_SHIFT);
+        uint64_t ex = 0;
+        if (tile == 0) { if (lane == 0) D[0] = D_FLAG_P | agg; }
+        else {
+            if (lane == 0) D[tile] = D_FLAG_A | agg;
+            int base = (int)tile - 1;
+            for (;;) {
+                const int idx = base - lane;
+                uint64_t d;
+                do { d = idx >= 0 ? D[idx] : D_FLAG_P; } while (__any_sync(0xffffffffu, (d >> 62) == 0));
+                const unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
+                uint64_t val = d & D_VAL;
+                if (pm) { const int first = __ffs(pm) - 1; ex += warp_sum64(lane <= first ? val : 0); break; }
+                ex += warp_sum64(val); base -= 32;
+            }
+            if (lane == 0) D[tile] = D_FLAG_P | (ex + agg);
+        }
+        if (lane == 0) s_prefix = ex;
+    }
+    __syncthreads();
+    const uint64_t ex = s_prefix;
+    const uint64_t gbase = ex & ((1ull << D_MISS_SHIFT) - 1);
+    const uint32_t mbase = (uint32_t)(ex >> D_MISS_SHIFT);
+    const bool overflow = gbase + tile_bytes > (uint64_t)P.out_cap;
+
+    // ---- per-query outputs ---------------------------------------------------------------------
+    if (tid < (int)nq) {
+        P.out_off[q0 + tid] = (uint32_t)(gbase + my_o);
+        P.status[q0 + tid] = r.status;
+        if (my_miss) P.miss_idx[mbase + my_mrank] = q0 + tid;
+        if (q0 + tid == P.n - 1) {
+            P.out_off[P.n] = (uint32_t)(gbase + tile_bytes);
+            P.totals[0] = (uint32_t)(gbase + tile_bytes); P.totals[1] = mbase + tile_miss;
+        }
+    }
+    if (overflow) { if (tid == 0) atomicExch(&P.totals[2], 1u); return; }
+
+    // ---- assemble in shared memory, flush with aligned 16-byte stores ---------------------------
+    const uint32_t nrounds = (tile_bytes + CAPW - 1) / CAPW;
+    for (uint32_t rd = 0; rd < nrounds; rd++) {
+        const uint32_t w0 = rd * CAPW;                                        // window start (tile offset)
+        const uint32_t shift = (uint32_t)((gbase + w0) & 15);                // same 16B phase in smem and global
+        const bool mine = my_len && my_o >= w0 && my_o < w0 + CAPW;
+        if (mine) emit_response(P, r, s_out + shift + (my_o - w0), qidx);
+        __syncthreads();
+        // bytes of this round: from the first response starting in the window to the end of the last
+        uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
+        if (rd > 0) {                                                         // skip the previous round's overhang
+            // first response start >= w0: binary search over the scan
+            int a = 0, b = T;
+            while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0) a = m + 1; else b = m; }
+            lo = a < T ? max(s_scan[a], w0) : tile_bytes;
+            lo = min(lo, tile_bytes);
+        }
+        if (hi < tile_bytes) {                                                // extend to the end of the last response that starts in the window
+            int a = 0, b = T;
+            while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0 + CAPW) a = m + 1; else b = m; }
+            hi = a < T ? s_scan[a] : tile_bytes;                              // start of the first response of the next round
+            // zero-length entries at the boundary share the same offset: fine, range is [lo, hi)
+        }
+        if (hi > lo) {
+            uint8_t* g = P.out + gbase;                                       // g[x] <-> s_out[shift + x - w0]
+            const uint8_t* s = s_out + shift - w0;
+            uint32_t x0 = lo, x1 = hi;
+            // head up to 16-byte alignment of the global address
+            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);
+            if (head > x1 - x0) head = x1 - x0;
+            if (tid < (int)head) g[x0 + tid] = s[x0 + tid];
+            x0 += head;
+            const uint32_t nv = (x1 - x0) >> 4;
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s + x0 + 16 * i);
+            x0 += nv << 4;
+            if (x0 + tid < x1) g[x0 + tid] = s[x0 + tid];
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace bbk
+
+// =================================================================================================
+// host side of the C ABI
+// =================================================================================================
+static thread_local std::string g_cuda_err;
+#define CK(call) do { cudaError_t _e = (call); if (_e != cudaSuccess) { g_cuda_err = std::string(#call) + ": " + cudaGetErrorString(_e); return BB_ERR_CUDA; } } while (0)
+
+namespace {
+constexpr int NSLOTS = 4;
+struct SlotCtx {
+    cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr;
+    uint8_t* d_pkts = nullptr; uint32_t* d_off = nullptr; uint8_t* d_out = nullptr; uint32_t* d_out_off = nullptr;
+    uint8_t* d_status = nullptr; uint32_t* d_miss = nullptr; uint32_t* d_totals = nullptr;
+    unsigned long long* d_desc = nullptr;        // [ntiles_max] + counter
+    uint32_t* h_totals = nullptr;                // pinned
+    // pending call
+    bool busy = false; uint32_t n = 0; uint8_t* out = nullptr; uint32_t out_cap = 0; uint32_t* miss_idx = nullptr; uint32_t* n_miss = nullptr;
+};
+}
+
+struct bb_engine {
+    bb::EngineConst hconst; bb::EngineConst* d_const = nullptr;
+    bb::Slot* d_table = nullptr; uint8_t* d_arena = nullptr; uint32_t mask = 0; int ready = 0;
+    int device = 0; uint32_t max_batch = 0, max_bytes = 0, out_dev_cap = 0, max_tiles = 0;
+    SlotCtx slots[NSLOTS];
+    unsigned long long* d_desc_dev = nullptr;    // scratch for bb_resolve_batch_device
+    uint64_t launches = 0;
+};
+
+static bool name_to_wire(const std::string& s, std::string& out) {
+    out.clear(); size_t st = 0;
+    if (s.empty()) return false;
+    for (size_t i = 0; i <= s.size(); i++) if (i == s.size() || s[i] == '.') {
+        size_t l = i - st; if (l < 1 || l > 63) return false;
+        out.push_back((char)l); out.append(s, st, l); st = i + 1;
+    }
+    return true;
+}
+
+extern "C" {
+
+const char* bb_strerror(int err) {
+    switch (err) {
+    case BB_OK: return "ok";
+    case BB_ERR_ARG: return "invalid argument";
+    case BB_ERR_SNAPSHOT: return "snapshot is not valid JSON-lines (or repeats a path)";
+    case BB_ERR_CUDA: return "CUDA error";
+    case BB_ERR_NOMEM: return "out of memory";
+    case BB_ERR_CAPACITY: return "output capacity too small for this batch";
+    case BB_ERR_NO_DEVICE: return "no CUDA device (binder_b200 has no CPU fallback)";
+    case BB_ERR_DOMAIN: return "dns_domain must be a lower-case, encodable DNS name";
+    }
+    return "unknown error";
+}
+const char* bb_last_cuda_error(void) { return g_cuda_err.c_str(); }
+int bb_abi_version(void) { return BB_ABI_VERSION; }
+
+void* bb_host_alloc(size_t bytes) { void* p = nullptr; return cudaMallocHost(&p, bytes ? bytes : 1) == cudaSuccess ? p : nullptr; }
+void bb_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+static int engine_alloc(bb_engine* e) {
+    CK(cudaSetDevice(e->device));
+    CK(cudaMalloc(&e->d_const, sizeof(bb::EngineConst)));
+    CK(cudaMemcpy(e->d_const, &e->hconst, sizeof(bb::EngineConst), cudaMemcpyHostToDevice));
+    e->max_tiles = (e->max_batch + bbk::T - 1) / bbk::T;
+    uint64_t cap = (uint64_t)e->max_batch * 512;                 // device-side response buffer per slot
+    if (cap < (1u << 20)) cap = 1u << 20;
+    if (cap > 0xFFFFFF00ull) cap = 0xFFFFFF00ull;
+    e->out_dev_cap = (uint32_t)cap;
+    for (auto& s : e->slots) {
+        CK(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&s.ev, cudaEventDisableTiming));
+        CK(cudaMalloc(&s.d_pkts, (size_t)e->max_bytes + 64));
+        CK(cudaMalloc(&s.d_off, ((size_t)e->max_batch + 1) * 4));
+        CK(cudaMalloc(&s.d_out, (size_t)e->out_dev_cap + 64));
+        CK(cudaMalloc(&s.d_out_off, ((size_t)e->max_batch + 1) * 4));
+        CK(cudaMalloc(&s.d_status, (size_t)e->max_batch + 16));
+        CK(cudaMalloc(&s.d_miss, (size_t)e->max_batch * 4 + 16));
+        CK(cudaMalloc(&s.d_totals, 16));
+        CK(cudaMalloc(&s.d_desc, ((size_t)e->max_tiles + 2) * 8));
+        CK(cudaMallocHost(&s.h_totals, 16));
+    }
+    CK(cudaMalloc(&e->d_desc_dev, ((size_t)e->max_tiles + 2) * 8));
+    return BB_OK;
+}
+
+bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
+    auto fail = [&](int c) -> bb_engine* { if (err) *err = c; return nullptr; };
+    if (err) *err = BB_OK;
+    if (!o || !o->dns_domain) return fail(BB_ERR_ARG);
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(BB_ERR_NO_DEVICE);
+    if (o->device < 0 || o->device >= ndev) return fail(BB_ERR_ARG);
+    std::string dom = o->dns_domain, w, hw;
+    for (char c : dom) if (c >= 'A' && c <= 'Z') return fail(BB_ERR_DOMAIN);
+    if (!name_to_wire(dom, w) || !name_to_wire("hostmaster." + dom, hw) || hw.size() + 1 > 255) return fail(BB_ERR_DOMAIN);
+    bb_engine* e = new bb_engine();
+    memset(&e->hconst, 0, sizeof e->hconst);
+    e->hconst.suffix_len = (uint32_t)dom.size() + 1;
+    e->hconst.suffix[0] = '.'; memcpy(e->hconst.suffix + 1, dom.data(), dom.size());
+    // SOARecord(dnsDomain): mname = dnsDomain, rname = hostmaster.<dnsDomain>, both uncompressed
+    memcpy(e->hconst.soa, w.data(), w.size()); e->hconst.soa[w.size()] = 0;
+    memcpy(e->hconst.soa + w.size() + 1, hw.data(), hw.size()); e->hconst.soa[w.size() + 1 + hw.size()] = 0;
+    e->hconst.soa_len = (uint32_t)(w.size() + 1 + hw.size() + 1);
+    e->hconst.recursion = o->recursion ? 1 : 0;
+    e->device = o->device;
+    e->max_batch = o->max_batch ? o->max_batch : (1u << 20);
+    if (e->max_batch > (1u << 22)) { delete e; return fail(BB_ERR_ARG); }
+    e->max_bytes = o->max_batch_bytes ? o->max_batch_bytes : e->max_batch * 64;
+    int rc = engine_alloc(e);
+    if (rc != BB_OK) { bb_engine_destroy(e); return fail(rc); }
+    return e;
+}
+
+void bb_engine_destroy(bb_engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaDeviceSynchronize();
+    for (auto& s : e->slots) {
+        cudaFree(s.d_pkts); cudaFree(s.d_off); cudaFree(s.d_out); cudaFree(s.d_out_off); cudaFree(s.d_status);
+        cudaFree(s.d_miss); cudaFree(s.d_totals); cudaFree(s.d_desc); if (s.h_totals) cudaFreeHost(s.h_totals);
+        if (s.ev) cudaEventDestroy(s.ev); if (s.stream) cudaStreamDestroy(s.stream);
+    }
+    cudaFree(e->d_desc_dev); cudaFree(e->d_const); cudaFree(e->d_table); cudaFree(e->d_arena);
+    delete e;
+}
+
+int bb_engine_swap_zone(bb_engine* e, const bb_zone* z) {
+    if (!e || !z) return BB_ERR_ARG;
+    const bb::ZoneImage* img = bb_zone_image(z);
+    CK(cudaSetDevice(e->device));
+    bb::Slot* nt = nullptr; uint8_t* na = nullptr;
+    CK(cudaMalloc(&nt, (size_t)img->nslots * sizeof(bb::Slot)));
+    CK(cudaMalloc(&na, (size_t)img->arena_len + 64));
+    CK(cudaMemcpy(nt, img->slots, (size_t)img->nslots * sizeof(bb::Slot), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(na, img->arena, (size_t)img->arena_len, cudaMemcpyHostToDevice));
+    CK(cudaDeviceSynchronize());                 // batches in flight finish on the old epoch
+    bb::Slot* ot = e->d_table; uint8_t* oa = e->d_arena;
+    e->d_table = nt; e->d_arena = na; e->mask = img->nslots - 1; e->ready = img->ready;
+    cudaFree(ot); cudaFree(oa);
+    return BB_OK;
+}
+int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }
+int bb_engine_slots(const bb_engine*) { return NSLOTS; }
+uint64_t bb_engine_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
+
+static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts, const uint32_t* d_off, uint32_t n,
+                  uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
+                  uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st) {
+    bbk::Params P;
+    P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
+    P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
+    P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table;
+    P.eng = e->d_const;
+    P.ntiles = (n + bbk::T - 1) / bbk::T;
+    P.desc = desc; P.counter = (uint32_t*)(desc + e->max_tiles);
+    CK(cudaMemsetAsync(desc, 0, ((size_t)P.ntiles) * 8, st));
+    CK(cudaMemsetAsync(desc + e->max_tiles, 0, 8, st));
+    CK(cudaMemsetAsync(d_totals, 0, 16, st));
+    if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); return BB_OK; }
+    bbk::resolve_kernel<<<P.ntiles, bbk::T, 0, st>>>(P);
+    CK(cudaGetLastError());
+    e->launches++;
+    return BB_OK;
+}
+
+int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
+                            uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
+                            uint8_t* d_status, uint32_t* d_miss_idx, uint32_t* d_totals, void* stream) {
+    if (!e || n > e->max_batch || ((uintptr_t)d_pkts & 15) || ((uintptr_t)d_out & 15)) return BB_ERR_ARG;
+    return launch(e, e->d_desc_dev, d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_status, d_miss_idx,
+                  d_totals, (cudaStream_t)stream);
+}
+
+int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
+                      uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                      uint32_t* miss_idx, uint32_t* n_miss) {
+    if (!e || slot < 0 || slot >= NSLOTS || !pkt_off || !out_off || !n_miss || (n && (!pkts || !status || !miss_idx))) return BB_ERR_ARG;
+    SlotCtx& s = e->slots[slot];
+    if (s.busy || n > e->max_batch) return BB_ERR_ARG;
+    const uint32_t total_in = pkt_off[n];
+    if (total_in > e->max_bytes) return BB_ERR_ARG;
+    CK(cudaSetDevice(e->device));
+    if (total_in) CK(cudaMemcpyAsync(s.d_pkts, pkts, total_in, cudaMemcpyHostToDevice, s.stream));
+    CK(cudaMemcpyAsync(s.d_off, pkt_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
+    uint32_t cap = out_cap < e->out_dev_cap ? out_cap : e->out_dev_cap;
+    int rc = launch(e, s.d_desc, s.d_pkts, s.d_off, n, seed, qidx_base, s.d_out, cap, s.d_out_off, s.d_status, s.d_miss, s.d_totals, s.stream);
+    if (rc != BB_OK) return rc;
+    CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 16, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaEventRecord(s.ev, s.stream));
+    CK(cudaMemcpyAsync(out_off, s.d_out_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
+    if (n) CK(cudaMemcpyAsync(status, s.d_status, n, cudaMemcpyDeviceToHost, s.stream));
+    s.busy = true; s.n = n; s.out = out; s.out_cap = out_cap; s.miss_idx = miss_idx; s.n_miss = n_miss;
+    return BB_OK;
+}
+
+int bb_resolve_wait(bb_engine* e, int slot) {
+    if (!e || slot < 0 || slot >= NSLOTS) return BB_ERR_ARG;
+    SlotCtx& s = e->slots[slot];
+    if (!s.busy) return BB_ERR_ARG;
+    s.busy = false;
+    CK(cudaSetDevice(e->device));
+    CK(cudaEventSynchronize(s.ev));
+    const uint32_t total = s.h_totals[0], nmiss = s.h_totals[1], ovf = s.h_totals[2];
+    if (ovf || total > s.out_cap) { cudaStreamSynchronize(s.stream); return BB_ERR_CAPACITY; }
+    if (total) CK(cudaMemcpyAsync(s.out, s.d_out, total, cudaMemcpyDeviceToHost, s.stream));
+    if (nmiss) CK(cudaMemcpyAsync(s.miss_idx, s.d_miss, (size_t)nmiss * 4, cudaMemcpyDeviceToHost, s.stream));
+    CK(cudaStreamSynchronize(s.stream));
+    *s.n_miss = nmiss;
+    return BB_OK;
+}
+
+int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
+                     uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                     uint32_t* miss_idx, uint32_t* n_miss) {
+    int rc = bb_resolve_submit(e, 0, pkts, pkt_off, n, seed, qidx_base, out, out_cap, out_off, status, miss_idx, n_miss);
+    if (rc != BB_OK) return rc;
+    return bb_resolve_wait(e, 0);
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// Zone image: the HBM-resident, flattened form of binder's ZKCache (lib/zk.js:20-119).
+//
+// One open-addressed table (linear probing, power-of-two, load factor <= 0.5) of 64-byte
+// slots holds BOTH of ZKCache's maps:
+//   forward  ca_treeNodes[lower-cased fqdn]  (lib/zk.js:62-64, keys written at :84,96)
+//   reverse  ca_revLookup[address string]    (lib/zk.js:65-67, keys written at :187-188)
+// distinguished by a namespace bit that also seeds the hash.  Everything lib/server.js
+// computes per query from the JSON record that does not depend on the query (record
+// validation :251-260, ttl selection :270-274, url.parse :297-298, the service child filter
+// :352-360 and per-child validation :366-393) is evaluated once at build time and stored as
+// a `kind` + payload, so the kernel never touches JSON.
+//
+// A slot is one 64-byte, 64-byte-aligned unit = two 32-byte DRAM sectors: a host A record
+// (the common case) resolves with exactly one random 64-byte read.
+#ifndef BB_ZONE_IMAGE_H
+#define BB_ZONE_IMAGE_H
+
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BB_HD __host__ __device__ __forceinline__
+#else
+#define BB_HD inline
+#endif
+
+namespace bb {
+
+enum : uint8_t {
+    K_EMPTY = 0,
+    // forward namespace
+    K_INVALID = 1,    // lib/server.js:251-260 fails (or a ttl mname would reject): SERVFAIL
+    K_ADDR = 2,       // host-like / database with a usable IPv4: one A record (:296-311)
+    K_ADDR_BAD = 3,   // typed + ttl fine, address unusable: A -> SERVFAIL, SRV -> NODATA (:276-292)
+    K_SERVICE = 4,    // val = arena offset of a SvcHdr (:313-417)
+    K_UNKNOWN = 5,    // record.type not in the switch (:419-424): A -> default rcode, SRV -> NODATA
+    // reverse namespace
+    K_PTR = 6,        // val = arena offset of {u8 wire_len, target name wire bytes} (:123-130)
+    K_PTR_BAD = 7,    // ttl / target unusable: SERVFAIL
+};
+
+constexpr uint32_t NS_FORWARD = 0;
+constexpr uint32_t NS_REVERSE = 1;
+constexpr uint32_t KEY_INLINE_MAX = 48;
+constexpr uint8_t  KLEN_OVERFLOW = 0xFF;      // key bytes live in the arena
+
+struct alignas(64) Slot {
+    uint32_t hash;       // full 32-bit key hash (compared before the key bytes)
+    uint8_t  klen;       // key length 1..48, or KLEN_OVERFLOW
+    uint8_t  kind;       // K_*
+    uint8_t  ns;         // NS_*
+    uint8_t  pad;
+    uint32_t ttl;        // record ttl (lib/server.js:270-274)
+    uint32_t val;        // IPv4 (network order bytes packed big-endian) or arena offset
+    uint8_t  key[48];    // inline key; overflow: key[0..3] = arena offset, key[4..7] = length
+};
+static_assert(sizeof(Slot) == 64, "slot must be one 64-byte unit");
+
+// ---- service record in the arena (4-byte aligned) --------------------------------------
+struct SvcHdr {
+    uint32_t ttl;            // after record.ttl / service.ttl / service.service.ttl (:270-274,331-332)
+    uint16_t nkids;          // children that pass the type filter (:352-360), in child order
+    uint8_t  srvce_len;      // 0xFF: s.srvce absent or not a string -> never equal (:334-335)
+    uint8_t  proto_len;      // same for s.proto
+    // followed by: srvce bytes, proto bytes, pad to 4, uint32_t kid_off[nkids] (arena offsets)
+};
+enum : uint8_t {
+    KID_BAD_A = 1,       // "bad zk info" when serving A        (:366-376 + contract)
+    KID_BAD_SRV = 2,     // "bad zk info" when serving SRV
+    KID_ADDR_NULL = 4,   // address === null -> skipped          (:378-381)
+    KID_HAS_RTTL = 8,    // child carries its own ttl            (:389-393)
+};
+struct KidRec {
+    uint32_t addr;           // IPv4 packed big-endian
+    uint32_t rttl;
+    uint8_t  flags;          // KID_*
+    uint8_t  wire_len;       // child name as wire labels, no terminator (knode.name, :396)
+    uint8_t  nports;         // SRV ports: krec[type].ports or [s.port]  (:383-385)
+    uint8_t  pad;
+    // followed by: uint16_t ports[nports], uint8_t wire[wire_len], pad to 4
+};
+
+// ---- key hash (murmur3-32 over little-endian words, zero-padded tail) ------------------
+BB_HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+BB_HD uint32_t fmix32(uint32_t h) {
+    h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h;
+}
+BB_HD uint32_t hash_init(uint32_t ns) { return ns ? 0x52455631u : 0x42494E44u; }
+BB_HD uint32_t hash_word(uint32_t h, uint32_t w) {
+    w *= 0xCC9E2D51u; w = rotl32(w, 15); w *= 0x1B873593u;
+    h ^= w; h = rotl32(h, 13); h = h * 5u + 0xE6546B64u;
+    return h;
+}
+BB_HD uint32_t hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ len); }
+
+inline uint32_t hash_key(uint32_t ns, const uint8_t* k, uint32_t len) {
+    uint32_t h = hash_init(ns);
+    uint32_t i = 0;
+    for (; i + 4 <= len; i += 4)
+        h = hash_word(h, (uint32_t)k[i] | (uint32_t)k[i + 1] << 8 | (uint32_t)k[i + 2] << 16 | (uint32_t)k[i + 3] << 24);
+    if (i < len) {
+        uint32_t w = 0;
+        for (uint32_t j = 0; i + j < len; j++) w |= (uint32_t)k[i + j] << (8 * j);
+        h = hash_word(h, w);
+    }
+    return hash_finish(h, len);
+}
+
+// ---- shuffle RNG: the seeded stand-in for Math.random() at lib/server.js:46 ------------
+BB_HD uint32_t shuffle_rand(uint64_t seed, uint32_t qidx, uint32_t i) {
+    uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);
+    uint32_t r = fmix32(fmix32(fmix32(lo) ^ hi ^ (qidx * 0x9E3779B1u)) + i * 0x85EBCA77u);
+    return (uint32_t)(((uint64_t)r * (i + 1)) >> 32);
+}
+
+// ---- per-engine constants (createServer options, lib/server.js:435-441) ----------------
+struct EngineConst {
+    uint32_t suffix_len;         // strlen('.' + dnsDomain); 0 when dnsDomain === '' (:157)
+    uint32_t soa_len;            // SOA rdata up to (not including) the trailing 5 x u32
+    uint32_t recursion;          // options.recursion present (:110,222)
+    uint32_t pad;
+    uint8_t  suffix[256];        // '.' + dnsDomain, as query.name() would spell it
+    uint8_t  soa[528];           // mname wire + rname wire of SOARecord(dnsDomain) (:286-287)
+};
+
+// host-side container of a built zone
+struct ZoneImage {
+    uint32_t  nslots;            // power of two
+    Slot*     slots;             // malloc'd, 64-byte aligned
+    uint8_t*  arena;
+    uint64_t  arena_len;
+    uint64_t  n_nodes, n_fwd, n_rev;
+    int       ready;             // root domain node exists (lib/zk.js:55-58)
+};
+
+}  // namespace bb
+#endif

@@ -1,0 +1,108 @@
+"""Python face of the C ABI: Zone (the ZKCache read side) and Engine (the query handler).
+
+Mirrors the objects binder wires together in main.js:154-217:
+    zkCache = new core.ZKCache({domain})          -> Zone(snapshot, domain)
+    server  = core.createServer({zkCache, dnsDomain, datacenterName, recursion})
+                                                  -> Engine(dns_domain, datacenter, recursion)
+Every call goes through libbinder_b200.so; nothing here computes a DNS answer.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+
+ANSWERED, MISS_RECURSE, DROPPED = 0, 1, 2
+
+
+class Zone(object):
+    """bb_zone: flattened image of the mirrored ZooKeeper subtree (lib/zk.js ZKCache)."""
+
+    def __init__(self, snapshot_jsonl, dns_domain):
+        if isinstance(snapshot_jsonl, str):
+            snapshot_jsonl = snapshot_jsonl.encode('utf-8')
+        err = ctypes.c_int(0)
+        self._h = lib().bb_zone_build(snapshot_jsonl, len(snapshot_jsonl), dns_domain.encode(), ctypes.byref(err))
+        if not self._h:
+            raise _lib.BinderError(err.value)
+
+    def stat(self):
+        L = lib()
+        keys = ('nodes', 'forward_keys', 'reverse_keys', 'slots', 'image_bytes', 'arena_bytes')
+        return {k: int(L.bb_zone_stat(self._h, i)) for i, k in enumerate(keys)}
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().bb_zone_free(self._h)
+            self._h = None
+
+    __del__ = close
+
+
+class Engine(object):
+    """bb_engine: the batched onQuery handler (lib/server.js:471-507) on one GPU."""
+
+    def __init__(self, dns_domain, datacenter='', recursion=False, snapshot=None, device=0,
+                 max_batch=1 << 16, max_batch_bytes=0):
+        self._keep = (dns_domain.encode(), datacenter.encode())
+        opts = _lib.EngineOpts(self._keep[0], self._keep[1], int(bool(recursion)), device, max_batch,
+                               max_batch_bytes)
+        err = ctypes.c_int(0)
+        self._h = lib().bb_engine_create(ctypes.byref(opts), ctypes.byref(err))
+        if not self._h:
+            raise _lib.BinderError(err.value)
+        self.dns_domain = dns_domain
+        self.max_batch = max_batch
+        if snapshot is not None:
+            self.load_snapshot(snapshot)
+
+    # -- zone ------------------------------------------------------------------------------
+    def load_snapshot(self, snapshot_jsonl):
+        z = Zone(snapshot_jsonl, self.dns_domain)
+        try:
+            self.swap_zone(z)
+            return z.stat()
+        finally:
+            z.close()
+
+    def swap_zone(self, zone):
+        check(lib().bb_engine_swap_zone(self._h, zone._h))
+
+    def is_ready(self):
+        return bool(lib().bb_engine_is_ready(self._h))
+
+    def launch_count(self):
+        return int(lib().bb_engine_launch_count(self._h))
+
+    # -- host-buffer path (bb_resolve_batch) -------------------------------------------------
+    def resolve_batch(self, data, off, seed=0, qidx_base=0, out_cap=None):
+        """data: uint8[...] packed packets, off: uint32[n+1] ->
+        (out uint8[total], out_off uint32[n+1], status uint8[n], miss uint32[m])"""
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n = len(off) - 1
+        if out_cap is None:
+            out_cap = max(4096, min(n * 1232, 0xFFFFFF00))
+        out = np.empty(out_cap, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        miss = np.zeros(max(n, 1), dtype=np.uint32)
+        n_miss = ctypes.c_uint32(0)
+        check(lib().bb_resolve_batch(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
+                                     out.ctypes.data, out_cap, out_off.ctypes.data, status.ctypes.data,
+                                     miss.ctypes.data, ctypes.byref(n_miss)))
+        return out[:out_off[n]].copy(), out_off, status[:n], miss[:n_miss.value].copy()
+
+    # -- device-buffer path (bb_resolve_batch_device); pointers are raw device addresses ------
+    def resolve_device(self, d_pkts, d_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_status, d_miss,
+                       d_totals, stream=0):
+        check(lib().bb_resolve_batch_device(self._h, d_pkts, d_off, n, seed, qidx_base, d_out, out_cap,
+                                            d_out_off, d_status, d_miss, d_totals, stream))
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().bb_engine_destroy(self._h)
+            self._h = None
+
+    __del__ = close

@@ -1,0 +1,152 @@
+/*
+ * binder_b200 — C ABI of the B200-native DNS resolve engine.
+ *
+ * This is the drop-in boundary for ONE path of TritonDataCenter/binder: raw DNS query
+ * packet -> parse -> zone-cache lookup -> answer wire bytes.  Each entry point names the
+ * reference interface it replaces (paths relative to the reference tree).  Plain pointers
+ * and sizes only; nothing here throws, allocates on behalf of the caller, or exposes torch
+ * / CUDA types (a stream is passed as an opaque pointer).
+ *
+ * A Node.js host binds these through an N-API addon (addon/binder_b200_napi.cc,
+ * INTEGRATION.md); the tests and bench bind them through ctypes.
+ */
+#ifndef BINDER_B200_H
+#define BINDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BB_ABI_VERSION 1
+
+/* ---- error codes (negative) ------------------------------------------------------- */
+enum {
+    BB_OK = 0,
+    BB_ERR_ARG = -1,        /* null / out-of-range argument                              */
+    BB_ERR_SNAPSHOT = -2,   /* snapshot is not valid JSON-lines                          */
+    BB_ERR_CUDA = -3,       /* CUDA runtime error (bb_last_cuda_error has the text)      */
+    BB_ERR_NOMEM = -4,      /* host or device allocation failed                          */
+    BB_ERR_CAPACITY = -5,   /* out_cap too small for this batch's responses              */
+    BB_ERR_NO_DEVICE = -6,  /* no CUDA device: there is NO CPU fallback                   */
+    BB_ERR_DOMAIN = -7      /* dns_domain is not an encodable DNS name                   */
+};
+const char* bb_strerror(int err);
+const char* bb_last_cuda_error(void);
+int bb_abi_version(void);
+
+/* ---- per-query status, written to status[i] ---------------------------------------- */
+enum {
+    BB_ANSWERED = 0,        /* out[out_off[i] .. out_off[i+1]) is the response packet:
+                               query.respond() was called (lib/server.js:75,...,427)      */
+    BB_MISS_RECURSE = 1,    /* cache miss, RD set, recursion enabled: no bytes; index is in
+                               miss_idx[] for options.recursion.resolve(query, cb)
+                               (lib/server.js:110-113, 222-225)                           */
+    BB_DROPPED = 2          /* not a decodable query (mname never emits 'query'): no bytes */
+};
+
+/* ---- zone: replaces the read side of lib/zk.js ZKCache ----------------------------- */
+/*
+ * An immutable, flattened image of the ZooKeeper subtree binder mirrors
+ * (lib/zk.js:20-48 ZKCache, :78-119 TreeNode, :139-194 onDataChanged ingest):
+ *   forward keys  = ca_treeNodes  (lower-cased fqdn  -> node)   lib/zk.js:62-64
+ *   reverse keys  = ca_revLookup  (address string    -> node)   lib/zk.js:65-67
+ * built from a snapshot: JSON lines {"path": "/com/foo/x", "data": <JSON.parse result>}
+ * (or "raw": "<znode bytes>"), parents before children, children in ZK child order.
+ * `dns_domain` is ZKCache's options.domain (main.js:158-162): the subtree root.
+ */
+typedef struct bb_zone bb_zone;
+bb_zone* bb_zone_build(const char* snapshot_jsonl, size_t len, const char* dns_domain, int* err);
+void     bb_zone_free(bb_zone* z);
+/* introspection: znodes mirrored (root included), forward keys, reverse keys, table bytes */
+uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 rev 3 slots 4 image bytes 5 arena bytes */
+
+/* ---- engine: replaces lib/server.js createServer()'s query handler ----------------- */
+/*
+ * Options mirror createServer(options) (lib/server.js:435-441, main.js:204-214):
+ *   dns_domain       options.dnsDomain        (suffix gate, SOA host)  lib/server.js:157-166,286
+ *   datacenter_name  options.datacenterName   (only read by dead code, lib/server.js:167-175)
+ *   recursion        options.recursion != null (miss hand-off)          lib/server.js:110,222
+ *   device           CUDA device ordinal
+ */
+typedef struct bb_engine bb_engine;
+typedef struct bb_engine_opts {
+    const char* dns_domain;
+    const char* datacenter_name;
+    int32_t     recursion;
+    int32_t     device;
+    uint32_t    max_batch;       /* largest n per call (0 -> 1<<20)                      */
+    uint32_t    max_batch_bytes; /* largest packed query bytes per call (0 -> 64*max_batch) */
+} bb_engine_opts;
+
+bb_engine* bb_engine_create(const bb_engine_opts* opts, int* err);
+void       bb_engine_destroy(bb_engine* e);
+
+/*
+ * Publish a zone (the "ZK session established / watcher fired" analogue,
+ * lib/zk.js:45-47,68-76).  Uploads the image to HBM and swaps it in; batches submitted
+ * afterwards see the new zone.  Until the first swap the engine is "not ready" and A / SRV /
+ * PTR queries that pass the early refusals are answered SERVFAIL (lib/server.js:86-92,186-192).
+ * The engine keeps its own device copy; the caller may free `z` afterwards.
+ */
+int bb_engine_swap_zone(bb_engine* e, const bb_zone* z);
+int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/zk.js:55-58 */
+
+/*
+ * Resolve one batch of raw DNS query packets held in HOST memory: the batched form of
+ * mname's 'query' event -> onQuery(query, cb) (lib/server.js:471-507) -> resolve /
+ * resolvePtr (lib/server.js:67-429) -> query.respond().
+ *
+ *   pkts, pkt_off[n+1]   packed packets; packet i = pkts[pkt_off[i] .. pkt_off[i+1])
+ *   shuffle_seed         seeds the service-answer shuffle (lib/server.js:40-53, Math.random
+ *                        replaced by a counter RNG keyed on (seed, qidx_base + i))
+ *   out, out_cap         response bytes, packed in query order
+ *   out_off[n+1]         response i = out[out_off[i] .. out_off[i+1])  (empty unless ANSWERED)
+ *   status[n]            BB_ANSWERED / BB_MISS_RECURSE / BB_DROPPED
+ *   miss_idx[n], n_miss  ascending indices of the BB_MISS_RECURSE queries
+ *
+ * Host<->device copies happen inside the call (pinned buffers from bb_host_alloc make
+ * them asynchronous DMA).  Returns BB_OK or a negative error; never partial results.
+ */
+int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
+                     uint64_t shuffle_seed, uint32_t qidx_base,
+                     uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                     uint32_t* miss_idx, uint32_t* n_miss);
+
+/*
+ * Pipelined form of bb_resolve_batch: up to bb_engine_slots() batches in flight, each on
+ * its own stream (H2D, kernel and D2H of different batches overlap).  submit() returns at
+ * once; wait() blocks until that slot's results are in the caller's buffers.
+ */
+int bb_engine_slots(const bb_engine* e);
+int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
+                      uint64_t shuffle_seed, uint32_t qidx_base,
+                      uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                      uint32_t* miss_idx, uint32_t* n_miss);
+int bb_resolve_wait(bb_engine* e, int slot);
+
+/*
+ * Device-resident form (inputs and outputs already in HBM; used for kernel-only timing and
+ * by the multi-GPU router).  All pointers are device pointers; d_pkts must be 16-byte
+ * aligned and readable up to the next multiple of 16 past pkt_off[n].  d_totals receives
+ * {total response bytes, n_miss, 0, 0}.  `stream` is a cudaStream_t (NULL = default
+ * stream).  Asynchronous: returns after the launch.
+ */
+int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
+                            uint64_t shuffle_seed, uint32_t qidx_base,
+                            uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint8_t* d_status,
+                            uint32_t* d_miss_idx, uint32_t* d_totals, void* stream);
+
+/* Number of kernel launches bb_* calls have issued so far on this engine. */
+uint64_t bb_engine_launch_count(const bb_engine* e);
+
+/* pinned host memory for the batch containers */
+void* bb_host_alloc(size_t bytes);
+void  bb_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BINDER_B200_H */
