@@ -30,6 +30,7 @@ SYMBOLS = {
                                            _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p,
                                            _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'bb_engine_launch_count': (_c.c_uint64, [_c.c_void_p]),
+    'bb_engine_launch_epoch': (_c.c_uint32, [_c.c_void_p]),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),
     'bb_host_free': (None, [_c.c_void_p]),
 }

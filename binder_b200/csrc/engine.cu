@@ -53,6 +53,7 @@ struct Params {
     const Slot* table; uint32_t mask; const uint8_t* arena; int ready;
     const EngineConst* eng;
     unsigned long long* desc; uint32_t* counter; uint32_t ntiles;
+    uint32_t epoch;          // launch number: marks totals[2] (overflow) / totals[3] (done) of THIS launch
 };
 
 // per-thread state carried from the sizing pass to the emit pass
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_tile, s_last;
     __shared__ unsigned long long s_prefix;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
@@ -581,13 +582,13 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         if (my_miss) P.miss_idx[mbase + my_mrank] = q0 + tid;
         if (q0 + tid == P.n - 1) {
             P.out_off[P.n] = (uint32_t)(gbase + tile_bytes);
-            P.totals[0] = (uint32_t)(gbase + tile_bytes); P.totals[1] = mbase + tile_miss;
+            P.totals[0] = (uint32_t)(gbase + tile_bytes); P.totals[1] = mbase + tile_miss; P.totals[3] = P.epoch;
         }
     }
-    if (overflow) { if (tid == 0) atomicExch(&P.totals[2], 1u); return; }
+    if (overflow && tid == 0) P.totals[2] = P.epoch;
 
     // ---- assemble in shared memory, flush with aligned 16-byte stores ---------------------------
-    const uint32_t nrounds = (tile_bytes + CAPW - 1) / CAPW;
+    const uint32_t nrounds = overflow ? 0 : (tile_bytes + CAPW - 1) / CAPW;
     for (uint32_t rd = 0; rd < nrounds; rd++) {
         const uint32_t w0 = rd * CAPW;                                        // window start (tile offset)
         const uint32_t shift = (uint32_t)((gbase + w0) & 15);                // same 16B phase in smem and global
@@ -625,6 +626,14 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         }
         __syncthreads();
     }
+
+    // ---- self-cleaning: the last tile to finish resets the look-back state for the next launch --
+    if (tid == 0) s_last = atomicAdd(P.counter + 1, 1u) == P.ntiles - 1;
+    __syncthreads();
+    if (s_last) {                                  // every tile has finished reading descriptors
+        for (uint32_t i = tid; i < P.ntiles; i += T) P.desc[i] = 0;
+        if (tid == 0) { P.counter[0] = 0; P.counter[1] = 0; }
+    }
 }
 
 }  // namespace bbk
@@ -644,7 +653,7 @@ struct SlotCtx {
     unsigned long long* d_desc = nullptr;        // [ntiles_max] + counter
     uint32_t* h_totals = nullptr;                // pinned
     // pending call
-    bool busy = false; uint32_t n = 0; uint8_t* out = nullptr; uint32_t out_cap = 0; uint32_t* miss_idx = nullptr; uint32_t* n_miss = nullptr;
+    bool busy = false; uint32_t n = 0, epoch = 0; uint8_t* out = nullptr; uint32_t out_cap = 0; uint32_t* miss_idx = nullptr; uint32_t* n_miss = nullptr;
 };
 }
 
@@ -654,7 +663,7 @@ struct bb_engine {
     int device = 0; uint32_t max_batch = 0, max_bytes = 0, out_dev_cap = 0, max_tiles = 0;
     SlotCtx slots[NSLOTS];
     unsigned long long* d_desc_dev = nullptr;    // scratch for bb_resolve_batch_device
-    uint64_t launches = 0;
+    uint64_t launches = 0, epoch = 0;
 };
 
 static bool name_to_wire(const std::string& s, std::string& out) {
@@ -708,9 +717,12 @@ static int engine_alloc(bb_engine* e) {
         CK(cudaMalloc(&s.d_miss, (size_t)e->max_batch * 4 + 16));
         CK(cudaMalloc(&s.d_totals, 16));
         CK(cudaMalloc(&s.d_desc, ((size_t)e->max_tiles + 2) * 8));
+        CK(cudaMemset(s.d_desc, 0, ((size_t)e->max_tiles + 2) * 8));
+        CK(cudaMemset(s.d_totals, 0, 16));
         CK(cudaMallocHost(&s.h_totals, 16));
     }
     CK(cudaMalloc(&e->d_desc_dev, ((size_t)e->max_tiles + 2) * 8));
+    CK(cudaMemset(e->d_desc_dev, 0, ((size_t)e->max_tiles + 2) * 8));
     return BB_OK;
 }
 
@@ -773,6 +785,7 @@ int bb_engine_swap_zone(bb_engine* e, const bb_zone* z) {
 int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }
 int bb_engine_slots(const bb_engine*) { return NSLOTS; }
 uint64_t bb_engine_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
+uint32_t bb_engine_launch_epoch(const bb_engine* e) { return e ? (uint32_t)e->epoch : 0; }
 
 static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts, const uint32_t* d_off, uint32_t n,
                   uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
@@ -784,10 +797,9 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.eng = e->d_const;
     P.ntiles = (n + bbk::T - 1) / bbk::T;
     P.desc = desc; P.counter = (uint32_t*)(desc + e->max_tiles);
-    CK(cudaMemsetAsync(desc, 0, ((size_t)P.ntiles) * 8, st));
-    CK(cudaMemsetAsync(desc + e->max_tiles, 0, 8, st));
-    CK(cudaMemsetAsync(d_totals, 0, 16, st));
-    if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); return BB_OK; }
+    P.epoch = (uint32_t)(++e->epoch);
+    if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
+    // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     bbk::resolve_kernel<<<P.ntiles, bbk::T, 0, st>>>(P);
     CK(cudaGetLastError());
     e->launches++;
@@ -820,7 +832,7 @@ int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_
     CK(cudaEventRecord(s.ev, s.stream));
     CK(cudaMemcpyAsync(out_off, s.d_out_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
     if (n) CK(cudaMemcpyAsync(status, s.d_status, n, cudaMemcpyDeviceToHost, s.stream));
-    s.busy = true; s.n = n; s.out = out; s.out_cap = out_cap; s.miss_idx = miss_idx; s.n_miss = n_miss;
+    s.busy = true; s.n = n; s.epoch = (uint32_t)e->epoch; s.out = out; s.out_cap = out_cap; s.miss_idx = miss_idx; s.n_miss = n_miss;
     return BB_OK;
 }
 
@@ -831,7 +843,8 @@ int bb_resolve_wait(bb_engine* e, int slot) {
     s.busy = false;
     CK(cudaSetDevice(e->device));
     CK(cudaEventSynchronize(s.ev));
-    const uint32_t total = s.h_totals[0], nmiss = s.h_totals[1], ovf = s.h_totals[2];
+    const uint32_t total = s.n ? s.h_totals[0] : 0, nmiss = s.n ? s.h_totals[1] : 0;
+    const bool ovf = s.n && s.h_totals[2] == s.epoch;
     if (ovf || total > s.out_cap) { cudaStreamSynchronize(s.stream); return BB_ERR_CAPACITY; }
     if (total) CK(cudaMemcpyAsync(s.out, s.d_out, total, cudaMemcpyDeviceToHost, s.stream));
     if (nmiss) CK(cudaMemcpyAsync(s.miss_idx, s.d_miss, (size_t)nmiss * 4, cudaMemcpyDeviceToHost, s.stream));

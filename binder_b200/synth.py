@@ -205,3 +205,31 @@ def batch_mixed(zone, n, seed, miss_frac=0.0):
         else:
             out.append(make_query(host_name(h), 28, int(q)))
     return out
+
+
+def batch_host_a_fast(zone, n, seed, miss_frac=0.0, rd=True):
+    """Vectorised batch_host_a: -> (uint8 data padded to 16, uint32 off[n+1]).  Every packet is
+    the 48-byte query for h%07d.g%04d.dc1.example.com, type A, class IN."""
+    rng = np.random.default_rng(seed)
+    idx = rng.integers(0, zone.n_hosts, size=n)
+    if miss_frac > 0:
+        miss = rng.random(n) < miss_frac
+        idx = np.where(miss, idx + zone.n_hosts + 7, idx)
+    ids = rng.integers(0, 65536, size=n)
+    tmpl = np.frombuffer(make_query(host_name(0), 1, 0, rd=rd), dtype=np.uint8)
+    assert tmpl.size == 48
+    pk = np.tile(tmpl, (n, 1))
+    pk[:, 0] = ids >> 8
+    pk[:, 1] = ids & 255
+    v = idx.copy()
+    for k in range(7):
+        pk[:, 20 - k] = 48 + v % 10
+        v //= 10
+    g = idx % N_GROUPS
+    for k in range(4):
+        pk[:, 26 - k] = 48 + g % 10
+        g //= 10
+    data = np.zeros((n * 48 + 15) // 16 * 16, dtype=np.uint8)
+    data[:n * 48] = pk.reshape(-1)
+    off = (np.arange(n + 1, dtype=np.uint64) * 48).astype(np.uint32)
+    return data, off

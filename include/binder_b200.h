@@ -130,8 +130,10 @@ int bb_resolve_wait(bb_engine* e, int slot);
 /*
  * Device-resident form (inputs and outputs already in HBM; used for kernel-only timing and
  * by the multi-GPU router).  All pointers are device pointers; d_pkts must be 16-byte
- * aligned and readable up to the next multiple of 16 past pkt_off[n].  d_totals receives
- * {total response bytes, n_miss, 0, 0}.  `stream` is a cudaStream_t (NULL = default
+ * aligned and readable up to the next multiple of 16 past pkt_off[n]; d_out must be 16-byte
+ * aligned.  d_totals[4] receives {total response bytes, n_miss, overflow marker, done
+ * marker}: the markers equal bb_engine_launch_epoch() of this call when set (out_cap too
+ * small / launch finished).  Calls on one engine must be issued in stream order.  `stream` is a cudaStream_t (NULL = default
  * stream).  Asynchronous: returns after the launch.
  */
 int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
@@ -141,6 +143,8 @@ int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t*
 
 /* Number of kernel launches bb_* calls have issued so far on this engine. */
 uint64_t bb_engine_launch_count(const bb_engine* e);
+/* Epoch (launch number, low 32 bits) of the most recent resolve call on this engine. */
+uint32_t bb_engine_launch_epoch(const bb_engine* e);
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);

@@ -81,6 +81,29 @@ class Oracle(object):
             raise RuntimeError('oracle resolve failed (%d)' % rc)
         return out[:out_off[n]].copy(), out_off, status[:n], miss[:n_miss.value].copy()
 
+    def timed_resolve(self, data, off, seed=0, nthreads=1, repeat=1):
+        """Seconds per call of orc_resolve_batch alone (buffers allocated and touched beforehand)."""
+        import time
+        data = np.ascontiguousarray(data, dtype=np.uint8)
+        off = np.ascontiguousarray(off, dtype=np.uint32)
+        n = len(off) - 1
+        out_cap = max(1, min(n * 600, 0xFFFFFFF0))
+        out = np.zeros(out_cap, dtype=np.uint8)
+        out_off = np.zeros(n + 1, dtype=np.uint32)
+        status = np.zeros(max(n, 1), dtype=np.uint8)
+        miss = np.zeros(max(n, 1), dtype=np.uint32)
+        n_miss = ctypes.c_uint32(0)
+        best = []
+        for _ in range(repeat):
+            t0 = time.perf_counter()
+            rc = lib().orc_resolve_batch(self._h, data.ctypes.data, off.ctypes.data, n, seed, 0,
+                                         out.ctypes.data, out_cap, out_off.ctypes.data, status.ctypes.data,
+                                         miss.ctypes.data, ctypes.byref(n_miss), nthreads)
+            best.append(time.perf_counter() - t0)
+            if rc != 0:
+                raise RuntimeError('oracle resolve failed (%d)' % rc)
+        return best
+
     def resolve_one(self, pkt, seed=0, qidx=0):
         data = np.frombuffer(pkt, dtype=np.uint8)
         off = np.array([0, len(pkt)], dtype=np.uint32)

@@ -96,7 +96,7 @@ def test_config2_full_size():
     # size-independent property at full size: every answer carries the address the generator
     # assigned to that host (10.x.y.z from the index in the name)
     out = g[0].reshape(65536, 64)
-    names = out[:, 13:20]
+    names = out[:, 14:21].astype(np.int64)      # \x08 'h' then 7 digits
     idx = np.zeros(65536, dtype=np.int64)
     for k in range(7):
         idx = idx * 10 + (names[:, k] - 48)
@@ -174,7 +174,7 @@ def test_device_resident_api():
     assert gpu.launch_count() == before + 1
     o = orc.resolve_batch(data, off, seed=5)
     tot = d_tot.cpu().numpy()
-    assert tot[0] == o[1][-1] and tot[2] == 0
+    assert tot[0] == o[1][-1] and tot[2] == 0 and tot[3] != 0
     assert np.array_equal(d_oo.cpu().numpy().view(np.uint32), o[1])
     assert np.array_equal(d_out.cpu().numpy()[:tot[0]], o[0])
     assert np.array_equal(d_st.cpu().numpy(), o[2])
