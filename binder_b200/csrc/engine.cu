@@ -59,6 +59,8 @@ struct Params {
 // per-thread state carried from the sizing pass to the emit pass
 struct Res {
     const uint8_t* p;        // packet bytes (shared memory, or global when the tile did not fit)
+    uint64_t lenmask;        // bit i set: QNAME byte i is a label-length byte (names <= 64 bytes)
+    uint32_t sp;             // shared-memory address of the packet (0 when not staged)
     uint32_t qn_len;         // QNAME wire length incl. terminator
     uint32_t ttl, val;
     uint64_t perm;           // shuffled child order, 4 bits each (nk <= 16)
@@ -94,14 +96,17 @@ __device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
     uint32_t qd = be16(p + 4), an = be16(p + 6), ns = be16(p + 8), ar = be16(p + 10);
     if (qd != 1 || an != 0 || ns != 0 || ar > 1) return false;
     uint32_t pos = 12;
+    uint64_t lm = 0;
     for (;;) {
         if (pos >= len) return false;
         uint32_t c = p[pos];
         if (c == 0) { ++pos; break; }
         if (c > 63 || pos + 1 + c > len) return false;
+        if (pos - 12 < 64) lm |= 1ull << (pos - 12);
         pos += 1 + c;
         if (pos - 12 + 1 > 255) return false;
     }
+    r.lenmask = lm;
     r.qn_len = pos - 12;
     if (pos + 4 > len) return false;
     r.qtype = (uint16_t)be16(p + pos);
@@ -266,6 +271,156 @@ __device__ __forceinline__ void size_single(Res& r, uint32_t fixed, uint32_t rr)
     else { r.rlen = (uint16_t)fixed; r.keep_ans = 0; r.tc = 1; }
 }
 
+// What resolve() does once zk.lookup() has answered (lib/server.js:219-424); shared by the
+// generic and the word-wise front ends.
+__device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed, bool srv, bool hit,
+                               uint32_t kind, uint32_t ttl, uint32_t val, uint32_t l0, uint32_t l1) {
+    const uint8_t* nm = r.p + 12;
+    const EngineConst* E = P.eng;
+    if (!hit) {                                                               // :219-247
+        if (E->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        r.rcode = RC_REFUSED; return;
+    }
+    r.ttl = ttl; r.val = val;
+    if (kind == K_INVALID) { r.rcode = RC_SERVFAIL; return; }                 // :251-260
+    if (srv && kind != K_SERVICE) {                                           // :276-292 NODATA + SOA
+        r.rcode = RC_NOERROR; r.rk = RK_SOA;
+        uint32_t rr = dom_owner_len(r) + 10 + E->soa_len + 20;
+        if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
+        else { r.keep_ans = 0; r.tc = 1; }
+        return;
+    }
+    if (kind == K_ADDR) { r.rcode = RC_NOERROR; r.rk = RK_A1; size_single(r, fixed, dom_owner_len(r) + 14); return; }
+    if (kind == K_ADDR_BAD) { r.rcode = RC_SERVFAIL; return; }                // contract
+    if (kind == K_UNKNOWN) { r.rcode = RC_NOTIMP; return; }                   // :419-424 + :346-350
+    // K_SERVICE (:313-417)
+    SvcView sv; sv.open(P.arena, val);
+    const SvcHdr* h = sv.hdr();
+    r.ttl = h->ttl;
+    if (srv) {
+        const uint8_t* sb = sv.base + sizeof(SvcHdr);
+        bool match = h->srvce_len == l0 && h->proto_len == l1;
+        for (uint32_t i = 0; match && i < l0; i++) if (sb[i] != nm[1 + i]) match = false;
+        for (uint32_t i = 0; match && i < l1; i++) if (sb[l0 + i] != nm[2 + l0 + i]) match = false;
+        if (!match) { r.rcode = RC_NXDOMAIN; return; }                        // :334-345
+    }
+    r.rcode = RC_NOERROR;                                                     // :351
+    r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
+    size_service(P, r, qidx, srv, fixed);
+}
+
+// ---- word-wise front end of resolve() -----------------------------------------------------
+// Same decisions as resolve_forward() below, four name bytes per step, for the common case:
+// packet staged in shared memory, QNAME <= 64 wire bytes, lookup key <= 48 bytes (inline slot
+// keys).  Anything else returns false and takes the generic path.
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+// unaligned 32-bit load from shared memory (the staging buffers carry read slack)
+__device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
+    const uint32_t b = a & ~3u;
+    return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) * 8);
+}
+// 0x80 in every byte of v that is zero
+__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); }
+// 0x80 in every byte of x7 (7-bit bytes) that is >= k
+__device__ __forceinline__ uint32_t ge7(uint32_t x7, uint32_t k) { return (x7 + (0x80u - k) * 0x01010101u) & 0x80808080u; }
+// 0x80 in every byte that is 'A'..'Z'
+__device__ __forceinline__ uint32_t upper_bytes(uint32_t x) {
+    const uint32_t x7 = x & 0x7F7F7F7Fu;
+    return ge7(x7, 0x41) & ~ge7(x7, 0x5B) & ~x;
+}
+
+__device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
+    const EngineConst* E = P.eng;
+    const uint32_t nm = r.sp + 12;
+    const bool srv = r.qtype == QT_SRV;
+    const uint32_t d_end = r.qn_len - 1;
+    uint32_t d_off = 0, l0 = 0, l1 = 0;
+    bool refuse = false;
+    if (srv) {                                                                // :141-154
+        l0 = lds8(nm);
+        if (l0 == 0) { r.rcode = RC_REFUSED; return true; }
+        const uint32_t p1 = 1 + l0; l1 = lds8(nm + p1);
+        if (l1 == 0) { r.rcode = RC_REFUSED; return true; }
+        for (uint32_t i = 1; i <= l0; i++) { const uint32_t c = lds8(nm + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
+        for (uint32_t i = 1; i <= l1; i++) { const uint32_t c = lds8(nm + p1 + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
+        d_off = p1 + 1 + l1;
+        if (lds8(nm + d_off) == 0) { r.rcode = RC_REFUSED; return true; }
+    }
+    if (d_end <= d_off + 1) { r.rcode = RC_REFUSED; return true; }            // root name (suffix_len > 0 always)
+    const uint32_t dl = d_end - d_off - 1;
+    if (dl > KEY_INLINE_MAX) return false;
+    const uint32_t sl = E->suffix_len;
+    const int j0 = (int)dl - (int)sl;
+    uint32_t kw[12];
+    uint32_t h = hash_init(NS_FORWARD);
+    uint32_t dotl = 0, nl = 0, inval = 0, sfx_bad = 0, last_up = 0xFFFFFFFFu;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+        kw[i] = 0;
+        if (4u * i < dl) {
+            const uint32_t x = ldsu32(nm + d_off + 1 + 4 * i);
+            const uint32_t nb = dl - 4 * i;
+            const uint32_t tm = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1);
+            const uint32_t tm80 = tm & 0x80808080u;
+            const uint32_t bits = (uint32_t)(r.lenmask >> (d_off + 1 + 4 * i)) & 0xFu;
+            const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // length-byte positions
+            dotl |= zero_bytes(x ^ 0x2E2E2E2Eu) & ~m8 & tm80;                         // '.' inside a label
+            nl |= (zero_bytes(x ^ 0x0A0A0A0Au) | zero_bytes(x ^ 0x0D0D0D0Du)) & ~m8 & tm80;
+            const uint32_t xd = ((x & ~m8) | (0x2E2E2E2Eu & m8)) & tm;                 // dotted view
+            if (j0 >= 0 && 4 * i + 4 > j0) {                                           // suffix gate, case-sensitive
+                const int sh = 4 * i - j0;
+                const uint32_t e = ldsu32((uint32_t)((int)s_sfx + 4 + sh));
+                const uint32_t cm = sh < 0 ? (0xFFFFFFFFu << (8 * (-sh))) : 0xFFFFFFFFu;
+                sfx_bad |= (xd ^ e) & cm & tm;
+            }
+            const uint32_t up = upper_bytes(xd) & tm80;
+            const uint32_t lo = xd | (up >> 2);                                        // toLowerCase (:207)
+            const uint32_t y7 = lo & 0x7F7F7F7Fu;
+            const uint32_t ok = ((ge7(y7, 0x61) & ~ge7(y7, 0x7B)) | (ge7(y7, 0x30) & ~ge7(y7, 0x3A)) |
+                                 (ge7(y7, 0x2D) & ~ge7(y7, 0x2F)) | zero_bytes(lo ^ 0x5F5F5F5Fu)) & ~lo;
+            inval |= ~ok & tm80;                                                       // /[^a-z0-9_.-]/ (:208)
+            if (up) last_up = 4 * i + ((31 - __clz(up)) >> 3);
+            kw[i] = lo;
+            h = hash_word(h, lo);
+        }
+    }
+    if (srv && nl) return false;                      // regex group 3 stops at a line terminator: generic path
+    if (dotl || refuse) { r.rcode = RC_REFUSED; return true; }                // in-label dot / SRV shape
+    if (j0 < 0 || sfx_bad) { r.rcode = RC_REFUSED; return true; }             // :157-166
+    if (!P.ready) { r.rcode = RC_SERVFAIL; return true; }                     // :186-192
+    if (inval) { r.rcode = RC_REFUSED; return true; }                         // :208-215
+    h = hash_finish(h, dl);
+    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
+    if (last_up == 0xFFFFFFFFu) r.ptr_tgt = (uint16_t)d_off;
+    else {
+        const uint32_t pu = d_off + 1 + last_up;                              // wire position of the last upper-case byte
+        const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
+        r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
+    }
+    // zk.lookup(domain): one 64-byte slot per probe, compared as words
+    uint32_t idx = h & P.mask, kind = 0, ttl = 0, val = 0;
+    bool hit = false;
+    const uint32_t want = dl | (NS_FORWARD << 16);
+    for (;;) {
+        const uint4* sq = (const uint4*)(P.table + idx);
+        const uint4 q0 = __ldg(sq), q1 = __ldg(sq + 1), q2 = __ldg(sq + 2), q3 = __ldg(sq + 3);
+        const uint32_t sk = (q0.y >> 8) & 0xFF;
+        if (sk == K_EMPTY) break;
+        if (q0.x == h && (q0.y & 0x00FF00FFu) == want) {
+            const uint32_t diff = (kw[0] ^ q1.x) | (kw[1] ^ q1.y) | (kw[2] ^ q1.z) | (kw[3] ^ q1.w) |
+                                  (kw[4] ^ q2.x) | (kw[5] ^ q2.y) | (kw[6] ^ q2.z) | (kw[7] ^ q2.w) |
+                                  (kw[8] ^ q3.x) | (kw[9] ^ q3.y) | (kw[10] ^ q3.z) | (kw[11] ^ q3.w);
+            if (diff == 0) { hit = true; kind = sk; ttl = q0.z; val = q0.w; break; }
+        }
+        idx = (idx + 1) & P.mask;
+    }
+    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
+    return true;
+}
+
 // ---- resolve (lib/server.js:136-429) -------------------------------------------------------
 __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed) {
     const uint8_t* nm = r.p + 12;
@@ -323,37 +478,9 @@ __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t
     r.lastlen = (uint16_t)lastlen;
 
     FwdKey kg; kg.nm = nm; kg.d_off = d_off; kg.d_end = d_end;
-    uint32_t kind, ttl, val;
-    if (!probe(P, NS_FORWARD, kg, kind, ttl, val)) {                          // :219-247
-        if (E->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
-        r.rcode = RC_REFUSED; return;
-    }
-    r.ttl = ttl; r.val = val;
-    if (kind == K_INVALID) { r.rcode = RC_SERVFAIL; return; }                 // :251-260
-    if (srv && kind != K_SERVICE) {                                           // :276-292 NODATA + SOA
-        r.rcode = RC_NOERROR; r.rk = RK_SOA;
-        uint32_t rr = dom_owner_len(r) + 10 + E->soa_len + 20;
-        if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
-        else { r.keep_ans = 0; r.tc = 1; }
-        return;
-    }
-    if (kind == K_ADDR) { r.rcode = RC_NOERROR; r.rk = RK_A1; size_single(r, fixed, dom_owner_len(r) + 14); return; }
-    if (kind == K_ADDR_BAD) { r.rcode = RC_SERVFAIL; return; }                // contract
-    if (kind == K_UNKNOWN) { r.rcode = RC_NOTIMP; return; }                   // :419-424 + :346-350
-    // K_SERVICE (:313-417)
-    SvcView sv; sv.open(P.arena, val);
-    const SvcHdr* h = sv.hdr();
-    r.ttl = h->ttl;
-    if (srv) {
-        const uint8_t* sb = sv.base + sizeof(SvcHdr);
-        bool match = h->srvce_len == l0 && h->proto_len == l1;
-        for (uint32_t i = 0; match && i < l0; i++) if (sb[i] != nm[1 + i]) match = false;
-        for (uint32_t i = 0; match && i < l1; i++) if (sb[l0 + i] != nm[2 + l0 + i]) match = false;
-        if (!match) { r.rcode = RC_NXDOMAIN; return; }                        // :334-345
-    }
-    r.rcode = RC_NOERROR;                                                     // :351
-    r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
-    size_service(P, r, qidx, srv, fixed);
+    uint32_t kind = 0, ttl = 0, val = 0;
+    const bool hit = probe(P, NS_FORWARD, kg, kind, ttl, val);
+    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
 }
 
 // ---- resolvePtr (lib/server.js:67-134) -----------------------------------------------------
@@ -380,7 +507,7 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 }
 
 // onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
-__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx) {
+__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
     r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
     r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
     if (!decode(r.p, len, r)) { r.status = ST_DROPPED; return; }
@@ -389,6 +516,7 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
     r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
     const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
     if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
+    if (r.sp && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, qidx, fixed)) return;
     const uint8_t* nm = r.p + 12;
     for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
         uint32_t l = nm[q];
@@ -482,6 +610,72 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
     if (!opt_done) w.copy(opt, 11);
 }
 
+// ---- word-wise response writer -------------------------------------------------------------
+// A byte stream into shared memory at an arbitrary byte address, stored as aligned 32-bit words;
+// only the bytes shared with the neighbouring responses (first / last partial word) go out as
+// single bytes, so two threads never write the same word.
+struct Wr {
+    uint32_t wp;         // shared address of the word being filled
+    uint64_t acc; uint32_t fill, head;
+    __device__ void begin(uint32_t dst) { head = dst & 3u; wp = dst - head; acc = 0; fill = head; }
+    __device__ __forceinline__ void flush() {
+        if (head) { for (uint32_t b = head; b < 4; b++) sts8(wp + b, (uint32_t)(acc >> (8 * b)) & 0xFF); head = 0; }
+        else sts32(wp, (uint32_t)acc);
+        wp += 4; acc >>= 32; fill -= 4;
+    }
+    // v holds n (1..4) bytes in memory order (little-endian integer)
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) { acc |= (uint64_t)v << (8 * fill); fill += n; if (fill >= 4) flush(); }
+    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(wp + b, (uint32_t)(acc >> (8 * b)) & 0xFF); }
+    // n bytes from shared memory
+    __device__ void copy(uint32_t src, uint32_t n) {
+        uint32_t i = 0;
+        for (; i + 4 <= n; i += 4) put(ldsu32(src + i), 4);
+        if (i < n) put(ldsu32(src + i) & ((1u << (8 * (n - i))) - 1), n - i);
+    }
+};
+__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
+
+// emit_response() for the two commonest shapes (rcode-only and one A record), word-wise.
+__device__ void emit_fast(const Res& r, uint32_t dst) {
+    Wr w; w.begin(dst);
+    const uint32_t p = r.sp;
+    const uint32_t an = r.rk == RK_A1 ? r.keep_ans : 0;
+    const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
+    w.put((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24), 4);   // id, QR AA TC RD, rcode
+    w.put(0x00000100u | (an << 24), 4);                                           // QDCOUNT=1, ANCOUNT
+    w.put(r.edns ? 0x01000000u : 0u, 4);                                          // NSCOUNT=0, ARCOUNT
+    w.copy(p + 12, r.qn_len + 4);                                                 // question, verbatim
+    if (an) {
+        if (r.ptr_tgt != NONE16) {
+            // literal labels before the pointer target, lower-cased (length bytes < 64 are unaffected)
+            const uint32_t n = (uint32_t)(r.ptr_tgt - r.d_off);
+            for (uint32_t i = 0; i < n; i += 4) {
+                uint32_t x = ldsu32(p + 12 + r.d_off + i);
+                x |= upper_bytes(x) >> 2;
+                const uint32_t nb = n - i;
+                w.put(nb >= 4 ? x : x & ((1u << (8 * nb)) - 1), nb >= 4 ? 4 : nb);
+            }
+            const uint32_t ptr = 0xC000u | (12u + r.ptr_tgt);
+            w.put((ptr >> 8) | ((ptr & 0xFF) << 8), 2);
+        } else {
+            const uint32_t n = (uint32_t)(r.d_end - r.d_off);
+            for (uint32_t i = 0; i < n; i += 4) {
+                uint32_t x = ldsu32(p + 12 + r.d_off + i);
+                x |= upper_bytes(x) >> 2;
+                const uint32_t nb = n - i;
+                w.put(nb >= 4 ? x : x & ((1u << (8 * nb)) - 1), nb >= 4 ? 4 : nb);
+            }
+            w.put(0, 1);
+        }
+        w.put(0x01000100u, 4);                      // TYPE A, CLASS IN
+        w.put(bswap32(r.ttl), 4);
+        w.put(0x0400u, 2);                          // RDLENGTH 4
+        w.put(bswap32(r.val), 4);
+    }
+    if (r.edns) { w.put(0x04290000u, 4); w.put(0x000000B0u, 4); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+    w.end();
+}
+
 // ---- the kernel ------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -496,9 +690,11 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_tile, s_last;
     __shared__ unsigned long long s_prefix;
+    __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];   // 4 pad bytes, '.' + dnsDomain, zero tail
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
     if (tid == 0) s_tile = atomicAdd(P.counter, 1u);                          // ticket = look-back order
+    if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
     __syncthreads();
     const uint32_t tile = s_tile;
     if (tile >= P.ntiles) return;
@@ -527,7 +723,8 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
         if (o1 >= o0 && o1 - o0 <= 65535u) {
             r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
-            resolve_query(P, r, o1 - o0, qidx);
+            r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
+            resolve_query(P, r, o1 - o0, qidx, (uint32_t)__cvta_generic_to_shared(s_sfx));
         }
     }
     const uint32_t my_len = r.rlen;
@@ -593,7 +790,11 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         const uint32_t w0 = rd * CAPW;                                        // window start (tile offset)
         const uint32_t shift = (uint32_t)((gbase + w0) & 15);                // same 16B phase in smem and global
         const bool mine = my_len && my_o >= w0 && my_o < w0 + CAPW;
-        if (mine) emit_response(P, r, s_out + shift + (my_o - w0), qidx);
+        if (mine) {
+            if (r.sp && (r.rk == RK_HEADER || r.rk == RK_A1))
+                emit_fast(r, (uint32_t)__cvta_generic_to_shared(s_out) + shift + (my_o - w0));
+            else emit_response(P, r, s_out + shift + (my_o - w0), qidx);
+        }
         __syncthreads();
         // bytes of this round: from the first response starting in the window to the end of the last
         uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
