@@ -152,6 +152,7 @@ def main():
     ap.add_argument('--batch', type=int, default=BATCH)
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e leg (profiling runs)')
+    ap.add_argument('--ordered', action='store_true', help='query-order packing (look-back) instead of arrival packing')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -170,7 +171,7 @@ def main():
         return bench_multi.main(args, rank, world, local_rank)
 
     import torch
-    from binder_b200.engine import Engine
+    from binder_b200.engine import Engine, repack
     from binder_b200 import build as bbuild
     bbuild.build()
     if not torch.cuda.is_available():
@@ -181,7 +182,7 @@ def main():
     t0 = time.time()
     zone = synth.gen_zone(args.zone_records)
     eng = Engine(zone.dns_domain, zone.datacenter, recursion=False, device=local_rank, max_batch=args.batch,
-                 max_batch_bytes=args.batch * 64)
+                 max_batch_bytes=args.batch * 64, ordered=args.ordered)
     zstat = eng.load_snapshot(zone.jsonl)
     log('[bench] zone: %d records, table %.0f MB, built+uploaded in %.1fs' % (zone.n_records, zstat['image_bytes'] / 1e6, time.time() - t0))
 
@@ -194,13 +195,14 @@ def main():
             pk=torch.from_numpy(data).to(dev), off=torch.from_numpy(off.view(np.int32)).to(dev),
             out=torch.empty(out_cap, dtype=torch.uint8, device=dev), oo=torch.empty(B + 1, dtype=torch.int32, device=dev),
             st=torch.empty(B, dtype=torch.uint8, device=dev), ms=torch.empty(B, dtype=torch.int32, device=dev),
+            ol=torch.empty(B, dtype=torch.int16, device=dev),
             tot=torch.zeros(4, dtype=torch.int32, device=dev)))
     stream = torch.cuda.current_stream()
 
     def step(k):
         b = d[k % RING]
         eng.resolve_device(b['pk'].data_ptr(), b['off'].data_ptr(), B, 0xB1DDE5, 0, b['out'].data_ptr(), out_cap,
-                           b['oo'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(),
+                           b['oo'].data_ptr(), b['ol'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(),
                            stream.cuda_stream)
 
     # ---- kernel path, device-resident -----------------------------------------------------------
@@ -229,7 +231,7 @@ def main():
             for k in range(args.steps):
                 b = d[(args.warmup + k) % RING]
                 eng.resolve_device(b['pk'].data_ptr(), b['off'].data_ptr(), B, 0xB1DDE5, 0, b['out'].data_ptr(), out_cap,
-                                   b['oo'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(), cs)
+                                   b['oo'].data_ptr(), b['ol'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(), cs)
         g.replay()
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -276,7 +278,7 @@ def main():
         hb = []
         for r in range(nslots * 2):
             data, off = ring[r % RING]
-            sizes = dict(pk=data.size, off=(B + 1) * 4, out=out_cap, oo=(B + 1) * 4, st=B, ms=B * 4)
+            sizes = dict(pk=data.size, off=(B + 1) * 4, out=out_cap, oo=(B + 1) * 4, ol=B * 2, st=B, ms=B * 4)
             ptr = {k: L.bb_host_alloc(v) for k, v in sizes.items()}
             ctypes.memmove(ptr['pk'], data.ctypes.data, data.size)
             ctypes.memmove(ptr['off'], off.ctypes.data, (B + 1) * 4)
@@ -284,7 +286,7 @@ def main():
 
         def submit(slot, h):
             check(L.bb_resolve_submit(eng._h, slot, h['ptr']['pk'], h['ptr']['off'], B, 0xB1DDE5, 0, h['ptr']['out'],
-                                      out_cap, h['ptr']['oo'], h['ptr']['st'], h['ptr']['ms'], ctypes.byref(h['nm'])))
+                                      out_cap, h['ptr']['oo'], h['ptr']['ol'], h['ptr']['st'], h['ptr']['ms'], ctypes.byref(h['nm'])))
         ksteps = max(args.steps, nslots * 4)
         for phase in ('warm', 'timed'):
             nst = max(args.warmup, nslots) if phase == 'warm' else ksteps
@@ -306,15 +308,18 @@ def main():
             e2e_launches = eng.launch_count() - l0
         h = hb[0]
         oo_h = np.ctypeslib.as_array(ctypes.cast(h['ptr']['oo'], ctypes.POINTER(ctypes.c_uint32)), shape=(B + 1,))
-        d2h = int(oo_h[B]) + (B + 1) * 4 + B + 16
+        d2h = int(oo_h[B]) + (B + 1) * 4 + B * 2 + B + 16
         e2e = {'value': B * ksteps / dt, 'unit': UNIT, 'h2d_bytes_per_step': h['in_bytes'], 'd2h_bytes_per_step': d2h,
                'steps': ksteps, 'in_flight': nslots, 'timing': 'wall clock bracketed by device synchronize',
                'api': 'bb_resolve_submit/bb_resolve_wait, pinned host buffers'}
         out_h = np.ctypeslib.as_array(ctypes.cast(h['ptr']['out'], ctypes.POINTER(ctypes.c_uint8)), shape=(int(oo_h[B]),))
+        ol_h = np.ctypeslib.as_array(ctypes.cast(h['ptr']['ol'], ctypes.POINTER(ctypes.c_uint16)), shape=(B,))
         # slot 0's host result must equal the device-resident result of the same batch
         step(0)
         torch.cuda.synchronize()
-        assert np.array_equal(out_h, d[0]['out'].cpu().numpy()[:int(oo_h[B])]), 'e2e result differs from kernel-path result'
+        dev_packed = repack(d[0]['out'].cpu().numpy(), d[0]['oo'].cpu().numpy().view(np.uint32),
+                            d[0]['ol'].cpu().numpy().view(np.uint16))[0]
+        assert np.array_equal(repack(out_h, oo_h, ol_h)[0], dev_packed), 'e2e result differs from kernel-path result'
 
     # ---- CPU baseline + bit-exact spot check of the timed workload --------------------------------
     cpu = None
@@ -323,9 +328,9 @@ def main():
         o = orc.resolve_batch(ring[0][0], ring[0][1], seed=0xB1DDE5)
         step(0)
         torch.cuda.synchronize()
-        got = d[0]['out'].cpu().numpy()[:len(o[0])]
-        assert np.array_equal(got, o[0]) and np.array_equal(d[0]['oo'].cpu().numpy().view(np.uint32), o[1]), \
-            'GPU answers differ from the CPU oracle'
+        got, goff = repack(d[0]['out'].cpu().numpy(), d[0]['oo'].cpu().numpy().view(np.uint32),
+                           d[0]['ol'].cpu().numpy().view(np.uint16))
+        assert np.array_equal(got, o[0]) and np.array_equal(goff, o[1]), 'GPU answers differ from the CPU oracle'
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
@@ -333,7 +338,7 @@ def main():
             'config': {'workload': WORKLOAD, 'zone_records': zone.n_records, 'batch': B, 'table_mb': zstat['image_bytes'] / 1e6,
                        'l2_policy': 'inputs larger than L2: ring of %d distinct batches (%.0f MB in+out) over a %.0f MB table'
                                     % (RING, RING * (ring[0][0].size + out_cap * 2 / 3 + 8 * B) / 1e6, zstat['image_bytes'] / 1e6),
-                       'parallelism': 'single GPU', 'graph_replay_ms_per_step': graph_ms / args.steps if graph_ms else None},
+                       'parallelism': 'single GPU', 'output_packing': 'query order (look-back)' if args.ordered else 'arrival (one atomic claim per 128-query tile)', 'graph_replay_ms_per_step': graph_ms / args.steps if graph_ms else None},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches + e2e_launches),
             'roofline': roofline, 'cpu_baseline': cpu}
     print(json.dumps(line), flush=True)

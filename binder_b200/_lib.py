@@ -20,17 +20,19 @@ SYMBOLS = {
     'bb_engine_swap_zone': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'bb_engine_is_ready': (_c.c_int, [_c.c_void_p]),
     'bb_resolve_batch': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_uint32,
-                                    _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+                                    _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                    _c.c_void_p]),
     'bb_engine_slots': (_c.c_int, [_c.c_void_p]),
     'bb_resolve_submit': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,
                                      _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
-                                     _c.c_void_p]),
+                                     _c.c_void_p, _c.c_void_p]),
     'bb_resolve_wait': (_c.c_int, [_c.c_void_p, _c.c_int]),
     'bb_resolve_batch_device': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,
                                            _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p,
-                                           _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+                                           _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'bb_engine_launch_count': (_c.c_uint64, [_c.c_void_p]),
     'bb_engine_launch_epoch': (_c.c_uint32, [_c.c_void_p]),
+    'bb_engine_set_stage_log': (None, [_c.c_void_p, _c.c_void_p]),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),
     'bb_host_free': (None, [_c.c_void_p]),
 }
@@ -38,7 +40,8 @@ SYMBOLS = {
 
 class EngineOpts(ctypes.Structure):
     _fields_ = [('dns_domain', _c.c_char_p), ('datacenter_name', _c.c_char_p), ('recursion', _c.c_int32),
-                ('device', _c.c_int32), ('max_batch', _c.c_uint32), ('max_batch_bytes', _c.c_uint32)]
+                ('device', _c.c_int32), ('max_batch', _c.c_uint32), ('max_batch_bytes', _c.c_uint32),
+                ('ordered_output', _c.c_int32)]
 
 
 _lib = None

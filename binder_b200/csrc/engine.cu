@@ -49,11 +49,12 @@ enum { RK_NONE = 0, RK_HEADER = 1, RK_A1 = 2, RK_PTR = 3, RK_SOA = 4, RK_SVC_A =
 struct Params {
     const uint8_t* pkts; const uint32_t* pkt_off; uint32_t n;
     uint64_t seed; uint32_t qidx_base;
-    uint8_t* out; uint32_t out_cap; uint32_t* out_off; uint8_t* status; uint32_t* miss_idx; uint32_t* totals;
+    uint8_t* out; uint32_t out_cap; uint32_t* out_off; uint16_t* out_len; uint8_t* status; uint32_t* miss_idx; uint32_t* totals;
     const Slot* table; uint32_t mask; const uint8_t* arena; int ready;
     const EngineConst* eng;
-    unsigned long long* desc; uint32_t* counter; uint32_t ntiles;
+    unsigned long long* desc; uint32_t* counter; uint32_t ntiles, ntiles_cap;   // desc[ntiles_cap] = arrival cursor
     uint32_t epoch;          // launch number: marks totals[2] (overflow) / totals[3] (done) of THIS launch
+    unsigned long long* stage_log;   // optional [ntiles][8] globaltimer stamps (bb_engine_set_stage_log)
 };
 
 // per-thread state carried from the sizing pass to the emit pass
@@ -682,28 +683,40 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     return v;
 }
 
-__global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
+#define STAMP(k) do { if (P.stage_log && tid == 0) P.stage_log[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
+
+#ifndef BB_MIN_BLOCKS
+#define BB_MIN_BLOCKS 4
+#endif
+// ORDERED: responses packed in query order (tile bases from a decoupled look-back; a tile waits
+// for its predecessors' sizes).  !ORDERED ("arrival" packing): a tile claims its output range
+// with one atomicAdd and never waits; response i is still out[out_off[i] .. +out_len[i]).
+template <bool ORDERED>
+__global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params P) {
     __shared__ __align__(16) uint8_t s_in[S_IN + 32];
     __shared__ __align__(16) uint8_t s_out[S_OUT];
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_tile, s_last;
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];   // 4 pad bytes, '.' + dnsDomain, zero tail
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    if (tid == 0) s_tile = atomicAdd(P.counter, 1u);                          // ticket = look-back order
+    // Tiles are taken in blockIdx order: like CUB's single-pass scan, the look-back below relies on
+    // thread blocks being dispatched in increasing blockIdx order (a block only ever waits for
+    // lower-numbered blocks, which are resident or finished).
     if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
-    __syncthreads();
-    const uint32_t tile = s_tile;
-    if (tile >= P.ntiles) return;
+    const uint32_t tile = blockIdx.x;
+    STAMP(0);
     const uint32_t q0 = tile * T;
     const uint32_t nq = min((uint32_t)T, P.n - q0);
 
     // ---- stage this tile's packets ---------------------------------------------------------
     for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
     __syncthreads();
+    STAMP(1);
     const uint32_t b0 = s_off[0], b1 = s_off[nq];
     const uint32_t a0 = b0 & ~15u;
     const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
@@ -715,6 +728,7 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     }
     __syncthreads();
 
+    STAMP(2);
     // ---- parse + lookup + size ----------------------------------------------------------------
     Res r;
     r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
@@ -730,6 +744,7 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     const uint32_t my_len = r.rlen;
     const uint32_t my_miss = (tid < (int)nq && r.status == ST_MISS) ? 1u : 0u;
 
+    STAMP(3);
     // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
     uint32_t v = my_len | (my_miss << 24);     // 128 x 1232 < 2^24
     uint32_t inc = v;
@@ -744,7 +759,12 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     s_scan[tid] = my_o;
     if (tid == 0) s_scan[T] = tile_bytes;
 
-    // ---- decoupled look-back: exclusive (bytes, misses) over all earlier tiles ---------------
+    STAMP(4);
+    // ---- where this tile's responses (and misses) go ------------------------------------------
+    if (!ORDERED) {
+        if (tid == 0)                                    // one claim per tile: bytes | misses << 40
+            s_prefix = atomicAdd(P.desc + P.ntiles_cap, (unsigned long long)tile_bytes | ((unsigned long long)tile_miss << D_MISS_SHIFT));
+    } else
     if (warp == 0) {
         volatile unsigned long long* D = P.desc;
         const uint64_t agg = (uint64_t)tile_bytes | ((uint64_t)tile_miss << D_MISS_SHIFT);
@@ -753,20 +773,36 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         else {
             if (lane == 0) D[tile] = D_FLAG_A | agg;
             int base = (int)tile - 1;
-            for (;;) {
-                const int idx = base - lane;
-                uint64_t d;
-                do { d = idx >= 0 ? D[idx] : D_FLAG_P; } while (__any_sync(0xffffffffu, (d >> 62) == 0));
-                const unsigned pm = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                uint64_t val = d & D_VAL;
-                if (pm) { const int first = __ffs(pm) - 1; ex += warp_sum64(lane <= first ? val : 0); break; }
-                ex += warp_sum64(val); base -= 32;
+            for (;;) {                                   // window of 128 predecessors, 4 independent loads per lane
+                uint64_t d[4];
+                bool ready;
+                do {
+                    ready = true;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int idx = base - lane - 32 * k;
+                        d[k] = idx >= 0 ? D[idx] : D_FLAG_P;
+                        ready &= (d[k] >> 62) != 0;
+                    }
+                } while (__any_sync(0xffffffffu, !ready));
+                uint32_t mypos = 0xFFFFFFFFu;            // distance of the nearest predecessor with an inclusive prefix
+#pragma unroll
+                for (int k = 3; k >= 0; k--) if ((d[k] >> 62) == 2) mypos = (uint32_t)(lane + 32 * k);
+                uint32_t minpos = mypos;
+                for (int o = 16; o; o >>= 1) minpos = min(minpos, __shfl_xor_sync(0xffffffffu, minpos, o));
+                uint64_t part = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++) if ((uint32_t)(lane + 32 * k) <= minpos) part += d[k] & D_VAL;
+                ex += warp_sum64(part);
+                if (minpos != 0xFFFFFFFFu) break;
+                base -= 128;
             }
             if (lane == 0) D[tile] = D_FLAG_P | (ex + agg);
         }
         if (lane == 0) s_prefix = ex;
     }
     __syncthreads();
+    STAMP(5);
     const uint64_t ex = s_prefix;
     const uint64_t gbase = ex & ((1ull << D_MISS_SHIFT) - 1);
     const uint32_t mbase = (uint32_t)(ex >> D_MISS_SHIFT);
@@ -775,9 +811,10 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
     // ---- per-query outputs ---------------------------------------------------------------------
     if (tid < (int)nq) {
         P.out_off[q0 + tid] = (uint32_t)(gbase + my_o);
+        P.out_len[q0 + tid] = (uint16_t)my_len;
         P.status[q0 + tid] = r.status;
         if (my_miss) P.miss_idx[mbase + my_mrank] = q0 + tid;
-        if (q0 + tid == P.n - 1) {
+        if (ORDERED && q0 + tid == P.n - 1) {
             P.out_off[P.n] = (uint32_t)(gbase + tile_bytes);
             P.totals[0] = (uint32_t)(gbase + tile_bytes); P.totals[1] = mbase + tile_miss; P.totals[3] = P.epoch;
         }
@@ -796,6 +833,7 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
             else emit_response(P, r, s_out + shift + (my_o - w0), qidx);
         }
         __syncthreads();
+        if (rd == 0) STAMP(6);
         // bytes of this round: from the first response starting in the window to the end of the last
         uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
         if (rd > 0) {                                                         // skip the previous round's overhang
@@ -828,12 +866,22 @@ __global__ void __launch_bounds__(T) resolve_kernel(const Params P) {
         __syncthreads();
     }
 
+    STAMP(7);
     // ---- self-cleaning: the last tile to finish resets the look-back state for the next launch --
-    if (tid == 0) s_last = atomicAdd(P.counter + 1, 1u) == P.ntiles - 1;
-    __syncthreads();
-    if (s_last) {                                  // every tile has finished reading descriptors
-        for (uint32_t i = tid; i < P.ntiles; i += T) P.desc[i] = 0;
-        if (tid == 0) { P.counter[0] = 0; P.counter[1] = 0; }
+    if (warp == 0) {
+        uint32_t last = 0;
+        if (lane == 0) last = atomicAdd(P.counter + 1, 1u) == P.ntiles - 1;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last) {                                // every tile has finished reading descriptors / claiming
+            if (ORDERED) { for (uint32_t i = lane; i < P.ntiles; i += 32) P.desc[i] = 0; }
+            else if (lane == 0) {
+                const unsigned long long cur = P.desc[P.ntiles_cap];
+                const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
+                P.out_off[P.n] = tb; P.totals[0] = tb; P.totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); P.totals[3] = P.epoch;
+                P.desc[P.ntiles_cap] = 0;
+            }
+            if (lane == 0) P.counter[1] = 0;
+        }
     }
 }
 
@@ -850,7 +898,7 @@ constexpr int NSLOTS = 4;
 struct SlotCtx {
     cudaStream_t stream = nullptr; cudaEvent_t ev = nullptr;
     uint8_t* d_pkts = nullptr; uint32_t* d_off = nullptr; uint8_t* d_out = nullptr; uint32_t* d_out_off = nullptr;
-    uint8_t* d_status = nullptr; uint32_t* d_miss = nullptr; uint32_t* d_totals = nullptr;
+    uint8_t* d_status = nullptr; uint32_t* d_miss = nullptr; uint32_t* d_totals = nullptr; uint16_t* d_out_len = nullptr;
     unsigned long long* d_desc = nullptr;        // [ntiles_max] + counter
     uint32_t* h_totals = nullptr;                // pinned
     // pending call
@@ -861,10 +909,11 @@ struct SlotCtx {
 struct bb_engine {
     bb::EngineConst hconst; bb::EngineConst* d_const = nullptr;
     bb::Slot* d_table = nullptr; uint8_t* d_arena = nullptr; uint32_t mask = 0; int ready = 0;
-    int device = 0; uint32_t max_batch = 0, max_bytes = 0, out_dev_cap = 0, max_tiles = 0;
+    int device = 0, ordered = 0; uint32_t max_batch = 0, max_bytes = 0, out_dev_cap = 0, max_tiles = 0;
     SlotCtx slots[NSLOTS];
     unsigned long long* d_desc_dev = nullptr;    // scratch for bb_resolve_batch_device
     uint64_t launches = 0, epoch = 0;
+    unsigned long long* stage_log = nullptr;
 };
 
 static bool name_to_wire(const std::string& s, std::string& out) {
@@ -915,15 +964,16 @@ static int engine_alloc(bb_engine* e) {
         CK(cudaMalloc(&s.d_out, (size_t)e->out_dev_cap + 64));
         CK(cudaMalloc(&s.d_out_off, ((size_t)e->max_batch + 1) * 4));
         CK(cudaMalloc(&s.d_status, (size_t)e->max_batch + 16));
+        CK(cudaMalloc(&s.d_out_len, (size_t)e->max_batch * 2 + 16));
         CK(cudaMalloc(&s.d_miss, (size_t)e->max_batch * 4 + 16));
         CK(cudaMalloc(&s.d_totals, 16));
-        CK(cudaMalloc(&s.d_desc, ((size_t)e->max_tiles + 2) * 8));
-        CK(cudaMemset(s.d_desc, 0, ((size_t)e->max_tiles + 2) * 8));
+        CK(cudaMalloc(&s.d_desc, ((size_t)e->max_tiles + 4) * 8));
+        CK(cudaMemset(s.d_desc, 0, ((size_t)e->max_tiles + 4) * 8));
         CK(cudaMemset(s.d_totals, 0, 16));
         CK(cudaMallocHost(&s.h_totals, 16));
     }
-    CK(cudaMalloc(&e->d_desc_dev, ((size_t)e->max_tiles + 2) * 8));
-    CK(cudaMemset(e->d_desc_dev, 0, ((size_t)e->max_tiles + 2) * 8));
+    CK(cudaMalloc(&e->d_desc_dev, ((size_t)e->max_tiles + 4) * 8));
+    CK(cudaMemset(e->d_desc_dev, 0, ((size_t)e->max_tiles + 4) * 8));
     return BB_OK;
 }
 
@@ -946,7 +996,7 @@ bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
     memcpy(e->hconst.soa + w.size() + 1, hw.data(), hw.size()); e->hconst.soa[w.size() + 1 + hw.size()] = 0;
     e->hconst.soa_len = (uint32_t)(w.size() + 1 + hw.size() + 1);
     e->hconst.recursion = o->recursion ? 1 : 0;
-    e->device = o->device;
+    e->device = o->device; e->ordered = o->ordered_output ? 1 : 0;
     e->max_batch = o->max_batch ? o->max_batch : (1u << 20);
     if (e->max_batch > (1u << 22)) { delete e; return fail(BB_ERR_ARG); }
     e->max_bytes = o->max_batch_bytes ? o->max_batch_bytes : e->max_batch * 64;
@@ -960,7 +1010,7 @@ void bb_engine_destroy(bb_engine* e) {
     cudaSetDevice(e->device);
     cudaDeviceSynchronize();
     for (auto& s : e->slots) {
-        cudaFree(s.d_pkts); cudaFree(s.d_off); cudaFree(s.d_out); cudaFree(s.d_out_off); cudaFree(s.d_status);
+        cudaFree(s.d_pkts); cudaFree(s.d_off); cudaFree(s.d_out); cudaFree(s.d_out_off); cudaFree(s.d_status); cudaFree(s.d_out_len);
         cudaFree(s.d_miss); cudaFree(s.d_totals); cudaFree(s.d_desc); if (s.h_totals) cudaFreeHost(s.h_totals);
         if (s.ev) cudaEventDestroy(s.ev); if (s.stream) cudaStreamDestroy(s.stream);
     }
@@ -987,21 +1037,24 @@ int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }
 int bb_engine_slots(const bb_engine*) { return NSLOTS; }
 uint64_t bb_engine_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
 uint32_t bb_engine_launch_epoch(const bb_engine* e) { return e ? (uint32_t)e->epoch : 0; }
+void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log) { if (e) e->stage_log = d_log; }
 
 static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts, const uint32_t* d_off, uint32_t n,
-                  uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
+                  uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint16_t* d_out_len,
                   uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st) {
     bbk::Params P;
     P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
-    P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
+    P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table;
     P.eng = e->d_const;
     P.ntiles = (n + bbk::T - 1) / bbk::T;
-    P.desc = desc; P.counter = (uint32_t*)(desc + e->max_tiles);
+    P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
+    P.stage_log = e->stage_log;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
-    bbk::resolve_kernel<<<P.ntiles, bbk::T, 0, st>>>(P);
+    if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, st>>>(P);
+    else bbk::resolve_kernel<false><<<P.ntiles, bbk::T, 0, st>>>(P);
     CK(cudaGetLastError());
     e->launches++;
     return BB_OK;
@@ -1009,16 +1062,16 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
 
 int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
                             uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
-                            uint8_t* d_status, uint32_t* d_miss_idx, uint32_t* d_totals, void* stream) {
+                            uint16_t* d_out_len, uint8_t* d_status, uint32_t* d_miss_idx, uint32_t* d_totals, void* stream) {
     if (!e || n > e->max_batch || ((uintptr_t)d_pkts & 15) || ((uintptr_t)d_out & 15)) return BB_ERR_ARG;
-    return launch(e, e->d_desc_dev, d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_status, d_miss_idx,
+    return launch(e, e->d_desc_dev, d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_out_len, d_status, d_miss_idx,
                   d_totals, (cudaStream_t)stream);
 }
 
 int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
-                      uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                      uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
                       uint32_t* miss_idx, uint32_t* n_miss) {
-    if (!e || slot < 0 || slot >= NSLOTS || !pkt_off || !out_off || !n_miss || (n && (!pkts || !status || !miss_idx))) return BB_ERR_ARG;
+    if (!e || slot < 0 || slot >= NSLOTS || !pkt_off || !out_off || !n_miss || (n && (!pkts || !status || !miss_idx || !out_len))) return BB_ERR_ARG;
     SlotCtx& s = e->slots[slot];
     if (s.busy || n > e->max_batch) return BB_ERR_ARG;
     const uint32_t total_in = pkt_off[n];
@@ -1027,12 +1080,13 @@ int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_
     if (total_in) CK(cudaMemcpyAsync(s.d_pkts, pkts, total_in, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_off, pkt_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
     uint32_t cap = out_cap < e->out_dev_cap ? out_cap : e->out_dev_cap;
-    int rc = launch(e, s.d_desc, s.d_pkts, s.d_off, n, seed, qidx_base, s.d_out, cap, s.d_out_off, s.d_status, s.d_miss, s.d_totals, s.stream);
+    int rc = launch(e, s.d_desc, s.d_pkts, s.d_off, n, seed, qidx_base, s.d_out, cap, s.d_out_off, s.d_out_len, s.d_status, s.d_miss, s.d_totals, s.stream);
     if (rc != BB_OK) return rc;
     CK(cudaMemcpyAsync(s.h_totals, s.d_totals, 16, cudaMemcpyDeviceToHost, s.stream));
     CK(cudaEventRecord(s.ev, s.stream));
     CK(cudaMemcpyAsync(out_off, s.d_out_off, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, s.stream));
     if (n) CK(cudaMemcpyAsync(status, s.d_status, n, cudaMemcpyDeviceToHost, s.stream));
+    if (n) CK(cudaMemcpyAsync(out_len, s.d_out_len, (size_t)n * 2, cudaMemcpyDeviceToHost, s.stream));
     s.busy = true; s.n = n; s.epoch = (uint32_t)e->epoch; s.out = out; s.out_cap = out_cap; s.miss_idx = miss_idx; s.n_miss = n_miss;
     return BB_OK;
 }
@@ -1055,9 +1109,9 @@ int bb_resolve_wait(bb_engine* e, int slot) {
 }
 
 int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
-                     uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                     uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
                      uint32_t* miss_idx, uint32_t* n_miss) {
-    int rc = bb_resolve_submit(e, 0, pkts, pkt_off, n, seed, qidx_base, out, out_cap, out_off, status, miss_idx, n_miss);
+    int rc = bb_resolve_submit(e, 0, pkts, pkt_off, n, seed, qidx_base, out, out_cap, out_off, out_len, status, miss_idx, n_miss);
     if (rc != BB_OK) return rc;
     return bb_resolve_wait(e, 0);
 }

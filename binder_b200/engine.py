@@ -16,6 +16,19 @@ from ._lib import check, lib
 ANSWERED, MISS_RECURSE, DROPPED = 0, 1, 2
 
 
+def repack(out, out_off, out_len):
+    """Responses re-packed in query order (what ordered_output=1 produces directly)."""
+    n = len(out_len)
+    lens = out_len.astype(np.int64)
+    total = int(lens.sum())
+    if total == 0:
+        return np.zeros(0, dtype=np.uint8), np.zeros(n + 1, dtype=np.uint32)
+    starts = np.zeros(n + 1, dtype=np.int64)
+    np.cumsum(lens, out=starts[1:])
+    idx = np.repeat(out_off[:n].astype(np.int64) - starts[:n], lens) + np.arange(total)
+    return out[idx], starts.astype(np.uint32)
+
+
 class Zone(object):
     """bb_zone: flattened image of the mirrored ZooKeeper subtree (lib/zk.js ZKCache)."""
 
@@ -37,17 +50,22 @@ class Zone(object):
             lib().bb_zone_free(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Engine(object):
     """bb_engine: the batched onQuery handler (lib/server.js:471-507) on one GPU."""
 
     def __init__(self, dns_domain, datacenter='', recursion=False, snapshot=None, device=0,
-                 max_batch=1 << 16, max_batch_bytes=0):
+                 max_batch=1 << 16, max_batch_bytes=0, ordered=False):
         self._keep = (dns_domain.encode(), datacenter.encode())
         opts = _lib.EngineOpts(self._keep[0], self._keep[1], int(bool(recursion)), device, max_batch,
-                               max_batch_bytes)
+                               max_batch_bytes, int(bool(ordered)))
+        self.ordered = bool(ordered)
         err = ctypes.c_int(0)
         self._h = lib().bb_engine_create(ctypes.byref(opts), ctypes.byref(err))
         if not self._h:
@@ -78,7 +96,8 @@ class Engine(object):
     # -- host-buffer path (bb_resolve_batch) -------------------------------------------------
     def resolve_batch(self, data, off, seed=0, qidx_base=0, out_cap=None):
         """data: uint8[...] packed packets, off: uint32[n+1] ->
-        (out uint8[total], out_off uint32[n+1], status uint8[n], miss uint32[m])"""
+        (out uint8[total], out_off uint32[n+1], out_len uint16[n], status uint8[n], miss uint32[m]);
+        response i = out[out_off[i] : out_off[i] + out_len[i]]"""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n = len(off) - 1
@@ -86,23 +105,28 @@ class Engine(object):
             out_cap = max(4096, min(n * 1232, 0xFFFFFF00))
         out = np.empty(out_cap, dtype=np.uint8)
         out_off = np.zeros(n + 1, dtype=np.uint32)
+        out_len = np.zeros(max(n, 1), dtype=np.uint16)
         status = np.zeros(max(n, 1), dtype=np.uint8)
         miss = np.zeros(max(n, 1), dtype=np.uint32)
         n_miss = ctypes.c_uint32(0)
         check(lib().bb_resolve_batch(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
-                                     out.ctypes.data, out_cap, out_off.ctypes.data, status.ctypes.data,
-                                     miss.ctypes.data, ctypes.byref(n_miss)))
-        return out[:out_off[n]].copy(), out_off, status[:n], miss[:n_miss.value].copy()
+                                     out.ctypes.data, out_cap, out_off.ctypes.data, out_len.ctypes.data,
+                                     status.ctypes.data, miss.ctypes.data, ctypes.byref(n_miss)))
+        return out[:out_off[n]].copy(), out_off, out_len[:n], status[:n], miss[:n_miss.value].copy()
 
     # -- device-buffer path (bb_resolve_batch_device); pointers are raw device addresses ------
-    def resolve_device(self, d_pkts, d_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_status, d_miss,
-                       d_totals, stream=0):
+    def resolve_device(self, d_pkts, d_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_out_len, d_status,
+                       d_miss, d_totals, stream=0):
         check(lib().bb_resolve_batch_device(self._h, d_pkts, d_off, n, seed, qidx_base, d_out, out_cap,
-                                            d_out_off, d_status, d_miss, d_totals, stream))
+                                            d_out_off, d_out_len, d_status, d_miss, d_totals, stream))
 
     def close(self):
         if getattr(self, '_h', None):
             lib().bb_engine_destroy(self._h)
             self._h = None
 
-    __del__ = close
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:      # interpreter shutdown
+            pass

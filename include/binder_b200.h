@@ -79,6 +79,10 @@ typedef struct bb_engine_opts {
     int32_t     device;
     uint32_t    max_batch;       /* largest n per call (0 -> 1<<20)                      */
     uint32_t    max_batch_bytes; /* largest packed query bytes per call (0 -> 64*max_batch) */
+    int32_t     ordered_output;  /* 0: "arrival" packing — responses packed in the order tiles of
+                                    128 queries finish (fastest; layout varies run to run, each
+                                    response's bytes do not).  1: packed in query order, out_off
+                                    monotonic, miss_idx ascending (tiles wait for predecessors). */
 } bb_engine_opts;
 
 bb_engine* bb_engine_create(const bb_engine_opts* opts, int* err);
@@ -102,17 +106,18 @@ int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/z
  *   pkts, pkt_off[n+1]   packed packets; packet i = pkts[pkt_off[i] .. pkt_off[i+1])
  *   shuffle_seed         seeds the service-answer shuffle (lib/server.js:40-53, Math.random
  *                        replaced by a counter RNG keyed on (seed, qidx_base + i))
- *   out, out_cap         response bytes, packed in query order
- *   out_off[n+1]         response i = out[out_off[i] .. out_off[i+1])  (empty unless ANSWERED)
+ *   out, out_cap         response bytes, packed (no gaps; see ordered_output)
+ *   out_off[n+1]         response i = out[out_off[i] .. out_off[i] + out_len[i]); out_off[n] = total bytes
+ *   out_len[n]           response length, 0 unless ANSWERED
  *   status[n]            BB_ANSWERED / BB_MISS_RECURSE / BB_DROPPED
- *   miss_idx[n], n_miss  ascending indices of the BB_MISS_RECURSE queries
+ *   miss_idx[n], n_miss  indices of the BB_MISS_RECURSE queries (ascending when ordered_output)
  *
  * Host<->device copies happen inside the call (pinned buffers from bb_host_alloc make
  * them asynchronous DMA).  Returns BB_OK or a negative error; never partial results.
  */
 int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
                      uint64_t shuffle_seed, uint32_t qidx_base,
-                     uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                     uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
                      uint32_t* miss_idx, uint32_t* n_miss);
 
 /*
@@ -123,7 +128,7 @@ int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off,
 int bb_engine_slots(const bb_engine* e);
 int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
                       uint64_t shuffle_seed, uint32_t qidx_base,
-                      uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                      uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
                       uint32_t* miss_idx, uint32_t* n_miss);
 int bb_resolve_wait(bb_engine* e, int slot);
 
@@ -138,13 +143,20 @@ int bb_resolve_wait(bb_engine* e, int slot);
  */
 int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
                             uint64_t shuffle_seed, uint32_t qidx_base,
-                            uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint8_t* d_status,
+                            uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint16_t* d_out_len, uint8_t* d_status,
                             uint32_t* d_miss_idx, uint32_t* d_totals, void* stream);
 
 /* Number of kernel launches bb_* calls have issued so far on this engine. */
 uint64_t bb_engine_launch_count(const bb_engine* e);
 /* Epoch (launch number, low 32 bits) of the most recent resolve call on this engine. */
 uint32_t bb_engine_launch_epoch(const bb_engine* e);
+/*
+ * Stage timers, the batched analogue of query._stamp() (lib/server.js:479-483): when d_log is
+ * a device buffer of ceil(n/128) x 8 uint64, every 128-query tile of later launches stores
+ * %globaltimer (ns) at: 0 start, 1 offsets in, 2 packets staged, 3 parsed+looked up+sized,
+ * 4 tile scan, 5 cross-tile look-back, 6 responses assembled, 7 flushed.  NULL turns it off.
+ */
+void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);

@@ -62,7 +62,7 @@ class Oracle(object):
 
     def resolve_batch(self, data, off, seed=0, qidx_base=0, nthreads=1, out_cap=None):
         """data: uint8 array of packed packets, off: uint32[n+1].
-        Returns (out uint8[total], out_off uint32[n+1], status uint8[n], miss uint32[m])."""
+        Returns (out uint8[total], out_off uint32[n+1], out_len uint16[n], status uint8[n], miss uint32[m])."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n = len(off) - 1
@@ -79,7 +79,8 @@ class Oracle(object):
                                      nthreads)
         if rc != 0:
             raise RuntimeError('oracle resolve failed (%d)' % rc)
-        return out[:out_off[n]].copy(), out_off, status[:n], miss[:n_miss.value].copy()
+        lens = np.diff(out_off.astype(np.int64)).astype(np.uint16)
+        return out[:out_off[n]].copy(), out_off, lens, status[:n], miss[:n_miss.value].copy()
 
     def timed_resolve(self, data, off, seed=0, nthreads=1, repeat=1):
         """Seconds per call of orc_resolve_batch alone (buffers allocated and touched beforehand)."""
@@ -107,7 +108,7 @@ class Oracle(object):
     def resolve_one(self, pkt, seed=0, qidx=0):
         data = np.frombuffer(pkt, dtype=np.uint8)
         off = np.array([0, len(pkt)], dtype=np.uint32)
-        out, out_off, status, miss = self.resolve_batch(data, off, seed, qidx)
+        out, out_off, lens, status, miss = self.resolve_batch(data, off, seed, qidx)
         return bytes(out), int(status[0])
 
     def close(self):

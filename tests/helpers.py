@@ -80,14 +80,14 @@ def ref_options(snap_bytes, dns_domain, recursion=False, datacenter=''):
 # ---------------------------------------------------------------------------------------
 # implementations under test, one calling convention
 # ---------------------------------------------------------------------------------------
-def make_impl(kind, dns_domain, snap_bytes, recursion=False, datacenter=''):
+def make_impl(kind, dns_domain, snap_bytes, recursion=False, datacenter='', **kw):
     """kind 'oracle' -> oracle/liboracle.so;  kind 'gpu' -> the product through its C ABI."""
     if kind == 'oracle':
         from oracle_lib import Oracle
         return Oracle(dns_domain, datacenter, recursion, snapshot=snap_bytes)
     if kind == 'gpu':
         from binder_b200.engine import Engine
-        return Engine(dns_domain, datacenter, recursion, snapshot=snap_bytes)
+        return Engine(dns_domain, datacenter, recursion, snapshot=snap_bytes, **kw)
     raise ValueError(kind)
 
 
@@ -95,6 +95,6 @@ def resolve_list(impl, pkts, seed=0, qidx_base=0):
     """[packet bytes] -> [(status, response bytes)], plus the miss index list."""
     from binder_b200.synth import pack_batch
     data, off = pack_batch(pkts)
-    out, out_off, status, miss = impl.resolve_batch(data, off, seed=seed, qidx_base=qidx_base)
-    res = [(int(status[i]), bytes(out[out_off[i]:out_off[i + 1]])) for i in range(len(pkts))]
-    return res, [int(x) for x in miss]
+    out, out_off, out_len, status, miss = impl.resolve_batch(data, off, seed=seed, qidx_base=qidx_base)
+    res = [(int(status[i]), bytes(out[out_off[i]:out_off[i] + out_len[i]])) for i in range(len(pkts))]
+    return res, sorted(int(x) for x in miss)
