@@ -23,7 +23,8 @@ def up_to_date():
 def build(force=False, verbose=False):
     if not force and up_to_date():
         return SO
-    cmd = [NVCC] + FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO] + SRCS
+    extra = os.environ.get('BB_NVCC_DEFINES', '').split()      # e.g. -DBB_MIN_BLOCKS=6 (tuning experiments)
+    cmd = [NVCC] + FLAGS + extra + (['-Xptxas', '-v'] if verbose else []) + ['-o', SO] + SRCS
     subprocess.check_call(cmd)
     return SO
 

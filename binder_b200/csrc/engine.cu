@@ -688,7 +688,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #define STAMP(k) do { if (P.stage_log && tid == 0) P.stage_log[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
 
 #ifndef BB_MIN_BLOCKS
-#define BB_MIN_BLOCKS 4
+#define BB_MIN_BLOCKS 8      /* 64 registers, no spills: 8 tiles (1024 threads) resident per SM */
 #endif
 // ORDERED: responses packed in query order (tile bases from a decoupled look-back; a tile waits
 // for its predecessors' sizes).  !ORDERED ("arrival" packing): a tile claims its output range
@@ -836,14 +836,14 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         if (rd == 0) STAMP(6);
         // bytes of this round: from the first response starting in the window to the end of the last
         uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
-        if (rd > 0) {                                                         // skip the previous round's overhang
+        if (nrounds > 1 && rd > 0) {                                                         // skip the previous round's overhang
             // first response start >= w0: binary search over the scan
             int a = 0, b = T;
             while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0) a = m + 1; else b = m; }
             lo = a < T ? max(s_scan[a], w0) : tile_bytes;
             lo = min(lo, tile_bytes);
         }
-        if (hi < tile_bytes) {                                                // extend to the end of the last response that starts in the window
+        if (nrounds > 1 && hi < tile_bytes) {                                 // extend to the end of the last response that starts in the window
             int a = 0, b = T;
             while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0 + CAPW) a = m + 1; else b = m; }
             hi = a < T ? s_scan[a] : tile_bytes;                              // start of the first response of the next round
@@ -911,7 +911,10 @@ struct bb_engine {
     bb::Slot* d_table = nullptr; uint8_t* d_arena = nullptr; uint32_t mask = 0; int ready = 0;
     int device = 0, ordered = 0; uint32_t max_batch = 0, max_bytes = 0, out_dev_cap = 0, max_tiles = 0;
     SlotCtx slots[NSLOTS];
-    unsigned long long* d_desc_dev = nullptr;    // scratch for bb_resolve_batch_device
+    // look-back / claim scratch of bb_resolve_batch_device, one per caller stream (launches on
+    // different streams may overlap)
+    static constexpr int MAX_DEV_STREAMS = 16;
+    void* dev_stream[MAX_DEV_STREAMS] = {}; unsigned long long* dev_desc[MAX_DEV_STREAMS] = {}; int n_dev_streams = 0;
     uint64_t launches = 0, epoch = 0;
     unsigned long long* stage_log = nullptr;
 };
@@ -972,8 +975,6 @@ static int engine_alloc(bb_engine* e) {
         CK(cudaMemset(s.d_totals, 0, 16));
         CK(cudaMallocHost(&s.h_totals, 16));
     }
-    CK(cudaMalloc(&e->d_desc_dev, ((size_t)e->max_tiles + 4) * 8));
-    CK(cudaMemset(e->d_desc_dev, 0, ((size_t)e->max_tiles + 4) * 8));
     return BB_OK;
 }
 
@@ -1014,7 +1015,8 @@ void bb_engine_destroy(bb_engine* e) {
         cudaFree(s.d_miss); cudaFree(s.d_totals); cudaFree(s.d_desc); if (s.h_totals) cudaFreeHost(s.h_totals);
         if (s.ev) cudaEventDestroy(s.ev); if (s.stream) cudaStreamDestroy(s.stream);
     }
-    cudaFree(e->d_desc_dev); cudaFree(e->d_const); cudaFree(e->d_table); cudaFree(e->d_arena);
+    for (int i = 0; i < e->n_dev_streams; i++) cudaFree(e->dev_desc[i]);
+    cudaFree(e->d_const); cudaFree(e->d_table); cudaFree(e->d_arena);
     delete e;
 }
 
@@ -1064,7 +1066,17 @@ int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t*
                             uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off,
                             uint16_t* d_out_len, uint8_t* d_status, uint32_t* d_miss_idx, uint32_t* d_totals, void* stream) {
     if (!e || n > e->max_batch || ((uintptr_t)d_pkts & 15) || ((uintptr_t)d_out & 15)) return BB_ERR_ARG;
-    return launch(e, e->d_desc_dev, d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_out_len, d_status, d_miss_idx,
+    int si = -1;
+    for (int i = 0; i < e->n_dev_streams; i++) if (e->dev_stream[i] == stream) si = i;
+    if (si < 0) {
+        if (e->n_dev_streams == bb_engine::MAX_DEV_STREAMS) return BB_ERR_ARG;
+        CK(cudaSetDevice(e->device));
+        unsigned long long* dsc = nullptr;
+        CK(cudaMalloc(&dsc, ((size_t)e->max_tiles + 4) * 8));
+        CK(cudaMemset(dsc, 0, ((size_t)e->max_tiles + 4) * 8));
+        si = e->n_dev_streams++; e->dev_stream[si] = stream; e->dev_desc[si] = dsc;
+    }
+    return launch(e, e->dev_desc[si], d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_out_len, d_status, d_miss_idx,
                   d_totals, (cudaStream_t)stream);
 }
 

@@ -138,7 +138,8 @@ int bb_resolve_wait(bb_engine* e, int slot);
  * aligned and readable up to the next multiple of 16 past pkt_off[n]; d_out must be 16-byte
  * aligned.  d_totals[4] receives {total response bytes, n_miss, overflow marker, done
  * marker}: the markers equal bb_engine_launch_epoch() of this call when set (out_cap too
- * small / launch finished).  Calls on one engine must be issued in stream order.  `stream` is a cudaStream_t (NULL = default
+ * small / launch finished).  Launches on up to 16 distinct streams may overlap; launches on one
+ * stream run in order.  `stream` is a cudaStream_t (NULL = default
  * stream).  Asynchronous: returns after the launch.
  */
 int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
