@@ -13,6 +13,8 @@ SYMBOLS = {
     'bb_last_cuda_error': (_c.c_char_p, []),
     'bb_abi_version': (_c.c_int, []),
     'bb_zone_build': (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_char_p, _c.POINTER(_c.c_int)]),
+    'bb_zone_build_shard': (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_uint32, _c.c_uint32,
+                                          _c.POINTER(_c.c_int)]),
     'bb_zone_free': (None, [_c.c_void_p]),
     'bb_zone_stat': (_c.c_uint64, [_c.c_void_p, _c.c_int]),
     'bb_engine_create': (_c.c_void_p, [_c.c_void_p, _c.POINTER(_c.c_int)]),
@@ -33,6 +35,16 @@ SYMBOLS = {
     'bb_engine_launch_count': (_c.c_uint64, [_c.c_void_p]),
     'bb_engine_launch_epoch': (_c.c_uint32, [_c.c_void_p]),
     'bb_engine_set_stage_log': (None, [_c.c_void_p, _c.c_void_p]),
+    'bb_shard_create': (_c.c_void_p, [_c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.c_uint32, _c.POINTER(_c.c_int)]),
+    'bb_shard_destroy': (None, [_c.c_void_p]),
+    'bb_shard_ipc_handle_size': (_c.c_uint32, []),
+    'bb_shard_region_capacity': (_c.c_uint32, [_c.c_void_p]),
+    'bb_shard_get_ipc_handle': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    'bb_shard_open_peers': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    'bb_shard_route_push': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_void_p]),
+    'bb_shard_resolve': (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    'bb_shard_fetch': (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                  _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),
     'bb_host_free': (None, [_c.c_void_p]),
 }

@@ -55,6 +55,9 @@ struct Params {
     unsigned long long* desc; uint32_t* counter; uint32_t ntiles, ntiles_cap;   // desc[ntiles_cap] = arrival cursor
     uint32_t epoch;          // launch number: marks totals[2] (overflow) / totals[3] (done) of THIS launch
     unsigned long long* stage_log;   // optional [ntiles][8] globaltimer stamps (bb_engine_set_stage_log)
+    const uint32_t* n_dev;           // when set, the batch size is read from device memory (routed batches)
+    const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
+    uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
 };
 
 // per-thread state carried from the sizing pass to the emit pass
@@ -71,6 +74,7 @@ struct Res {
     uint16_t lastlen;        // position of the domain's last length byte
     uint16_t keep_ans, keep_add, n_walk, nk;
     uint8_t status, rk, rcode, tc, opcode, rd, edns, trunc;
+    uint8_t owner;           // route mode: rank that owns this query's lookup key
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -155,12 +159,13 @@ struct RevKey {
 };
 
 template <class KG>
-__device__ bool probe(const Params& P, uint32_t ns, KG& kg, uint32_t& kind, uint32_t& ttl, uint32_t& val) {
+__device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& kind, uint32_t& ttl, uint32_t& val) {
     uint32_t klen = kg.length();
     KeyHash kh; kh.init(ns);
     kg.start();
     for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
     uint32_t h = kh.finish();
+    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return false; }   // sharding: who would answer
     uint32_t i = h & P.mask;
     for (;;) {
         const Slot* s = P.table + i;
@@ -391,7 +396,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     if (srv && nl) return false;                      // regex group 3 stops at a line terminator: generic path
     if (dotl || refuse) { r.rcode = RC_REFUSED; return true; }                // in-label dot / SRV shape
     if (j0 < 0 || sfx_bad) { r.rcode = RC_REFUSED; return true; }             // :157-166
-    if (!P.ready) { r.rcode = RC_SERVFAIL; return true; }                     // :186-192
+    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return true; }         // :186-192
     if (inval) { r.rcode = RC_REFUSED; return true; }                         // :208-215
     h = hash_finish(h, dl);
     r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
@@ -401,6 +406,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
         r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
     }
+    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
     // zk.lookup(domain): one 64-byte slot per probe, compared as words
     uint32_t idx = h & P.mask, kind = 0, ttl = 0, val = 0;
     bool hit = false;
@@ -473,14 +479,14 @@ __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t
         }
     }
     if (!suffix_ok) { r.rcode = RC_REFUSED; return; }
-    if (!P.ready) { r.rcode = RC_SERVFAIL; return; }                         // :186-192
+    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return; }             // :186-192
     if (!charset_ok) { r.rcode = RC_REFUSED; return; }
     r.ptr_tgt = (need_b || r.trunc) ? (uint16_t)NONE16 : (uint16_t)ptr_tgt;
     r.lastlen = (uint16_t)lastlen;
 
     FwdKey kg; kg.nm = nm; kg.d_off = d_off; kg.d_end = d_end;
     uint32_t kind = 0, ttl = 0, val = 0;
-    const bool hit = probe(P, NS_FORWARD, kg, kind, ttl, val);
+    const bool hit = probe(P, r, NS_FORWARD, kg, kind, ttl, val);
     finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
 }
 
@@ -494,10 +500,10 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
               nm[prev] == 7 && nm[prev + 1] == 'i' && nm[prev + 2] == 'n' && nm[prev + 3] == '-' && nm[prev + 4] == 'a' &&
               nm[prev + 5] == 'd' && nm[prev + 6] == 'd' && nm[prev + 7] == 'r';
     if (!ok) { r.rcode = RC_REFUSED; return; }
-    if (!P.ready) { r.rcode = RC_SERVFAIL; return; }                          // :86-92
+    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return; }              // :86-92
     RevKey kg; kg.nm = nm; kg.nlab = nlab - 2; kg.measure();
     uint32_t kind = 0, ttl = 0, val = 0;
-    bool hit = kg.length() > 0 && probe(P, NS_REVERSE, kg, kind, ttl, val);
+    bool hit = kg.length() > 0 && probe(P, r, NS_REVERSE, kg, kind, ttl, val);
     if (!hit) {                                                               // :107-121
         if (P.eng->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
         r.rcode = RC_REFUSED; return;
@@ -710,8 +716,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
     const uint32_t tile = blockIdx.x;
     STAMP(0);
+    const uint32_t n = P.n_dev ? *P.n_dev : P.n;           // routed batches: size known only on the device
+    const uint32_t ntiles = (n + T - 1) / T;
+    if (tile < ntiles) {
     const uint32_t q0 = tile * T;
-    const uint32_t nq = min((uint32_t)T, P.n - q0);
+    const uint32_t nq = min((uint32_t)T, n - q0);
 
     // ---- stage this tile's packets ---------------------------------------------------------
     for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
@@ -732,7 +741,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // ---- parse + lookup + size ----------------------------------------------------------------
     Res r;
     r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
-    const uint32_t qidx = P.qidx_base + q0 + tid;
+    const uint32_t qidx = (P.qidx_map && tid < (int)nq) ? P.qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
     if (tid < (int)nq) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
         if (o1 >= o0 && o1 - o0 <= 65535u) {
@@ -814,10 +823,6 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         P.out_len[q0 + tid] = (uint16_t)my_len;
         P.status[q0 + tid] = r.status;
         if (my_miss) P.miss_idx[mbase + my_mrank] = q0 + tid;
-        if (ORDERED && q0 + tid == P.n - 1) {
-            P.out_off[P.n] = (uint32_t)(gbase + tile_bytes);
-            P.totals[0] = (uint32_t)(gbase + tile_bytes); P.totals[1] = mbase + tile_miss; P.totals[3] = P.epoch;
-        }
     }
     if (overflow && tid == 0) P.totals[2] = P.epoch;
 
@@ -867,21 +872,134 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     }
 
     STAMP(7);
-    // ---- self-cleaning: the last tile to finish resets the look-back state for the next launch --
+    }   // tile < ntiles
+    // ---- self-cleaning: the last block to finish publishes the totals and resets the placement
+    // state for the next launch (blocks beyond ntiles only take part in this count) ------------
     if (warp == 0) {
         uint32_t last = 0;
-        if (lane == 0) last = atomicAdd(P.counter + 1, 1u) == P.ntiles - 1;
+        if (lane == 0) { __threadfence(); last = atomicAdd(P.counter + 1, 1u) == gridDim.x - 1; }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                // every tile has finished reading descriptors / claiming
-            if (ORDERED) { for (uint32_t i = lane; i < P.ntiles; i += 32) P.desc[i] = 0; }
-            else if (lane == 0) {
-                const unsigned long long cur = P.desc[P.ntiles_cap];
+            __threadfence();
+            volatile unsigned long long* D = P.desc;
+            unsigned long long cur = 0;
+            if (ORDERED) { if (ntiles) cur = D[ntiles - 1] & D_VAL; }            // inclusive prefix of the last tile
+            else cur = D[P.ntiles_cap];
+            if (lane == 0) {
                 const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
-                P.out_off[P.n] = tb; P.totals[0] = tb; P.totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); P.totals[3] = P.epoch;
-                P.desc[P.ntiles_cap] = 0;
+                P.out_off[n] = tb; P.totals[0] = tb; P.totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); P.totals[3] = P.epoch;
             }
+            __syncwarp();
+            if (ORDERED) { for (uint32_t i = lane; i < ntiles; i += 32) P.desc[i] = 0; }
+            else if (lane == 0) P.desc[P.ntiles_cap] = 0;
             if (lane == 0) P.counter[1] = 0;
         }
+    }
+}
+
+
+// ---- multi-GPU: route + push ----------------------------------------------------------------
+// Ingress side of the sharded design.  Each query is parsed just far enough to
+// know its lookup key (the same code as resolve, in route mode) and is then written straight
+// into the receive region (this rank -> owner rank) in the OWNER's HBM with peer-to-peer stores
+// over NVLink: no staging buffer, no separate collective.  Space inside a region is claimed
+// with sender-local atomics (a region has exactly one writer rank), so nothing atomic ever
+// crosses the link.  A region is laid out as an ordinary batch (packed packets + u32 offsets)
+// plus the original query index of each packet, so the owner resolves it with resolve_kernel.
+constexpr int MAX_RANKS = 8;
+constexpr int PUSH_CNT_SHIFT = 40;
+struct PushParams {
+    Params P;                              // pkts, pkt_off, n, eng, route = 1, nranks, rank
+    uint8_t* region[MAX_RANKS];            // region (rank -> d) inside rank d's receive buffer (peer-mapped)
+    uint32_t cap_q, cap_b;                 // capacity of one region: queries, packet bytes
+    unsigned long long* cursor;            // [nranks], local: count << 40 | bytes
+    uint32_t* done;                        // finished-block counter
+    uint32_t* err;                         // set when a region overflows
+    uint32_t qidx_base, epoch;
+};
+__host__ __device__ inline size_t region_off_array(uint32_t) { return 16; }
+__host__ __device__ inline size_t region_qidx_array(uint32_t cap_q) { return 16 + 4 * ((size_t)cap_q + 1); }
+__host__ __device__ inline size_t region_bytes(uint32_t cap_q) { return (16 + 4 * ((size_t)cap_q + 1) + 4 * (size_t)cap_q + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t region_size(uint32_t cap_q, uint32_t cap_b) { return (region_bytes(cap_q) + cap_b + 64 + 255) & ~(size_t)255; }
+
+__global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const PushParams A) {
+    const Params& P = A.P;
+    __shared__ __align__(16) uint8_t s_in[S_IN + 32];
+    __shared__ uint32_t s_off[T + 1];
+    __shared__ unsigned long long s_cur[MAX_RANKS], s_base[MAX_RANKS];
+    __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
+    if (tid < MAX_RANKS) s_cur[tid] = 0;
+    const uint32_t q0 = blockIdx.x * T;
+    const uint32_t nq = min((uint32_t)T, P.n - q0);
+    for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
+    __syncthreads();
+    const uint32_t b0 = s_off[0], b1 = s_off[nq];
+    const uint32_t a0 = b0 & ~15u;
+    const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
+    if (staged) {
+        const uint4* src = (const uint4*)(P.pkts + a0);
+        uint4* dst = (uint4*)s_in;
+        const uint32_t nv = (b1 - a0 + 15) >> 4;
+        for (uint32_t i = tid; i < nv; i += T) dst[i] = __ldg(src + i);
+    }
+    __syncthreads();
+    Res r;
+    r.owner = (uint8_t)P.rank;                     // queries that need no lookup are answered where they arrived
+    uint32_t len = 0, k = 0, boff = 0;
+    const bool have = tid < (int)nq;
+    if (have) {
+        const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
+        if (o1 >= o0 && o1 - o0 <= 65535u) {
+            len = o1 - o0;
+            r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
+            r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
+            resolve_query(P, r, len, 0, (uint32_t)__cvta_generic_to_shared(s_sfx));
+            if (r.owner >= P.nranks) r.owner = (uint8_t)P.rank;
+        }
+        const unsigned long long old = atomicAdd(&s_cur[r.owner], (1ull << PUSH_CNT_SHIFT) | len);
+        k = (uint32_t)(old >> PUSH_CNT_SHIFT); boff = (uint32_t)(old & ((1ull << PUSH_CNT_SHIFT) - 1));
+    }
+    __syncthreads();
+    if (tid < (int)P.nranks) { const unsigned long long t = s_cur[tid]; s_base[tid] = t ? atomicAdd(A.cursor + tid, t) : 0ull; }
+    __syncthreads();
+    if (have) {
+        const unsigned long long base = s_base[r.owner];
+        const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT) + k;
+        const unsigned long long gb = (base & ((1ull << PUSH_CNT_SHIFT) - 1)) + boff;
+        if (gk >= A.cap_q || gb + len > A.cap_b) *A.err = 1;
+        else {
+            uint8_t* reg = A.region[r.owner];
+            ((uint32_t*)(reg + region_off_array(A.cap_q)))[gk] = (uint32_t)gb;
+            ((uint32_t*)(reg + region_qidx_array(A.cap_q)))[gk] = A.qidx_base + q0 + tid;
+            uint8_t* dst = reg + region_bytes(A.cap_q) + gb;
+            const uint8_t* src = r.p;
+            uint32_t i = 0;
+            // peer stores: bytes up to 4-byte alignment of the destination, then words
+            for (; i < len && ((uintptr_t)(dst + i) & 3); i++) dst[i] = src[i];
+            if (r.sp) for (; i + 4 <= len; i += 4) *(uint32_t*)(dst + i) = ldsu32(r.sp + i);
+            for (; i < len; i++) dst[i] = src[i];
+        }
+    }
+    // the last block publishes the region headers (count, bytes, end-of-offsets sentinel)
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t last = 0;
+        if (lane == 0) { __threadfence(); last = atomicAdd(A.done, 1u) == gridDim.x - 1; }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (last && lane < (int)P.nranks) {
+            __threadfence();
+            const unsigned long long c = *(volatile unsigned long long*)(A.cursor + lane);
+            const uint32_t cnt = min((uint32_t)(c >> PUSH_CNT_SHIFT), A.cap_q);
+            const uint32_t nb = (uint32_t)min(c & ((1ull << PUSH_CNT_SHIFT) - 1), (unsigned long long)A.cap_b);
+            uint8_t* reg = A.region[lane];
+            ((uint32_t*)(reg + region_off_array(A.cap_q)))[cnt] = nb;
+            uint32_t* hdr = (uint32_t*)reg;
+            hdr[0] = cnt; hdr[1] = nb; hdr[2] = A.epoch; hdr[3] = *A.err;
+            A.cursor[lane] = 0;
+        }
+        if (last && lane == 0) *A.done = 0;
     }
 }
 
@@ -1053,6 +1171,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
     P.stage_log = e->stage_log;
+    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, st>>>(P);
@@ -1126,6 +1245,174 @@ int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off,
     int rc = bb_resolve_submit(e, 0, pkts, pkt_off, n, seed, qidx_base, out, out_cap, out_off, out_len, status, miss_idx, n_miss);
     if (rc != BB_OK) return rc;
     return bb_resolve_wait(e, 0);
+}
+
+}  // extern "C"
+
+// =================================================================================================
+// multi-GPU shard: receive regions in peer-mapped HBM, route + push, region resolves
+// =================================================================================================
+struct bb_shard {
+    bb_engine* e = nullptr; uint32_t nranks = 1, rank = 0, max_batch = 0, cap_q = 0, cap_b = 0;
+    size_t reg_size = 0;
+    uint8_t* recv = nullptr;                       // nranks regions: region s = queries pushed by rank s
+    uint8_t* peer_recv[bbk::MAX_RANKS] = {};       // rank d's receive buffer as mapped here
+    unsigned long long* cursor = nullptr; uint32_t* done = nullptr; uint32_t* err = nullptr;
+    uint32_t epoch = 0;
+    // owner side: one output set + stream per source region
+    cudaStream_t st[bbk::MAX_RANKS] = {}; cudaEvent_t ev_fork = nullptr, ev_join[bbk::MAX_RANKS] = {};
+    unsigned long long* desc[bbk::MAX_RANKS] = {};
+    uint8_t* d_out[bbk::MAX_RANKS] = {}; uint32_t* d_out_off[bbk::MAX_RANKS] = {}; uint16_t* d_out_len[bbk::MAX_RANKS] = {};
+    uint8_t* d_status[bbk::MAX_RANKS] = {}; uint32_t* d_miss[bbk::MAX_RANKS] = {}; uint32_t* d_totals[bbk::MAX_RANKS] = {};
+    uint32_t out_cap = 0;
+};
+
+extern "C" {
+
+bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t max_batch, uint32_t bytes_per_query, int* err) {
+    auto fail = [&](int c) -> bb_shard* { if (err) *err = c; return nullptr; };
+    if (err) *err = BB_OK;
+    if (!e || nranks == 0 || nranks > bbk::MAX_RANKS || rank >= nranks || max_batch == 0 || max_batch > e->max_batch) return fail(BB_ERR_ARG);
+    bb_shard* s = new bb_shard();
+    s->e = e; s->nranks = nranks; s->rank = rank; s->max_batch = max_batch;
+    // a region holds this rank's share of one ingress batch: B/nranks on average, +50 % and a floor
+    // for hash imbalance (a full batch when there is one rank)
+    s->cap_q = nranks == 1 ? max_batch : max_batch / nranks + max_batch / (2 * nranks) + 1024;
+    if (s->cap_q > max_batch) s->cap_q = max_batch;
+    s->cap_b = s->cap_q * (bytes_per_query ? bytes_per_query : 64);
+    s->reg_size = bbk::region_size(s->cap_q, s->cap_b);
+    s->out_cap = s->cap_q * 512u;
+    auto ck = [&](cudaError_t c) { if (c != cudaSuccess) { g_cuda_err = cudaGetErrorString(c); return false; } return true; };
+    bool ok = ck(cudaSetDevice(e->device)) && ck(cudaMalloc(&s->recv, s->reg_size * nranks)) && ck(cudaMemset(s->recv, 0, s->reg_size * nranks)) &&
+              ck(cudaMalloc(&s->cursor, 8 * bbk::MAX_RANKS)) && ck(cudaMemset(s->cursor, 0, 8 * bbk::MAX_RANKS)) &&
+              ck(cudaMalloc(&s->done, 16)) && ck(cudaMemset(s->done, 0, 16)) && ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    s->err = s->done ? s->done + 2 : nullptr;
+    const uint32_t tiles = (s->cap_q + bbk::T - 1) / bbk::T;
+    for (uint32_t r = 0; ok && r < nranks; r++) {
+        ok = ck(cudaStreamCreateWithFlags(&s->st[r], cudaStreamNonBlocking)) && ck(cudaEventCreateWithFlags(&s->ev_join[r], cudaEventDisableTiming)) &&
+             ck(cudaMalloc(&s->desc[r], ((size_t)e->max_tiles + 4) * 8)) && ck(cudaMemset(s->desc[r], 0, ((size_t)e->max_tiles + 4) * 8)) &&
+             ck(cudaMalloc(&s->d_out[r], (size_t)s->out_cap + 64)) && ck(cudaMalloc(&s->d_out_off[r], ((size_t)s->cap_q + 1) * 4)) &&
+             ck(cudaMalloc(&s->d_out_len[r], (size_t)s->cap_q * 2 + 16)) && ck(cudaMalloc(&s->d_status[r], (size_t)s->cap_q + 16)) &&
+             ck(cudaMalloc(&s->d_miss[r], (size_t)s->cap_q * 4 + 16)) && ck(cudaMalloc(&s->d_totals[r], 16)) && ck(cudaMemset(s->d_totals[r], 0, 16));
+    }
+    (void)tiles;
+    if (!ok) { bb_shard_destroy(s); return fail(BB_ERR_CUDA); }
+    s->peer_recv[rank] = s->recv;
+    return s;
+}
+
+void bb_shard_destroy(bb_shard* s) {
+    if (!s) return;
+    cudaSetDevice(s->e->device); cudaDeviceSynchronize();
+    for (uint32_t r = 0; r < s->nranks; r++) {
+        if (r != s->rank && s->peer_recv[r]) cudaIpcCloseMemHandle(s->peer_recv[r]);
+        if (s->st[r]) cudaStreamDestroy(s->st[r]); if (s->ev_join[r]) cudaEventDestroy(s->ev_join[r]);
+        cudaFree(s->desc[r]); cudaFree(s->d_out[r]); cudaFree(s->d_out_off[r]); cudaFree(s->d_out_len[r]);
+        cudaFree(s->d_status[r]); cudaFree(s->d_miss[r]); cudaFree(s->d_totals[r]);
+    }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    cudaFree(s->recv); cudaFree(s->cursor); cudaFree(s->done);
+    delete s;
+}
+
+uint32_t bb_shard_ipc_handle_size(void) { return (uint32_t)sizeof(cudaIpcMemHandle_t); }
+uint32_t bb_shard_region_capacity(const bb_shard* s) { return s ? s->cap_q : 0; }
+
+int bb_shard_get_ipc_handle(bb_shard* s, void* out) {
+    if (!s || !out) return BB_ERR_ARG;
+    CK(cudaSetDevice(s->e->device));
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, s->recv));
+    memcpy(out, &h, sizeof h);
+    return BB_OK;
+}
+
+// handles: nranks x bb_shard_ipc_handle_size() bytes, rank-major (this rank's own entry is ignored)
+int bb_shard_open_peers(bb_shard* s, const void* handles) {
+    if (!s || !handles) return BB_ERR_ARG;
+    CK(cudaSetDevice(s->e->device));
+    for (uint32_t r = 0; r < s->nranks; r++) {
+        if (r == s->rank) continue;
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t*)handles + (size_t)r * sizeof h, sizeof h);
+        void* p = nullptr;
+        CK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        s->peer_recv[r] = (uint8_t*)p;
+    }
+    return BB_OK;
+}
+
+// Ingress: route every query of a device-resident batch to its owner and push it there.
+int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n, uint32_t qidx_base, void* stream) {
+    if (!s || n > s->max_batch || ((uintptr_t)d_pkts & 15)) return BB_ERR_ARG;
+    for (uint32_t r = 0; r < s->nranks; r++) if (!s->peer_recv[r]) return BB_ERR_ARG;
+    bb_engine* e = s->e;
+    bbk::PushParams A; memset(&A, 0, sizeof A);
+    A.P.pkts = d_pkts; A.P.pkt_off = d_pkt_off; A.P.n = n; A.P.eng = e->d_const; A.P.ready = 1;
+    A.P.route = 1; A.P.nranks = s->nranks; A.P.rank = s->rank; A.P.table = e->d_table; A.P.mask = e->mask; A.P.arena = e->d_arena;
+    for (uint32_t r = 0; r < s->nranks; r++) A.region[r] = s->peer_recv[r] + (size_t)s->rank * s->reg_size;
+    A.cap_q = s->cap_q; A.cap_b = s->cap_b; A.cursor = s->cursor; A.done = s->done; A.err = s->err;
+    A.qidx_base = qidx_base; A.epoch = ++s->epoch;
+    // n == 0 still publishes empty region headers (one block, no queries)
+    const uint32_t grid = n ? (n + bbk::T - 1) / bbk::T : 1;
+    bbk::route_push_kernel<<<grid, bbk::T, 0, (cudaStream_t)stream>>>(A);
+    CK(cudaGetLastError());
+    e->launches++;
+    return BB_OK;
+}
+
+// Owner: resolve the nranks receive regions (after the caller's cross-rank barrier), one launch
+// per region on forked streams that join back into `stream`.
+int bb_shard_resolve(bb_shard* s, uint64_t seed, void* stream) {
+    if (!s) return BB_ERR_ARG;
+    bb_engine* e = s->e;
+    cudaStream_t main = (cudaStream_t)stream;
+    CK(cudaEventRecord(s->ev_fork, main));
+    for (uint32_t r = 0; r < s->nranks; r++) {
+        CK(cudaStreamWaitEvent(s->st[r], s->ev_fork, 0));
+        uint8_t* reg = s->recv + (size_t)r * s->reg_size;
+        bbk::Params P; memset(&P, 0, sizeof P);
+        P.pkts = reg + bbk::region_bytes(s->cap_q); P.pkt_off = (const uint32_t*)(reg + bbk::region_off_array(s->cap_q));
+        P.n = 0; P.n_dev = (const uint32_t*)reg; P.qidx_map = (const uint32_t*)(reg + bbk::region_qidx_array(s->cap_q));
+        P.seed = seed; P.qidx_base = 0;
+        P.out = s->d_out[r]; P.out_cap = s->out_cap; P.out_off = s->d_out_off[r]; P.out_len = s->d_out_len[r];
+        P.status = s->d_status[r]; P.miss_idx = s->d_miss[r]; P.totals = s->d_totals[r];
+        P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
+        P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
+        P.desc = s->desc[r]; P.counter = (uint32_t*)(s->desc[r] + e->max_tiles + 1);
+        P.epoch = (uint32_t)(++e->epoch); P.stage_log = nullptr; P.route = 0; P.nranks = s->nranks; P.rank = s->rank;
+        if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, s->st[r]>>>(P);
+        else bbk::resolve_kernel<false><<<P.ntiles, bbk::T, 0, s->st[r]>>>(P);
+        CK(cudaGetLastError());
+        e->launches++;
+        CK(cudaEventRecord(s->ev_join[r], s->st[r]));
+        CK(cudaStreamWaitEvent(main, s->ev_join[r], 0));
+    }
+    return BB_OK;
+}
+
+// Results of region `src` to host memory (synchronous).  qidx[i] is the index the query had in
+// rank src's ingress numbering (qidx_base + position).  Returns the region's query count in *n_out.
+int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
+                   uint8_t* status, uint32_t* qidx, uint32_t* miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out) {
+    if (!s || src >= s->nranks) return BB_ERR_ARG;
+    CK(cudaSetDevice(s->e->device));
+    uint8_t* reg = s->recv + (size_t)src * s->reg_size;
+    uint32_t hdr[4], tot[4];
+    CK(cudaMemcpy(hdr, reg, 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tot, s->d_totals[src], 16, cudaMemcpyDeviceToHost));
+    if (hdr[3]) return BB_ERR_CAPACITY;                          // a sender overflowed this region
+    const uint32_t n = hdr[0];
+    *n_out = n; *n_miss = n ? tot[1] : 0; *total_out = n ? tot[0] : 0;
+    if (!n) return BB_OK;
+    if (tot[0] > out_cap) return BB_ERR_CAPACITY;
+    CK(cudaMemcpy(out, s->d_out[src], tot[0], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_off, s->d_out_off[src], ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_len, s->d_out_len[src], (size_t)n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(status, s->d_status[src], n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qidx, reg + bbk::region_qidx_array(s->cap_q), (size_t)n * 4, cudaMemcpyDeviceToHost));
+    if (tot[1]) CK(cudaMemcpy(miss_idx, s->d_miss[src], (size_t)tot[1] * 4, cudaMemcpyDeviceToHost));
+    return BB_OK;
 }
 
 }  // extern "C"

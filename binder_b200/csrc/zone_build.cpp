@@ -411,6 +411,8 @@ struct TableBuilder {
         return l == len && memcmp(arena.data() + off, k, len) == 0;
     }
     // insert or overwrite ("last writer wins", like assigning into a JS object)
+    uint32_t nranks = 1, rank = 0;
+    bool mine(uint32_t ns, const uint8_t* k, uint32_t len) const { return nranks == 1 || owner_of(hash_key(ns, k, len), nranks) == rank; }
     bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
         uint32_t h = hash_key(ns, k, len);
         uint32_t i = h & mask;
@@ -436,10 +438,11 @@ struct TableBuilder {
 // ---------------------------------------------------------------------------------------
 struct bb_zone { bb::ZoneImage img; };
 
-extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_domain, int* err) {
+extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char* dns_domain, uint32_t nranks,
+                                        uint32_t rank, int* err) {
     auto fail = [&](int e) -> bb_zone* { if (err) *err = e; return nullptr; };
     if (err) *err = BB_OK;
-    if ((!buf && len) || !dns_domain) return fail(BB_ERR_ARG);
+    if ((!buf && len) || !dns_domain || nranks == 0 || rank >= nranks) return fail(BB_ERR_ARG);
     Builder B;
     B.dns_domain = dns_domain;
     // ZKCache.isReady() compares with options.domain verbatim (lib/zk.js:55-58) while keys are
@@ -512,13 +515,14 @@ extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_d
     memset(&Z, 0, sizeof Z);
     uint64_t nkeys = 0;
     for (auto& nd : B.nodes) nkeys += 1 + ((nd.flags & NF_REV) ? 1 : 0);
-    uint64_t want = nkeys * 2; uint32_t ns = 64;
+    // load factor <= 0.5; a shard holds ~1/nranks of the keys (+ 12 % slack for hash imbalance)
+    uint64_t want = nranks == 1 ? nkeys * 2 : nkeys * 2 / nranks + nkeys / (4 * nranks) + 64; uint32_t ns = 64;
     while (ns < want) { ns <<= 1; if (ns == 0) { delete zone; return fail(BB_ERR_NOMEM); } }
     Z.nslots = ns;
     Z.slots = (Slot*)aligned_alloc(64, (size_t)ns * sizeof(Slot));
     if (!Z.slots) { delete zone; return fail(BB_ERR_NOMEM); }
     memset(Z.slots, 0, (size_t)ns * sizeof(Slot));
-    TableBuilder T; T.z = &Z; T.mask = ns - 1;
+    TableBuilder T; T.z = &Z; T.mask = ns - 1; T.nranks = nranks; T.rank = rank;
     T.arena.assign(4, 0);                                     // offset 0 is never a valid record
     Z.n_nodes = B.nodes.size();
     std::string dom, kw, tmp;
@@ -528,7 +532,7 @@ extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_d
         bool dom_ok = to_wire(dom.data(), dom.size(), tmp) && tmp.size() + 1 <= 255;
         std::string dom_wire = tmp;
         // ---- forward key (lib/zk.js:96) -------------------------------------------------
-        if (dom_ok) {                                         // a name no query can spell is unreachable
+        if (dom_ok && T.mine(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size())) {   // unspellable names are unreachable; other ranks own the rest
             uint32_t val = nd.addr;
             if (nd.kind == K_SERVICE) {
                 const SvcInfo& si = B.svcs[nd.extra];
@@ -581,7 +585,7 @@ extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_d
             if (T.put(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size(), nd.kind, ttl, val)) Z.n_fwd++;
         }
         // ---- reverse key (lib/zk.js:183-188) ---------------------------------------------
-        if ((nd.flags & NF_REV) && nd.rev_len <= 253) {
+        if ((nd.flags & NF_REV) && nd.rev_len <= 253 && T.mine(NS_REVERSE, (const uint8_t*)B.pool.data() + nd.rev_off, nd.rev_len)) {
             uint8_t kind = K_PTR_BAD; uint32_t val = 0;
             if ((nd.flags & NF_TTL_OK) && dom_ok) {          // lib/server.js:123-130
                 std::string t; t.push_back((char)(dom_wire.size() + 1)); t += dom_wire; t.push_back(0);
@@ -597,6 +601,10 @@ extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_d
     memcpy(Z.arena, T.arena.data(), Z.arena_len);
     Z.ready = 1;                                              // the root TreeNode exists (lib/zk.js:55-58)
     return zone;
+}
+
+extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_domain, int* err) {
+    return bb_zone_build_shard(buf, len, dns_domain, 1, 0, err);
 }
 
 extern "C" void bb_zone_free(bb_zone* z) {

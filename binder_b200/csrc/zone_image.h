@@ -105,6 +105,12 @@ inline uint32_t hash_key(uint32_t ns, const uint8_t* k, uint32_t len) {
     return hash_finish(h, len);
 }
 
+// ---- sharding: which rank owns a key (multi-GPU) -------------------------------
+// A second mix decorrelates the owner from the slot index (both derive from the key hash).
+BB_HD uint32_t owner_of(uint32_t key_hash, uint32_t nranks) {
+    return (uint32_t)(((uint64_t)fmix32(key_hash * 0x9E3779B1u + 0x7F4A7C15u) * nranks) >> 32);
+}
+
 // ---- shuffle RNG: the seeded stand-in for Math.random() at lib/server.js:46 ------------
 BB_HD uint32_t shuffle_rand(uint64_t seed, uint32_t qidx, uint32_t i) {
     uint32_t lo = (uint32_t)seed, hi = (uint32_t)(seed >> 32);

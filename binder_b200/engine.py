@@ -32,11 +32,12 @@ def repack(out, out_off, out_len):
 class Zone(object):
     """bb_zone: flattened image of the mirrored ZooKeeper subtree (lib/zk.js ZKCache)."""
 
-    def __init__(self, snapshot_jsonl, dns_domain):
+    def __init__(self, snapshot_jsonl, dns_domain, nranks=1, rank=0):
         if isinstance(snapshot_jsonl, str):
             snapshot_jsonl = snapshot_jsonl.encode('utf-8')
         err = ctypes.c_int(0)
-        self._h = lib().bb_zone_build(snapshot_jsonl, len(snapshot_jsonl), dns_domain.encode(), ctypes.byref(err))
+        self._h = lib().bb_zone_build_shard(snapshot_jsonl, len(snapshot_jsonl), dns_domain.encode(), nranks, rank,
+                                            ctypes.byref(err))
         if not self._h:
             raise _lib.BinderError(err.value)
 
@@ -76,8 +77,8 @@ class Engine(object):
             self.load_snapshot(snapshot)
 
     # -- zone ------------------------------------------------------------------------------
-    def load_snapshot(self, snapshot_jsonl):
-        z = Zone(snapshot_jsonl, self.dns_domain)
+    def load_snapshot(self, snapshot_jsonl, nranks=1, rank=0):
+        z = Zone(snapshot_jsonl, self.dns_domain, nranks, rank)
         try:
             self.swap_zone(z)
             return z.stat()

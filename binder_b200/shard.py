@@ -1,0 +1,114 @@
+"""Multi-GPU face of the engine: one process per GPU, zone sharded by key hash, queries routed
+to their owner with one exchange over NVLink peer memory (include/binder_b200.h, bb_shard_*).
+
+torch.distributed is plumbing only: it carries the opaque CUDA IPC handles between the
+processes once, and provides the cross-rank barrier between "everyone has pushed" and "owners
+resolve" (a 1-element all-reduce on the compute stream).
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib
+from .engine import Engine
+
+
+def fmix32(h):
+    h = h.astype(np.uint64)
+    h ^= h >> np.uint64(16); h = (h * np.uint64(0x85EBCA6B)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(13); h = (h * np.uint64(0xC2B2AE35)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(16)
+    return h
+
+
+def hash_keys(keys, ns=0):
+    """bb::hash_key (zone_image.h) for a list of equal-length byte keys, vectorised."""
+    arr = np.frombuffer(b''.join(keys), dtype=np.uint8).reshape(len(keys), -1)
+    n, L = arr.shape
+    pad = (-L) % 4
+    if pad:
+        arr = np.concatenate([arr, np.zeros((n, pad), np.uint8)], axis=1)
+    words = arr.reshape(n, -1, 4).astype(np.uint64)
+    w = words[:, :, 0] | words[:, :, 1] << np.uint64(8) | words[:, :, 2] << np.uint64(16) | words[:, :, 3] << np.uint64(24)
+    M = np.uint64(0xFFFFFFFF)
+    h = np.full(n, 0x52455631 if ns else 0x42494E44, dtype=np.uint64)
+    for i in range(w.shape[1]):
+        x = (w[:, i] * np.uint64(0xCC9E2D51)) & M
+        x = ((x << np.uint64(15)) | (x >> np.uint64(17))) & M
+        x = (x * np.uint64(0x1B873593)) & M
+        h ^= x
+        h = ((h << np.uint64(13)) | (h >> np.uint64(19))) & M
+        h = (h * np.uint64(5) + np.uint64(0xE6546B64)) & M
+    return fmix32(h ^ np.uint64(L))
+
+
+def owner_of(key_hash, nranks):
+    """bb::owner_of (zone_image.h)."""
+    h = (key_hash * np.uint64(0x9E3779B1) + np.uint64(0x7F4A7C15)) & np.uint64(0xFFFFFFFF)
+    return ((fmix32(h) * np.uint64(nranks)) >> np.uint64(32)).astype(np.int64)
+
+
+class ShardedEngine(object):
+    """One rank of the sharded resolver."""
+
+    def __init__(self, dns_domain, datacenter, snapshot, rank, world, device, max_batch, recursion=False,
+                 ordered=False, bytes_per_query=64, dist=None):
+        self.rank, self.world = rank, world
+        self.engine = Engine(dns_domain, datacenter, recursion=recursion, device=device, max_batch=max_batch,
+                             max_batch_bytes=max_batch * bytes_per_query, ordered=ordered)
+        self.zone_stat = self.engine.load_snapshot(snapshot, world, rank)
+        err = ctypes.c_int(0)
+        self._h = lib().bb_shard_create(self.engine._h, world, rank, max_batch, bytes_per_query, ctypes.byref(err))
+        if not self._h:
+            raise _lib.BinderError(err.value)
+        self.cap_q = lib().bb_shard_region_capacity(self._h)
+        self.dist = dist
+        self._flag = None
+        if world > 1:
+            hs = lib().bb_shard_ipc_handle_size()
+            mine = (ctypes.c_uint8 * hs)()
+            check(lib().bb_shard_get_ipc_handle(self._h, mine))
+            gathered = [None] * world
+            dist.all_gather_object(gathered, bytes(mine))
+            blob = b''.join(gathered)
+            check(lib().bb_shard_open_peers(self._h, blob))
+            dist.barrier()
+
+    def route_push(self, d_pkts, d_off, n, qidx_base, stream):
+        check(lib().bb_shard_route_push(self._h, d_pkts, d_off, n, qidx_base, stream))
+
+    def barrier(self):
+        """Cross-rank barrier in stream order: every rank's pushes are complete before any owner resolves."""
+        if self.world > 1:
+            import torch
+            if self._flag is None:
+                self._flag = torch.zeros(1, dtype=torch.int32, device='cuda')
+            self.dist.all_reduce(self._flag)
+
+    def resolve(self, seed, stream):
+        check(lib().bb_shard_resolve(self._h, seed, stream))
+
+    def step(self, d_pkts, d_off, n, qidx_base, seed, stream):
+        self.route_push(d_pkts, d_off, n, qidx_base, stream)
+        self.barrier()
+        self.resolve(seed, stream)
+
+    def fetch(self, src):
+        """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays."""
+        cap = self.cap_q
+        out = np.empty(cap * 512, np.uint8); out_off = np.zeros(cap + 1, np.uint32); out_len = np.zeros(cap, np.uint16)
+        status = np.zeros(cap, np.uint8); qidx = np.zeros(cap, np.uint32); miss = np.zeros(cap, np.uint32)
+        n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        check(lib().bb_shard_fetch(self._h, src, out.ctypes.data, out.size, out_off.ctypes.data, out_len.ctypes.data,
+                                   status.ctypes.data, qidx.ctypes.data, miss.ctypes.data, ctypes.byref(n),
+                                   ctypes.byref(nm), ctypes.byref(tot)))
+        n = n.value
+        return dict(n=n, out=out[:tot.value], out_off=out_off[:n + 1], out_len=out_len[:n], status=status[:n],
+                    qidx=qidx[:n], miss=miss[:nm.value])
+
+    def close(self):
+        if getattr(self, '_h', None):
+            lib().bb_shard_destroy(self._h)
+            self._h = None
+        self.engine.close()

@@ -59,6 +59,10 @@ enum {
  */
 typedef struct bb_zone bb_zone;
 bb_zone* bb_zone_build(const char* snapshot_jsonl, size_t len, const char* dns_domain, int* err);
+/* Shard `rank` of `nranks` of the same zone: only the keys this rank owns are inserted
+ * (owner = owner_of(hash(key)), zone_image.h); a service's child list lives with the service. */
+bb_zone* bb_zone_build_shard(const char* snapshot_jsonl, size_t len, const char* dns_domain,
+                             uint32_t nranks, uint32_t rank, int* err);
 void     bb_zone_free(bb_zone* z);
 /* introspection: znodes mirrored (root included), forward keys, reverse keys, table bytes */
 uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 rev 3 slots 4 image bytes 5 arena bytes */
@@ -158,6 +162,40 @@ uint32_t bb_engine_launch_epoch(const bb_engine* e);
  * 4 tile scan, 5 cross-tile look-back, 6 responses assembled, 7 flushed.  NULL turns it off.
  */
 void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
+
+/* ---- multi-GPU: hash-sharded zone, one process per GPU ------------------ */
+/*
+ * The reference scales out with full replicas behind a balancer (boot/setup.sh:136-149); here the
+ * zone is sharded by key hash and a batch is routed with ONE exchange: the ingress rank parses
+ * each query far enough to know its lookup key and stores the packet directly into the owner
+ * rank's HBM over NVLink peer memory (route + push, one kernel); the owner resolves and answers.
+ * Queries that need no lookup (NOTIMP, refusals, malformed) are answered on the ingress rank.
+ *
+ *   bb_shard_create        receive regions (one per source rank) + per-region output buffers
+ *   bb_shard_get_ipc_handle / bb_shard_open_peers
+ *                          exchange CUDA IPC handles of the receive buffers (the host passes the
+ *                          opaque bytes between processes, e.g. torch.distributed.all_gather)
+ *   bb_shard_route_push    ingress: device-resident batch -> owners' regions (asynchronous)
+ *   -- cross-rank barrier on the same stream (e.g. a 1-element NCCL all-reduce) --
+ *   bb_shard_resolve       owner: resolve all regions (asynchronous; joins back into `stream`)
+ *   bb_shard_fetch         one region's results to host memory; qidx[] = ingress index of each
+ *                          query on the source rank (qidx_base + position), which also keys the
+ *                          service shuffle, so answers are identical to the unsharded engine's.
+ */
+typedef struct bb_shard bb_shard;
+bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t max_batch,
+                          uint32_t bytes_per_query, int* err);
+void      bb_shard_destroy(bb_shard* s);
+uint32_t  bb_shard_ipc_handle_size(void);
+uint32_t  bb_shard_region_capacity(const bb_shard* s);
+int bb_shard_get_ipc_handle(bb_shard* s, void* handle_out);
+int bb_shard_open_peers(bb_shard* s, const void* handles);
+int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
+                        uint32_t qidx_base, void* stream);
+int bb_shard_resolve(bb_shard* s, uint64_t shuffle_seed, void* stream);
+int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, uint32_t* out_off,
+                   uint16_t* out_len, uint8_t* status, uint32_t* qidx, uint32_t* miss_idx,
+                   uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);
