@@ -1255,7 +1255,10 @@ int bb_resolve_batch(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off,
 struct bb_shard {
     bb_engine* e = nullptr; uint32_t nranks = 1, rank = 0, max_batch = 0, cap_q = 0, cap_b = 0;
     size_t reg_size = 0;
-    uint8_t* recv = nullptr;                       // nranks regions: region s = queries pushed by rank s
+    // 2 x nranks regions: set (step & 1), region s = queries pushed by rank s.  Double-buffered so that
+    // a fast rank's push of step k+1 never lands in a region a slower owner is still resolving (step k);
+    // by the time step k+2 reuses the set, every rank has passed barrier k+1, i.e. finished resolve k.
+    uint8_t* recv = nullptr;
     uint8_t* peer_recv[bbk::MAX_RANKS] = {};       // rank d's receive buffer as mapped here
     unsigned long long* cursor = nullptr; uint32_t* done = nullptr; uint32_t* err = nullptr;
     uint32_t epoch = 0;
@@ -1283,7 +1286,7 @@ bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t
     s->reg_size = bbk::region_size(s->cap_q, s->cap_b);
     s->out_cap = s->cap_q * 512u;
     auto ck = [&](cudaError_t c) { if (c != cudaSuccess) { g_cuda_err = cudaGetErrorString(c); return false; } return true; };
-    bool ok = ck(cudaSetDevice(e->device)) && ck(cudaMalloc(&s->recv, s->reg_size * nranks)) && ck(cudaMemset(s->recv, 0, s->reg_size * nranks)) &&
+    bool ok = ck(cudaSetDevice(e->device)) && ck(cudaMalloc(&s->recv, s->reg_size * nranks * 2)) && ck(cudaMemset(s->recv, 0, s->reg_size * nranks * 2)) &&
               ck(cudaMalloc(&s->cursor, 8 * bbk::MAX_RANKS)) && ck(cudaMemset(s->cursor, 0, 8 * bbk::MAX_RANKS)) &&
               ck(cudaMalloc(&s->done, 16)) && ck(cudaMemset(s->done, 0, 16)) && ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     s->err = s->done ? s->done + 2 : nullptr;
@@ -1350,9 +1353,11 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
     bbk::PushParams A; memset(&A, 0, sizeof A);
     A.P.pkts = d_pkts; A.P.pkt_off = d_pkt_off; A.P.n = n; A.P.eng = e->d_const; A.P.ready = 1;
     A.P.route = 1; A.P.nranks = s->nranks; A.P.rank = s->rank; A.P.table = e->d_table; A.P.mask = e->mask; A.P.arena = e->d_arena;
-    for (uint32_t r = 0; r < s->nranks; r++) A.region[r] = s->peer_recv[r] + (size_t)s->rank * s->reg_size;
+    A.epoch = ++s->epoch;
+    const size_t set = (size_t)(s->epoch & 1) * s->nranks;
+    for (uint32_t r = 0; r < s->nranks; r++) A.region[r] = s->peer_recv[r] + (set + s->rank) * s->reg_size;
     A.cap_q = s->cap_q; A.cap_b = s->cap_b; A.cursor = s->cursor; A.done = s->done; A.err = s->err;
-    A.qidx_base = qidx_base; A.epoch = ++s->epoch;
+    A.qidx_base = qidx_base;
     // n == 0 still publishes empty region headers (one block, no queries)
     const uint32_t grid = n ? (n + bbk::T - 1) / bbk::T : 1;
     bbk::route_push_kernel<<<grid, bbk::T, 0, (cudaStream_t)stream>>>(A);
@@ -1370,7 +1375,7 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, void* stream) {
     CK(cudaEventRecord(s->ev_fork, main));
     for (uint32_t r = 0; r < s->nranks; r++) {
         CK(cudaStreamWaitEvent(s->st[r], s->ev_fork, 0));
-        uint8_t* reg = s->recv + (size_t)r * s->reg_size;
+        uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + r) * s->reg_size;      // the set of the step just pushed
         bbk::Params P; memset(&P, 0, sizeof P);
         P.pkts = reg + bbk::region_bytes(s->cap_q); P.pkt_off = (const uint32_t*)(reg + bbk::region_off_array(s->cap_q));
         P.n = 0; P.n_dev = (const uint32_t*)reg; P.qidx_map = (const uint32_t*)(reg + bbk::region_qidx_array(s->cap_q));
@@ -1397,7 +1402,7 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
                    uint8_t* status, uint32_t* qidx, uint32_t* miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out) {
     if (!s || src >= s->nranks) return BB_ERR_ARG;
     CK(cudaSetDevice(s->e->device));
-    uint8_t* reg = s->recv + (size_t)src * s->reg_size;
+    uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + src) * s->reg_size;
     uint32_t hdr[4], tot[4];
     CK(cudaMemcpy(hdr, reg, 16, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tot, s->d_totals[src], 16, cudaMemcpyDeviceToHost));

@@ -1,0 +1,22 @@
+"""Sharded multi-GPU parity (needs >= 2 GPUs; skipped on a 1-GPU box): tools/multi_check.py under
+torchrun compares every routed query's answer with the single-engine CPU oracle."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('ordered', ['0', '1'])
+def test_sharded_two_ranks(ordered):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    env = dict(os.environ, BB_ORDERED=ordered, BB_BATCH='20000', BB_ZONE='100000')
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'tools', 'multi_check.py')],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert 'MULTI_CHECK_OK world=2' in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
