@@ -26,34 +26,53 @@ def main(args, rank, world, local_rank):
     dist.barrier()
     B = args.batch
     zone = synth.gen_zone(args.zone_records)
+    LANES = 4
+    sync = os.environ.get('BB_SYNC', 'flags')
     se = ShardedEngine(zone.dns_domain, zone.datacenter, zone.jsonl, rank, world, local_rank, max_batch=B,
-                       ordered=args.ordered, dist=dist)
+                       ordered=args.ordered, dist=dist, lanes=LANES, sync=sync)
     RING = 8
     ring = [synth.batch_host_a_fast(zone, B, seed=5000 + 97 * rank + r) for r in range(RING)]
     d = [(torch.from_numpy(x).to(dev), torch.from_numpy(o.view(np.int32)).to(dev)) for x, o in ring]
     stream = torch.cuda.current_stream()
 
-    def step(k):
-        pk, off = d[k % RING]
-        se.step(pk.data_ptr(), off.data_ptr(), B, rank * B, 0xB1DDE5, stream.cuda_stream)
+    lane_streams = [torch.cuda.Stream(device=dev) for _ in range(LANES)]
 
-    for k in range(args.warmup):
-        step(k)
+    def step(k, lane=None):
+        """Step k on lane k % LANES (its own stream and receive regions): LANES steps in flight."""
+        lane = k % LANES if lane is None else lane
+        pk, off = d[k % RING]
+        with torch.cuda.stream(lane_streams[lane]):
+            se.step(pk.data_ptr(), off.data_ptr(), B, rank * B, 0xB1DDE5, lane_streams[lane].cuda_stream, lane)
+
+    def timed(k0, nsteps):
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(stream)
+        for st in lane_streams:
+            st.wait_event(ea)
+        for k in range(nsteps):
+            step(k0 + k)
+        for st in lane_streams:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            stream.wait_event(ev)
+        eb.record(stream)
+        torch.cuda.synchronize()
+        return ea.elapsed_time(eb)
+
+    timed(0, max(args.warmup, LANES))
     torch.cuda.synchronize()
     dist.barrier()
     sampler = B1.ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     l0 = se.engine.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    # all ranks issue the same number of steps per lane (the peer flags count steps)
+    nsteps = (args.steps + LANES - 1) // LANES * LANES
     torch.cuda.synchronize()
     dist.barrier()
-    e0.record(stream)
-    for k in range(args.steps):
-        step(args.warmup + k)
-    e1.record(stream)
-    torch.cuda.synchronize()
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    elapsed = timed(nsteps, nsteps)
+    args.steps = nsteps
+    ms = torch.tensor([elapsed], device=dev)
     dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     launches = se.engine.launch_count() - l0
@@ -61,8 +80,9 @@ def main(args, rank, world, local_rank):
 
     # what the last timed step produced: every query answered exactly once somewhere
     owned = 0
+    last_lane = (2 * nsteps - 1) % LANES
     for src in range(world):
-        reg = se.fetch(src)
+        reg = se.fetch(src, last_lane)
         owned += reg['n']
         assert (reg['status'] == 0).all() and (reg['out_len'] == 64).all(), 'unexpected result in timed batch'
     tot = torch.tensor([owned], device=dev, dtype=torch.int64)
@@ -77,10 +97,10 @@ def main(args, rank, world, local_rank):
     def e2e_step(k):
         hp, ho = h_ring[k % len(h_ring)]
         d_pk.copy_(hp, non_blocking=True); d_off.copy_(ho, non_blocking=True)
-        se.step(d_pk.data_ptr(), d_off.data_ptr(), B, rank * B, 0xB1DDE5, stream.cuda_stream)
+        se.step(d_pk.data_ptr(), d_off.data_ptr(), B, rank * B, 0xB1DDE5, stream.cuda_stream, 0)
         n_out = 0
         for src in range(world):
-            n_out += int(se.fetch(src)['out_len'].sum())
+            n_out += int(se.fetch(src, 0)['out_len'].sum())
         return n_out
 
     e2e_step(0)
@@ -103,7 +123,7 @@ def main(args, rank, world, local_rank):
                 'config': {'workload': B1.WORKLOAD + '; zone hash-sharded over %d ranks, each rank ingests its own batch' % world,
                            'zone_records': zone.n_records, 'batch_per_rank': B, 'global_batch': B * world,
                            'shard_table_mb': se.zone_stat['image_bytes'] / 1e6,
-                           'parallelism': 'shard%d: route+push over NVLink peer memory (P2P stores), 1-element NCCL all-reduce as barrier, owner resolves' % world,
+                           'parallelism': 'shard%d: route+push kernel stores each query into its owner rank over NVLink peer memory; %s; owner resolves; %d steps in flight' % (world, 'per-region epoch flags + device-side wait (no collective)' if sync == 'flags' else '1-element NCCL all-reduce as barrier', LANES),
                            'l2_policy': 'ring of %d distinct batches per rank; shard table %.0f MB' % (RING, se.zone_stat['image_bytes'] / 1e6),
                            'output_packing': 'query order' if args.ordered else 'arrival'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': None, 'cpu_baseline': None}

@@ -42,7 +42,7 @@ SYMBOLS = {
     'bb_shard_get_ipc_handle': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'bb_shard_open_peers': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'bb_shard_route_push': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint32, _c.c_void_p]),
-    'bb_shard_resolve': (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_void_p]),
+    'bb_shard_resolve': (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p]),
     'bb_shard_fetch': (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                   _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),

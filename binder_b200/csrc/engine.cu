@@ -981,8 +981,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             if (r.sp) for (; i + 4 <= len; i += 4) *(uint32_t*)(dst + i) = ldsu32(r.sp + i);
             for (; i < len; i++) dst[i] = src[i];
         }
+        __threadfence_system();                    // this thread's peer stores are performed before the block counts itself done
     }
-    // the last block publishes the region headers (count, bytes, end-of-offsets sentinel)
+    // The last block publishes the region headers (count, bytes, end-of-offsets sentinel) and then,
+    // after a system-scope fence, the epoch flag the owner's wait kernel spins on: the exchange
+    // needs no collective, only this ordered pair of peer stores per (source, owner).
     __syncthreads();
     if (warp == 0) {
         uint32_t last = 0;
@@ -995,12 +998,28 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             const uint32_t nb = (uint32_t)min(c & ((1ull << PUSH_CNT_SHIFT) - 1), (unsigned long long)A.cap_b);
             uint8_t* reg = A.region[lane];
             ((uint32_t*)(reg + region_off_array(A.cap_q)))[cnt] = nb;
-            uint32_t* hdr = (uint32_t*)reg;
-            hdr[0] = cnt; hdr[1] = nb; hdr[2] = A.epoch; hdr[3] = *A.err;
+            volatile uint32_t* hdr = (volatile uint32_t*)reg;
+            hdr[0] = cnt; hdr[1] = nb; hdr[3] = *A.err;
+            __threadfence_system();
+            hdr[2] = A.epoch;                      // the flag: everything above is visible to whoever sees it
             A.cursor[lane] = 0;
         }
         if (last && lane == 0) *A.done = 0;
     }
+}
+
+// Owner side: wait (bounded) until every source rank has published `epoch` in its region header.
+__global__ void wait_regions_kernel(const uint8_t* recv_set, size_t reg_size, uint32_t nranks, uint32_t epoch, uint32_t* err) {
+    const uint32_t r = threadIdx.x;
+    if (r < nranks) {
+        const volatile uint32_t* hdr = (const volatile uint32_t*)(recv_set + (size_t)r * reg_size);
+        unsigned long long spins = 0;
+        while (hdr[2] != epoch) {
+            if (++spins > (1ull << 28)) { *err = 2; break; }      // ~seconds: a peer died; fail instead of hanging
+            __nanosleep(64);
+        }
+    }
+    __threadfence_system();
 }
 
 }  // namespace bbk
@@ -1368,10 +1387,15 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
 
 // Owner: resolve the nranks receive regions (after the caller's cross-rank barrier), one launch
 // per region on forked streams that join back into `stream`.
-int bb_shard_resolve(bb_shard* s, uint64_t seed, void* stream) {
+int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* stream) {
     if (!s) return BB_ERR_ARG;
     bb_engine* e = s->e;
     cudaStream_t main = (cudaStream_t)stream;
+    if (wait_for_peers) {
+        bbk::wait_regions_kernel<<<1, 32, 0, main>>>(s->recv + (size_t)(s->epoch & 1) * s->nranks * s->reg_size, s->reg_size, s->nranks,
+                                                      s->epoch, s->err);
+        CK(cudaGetLastError());
+    }
     CK(cudaEventRecord(s->ev_fork, main));
     for (uint32_t r = 0; r < s->nranks; r++) {
         CK(cudaStreamWaitEvent(s->st[r], s->ev_fork, 0));
@@ -1407,6 +1431,7 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
     CK(cudaMemcpy(hdr, reg, 16, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tot, s->d_totals[src], 16, cudaMemcpyDeviceToHost));
     if (hdr[3]) return BB_ERR_CAPACITY;                          // a sender overflowed this region
+    { uint32_t werr = 0; CK(cudaMemcpy(&werr, s->err, 4, cudaMemcpyDeviceToHost)); if (werr == 2) { g_cuda_err = "timed out waiting for a peer rank's push"; return BB_ERR_CUDA; } }
     const uint32_t n = hdr[0];
     *n_out = n; *n_miss = n ? tot[1] : 0; *total_out = n ? tot[0] : 0;
     if (!n) return BB_OK;

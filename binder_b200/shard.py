@@ -50,65 +50,72 @@ def owner_of(key_hash, nranks):
 
 
 class ShardedEngine(object):
-    """One rank of the sharded resolver."""
+    """One rank of the sharded resolver.  `lanes` independent exchange contexts (each with its own
+    double-buffered receive regions) let several steps be in flight on different streams."""
 
     def __init__(self, dns_domain, datacenter, snapshot, rank, world, device, max_batch, recursion=False,
-                 ordered=False, bytes_per_query=64, dist=None):
-        self.rank, self.world = rank, world
+                 ordered=False, bytes_per_query=64, dist=None, lanes=1, sync='flags'):
+        self.rank, self.world, self.sync = rank, world, sync
         self.engine = Engine(dns_domain, datacenter, recursion=recursion, device=device, max_batch=max_batch,
                              max_batch_bytes=max_batch * bytes_per_query, ordered=ordered)
         self.zone_stat = self.engine.load_snapshot(snapshot, world, rank)
-        err = ctypes.c_int(0)
-        self._h = lib().bb_shard_create(self.engine._h, world, rank, max_batch, bytes_per_query, ctypes.byref(err))
-        if not self._h:
-            raise _lib.BinderError(err.value)
-        self.cap_q = lib().bb_shard_region_capacity(self._h)
         self.dist = dist
         self._flag = None
+        self._lanes = []
+        for _ in range(lanes):
+            err = ctypes.c_int(0)
+            h = lib().bb_shard_create(self.engine._h, world, rank, max_batch, bytes_per_query, ctypes.byref(err))
+            if not h:
+                raise _lib.BinderError(err.value)
+            self._lanes.append(h)
+        self._h = self._lanes[0]
+        self.cap_q = lib().bb_shard_region_capacity(self._h)
         if world > 1:
             hs = lib().bb_shard_ipc_handle_size()
-            mine = (ctypes.c_uint8 * hs)()
-            check(lib().bb_shard_get_ipc_handle(self._h, mine))
-            gathered = [None] * world
-            dist.all_gather_object(gathered, bytes(mine))
-            blob = b''.join(gathered)
-            check(lib().bb_shard_open_peers(self._h, blob))
+            for h in self._lanes:
+                mine = (ctypes.c_uint8 * hs)()
+                check(lib().bb_shard_get_ipc_handle(h, mine))
+                gathered = [None] * world
+                dist.all_gather_object(gathered, bytes(mine))
+                check(lib().bb_shard_open_peers(h, b''.join(gathered)))
             dist.barrier()
 
-    def route_push(self, d_pkts, d_off, n, qidx_base, stream):
-        check(lib().bb_shard_route_push(self._h, d_pkts, d_off, n, qidx_base, stream))
+    def route_push(self, d_pkts, d_off, n, qidx_base, stream, lane=0):
+        check(lib().bb_shard_route_push(self._lanes[lane], d_pkts, d_off, n, qidx_base, stream))
 
     def barrier(self):
-        """Cross-rank barrier in stream order: every rank's pushes are complete before any owner resolves."""
+        """sync='nccl': cross-rank barrier in stream order (1-element all-reduce)."""
         if self.world > 1:
             import torch
             if self._flag is None:
                 self._flag = torch.zeros(1, dtype=torch.int32, device='cuda')
             self.dist.all_reduce(self._flag)
 
-    def resolve(self, seed, stream):
-        check(lib().bb_shard_resolve(self._h, seed, stream))
+    def resolve(self, seed, stream, lane=0):
+        wait = 1 if (self.sync == 'flags' and self.world > 1) else 0
+        check(lib().bb_shard_resolve(self._lanes[lane], seed, wait, stream))
 
-    def step(self, d_pkts, d_off, n, qidx_base, seed, stream):
-        self.route_push(d_pkts, d_off, n, qidx_base, stream)
-        self.barrier()
-        self.resolve(seed, stream)
+    def step(self, d_pkts, d_off, n, qidx_base, seed, stream, lane=0):
+        self.route_push(d_pkts, d_off, n, qidx_base, stream, lane)
+        if self.sync == 'nccl':
+            self.barrier()
+        self.resolve(seed, stream, lane)
 
-    def fetch(self, src):
+    def fetch(self, src, lane=0):
         """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays."""
         cap = self.cap_q
         out = np.empty(cap * 512, np.uint8); out_off = np.zeros(cap + 1, np.uint32); out_len = np.zeros(cap, np.uint16)
         status = np.zeros(cap, np.uint8); qidx = np.zeros(cap, np.uint32); miss = np.zeros(cap, np.uint32)
         n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
-        check(lib().bb_shard_fetch(self._h, src, out.ctypes.data, out.size, out_off.ctypes.data, out_len.ctypes.data,
-                                   status.ctypes.data, qidx.ctypes.data, miss.ctypes.data, ctypes.byref(n),
-                                   ctypes.byref(nm), ctypes.byref(tot)))
+        check(lib().bb_shard_fetch(self._lanes[lane], src, out.ctypes.data, out.size, out_off.ctypes.data,
+                                   out_len.ctypes.data, status.ctypes.data, qidx.ctypes.data, miss.ctypes.data,
+                                   ctypes.byref(n), ctypes.byref(nm), ctypes.byref(tot)))
         n = n.value
         return dict(n=n, out=out[:tot.value], out_off=out_off[:n + 1], out_len=out_len[:n], status=status[:n],
                     qidx=qidx[:n], miss=miss[:nm.value])
 
     def close(self):
-        if getattr(self, '_h', None):
-            lib().bb_shard_destroy(self._h)
-            self._h = None
+        for h in self._lanes:
+            lib().bb_shard_destroy(h)
+        self._lanes = []
         self.engine.close()

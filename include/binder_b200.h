@@ -175,9 +175,13 @@ void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
  *   bb_shard_get_ipc_handle / bb_shard_open_peers
  *                          exchange CUDA IPC handles of the receive buffers (the host passes the
  *                          opaque bytes between processes, e.g. torch.distributed.all_gather)
- *   bb_shard_route_push    ingress: device-resident batch -> owners' regions (asynchronous)
- *   -- cross-rank barrier on the same stream (e.g. a 1-element NCCL all-reduce) --
- *   bb_shard_resolve       owner: resolve all regions (asynchronous; joins back into `stream`)
+ *   bb_shard_route_push    ingress: device-resident batch -> owners' regions (asynchronous); its last
+ *                          block publishes, after system-scope fences, an epoch flag per region
+ *   bb_shard_resolve       owner: resolve all regions (asynchronous; joins back into `stream`).
+ *                          wait_for_peers=1: first waits on the device (bounded spin) for every
+ *                          source's flag of this step — no collective anywhere on the data path;
+ *                          wait_for_peers=0: the caller has put its own cross-rank barrier on the
+ *                          stream.  All ranks must call route_push/resolve the same number of times.
  *   bb_shard_fetch         one region's results to host memory; qidx[] = ingress index of each
  *                          query on the source rank (qidx_base + position), which also keys the
  *                          service shuffle, so answers are identical to the unsharded engine's.
@@ -192,7 +196,7 @@ int bb_shard_get_ipc_handle(bb_shard* s, void* handle_out);
 int bb_shard_open_peers(bb_shard* s, const void* handles);
 int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n,
                         uint32_t qidx_base, void* stream);
-int bb_shard_resolve(bb_shard* s, uint64_t shuffle_seed, void* stream);
+int bb_shard_resolve(bb_shard* s, uint64_t shuffle_seed, int wait_for_peers, void* stream);
 int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, uint32_t* out_off,
                    uint16_t* out_len, uint8_t* status, uint32_t* qidx, uint32_t* miss_idx,
                    uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
