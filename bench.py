@@ -45,6 +45,24 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL prints its version there) must not
+    add to it: fd 1 is pointed at stderr for the whole run and only emit() writes to the real one."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 class ClockSampler(object):
     """nvidia-smi clocks + throttle reasons sampled during the timed region."""
     Q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
@@ -140,7 +158,7 @@ def run_reference(args, zone):
                              'sample': '%d steps x one %d-query batch, all %d host threads' % (args.steps, BATCH, cores)},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -156,6 +174,7 @@ def main():
     ap.add_argument('--ordered', action='store_true', help='query-order packing (look-back) instead of arrival packing')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    claim_stdout()
 
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
@@ -375,7 +394,7 @@ def main():
                        'parallelism': 'single GPU', 'batches_in_flight': IN_FLIGHT, 'serial_ms_per_step': serial_ms, 'output_packing': 'query order (look-back)' if args.ordered else 'arrival (one atomic claim per 128-query tile)', 'graph_replay_ms_per_step': graph_ms / args.steps if graph_ms else None},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches + e2e_launches),
             'roofline': roofline, 'cpu_baseline': cpu}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 if __name__ == '__main__':

@@ -127,6 +127,6 @@ def main(args, rank, world, local_rank):
                            'l2_policy': 'ring of %d distinct batches per rank; shard table %.0f MB' % (RING, se.zone_stat['image_bytes'] / 1e6),
                            'output_packing': 'query order' if args.ordered else 'arrival'},
                 'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': None, 'cpu_baseline': None}
-        print(json.dumps(line), flush=True)
+        B1.emit(line)
     dist.barrier()
     dist.destroy_process_group()

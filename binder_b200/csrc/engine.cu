@@ -58,6 +58,9 @@ struct Params {
     const uint32_t* n_dev;           // when set, the batch size is read from device memory (routed batches)
     const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
     uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
+    // multi-region launch (grid.y = regions): every per-batch pointer advances by its stride per region
+    uint32_t regions;
+    size_t in_stride, out_stride, off_stride, len_stride, status_stride, miss_stride, totals_stride, desc_stride;
 };
 
 // per-thread state carried from the sizing pass to the emit pass
@@ -709,6 +712,20 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];   // 4 pad bytes, '.' + dnsDomain, zero tail
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // region of a multi-region launch (routed batches: one region per source rank)
+    const size_t ry = P.regions ? blockIdx.y : 0;
+    const uint8_t* const r_pkts = P.pkts + ry * P.in_stride;
+    const uint32_t* const r_pkt_off = (const uint32_t*)((const uint8_t*)P.pkt_off + ry * P.in_stride);
+    const uint32_t* const r_n_dev = P.n_dev ? (const uint32_t*)((const uint8_t*)P.n_dev + ry * P.in_stride) : nullptr;
+    const uint32_t* const r_qidx_map = P.qidx_map ? (const uint32_t*)((const uint8_t*)P.qidx_map + ry * P.in_stride) : nullptr;
+    uint8_t* const r_out = P.out + ry * P.out_stride;
+    uint32_t* const r_out_off = (uint32_t*)((uint8_t*)P.out_off + ry * P.off_stride);
+    uint16_t* const r_out_len = (uint16_t*)((uint8_t*)P.out_len + ry * P.len_stride);
+    uint8_t* const r_status = P.status + ry * P.status_stride;
+    uint32_t* const r_miss_idx = (uint32_t*)((uint8_t*)P.miss_idx + ry * P.miss_stride);
+    uint32_t* const r_totals = (uint32_t*)((uint8_t*)P.totals + ry * P.totals_stride);
+    unsigned long long* const r_desc = (unsigned long long*)((uint8_t*)P.desc + ry * P.desc_stride);
+    uint32_t* const r_counter = (uint32_t*)((uint8_t*)P.counter + ry * P.desc_stride);
 
     // Tiles are taken in blockIdx order: like CUB's single-pass scan, the look-back below relies on
     // thread blocks being dispatched in increasing blockIdx order (a block only ever waits for
@@ -716,21 +733,21 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
     const uint32_t tile = blockIdx.x;
     STAMP(0);
-    const uint32_t n = P.n_dev ? *P.n_dev : P.n;           // routed batches: size known only on the device
+    const uint32_t n = r_n_dev ? *r_n_dev : P.n;           // routed batches: size known only on the device
     const uint32_t ntiles = (n + T - 1) / T;
     if (tile < ntiles) {
     const uint32_t q0 = tile * T;
     const uint32_t nq = min((uint32_t)T, n - q0);
 
     // ---- stage this tile's packets ---------------------------------------------------------
-    for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
+    for (int i = tid; i <= (int)nq; i += T) s_off[i] = r_pkt_off[q0 + i];
     __syncthreads();
     STAMP(1);
     const uint32_t b0 = s_off[0], b1 = s_off[nq];
     const uint32_t a0 = b0 & ~15u;
     const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
     if (staged) {
-        const uint4* src = (const uint4*)(P.pkts + a0);
+        const uint4* src = (const uint4*)(r_pkts + a0);
         uint4* dst = (uint4*)s_in;
         const uint32_t nv = (b1 - a0 + 15) >> 4;
         for (uint32_t i = tid; i < nv; i += T) dst[i] = __ldg(src + i);
@@ -741,11 +758,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // ---- parse + lookup + size ----------------------------------------------------------------
     Res r;
     r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
-    const uint32_t qidx = (P.qidx_map && tid < (int)nq) ? P.qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
+    const uint32_t qidx = (r_qidx_map && tid < (int)nq) ? r_qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
     if (tid < (int)nq) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
         if (o1 >= o0 && o1 - o0 <= 65535u) {
-            r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
+            r.p = staged ? s_in + (o0 - a0) : r_pkts + o0;
             r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
             resolve_query(P, r, o1 - o0, qidx, (uint32_t)__cvta_generic_to_shared(s_sfx));
         }
@@ -772,10 +789,10 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // ---- where this tile's responses (and misses) go ------------------------------------------
     if (!ORDERED) {
         if (tid == 0)                                    // one claim per tile: bytes | misses << 40
-            s_prefix = atomicAdd(P.desc + P.ntiles_cap, (unsigned long long)tile_bytes | ((unsigned long long)tile_miss << D_MISS_SHIFT));
+            s_prefix = atomicAdd(r_desc + P.ntiles_cap, (unsigned long long)tile_bytes | ((unsigned long long)tile_miss << D_MISS_SHIFT));
     } else
     if (warp == 0) {
-        volatile unsigned long long* D = P.desc;
+        volatile unsigned long long* D = r_desc;
         const uint64_t agg = (uint64_t)tile_bytes | ((uint64_t)tile_miss << D_MISS_SHIFT);
         uint64_t ex = 0;
         if (tile == 0) { if (lane == 0) D[0] = D_FLAG_P | agg; }
@@ -819,12 +836,12 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
 
     // ---- per-query outputs ---------------------------------------------------------------------
     if (tid < (int)nq) {
-        P.out_off[q0 + tid] = (uint32_t)(gbase + my_o);
-        P.out_len[q0 + tid] = (uint16_t)my_len;
-        P.status[q0 + tid] = r.status;
-        if (my_miss) P.miss_idx[mbase + my_mrank] = q0 + tid;
+        r_out_off[q0 + tid] = (uint32_t)(gbase + my_o);
+        r_out_len[q0 + tid] = (uint16_t)my_len;
+        r_status[q0 + tid] = r.status;
+        if (my_miss) r_miss_idx[mbase + my_mrank] = q0 + tid;
     }
-    if (overflow && tid == 0) P.totals[2] = P.epoch;
+    if (overflow && tid == 0) r_totals[2] = P.epoch;
 
     // ---- assemble in shared memory, flush with aligned 16-byte stores ---------------------------
     const uint32_t nrounds = overflow ? 0 : (tile_bytes + CAPW - 1) / CAPW;
@@ -855,7 +872,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             // zero-length entries at the boundary share the same offset: fine, range is [lo, hi)
         }
         if (hi > lo) {
-            uint8_t* g = P.out + gbase;                                       // g[x] <-> s_out[shift + x - w0]
+            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[shift + x - w0]
             const uint8_t* s = s_out + shift - w0;
             uint32_t x0 = lo, x1 = hi;
             // head up to 16-byte alignment of the global address
@@ -877,22 +894,22 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // state for the next launch (blocks beyond ntiles only take part in this count) ------------
     if (warp == 0) {
         uint32_t last = 0;
-        if (lane == 0) { __threadfence(); last = atomicAdd(P.counter + 1, 1u) == gridDim.x - 1; }
+        if (lane == 0) { __threadfence(); last = atomicAdd(r_counter + 1, 1u) == gridDim.x - 1; }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                // every tile has finished reading descriptors / claiming
             __threadfence();
-            volatile unsigned long long* D = P.desc;
+            volatile unsigned long long* D = r_desc;
             unsigned long long cur = 0;
             if (ORDERED) { if (ntiles) cur = D[ntiles - 1] & D_VAL; }            // inclusive prefix of the last tile
             else cur = D[P.ntiles_cap];
             if (lane == 0) {
                 const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
-                P.out_off[n] = tb; P.totals[0] = tb; P.totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); P.totals[3] = P.epoch;
+                r_out_off[n] = tb; r_totals[0] = tb; r_totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); r_totals[3] = P.epoch;
             }
             __syncwarp();
-            if (ORDERED) { for (uint32_t i = lane; i < ntiles; i += 32) P.desc[i] = 0; }
-            else if (lane == 0) P.desc[P.ntiles_cap] = 0;
-            if (lane == 0) P.counter[1] = 0;
+            if (ORDERED) { for (uint32_t i = lane; i < ntiles; i += 32) r_desc[i] = 0; }
+            else if (lane == 0) r_desc[P.ntiles_cap] = 0;
+            if (lane == 0) r_counter[1] = 0;
         }
     }
 }
@@ -1190,7 +1207,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
     P.stage_log = e->stage_log;
-    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0;
+    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, st>>>(P);
@@ -1281,11 +1298,11 @@ struct bb_shard {
     uint8_t* peer_recv[bbk::MAX_RANKS] = {};       // rank d's receive buffer as mapped here
     unsigned long long* cursor = nullptr; uint32_t* done = nullptr; uint32_t* err = nullptr;
     uint32_t epoch = 0;
-    // owner side: one output set + stream per source region
-    cudaStream_t st[bbk::MAX_RANKS] = {}; cudaEvent_t ev_fork = nullptr, ev_join[bbk::MAX_RANKS] = {};
-    unsigned long long* desc[bbk::MAX_RANKS] = {};
-    uint8_t* d_out[bbk::MAX_RANKS] = {}; uint32_t* d_out_off[bbk::MAX_RANKS] = {}; uint16_t* d_out_len[bbk::MAX_RANKS] = {};
-    uint8_t* d_status[bbk::MAX_RANKS] = {}; uint32_t* d_miss[bbk::MAX_RANKS] = {}; uint32_t* d_totals[bbk::MAX_RANKS] = {};
+    // owner side: one output set per source region, each kind contiguous with a fixed stride so that
+    // all regions resolve in ONE launch (grid.y = region)
+    uint8_t* d_out = nullptr; uint8_t* d_out_off = nullptr; uint8_t* d_out_len = nullptr; uint8_t* d_status = nullptr;
+    uint8_t* d_miss = nullptr; uint8_t* d_totals = nullptr; uint8_t* d_desc = nullptr;
+    size_t out_stride = 0, off_stride = 0, len_stride = 0, status_stride = 0, miss_stride = 0, totals_stride = 16, desc_stride = 0;
     uint32_t out_cap = 0;
 };
 
@@ -1305,19 +1322,18 @@ bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t
     s->reg_size = bbk::region_size(s->cap_q, s->cap_b);
     s->out_cap = s->cap_q * 512u;
     auto ck = [&](cudaError_t c) { if (c != cudaSuccess) { g_cuda_err = cudaGetErrorString(c); return false; } return true; };
+    auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+    s->out_stride = up((size_t)s->out_cap + 64); s->off_stride = up(((size_t)s->cap_q + 1) * 4); s->len_stride = up((size_t)s->cap_q * 2 + 16);
+    s->status_stride = up((size_t)s->cap_q + 16); s->miss_stride = up((size_t)s->cap_q * 4 + 16); s->desc_stride = up(((size_t)e->max_tiles + 4) * 8);
     bool ok = ck(cudaSetDevice(e->device)) && ck(cudaMalloc(&s->recv, s->reg_size * nranks * 2)) && ck(cudaMemset(s->recv, 0, s->reg_size * nranks * 2)) &&
               ck(cudaMalloc(&s->cursor, 8 * bbk::MAX_RANKS)) && ck(cudaMemset(s->cursor, 0, 8 * bbk::MAX_RANKS)) &&
-              ck(cudaMalloc(&s->done, 16)) && ck(cudaMemset(s->done, 0, 16)) && ck(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+              ck(cudaMalloc(&s->done, 16)) && ck(cudaMemset(s->done, 0, 16)) &&
+              ck(cudaMalloc(&s->d_out, s->out_stride * nranks)) && ck(cudaMalloc(&s->d_out_off, s->off_stride * nranks)) &&
+              ck(cudaMalloc(&s->d_out_len, s->len_stride * nranks)) && ck(cudaMalloc(&s->d_status, s->status_stride * nranks)) &&
+              ck(cudaMalloc(&s->d_miss, s->miss_stride * nranks)) && ck(cudaMalloc(&s->d_totals, s->totals_stride * nranks)) &&
+              ck(cudaMemset(s->d_totals, 0, s->totals_stride * nranks)) &&
+              ck(cudaMalloc(&s->d_desc, s->desc_stride * nranks)) && ck(cudaMemset(s->d_desc, 0, s->desc_stride * nranks));
     s->err = s->done ? s->done + 2 : nullptr;
-    const uint32_t tiles = (s->cap_q + bbk::T - 1) / bbk::T;
-    for (uint32_t r = 0; ok && r < nranks; r++) {
-        ok = ck(cudaStreamCreateWithFlags(&s->st[r], cudaStreamNonBlocking)) && ck(cudaEventCreateWithFlags(&s->ev_join[r], cudaEventDisableTiming)) &&
-             ck(cudaMalloc(&s->desc[r], ((size_t)e->max_tiles + 4) * 8)) && ck(cudaMemset(s->desc[r], 0, ((size_t)e->max_tiles + 4) * 8)) &&
-             ck(cudaMalloc(&s->d_out[r], (size_t)s->out_cap + 64)) && ck(cudaMalloc(&s->d_out_off[r], ((size_t)s->cap_q + 1) * 4)) &&
-             ck(cudaMalloc(&s->d_out_len[r], (size_t)s->cap_q * 2 + 16)) && ck(cudaMalloc(&s->d_status[r], (size_t)s->cap_q + 16)) &&
-             ck(cudaMalloc(&s->d_miss[r], (size_t)s->cap_q * 4 + 16)) && ck(cudaMalloc(&s->d_totals[r], 16)) && ck(cudaMemset(s->d_totals[r], 0, 16));
-    }
-    (void)tiles;
     if (!ok) { bb_shard_destroy(s); return fail(BB_ERR_CUDA); }
     s->peer_recv[rank] = s->recv;
     return s;
@@ -1326,13 +1342,9 @@ bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t
 void bb_shard_destroy(bb_shard* s) {
     if (!s) return;
     cudaSetDevice(s->e->device); cudaDeviceSynchronize();
-    for (uint32_t r = 0; r < s->nranks; r++) {
-        if (r != s->rank && s->peer_recv[r]) cudaIpcCloseMemHandle(s->peer_recv[r]);
-        if (s->st[r]) cudaStreamDestroy(s->st[r]); if (s->ev_join[r]) cudaEventDestroy(s->ev_join[r]);
-        cudaFree(s->desc[r]); cudaFree(s->d_out[r]); cudaFree(s->d_out_off[r]); cudaFree(s->d_out_len[r]);
-        cudaFree(s->d_status[r]); cudaFree(s->d_miss[r]); cudaFree(s->d_totals[r]);
-    }
-    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    for (uint32_t r = 0; r < s->nranks; r++) if (r != s->rank && s->peer_recv[r]) cudaIpcCloseMemHandle(s->peer_recv[r]);
+    cudaFree(s->d_out); cudaFree(s->d_out_off); cudaFree(s->d_out_len); cudaFree(s->d_status); cudaFree(s->d_miss);
+    cudaFree(s->d_totals); cudaFree(s->d_desc);
     cudaFree(s->recv); cudaFree(s->cursor); cudaFree(s->done);
     delete s;
 }
@@ -1396,27 +1408,24 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
                                                       s->epoch, s->err);
         CK(cudaGetLastError());
     }
-    CK(cudaEventRecord(s->ev_fork, main));
-    for (uint32_t r = 0; r < s->nranks; r++) {
-        CK(cudaStreamWaitEvent(s->st[r], s->ev_fork, 0));
-        uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + r) * s->reg_size;      // the set of the step just pushed
-        bbk::Params P; memset(&P, 0, sizeof P);
-        P.pkts = reg + bbk::region_bytes(s->cap_q); P.pkt_off = (const uint32_t*)(reg + bbk::region_off_array(s->cap_q));
-        P.n = 0; P.n_dev = (const uint32_t*)reg; P.qidx_map = (const uint32_t*)(reg + bbk::region_qidx_array(s->cap_q));
-        P.seed = seed; P.qidx_base = 0;
-        P.out = s->d_out[r]; P.out_cap = s->out_cap; P.out_off = s->d_out_off[r]; P.out_len = s->d_out_len[r];
-        P.status = s->d_status[r]; P.miss_idx = s->d_miss[r]; P.totals = s->d_totals[r];
-        P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
-        P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
-        P.desc = s->desc[r]; P.counter = (uint32_t*)(s->desc[r] + e->max_tiles + 1);
-        P.epoch = (uint32_t)(++e->epoch); P.stage_log = nullptr; P.route = 0; P.nranks = s->nranks; P.rank = s->rank;
-        if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, s->st[r]>>>(P);
-        else bbk::resolve_kernel<false><<<P.ntiles, bbk::T, 0, s->st[r]>>>(P);
-        CK(cudaGetLastError());
-        e->launches++;
-        CK(cudaEventRecord(s->ev_join[r], s->st[r]));
-        CK(cudaStreamWaitEvent(main, s->ev_join[r], 0));
-    }
+    uint8_t* reg = s->recv + (size_t)(s->epoch & 1) * s->nranks * s->reg_size;          // region 0 of the set just pushed
+    bbk::Params P; memset(&P, 0, sizeof P);
+    P.pkts = reg + bbk::region_bytes(s->cap_q); P.pkt_off = (const uint32_t*)(reg + bbk::region_off_array(s->cap_q));
+    P.n = 0; P.n_dev = (const uint32_t*)reg; P.qidx_map = (const uint32_t*)(reg + bbk::region_qidx_array(s->cap_q));
+    P.seed = seed; P.qidx_base = 0;
+    P.out = s->d_out; P.out_cap = s->out_cap; P.out_off = (uint32_t*)s->d_out_off; P.out_len = (uint16_t*)s->d_out_len;
+    P.status = s->d_status; P.miss_idx = (uint32_t*)s->d_miss; P.totals = (uint32_t*)s->d_totals;
+    P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
+    P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
+    P.desc = (unsigned long long*)s->d_desc; P.counter = (uint32_t*)((unsigned long long*)s->d_desc + e->max_tiles + 1);
+    P.epoch = (uint32_t)(++e->epoch); P.stage_log = nullptr; P.route = 0; P.nranks = s->nranks; P.rank = s->rank;
+    P.regions = 1; P.in_stride = s->reg_size; P.out_stride = s->out_stride; P.off_stride = s->off_stride; P.len_stride = s->len_stride;
+    P.status_stride = s->status_stride; P.miss_stride = s->miss_stride; P.totals_stride = s->totals_stride; P.desc_stride = s->desc_stride;
+    const dim3 grid(P.ntiles, s->nranks);
+    if (e->ordered) bbk::resolve_kernel<true><<<grid, bbk::T, 0, main>>>(P);
+    else bbk::resolve_kernel<false><<<grid, bbk::T, 0, main>>>(P);
+    CK(cudaGetLastError());
+    e->launches++;
     return BB_OK;
 }
 
@@ -1429,19 +1438,19 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
     uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + src) * s->reg_size;
     uint32_t hdr[4], tot[4];
     CK(cudaMemcpy(hdr, reg, 16, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(tot, s->d_totals[src], 16, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(tot, s->d_totals + src * s->totals_stride, 16, cudaMemcpyDeviceToHost));
     if (hdr[3]) return BB_ERR_CAPACITY;                          // a sender overflowed this region
     { uint32_t werr = 0; CK(cudaMemcpy(&werr, s->err, 4, cudaMemcpyDeviceToHost)); if (werr == 2) { g_cuda_err = "timed out waiting for a peer rank's push"; return BB_ERR_CUDA; } }
     const uint32_t n = hdr[0];
     *n_out = n; *n_miss = n ? tot[1] : 0; *total_out = n ? tot[0] : 0;
     if (!n) return BB_OK;
     if (tot[0] > out_cap) return BB_ERR_CAPACITY;
-    CK(cudaMemcpy(out, s->d_out[src], tot[0], cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out_off, s->d_out_off[src], ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(out_len, s->d_out_len[src], (size_t)n * 2, cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(status, s->d_status[src], n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out, s->d_out + src * s->out_stride, tot[0], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_off, s->d_out_off + src * s->off_stride, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(out_len, s->d_out_len + src * s->len_stride, (size_t)n * 2, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(status, s->d_status + src * s->status_stride, n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(qidx, reg + bbk::region_qidx_array(s->cap_q), (size_t)n * 4, cudaMemcpyDeviceToHost));
-    if (tot[1]) CK(cudaMemcpy(miss_idx, s->d_miss[src], (size_t)tot[1] * 4, cudaMemcpyDeviceToHost));
+    if (tot[1]) CK(cudaMemcpy(miss_idx, s->d_miss + src * s->miss_stride, (size_t)tot[1] * 4, cudaMemcpyDeviceToHost));
     return BB_OK;
 }
 
