@@ -16,7 +16,7 @@ def main(args, rank, world, local_rank):
     import torch.distributed as dist
     from binder_b200 import synth, build
     from binder_b200.shard import ShardedEngine
-    import bench as B1
+    B1 = sys.modules['__main__']            # bench.py itself (it owns the real stdout)
 
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
@@ -36,13 +36,18 @@ def main(args, rank, world, local_rank):
     stream = torch.cuda.current_stream()
 
     lane_streams = [torch.cuda.Stream(device=dev) for _ in range(LANES)]
+    lane_handles = [st.cuda_stream for st in lane_streams]
+    d_ptrs = [(a.data_ptr(), b.data_ptr()) for a, b in d]
 
     def step(k, lane=None):
         """Step k on lane k % LANES (its own stream and receive regions): LANES steps in flight."""
         lane = k % LANES if lane is None else lane
-        pk, off = d[k % RING]
-        with torch.cuda.stream(lane_streams[lane]):
-            se.step(pk.data_ptr(), off.data_ptr(), B, rank * B, 0xB1DDE5, lane_streams[lane].cuda_stream, lane)
+        pk, off = d_ptrs[k % RING]
+        if sync == 'nccl':
+            with torch.cuda.stream(lane_streams[lane]):
+                se.step(pk, off, B, rank * B, 0xB1DDE5, lane_handles[lane], lane)
+        else:
+            se.step(pk, off, B, rank * B, 0xB1DDE5, lane_handles[lane], lane)
 
     def timed(k0, nsteps):
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
