@@ -733,7 +733,8 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
     const uint32_t tile = blockIdx.x;
     STAMP(0);
-    const uint32_t n = r_n_dev ? *r_n_dev : P.n;           // routed batches: size known only on the device
+    // routed batches: size known only on the device (header: count, bytes, epoch, sender overflow flag)
+    const uint32_t n = r_n_dev ? (r_n_dev[3] ? 0u : r_n_dev[0]) : P.n;
     const uint32_t ntiles = (n + T - 1) / T;
     if (tile < ntiles) {
     const uint32_t q0 = tile * T;
@@ -942,12 +943,17 @@ __host__ __device__ inline size_t region_size(uint32_t cap_q, uint32_t cap_b) { 
 __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const PushParams A) {
     const Params& P = A.P;
     __shared__ __align__(16) uint8_t s_in[S_IN + 32];
+    __shared__ __align__(16) uint8_t s_sorted[S_IN + 16 * MAX_RANKS + 32];     // the tile's packets grouped by owner
+    __shared__ uint32_t s_moff[T], s_mq[T];                                    // per-owner-grouped offsets / query indices
     __shared__ uint32_t s_off[T + 1];
     __shared__ unsigned long long s_cur[MAX_RANKS], s_base[MAX_RANKS];
+    __shared__ uint32_t s_kstart[MAX_RANKS + 1], s_bstart[MAX_RANKS];
+    __shared__ uint32_t s_ovf;
     __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
     if (tid < MAX_RANKS) s_cur[tid] = 0;
+    if (tid == 0) s_ovf = 0;
     const uint32_t q0 = blockIdx.x * T;
     const uint32_t nq = min((uint32_t)T, P.n - q0);
     for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
@@ -964,6 +970,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     __syncthreads();
     Res r;
     r.owner = (uint8_t)P.rank;                     // queries that need no lookup are answered where they arrived
+    r.sp = 0; r.p = nullptr;
     uint32_t len = 0, k = 0, boff = 0;
     const bool have = tid < (int)nq;
     if (have) {
@@ -979,27 +986,71 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         k = (uint32_t)(old >> PUSH_CNT_SHIFT); boff = (uint32_t)(old & ((1ull << PUSH_CNT_SHIFT) - 1));
     }
     __syncthreads();
+    // one claim per (tile, owner) in the sender-local cursor of region (this rank -> owner)
     if (tid < (int)P.nranks) { const unsigned long long t = s_cur[tid]; s_base[tid] = t ? atomicAdd(A.cursor + tid, t) : 0ull; }
     __syncthreads();
-    if (have) {
+    if (tid == 0) {
+        uint32_t kk = 0, bb = 0;
+        for (uint32_t d = 0; d < P.nranks; d++) {
+            const unsigned long long t = s_cur[d], base = s_base[d];
+            const uint32_t cnt = (uint32_t)(t >> PUSH_CNT_SHIFT), nb = (uint32_t)(t & ((1ull << PUSH_CNT_SHIFT) - 1));
+            const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT);
+            const unsigned long long gb = base & ((1ull << PUSH_CNT_SHIFT) - 1);
+            if (cnt && (gk + cnt > A.cap_q || gb + nb > A.cap_b)) { s_ovf = 1; *A.err = 1; }
+            s_kstart[d] = kk; kk += cnt;
+            bb += (uint32_t)((gb - bb) & 15);      // group start has the 16-byte phase of its destination
+            s_bstart[d] = bb; bb += nb;
+        }
+        s_kstart[P.nranks] = kk;
+    }
+    __syncthreads();
+    const bool ovf = s_ovf != 0;
+    if (have && !ovf) {
         const unsigned long long base = s_base[r.owner];
-        const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT) + k;
-        const unsigned long long gb = (base & ((1ull << PUSH_CNT_SHIFT) - 1)) + boff;
-        if (gk >= A.cap_q || gb + len > A.cap_b) *A.err = 1;
-        else {
+        const uint32_t gb = (uint32_t)(base & ((1ull << PUSH_CNT_SHIFT) - 1)) + boff;
+        if (staged) {
+            s_moff[s_kstart[r.owner] + k] = gb;
+            s_mq[s_kstart[r.owner] + k] = A.qidx_base + q0 + tid;
+            Wr w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted) + s_bstart[r.owner] + boff);
+            w.copy(r.sp, len);
+            w.end();
+        } else {                                   // oversized tile: plain peer stores from global memory
+            const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT) + k;
             uint8_t* reg = A.region[r.owner];
-            ((uint32_t*)(reg + region_off_array(A.cap_q)))[gk] = (uint32_t)gb;
+            ((uint32_t*)(reg + region_off_array(A.cap_q)))[gk] = gb;
             ((uint32_t*)(reg + region_qidx_array(A.cap_q)))[gk] = A.qidx_base + q0 + tid;
             uint8_t* dst = reg + region_bytes(A.cap_q) + gb;
-            const uint8_t* src = r.p;
-            uint32_t i = 0;
-            // peer stores: bytes up to 4-byte alignment of the destination, then words
-            for (; i < len && ((uintptr_t)(dst + i) & 3); i++) dst[i] = src[i];
-            if (r.sp) for (; i + 4 <= len; i += 4) *(uint32_t*)(dst + i) = ldsu32(r.sp + i);
-            for (; i < len; i++) dst[i] = src[i];
+            const uint8_t* src = P.pkts + s_off[tid];
+            for (uint32_t i = 0; i < len; i++) dst[i] = src[i];
         }
-        __threadfence_system();                    // this thread's peer stores are performed before the block counts itself done
     }
+    __syncthreads();
+    if (staged && !ovf) {
+        // per owner: one contiguous chunk of packets and of metadata, pushed with coalesced peer stores
+        for (uint32_t d = 0; d < P.nranks; d++) {
+            const unsigned long long t = s_cur[d], base = s_base[d];
+            const uint32_t cnt = (uint32_t)(t >> PUSH_CNT_SHIFT), nb = (uint32_t)(t & ((1ull << PUSH_CNT_SHIFT) - 1));
+            if (!cnt) continue;
+            uint8_t* reg = A.region[d];
+            const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT);
+            const unsigned long long gb = base & ((1ull << PUSH_CNT_SHIFT) - 1);
+            uint32_t* go = (uint32_t*)(reg + region_off_array(A.cap_q)) + gk;
+            uint32_t* gq = (uint32_t*)(reg + region_qidx_array(A.cap_q)) + gk;
+            for (uint32_t i = tid; i < cnt; i += T) { go[i] = s_moff[s_kstart[d] + i]; gq[i] = s_mq[s_kstart[d] + i]; }
+            uint8_t* g = reg + region_bytes(A.cap_q) + gb;                    // g[x] <-> s_sorted[s_bstart[d] + x]
+            const uint8_t* sm = s_sorted + s_bstart[d];
+            uint32_t x0 = 0;
+            uint32_t head = (uint32_t)((16 - (gb & 15)) & 15);
+            if (head > nb) head = nb;
+            if (tid < (int)head) g[tid] = sm[tid];
+            x0 = head;
+            const uint32_t nv = (nb - x0) >> 4;
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(sm + x0 + 16 * i);
+            x0 += nv << 4;
+            if (x0 + tid < nb) g[x0 + tid] = sm[x0 + tid];
+        }
+    }
+    __threadfence_system();                        // this block's peer stores are performed before it counts itself done
     // The last block publishes the region headers (count, bytes, end-of-offsets sentinel) and then,
     // after a system-scope fence, the epoch flag the owner's wait kernel spins on: the exchange
     // needs no collective, only this ordered pair of peer stores per (source, owner).
