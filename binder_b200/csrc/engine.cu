@@ -1365,13 +1365,12 @@ bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t
     if (!e || nranks == 0 || nranks > bbk::MAX_RANKS || rank >= nranks || max_batch == 0 || max_batch > e->max_batch) return fail(BB_ERR_ARG);
     bb_shard* s = new bb_shard();
     s->e = e; s->nranks = nranks; s->rank = rank; s->max_batch = max_batch;
-    // a region holds this rank's share of one ingress batch: B/nranks on average, +50 % and a floor
-    // for hash imbalance (a full batch when there is one rank)
-    s->cap_q = nranks == 1 ? max_batch : max_batch / nranks + max_batch / (2 * nranks) + 1024;
-    if (s->cap_q > max_batch) s->cap_q = max_batch;
+    // A region must be able to hold a whole ingress batch: queries that need no lookup stay on the
+    // ingress rank, and real DNS traffic is skewed (one hot name sends a full batch to one owner).
+    s->cap_q = max_batch;
     s->cap_b = s->cap_q * (bytes_per_query ? bytes_per_query : 64);
     s->reg_size = bbk::region_size(s->cap_q, s->cap_b);
-    s->out_cap = s->cap_q * 512u;
+    s->out_cap = s->cap_q * 256u;
     auto ck = [&](cudaError_t c) { if (c != cudaSuccess) { g_cuda_err = cudaGetErrorString(c); return false; } return true; };
     auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
     s->out_stride = up((size_t)s->out_cap + 64); s->off_stride = up(((size_t)s->cap_q + 1) * 4); s->len_stride = up((size_t)s->cap_q * 2 + 16);

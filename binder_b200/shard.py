@@ -104,7 +104,7 @@ class ShardedEngine(object):
     def fetch(self, src, lane=0):
         """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays."""
         cap = self.cap_q
-        out = np.empty(cap * 512, np.uint8); out_off = np.zeros(cap + 1, np.uint32); out_len = np.zeros(cap, np.uint16)
+        out = np.empty(cap * 256, np.uint8); out_off = np.zeros(cap + 1, np.uint32); out_len = np.zeros(cap, np.uint16)
         status = np.zeros(cap, np.uint8); qidx = np.zeros(cap, np.uint32); miss = np.zeros(cap, np.uint32)
         n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
         check(lib().bb_shard_fetch(self._lanes[lane], src, out.ctypes.data, out.size, out_off.ctypes.data,
