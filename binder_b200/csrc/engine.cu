@@ -175,7 +175,7 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
         uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,pad | ttl | val
         uint32_t sk = (hd.y >> 8) & 0xFF;
         if (sk == K_EMPTY) return false;
-        if (hd.x == h && ((hd.y >> 16) & 0xFF) == ns) {
+        if (hd.x == h && ((hd.y >> 16) & 1) == ns) {
             uint32_t sl = hd.y & 0xFF;
             const uint8_t* kb = nullptr;
             if (sl == KLEN_OVERFLOW) {
@@ -341,8 +341,58 @@ __device__ __forceinline__ uint32_t upper_bytes(uint32_t x) {
     return ge7(x7, 0x41) & ~ge7(x7, 0x5B) & ~x;
 }
 
+// Decode of a packet staged in shared memory, word-wise (same acceptance as decode()).
+__device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
+    if (len < 17) return false;                                               // header + root name + type/class at least
+    const uint32_t w0 = ldsu32(sp), w1 = ldsu32(sp + 4), w2 = ldsu32(sp + 8);
+    const uint32_t fl = (w0 >> 16) & 0xFF;                                    // byte 2: QR opcode AA TC RD
+    if (fl & 0x80) return false;
+    r.opcode = (fl >> 3) & 0xF; r.rd = fl & 1;
+    if (w1 != 0x00000100u) return false;                                      // QDCOUNT=1, ANCOUNT=0
+    if (w2 != 0u && w2 != 0x01000000u) return false;                          // NSCOUNT=0, ARCOUNT<=1
+    const uint32_t nm = sp + 12, lim = len - 12;                              // name bytes available
+    uint32_t pos = 0, lo = 0, hi = 0;
+    for (;;) {
+        if (pos >= lim) return false;
+        const uint32_t c = lds8(nm + pos);
+        if (c == 0) break;
+        if (c > 63) return false;
+        if (pos < 32) lo |= 1u << pos; else if (pos < 64) hi |= 1u << (pos - 32);
+        pos += 1 + c;
+        if (pos > 254) return false;
+    }
+    if (pos + 1 + 4 > lim) return false;
+    r.qn_len = pos + 1;
+    r.lenmask = (uint64_t)lo | ((uint64_t)hi << 32);
+    const uint32_t tc = ldsu32(nm + pos + 1);                                 // QTYPE, QCLASS (big-endian)
+    r.qtype = (uint16_t)(((tc & 0xFF) << 8) | ((tc >> 8) & 0xFF));
+    if ((tc >> 16) != 0x0100u) return false;                                  // class IN
+    r.edns = 0; r.adv = 0;
+    if (w2) {
+        const uint32_t q = nm + pos + 5;                                      // the one additional RR
+        if (pos + 5 + 11 > lim) return false;
+        const uint32_t a = ldsu32(q), b = ldsu32(q + 4), c2 = ldsu32(q + 8);
+        if ((a & 0xFFFFFF) != 0x290000u) return false;                        // root owner, TYPE 41
+        r.adv = (uint16_t)(((a >> 24) << 8) | (b & 0xFF));
+        const uint32_t rdlen = (((c2 >> 8) & 0xFF) << 8) | ((c2 >> 16) & 0xFF);
+        if (pos + 5 + 11 + rdlen > lim) return false;
+        r.edns = 1;
+    }
+    return true;
+}
+
+// 0x80 in every byte of the lower-cased dotted word `lo` that is NOT in [a-z0-9_-] ('.' counts as bad:
+// the caller masks out the label-boundary positions)
+__device__ __forceinline__ uint32_t bad_chars(uint32_t lo) {
+    const uint32_t y7 = lo & 0x7F7F7F7Fu;
+    const uint32_t ok = ((ge7(y7, 0x61) & ~ge7(y7, 0x7B)) | (ge7(y7, 0x30) & ~ge7(y7, 0x3A)) |
+                         zero_bytes(lo ^ 0x2D2D2D2Du) | zero_bytes(lo ^ 0x5F5F5F5Fu)) & ~lo;
+    return ~ok & 0x80808080u;
+}
+
 __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
     const EngineConst* E = P.eng;
+    if (!P.ready && !P.route) return false;            // not-ready engines: exact ordering of refusals lives in the generic path
     const uint32_t nm = r.sp + 12;
     const bool srv = r.qtype == QT_SRV;
     const uint32_t d_end = r.qn_len - 1;
@@ -358,62 +408,66 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         d_off = p1 + 1 + l1;
         if (lds8(nm + d_off) == 0) { r.rcode = RC_REFUSED; return true; }
     }
-    if (d_end <= d_off + 1) { r.rcode = RC_REFUSED; return true; }            // root name (suffix_len > 0 always)
+    if (d_end <= d_off + 1) { r.rcode = RC_REFUSED; return true; }            // root name
     const uint32_t dl = d_end - d_off - 1;
     if (dl > KEY_INLINE_MAX) return false;
+    // suffix gate (:157-166), case-sensitive, on the raw wire bytes: the domain's last sl bytes must be
+    // dnsDomain's wire labels and start at a label boundary ('.' + dnsDomain in the dotted view)
     const uint32_t sl = E->suffix_len;
-    const int j0 = (int)dl - (int)sl;
+    if (dl < sl) { r.rcode = RC_REFUSED; return true; }
+    {
+        const uint32_t t0 = d_end - sl;                                       // where the suffix's first length byte must sit
+        uint32_t bad = ((r.lenmask >> t0) & 1ull) ? 0u : 1u;
+        const uint32_t nw = (sl + 3) >> 2;
+        for (uint32_t j = 0; j < nw; j++) {                                   // words right-aligned to the end of the name
+            const uint32_t x = ldsu32(nm + d_end - 4 * (j + 1));
+            const uint32_t e = lds32(s_sfx + 256 - 4 * (j + 1));
+            const uint32_t rem = sl - 4 * j;                                  // bytes of this word that belong to the suffix
+            const uint32_t cm = rem >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - rem)));
+            bad |= (x ^ e) & cm;
+        }
+        if (bad) { r.rcode = RC_REFUSED; return true; }
+    }
+    // normalise (dotted view, toLowerCase :207) + hash, four bytes per step
+    const uint64_t lm = r.lenmask >> (d_off + 1);
+    const uint32_t nwords = (dl + 3) >> 2;
+    const uint32_t tailm = (dl & 3) ? ((1u << (8 * (dl & 3))) - 1) : 0xFFFFFFFFu;
     uint32_t kw[12];
     uint32_t h = hash_init(NS_FORWARD);
-    uint32_t dotl = 0, nl = 0, inval = 0, sfx_bad = 0, last_up = 0xFFFFFFFFu;
+    uint32_t upw = 0, upi = 0;
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         kw[i] = 0;
-        if (4u * i < dl) {
+        if ((uint32_t)i < nwords) {
             const uint32_t x = ldsu32(nm + d_off + 1 + 4 * i);
-            const uint32_t nb = dl - 4 * i;
-            const uint32_t tm = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1);
-            const uint32_t tm80 = tm & 0x80808080u;
-            const uint32_t bits = (uint32_t)(r.lenmask >> (d_off + 1 + 4 * i)) & 0xFu;
-            const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // length-byte positions
-            dotl |= zero_bytes(x ^ 0x2E2E2E2Eu) & ~m8 & tm80;                         // '.' inside a label
-            nl |= (zero_bytes(x ^ 0x0A0A0A0Au) | zero_bytes(x ^ 0x0D0D0D0Du)) & ~m8 & tm80;
-            const uint32_t xd = ((x & ~m8) | (0x2E2E2E2Eu & m8)) & tm;                 // dotted view
-            if (j0 >= 0 && 4 * i + 4 > j0) {                                           // suffix gate, case-sensitive
-                const int sh = 4 * i - j0;
-                const uint32_t e = ldsu32((uint32_t)((int)s_sfx + 4 + sh));
-                const uint32_t cm = sh < 0 ? (0xFFFFFFFFu << (8 * (-sh))) : 0xFFFFFFFFu;
-                sfx_bad |= (xd ^ e) & cm & tm;
-            }
-            const uint32_t up = upper_bytes(xd) & tm80;
-            const uint32_t lo = xd | (up >> 2);                                        // toLowerCase (:207)
-            const uint32_t y7 = lo & 0x7F7F7F7Fu;
-            const uint32_t ok = ((ge7(y7, 0x61) & ~ge7(y7, 0x7B)) | (ge7(y7, 0x30) & ~ge7(y7, 0x3A)) |
-                                 (ge7(y7, 0x2D) & ~ge7(y7, 0x2F)) | zero_bytes(lo ^ 0x5F5F5F5Fu)) & ~lo;
-            inval |= ~ok & tm80;                                                       // /[^a-z0-9_.-]/ (:208)
-            if (up) last_up = 4 * i + ((31 - __clz(up)) >> 3);
+            const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
+            const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // label-boundary positions
+            uint32_t xd = (x & ~m8) | (0x2E2E2E2Eu & m8);
+            if ((uint32_t)i == nwords - 1) xd &= tailm;
+            const uint32_t up = upper_bytes(xd);
+            if (up) { upw = up; upi = i; }
+            const uint32_t lo = xd | (up >> 2);
             kw[i] = lo;
             h = hash_word(h, lo);
         }
     }
-    if (srv && nl) return false;                      // regex group 3 stops at a line terminator: generic path
-    if (dotl || refuse) { r.rcode = RC_REFUSED; return true; }                // in-label dot / SRV shape
-    if (j0 < 0 || sfx_bad) { r.rcode = RC_REFUSED; return true; }             // :157-166
-    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return true; }         // :186-192
-    if (inval) { r.rcode = RC_REFUSED; return true; }                         // :208-215
     h = hash_finish(h, dl);
+    if (refuse) { r.rcode = RC_REFUSED; return true; }
+    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
     r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
-    if (last_up == 0xFFFFFFFFu) r.ptr_tgt = (uint16_t)d_off;
+    if (!upw) r.ptr_tgt = (uint16_t)d_off;
     else {
-        const uint32_t pu = d_off + 1 + last_up;                              // wire position of the last upper-case byte
+        const uint32_t pu = d_off + 1 + 4 * upi + ((31 - __clz(upw)) >> 3);  // wire position of the last upper-case byte
         const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
         r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
     }
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
-    // zk.lookup(domain): one 64-byte slot per probe, compared as words
+    // zk.lookup(domain): one 64-byte slot per probe, compared as words.  The header compare also
+    // carries the key's dot count: a query with a '.' inside a label has fewer label boundaries than
+    // any key that spells the same, so it can never match here.
+    const uint32_t ndots = (uint32_t)__popcll(r.lenmask >> (d_off + 1));
+    const uint32_t want = dl | ((NS_FORWARD | (ndots << 1)) << 16);
     uint32_t idx = h & P.mask, kind = 0, ttl = 0, val = 0;
-    bool hit = false;
-    const uint32_t want = dl | (NS_FORWARD << 16);
+    bool hit = false, clean = false;
     for (;;) {
         const uint4* sq = (const uint4*)(P.table + idx);
         const uint4 q0 = __ldg(sq), q1 = __ldg(sq + 1), q2 = __ldg(sq + 2), q3 = __ldg(sq + 3);
@@ -423,9 +477,27 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
             const uint32_t diff = (kw[0] ^ q1.x) | (kw[1] ^ q1.y) | (kw[2] ^ q1.z) | (kw[3] ^ q1.w) |
                                   (kw[4] ^ q2.x) | (kw[5] ^ q2.y) | (kw[6] ^ q2.z) | (kw[7] ^ q2.w) |
                                   (kw[8] ^ q3.x) | (kw[9] ^ q3.y) | (kw[10] ^ q3.z) | (kw[11] ^ q3.w);
-            if (diff == 0) { hit = true; kind = sk; ttl = q0.z; val = q0.w; break; }
+            if (diff == 0) { hit = true; kind = sk; ttl = q0.z; val = q0.w; clean = (q0.y >> 24) & SLOT_KEY_CLEAN; break; }
         }
         idx = (idx + 1) & P.mask;
+    }
+    if (!(hit && clean)) {
+        // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a
+        // label, a character outside [a-z0-9_.-] (:208-215) -> REFUSED; an SRV name with a
+        // line terminator goes to the generic path (its regex group stops there, :141).
+        uint32_t bad = 0, nlc = 0;
+#pragma unroll
+        for (int i = 0; i < 12; i++) {
+            if ((uint32_t)i < nwords) {
+                const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
+                const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t tm = ((uint32_t)i == nwords - 1) ? tailm : 0xFFFFFFFFu;
+                bad |= bad_chars(kw[i]) & ~m8 & tm;
+                nlc |= (zero_bytes(kw[i] ^ 0x0A0A0A0Au) | zero_bytes(kw[i] ^ 0x0D0D0D0Du)) & ~m8 & tm;
+            }
+        }
+        if (srv && nlc) return false;
+        if (bad) { r.rcode = RC_REFUSED; return true; }
     }
     finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
     return true;
@@ -520,7 +592,7 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
     r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
     r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
-    if (!decode(r.p, len, r)) { r.status = ST_DROPPED; return; }
+    if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
     r.maxsz = r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
     const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
     r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
@@ -710,7 +782,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
     __shared__ uint32_t s_wsum[8];
     __shared__ unsigned long long s_prefix;
-    __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];   // 4 pad bytes, '.' + dnsDomain, zero tail
+    __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     // region of a multi-region launch (routed batches: one region per source rank)
     const size_t ry = P.regions ? blockIdx.y : 0;
@@ -730,7 +802,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // Tiles are taken in blockIdx order: like CUB's single-pass scan, the look-back below relies on
     // thread blocks being dispatched in increasing blockIdx order (a block only ever waits for
     // lower-numbered blocks, which are resident or finished).
-    if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
+    for (int i = tid; i < 64; i += T) ((uint32_t*)s_sfx)[i] = __ldg((const uint32_t*)P.eng->wire_tail + i);
     const uint32_t tile = blockIdx.x;
     STAMP(0);
     // routed batches: size known only on the device (header: count, bytes, epoch, sender overflow flag)
@@ -949,9 +1021,9 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     __shared__ unsigned long long s_cur[MAX_RANKS], s_base[MAX_RANKS];
     __shared__ uint32_t s_kstart[MAX_RANKS + 1], s_bstart[MAX_RANKS];
     __shared__ uint32_t s_ovf;
-    __shared__ __align__(16) uint8_t s_sfx[4 + 256 + 12];
+    __shared__ __align__(16) uint8_t s_sfx[256];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (tid < 68) ((uint32_t*)s_sfx)[tid] = (tid >= 1 && tid <= 64) ? __ldg((const uint32_t*)P.eng->suffix + (tid - 1)) : 0u;
+    for (int i = tid; i < 64; i += T) ((uint32_t*)s_sfx)[i] = __ldg((const uint32_t*)P.eng->wire_tail + i);
     if (tid < MAX_RANKS) s_cur[tid] = 0;
     if (tid == 0) s_ovf = 0;
     const uint32_t q0 = blockIdx.x * T;
@@ -1201,6 +1273,7 @@ bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
     memcpy(e->hconst.soa, w.data(), w.size()); e->hconst.soa[w.size()] = 0;
     memcpy(e->hconst.soa + w.size() + 1, hw.data(), hw.size()); e->hconst.soa[w.size() + 1 + hw.size()] = 0;
     e->hconst.soa_len = (uint32_t)(w.size() + 1 + hw.size() + 1);
+    memcpy(e->hconst.wire_tail + 256 - w.size(), w.data(), w.size());   // word-wise suffix gate compares the name's tail with this
     e->hconst.recursion = o->recursion ? 1 : 0;
     e->device = o->device; e->ordered = o->ordered_output ? 1 : 0;
     e->max_batch = o->max_batch ? o->max_batch : (1u << 20);

@@ -404,7 +404,7 @@ struct TableBuilder {
         return off;
     }
     bool key_eq(const Slot& s, uint32_t ns, const uint8_t* k, uint32_t len) const {
-        if (s.ns != ns) return false;
+        if ((uint32_t)(s.ns & 1) != ns) return false;
         if (len <= KEY_INLINE_MAX) return s.klen == len && memcmp(s.key, k, len) == 0;
         if (s.klen != KLEN_OVERFLOW) return false;
         uint32_t off, l; memcpy(&off, s.key, 4); memcpy(&l, s.key + 4, 4);
@@ -419,7 +419,15 @@ struct TableBuilder {
         for (;;) {
             Slot& s = z->slots[i];
             if (s.kind == K_EMPTY) {
-                s.hash = h; s.ns = (uint8_t)ns;
+                s.hash = h;
+                uint32_t dots = 0; bool clean = true;
+                for (uint32_t i = 0; i < len; i++) {
+                    const uint8_t c = k[i];
+                    dots += c == '.';
+                    if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-' || c == '.')) clean = false;
+                }
+                s.ns = (uint8_t)(ns | (ns == NS_FORWARD ? (dots & 127) << 1 : 0));
+                s.flags = (ns == NS_FORWARD && clean) ? SLOT_KEY_CLEAN : 0;
                 if (len <= KEY_INLINE_MAX) { s.klen = (uint8_t)len; memcpy(s.key, k, len); }
                 else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); }
                 s.kind = kind; s.ttl = ttl; s.val = val;

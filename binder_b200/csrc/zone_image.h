@@ -42,13 +42,15 @@ constexpr uint32_t NS_FORWARD = 0;
 constexpr uint32_t NS_REVERSE = 1;
 constexpr uint32_t KEY_INLINE_MAX = 48;
 constexpr uint8_t  KLEN_OVERFLOW = 0xFF;      // key bytes live in the arena
+constexpr uint8_t  SLOT_KEY_CLEAN = 1;
 
 struct alignas(64) Slot {
     uint32_t hash;       // full 32-bit key hash (compared before the key bytes)
     uint8_t  klen;       // key length 1..48, or KLEN_OVERFLOW
     uint8_t  kind;       // K_*
-    uint8_t  ns;         // NS_*
-    uint8_t  pad;
+    uint8_t  ns;         // bit 0: NS_*; bits 1..7: number of '.' in a forward key (a query whose label
+                         // count disagrees cannot be this key: it carries a '.' inside a label)
+    uint8_t  flags;      // SLOT_KEY_CLEAN: every key byte is in [a-z0-9_.-] (lib/server.js:208)
     uint32_t ttl;        // record ttl (lib/server.js:270-274)
     uint32_t val;        // IPv4 (network order bytes packed big-endian) or arena offset
     uint8_t  key[48];    // inline key; overflow: key[0..3] = arena offset, key[4..7] = length
@@ -126,6 +128,7 @@ struct EngineConst {
     uint32_t pad;
     uint8_t  suffix[256];        // '.' + dnsDomain, as query.name() would spell it
     uint8_t  soa[528];           // mname wire + rname wire of SOARecord(dnsDomain) (:286-287)
+    uint8_t  wire_tail[256];     // dnsDomain as wire labels (no terminator), right-aligned: ends at wire_tail[256]
 };
 
 // host-side container of a built zone
