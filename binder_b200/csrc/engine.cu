@@ -169,12 +169,13 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
     for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
     uint32_t h = kh.finish();
     if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return false; }   // sharding: who would answer
-    uint32_t i = h & P.mask;
-    for (;;) {
-        const Slot* s = P.table + i;
-        uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,pad | ttl | val
+    // 2-choice cuckoo: the key is in slot1_of(h) or slot2_of(h) or nowhere
+    const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, P.mask) };
+    for (int c = 0; c < 2; c++) {
+        const Slot* s = P.table + cand[c];
+        uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,flags | ttl | val
         uint32_t sk = (hd.y >> 8) & 0xFF;
-        if (sk == K_EMPTY) return false;
+        if (sk == K_EMPTY) continue;
         if (hd.x == h && ((hd.y >> 16) & 1) == ns) {
             uint32_t sl = hd.y & 0xFF;
             const uint8_t* kb = nullptr;
@@ -189,8 +190,8 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
                 if (eq) { kind = sk; ttl = hd.z; val = hd.w; return true; }
             }
         }
-        i = (i + 1) & P.mask;
     }
+    return false;
 }
 
 // ---- shuffle (lib/server.js:40-53) --------------------------------------------------------
@@ -414,7 +415,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     // suffix gate (:157-166), case-sensitive, on the raw wire bytes: the domain's last sl bytes must be
     // dnsDomain's wire labels and start at a label boundary ('.' + dnsDomain in the dotted view)
     const uint32_t sl = E->suffix_len;
-    if (dl < sl) { r.rcode = RC_REFUSED; return true; }
+    if (dl < sl) { r.rcode = RC_REFUSED; return true; }       // (a truncated SRV domain is shorter still)
     {
         const uint32_t t0 = d_end - sl;                                       // where the suffix's first length byte must sit
         uint32_t bad = ((r.lenmask >> t0) & 1ull) ? 0u : 1u;
@@ -426,7 +427,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
             const uint32_t cm = rem >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - rem)));
             bad |= (x ^ e) & cm;
         }
-        if (bad) { r.rcode = RC_REFUSED; return true; }
+        if (bad) { if (srv) return false; r.rcode = RC_REFUSED; return true; }   // SRV: the regex group may stop at a line terminator (:141) -> generic path
     }
     // normalise (dotted view, toLowerCase :207) + hash, four bytes per step
     const uint64_t lm = r.lenmask >> (d_off + 1);
@@ -466,20 +467,26 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     // any key that spells the same, so it can never match here.
     const uint32_t ndots = (uint32_t)__popcll(r.lenmask >> (d_off + 1));
     const uint32_t want = dl | ((NS_FORWARD | (ndots << 1)) << 16);
-    uint32_t idx = h & P.mask, kind = 0, ttl = 0, val = 0;
+    uint32_t kind = 0, ttl = 0, val = 0;
     bool hit = false, clean = false;
-    for (;;) {
-        const uint4* sq = (const uint4*)(P.table + idx);
-        const uint4 q0 = __ldg(sq), q1 = __ldg(sq + 1), q2 = __ldg(sq + 2), q3 = __ldg(sq + 3);
-        const uint32_t sk = (q0.y >> 8) & 0xFF;
-        if (sk == K_EMPTY) break;
-        if (q0.x == h && (q0.y & 0x00FF00FFu) == want) {
-            const uint32_t diff = (kw[0] ^ q1.x) | (kw[1] ^ q1.y) | (kw[2] ^ q1.z) | (kw[3] ^ q1.w) |
-                                  (kw[4] ^ q2.x) | (kw[5] ^ q2.y) | (kw[6] ^ q2.z) | (kw[7] ^ q2.w) |
-                                  (kw[8] ^ q3.x) | (kw[9] ^ q3.y) | (kw[10] ^ q3.z) | (kw[11] ^ q3.w);
-            if (diff == 0) { hit = true; kind = sk; ttl = q0.z; val = q0.w; clean = (q0.y >> 24) & SLOT_KEY_CLEAN; break; }
-        }
-        idx = (idx + 1) & P.mask;
+    {
+        // 2-choice cuckoo: both candidate slots are fetched together — one DRAM round trip per lookup,
+        // hit or miss, for every lane of the warp
+        const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
+        const uint4* sb = (const uint4*)(P.table + slot2_of(h, P.mask));
+        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
+        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
+        const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |
+                            (kw[0] ^ a1.x) | (kw[1] ^ a1.y) | (kw[2] ^ a1.z) | (kw[3] ^ a1.w) |
+                            (kw[4] ^ a2.x) | (kw[5] ^ a2.y) | (kw[6] ^ a2.z) | (kw[7] ^ a2.w) |
+                            (kw[8] ^ a3.x) | (kw[9] ^ a3.y) | (kw[10] ^ a3.z) | (kw[11] ^ a3.w);
+        const uint32_t db = (b0.x ^ h) | ((b0.y & 0x00FF00FFu) ^ want) |
+                            (kw[0] ^ b1.x) | (kw[1] ^ b1.y) | (kw[2] ^ b1.z) | (kw[3] ^ b1.w) |
+                            (kw[4] ^ b2.x) | (kw[5] ^ b2.y) | (kw[6] ^ b2.z) | (kw[7] ^ b2.w) |
+                            (kw[8] ^ b3.x) | (kw[9] ^ b3.y) | (kw[10] ^ b3.z) | (kw[11] ^ b3.w);
+        // an empty slot has kind 0 and klen 0, so it can never equal `want` (dl >= 1)
+        if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
+        else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
     }
     if (!(hit && clean)) {
         // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a

@@ -410,32 +410,43 @@ struct TableBuilder {
         uint32_t off, l; memcpy(&off, s.key, 4); memcpy(&l, s.key + 4, 4);
         return l == len && memcmp(arena.data() + off, k, len) == 0;
     }
-    // insert or overwrite ("last writer wins", like assigning into a JS object)
     uint32_t nranks = 1, rank = 0;
     bool mine(uint32_t ns, const uint8_t* k, uint32_t len) const { return nranks == 1 || owner_of(hash_key(ns, k, len), nranks) == rank; }
-    bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
-        uint32_t h = hash_key(ns, k, len);
-        uint32_t i = h & mask;
-        for (;;) {
-            Slot& s = z->slots[i];
-            if (s.kind == K_EMPTY) {
-                s.hash = h;
-                uint32_t dots = 0; bool clean = true;
-                for (uint32_t i = 0; i < len; i++) {
-                    const uint8_t c = k[i];
-                    dots += c == '.';
-                    if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-' || c == '.')) clean = false;
-                }
-                s.ns = (uint8_t)(ns | (ns == NS_FORWARD ? (dots & 127) << 1 : 0));
-                s.flags = (ns == NS_FORWARD && clean) ? SLOT_KEY_CLEAN : 0;
-                if (len <= KEY_INLINE_MAX) { s.klen = (uint8_t)len; memcpy(s.key, k, len); }
-                else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); }
-                s.kind = kind; s.ttl = ttl; s.val = val;
-                return true;
-            }
-            if (s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; return false; }
-            i = (i + 1) & mask;
+    bool failed = false;         // a cuckoo insertion ran out of kicks: the caller rebuilds with a larger table
+    void fill(Slot& s, uint32_t h, uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
+        memset(&s, 0, sizeof s);
+        s.hash = h;
+        uint32_t dots = 0; bool clean = true;
+        for (uint32_t i = 0; i < len; i++) {
+            const uint8_t c = k[i];
+            dots += c == '.';
+            if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-' || c == '.')) clean = false;
         }
+        s.ns = (uint8_t)(ns | (ns == NS_FORWARD ? (dots & 127) << 1 : 0));
+        s.flags = (ns == NS_FORWARD && clean) ? SLOT_KEY_CLEAN : 0;
+        if (len <= KEY_INLINE_MAX) { s.klen = (uint8_t)len; memcpy(s.key, k, len); }
+        else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); }
+        s.kind = kind; s.ttl = ttl; s.val = val;
+    }
+    // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo
+    bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
+        const uint32_t h = hash_key(ns, k, len);
+        const uint32_t i1 = slot1_of(h, mask), i2 = slot2_of(h, mask);
+        for (uint32_t i : { i1, i2 }) {
+            Slot& s = z->slots[i];
+            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; return false; }
+        }
+        Slot cur; fill(cur, h, ns, k, len, kind, ttl, val);
+        uint32_t pos = z->slots[i1].kind == K_EMPTY ? i1 : (z->slots[i2].kind == K_EMPTY ? i2 : i1);
+        for (int kick = 0; kick < 2000; kick++) {
+            Slot& s = z->slots[pos];
+            if (s.kind == K_EMPTY) { s = cur; return true; }
+            Slot ev = s; s = cur; cur = ev;                          // evict the resident, move it to its other slot
+            const uint32_t a = slot1_of(cur.hash, mask), b = slot2_of(cur.hash, mask);
+            pos = pos == a ? b : a;
+        }
+        failed = true;
+        return true;
     }
 };
 
@@ -521,16 +532,20 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
     bb_zone* zone = new bb_zone();
     ZoneImage& Z = zone->img;
     memset(&Z, 0, sizeof Z);
+    TableBuilder T;
+    for (uint32_t grow = 0;; grow++) {      // cuckoo insertion can (rarely) fail: rebuild one size up
     uint64_t nkeys = 0;
     for (auto& nd : B.nodes) nkeys += 1 + ((nd.flags & NF_REV) ? 1 : 0);
-    // load factor <= 0.5; a shard holds ~1/nranks of the keys (+ 12 % slack for hash imbalance)
-    uint64_t want = nranks == 1 ? nkeys * 2 : nkeys * 2 / nranks + nkeys / (4 * nranks) + 64; uint32_t ns = 64;
+    // 2-choice cuckoo needs a load factor below 0.5: size for <= 0.45 (a shard holds ~1/nranks of the keys)
+    uint64_t want = (nkeys * 22 / 10) / nranks + (nranks > 1 ? nkeys / (4 * nranks) : 0) + 64; uint32_t ns = 64;
     while (ns < want) { ns <<= 1; if (ns == 0) { delete zone; return fail(BB_ERR_NOMEM); } }
+    ns <<= grow;
+    free(Z.slots); Z.slots = nullptr; Z.n_fwd = Z.n_rev = 0;
     Z.nslots = ns;
     Z.slots = (Slot*)aligned_alloc(64, (size_t)ns * sizeof(Slot));
     if (!Z.slots) { delete zone; return fail(BB_ERR_NOMEM); }
     memset(Z.slots, 0, (size_t)ns * sizeof(Slot));
-    TableBuilder T; T.z = &Z; T.mask = ns - 1; T.nranks = nranks; T.rank = rank;
+    T = TableBuilder(); T.z = &Z; T.mask = ns - 1; T.nranks = nranks; T.rank = rank;
     T.arena.assign(4, 0);                                     // offset 0 is never a valid record
     Z.n_nodes = B.nodes.size();
     std::string dom, kw, tmp;
@@ -602,6 +617,9 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
             if (T.put(NS_REVERSE, (const uint8_t*)B.pool.data() + nd.rev_off, nd.rev_len, kind, nd.ttl, val)) Z.n_rev++;
         }
     }
+    if (!T.failed) break;
+    if (grow > 3) { bb_zone_free(zone); return fail(BB_ERR_NOMEM); }
+    }   // grow
     while (T.arena.size() & 15) T.arena.push_back(0);
     Z.arena_len = T.arena.size();
     Z.arena = (uint8_t*)aligned_alloc(64, (Z.arena_len + 63) & ~(uint64_t)63);

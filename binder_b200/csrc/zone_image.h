@@ -1,7 +1,8 @@
 // Zone image: the HBM-resident, flattened form of binder's ZKCache (lib/zk.js:20-119).
 //
-// One open-addressed table (linear probing, power-of-two, load factor <= 0.5) of 64-byte
-// slots holds BOTH of ZKCache's maps:
+// One 2-choice cuckoo table (power-of-two, load factor < 0.46) of 64-byte slots holds BOTH of
+// ZKCache's maps (a key lives in slot h1 or slot h2, never anywhere else, so a lookup — hit or
+// miss — is two independent 64-byte reads issued together: one DRAM round trip per warp):
 //   forward  ca_treeNodes[lower-cased fqdn]  (lib/zk.js:62-64, keys written at :84,96)
 //   reverse  ca_revLookup[address string]    (lib/zk.js:65-67, keys written at :187-188)
 // distinguished by a namespace bit that also seeds the hash.  Everything lib/server.js
@@ -105,6 +106,13 @@ inline uint32_t hash_key(uint32_t ns, const uint8_t* k, uint32_t len) {
         h = hash_word(h, w);
     }
     return hash_finish(h, len);
+}
+
+// ---- cuckoo: the two slots a key may live in -------------------------------------------------
+BB_HD uint32_t slot1_of(uint32_t key_hash, uint32_t mask) { return key_hash & mask; }
+BB_HD uint32_t slot2_of(uint32_t key_hash, uint32_t mask) {
+    const uint32_t a = key_hash & mask, b = fmix32(key_hash ^ 0x5BD1E995u) & mask;
+    return b != a ? b : (a ^ 1u) & mask;
 }
 
 // ---- sharding: which rank owns a key (multi-GPU) -------------------------------
