@@ -35,7 +35,7 @@ constexpr int T = 128;                    // queries (= threads) per tile
 constexpr int S_IN = 8192;                // staged input bytes per tile
 constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
-constexpr int S_OUT = CAPW + MAXRESP + 32;
+constexpr int S_OUT = ((CAPW + MAXRESP + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -58,6 +58,7 @@ struct Params {
     const uint32_t* n_dev;           // when set, the batch size is read from device memory (routed batches)
     const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
     uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
+    uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
     // multi-region launch (grid.y = regions): every per-batch pointer advances by its stride per region
     uint32_t regions;
     size_t in_stride, out_stride, off_stride, len_stride, status_stride, miss_stride, totals_stride, desc_stride;
@@ -288,7 +289,7 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     const uint8_t* nm = r.p + 12;
     const EngineConst* E = P.eng;
     if (!hit) {                                                               // :219-247
-        if (E->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        if (P.recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
         r.rcode = RC_REFUSED; return;
     }
     r.ttl = ttl; r.val = val;
@@ -318,6 +319,11 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
     size_service(P, r, qidx, srv, fixed);
 }
+
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+// per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
+constexpr int NSTAGE = 12;
+#define STAMP(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * NSTAGE + (k)] = gtime(); } while (0)
 
 // ---- word-wise front end of resolve() -----------------------------------------------------
 // Same decisions as resolve_forward() below, four name bytes per step, for the common case:
@@ -414,7 +420,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     if (dl > KEY_INLINE_MAX) return false;
     // suffix gate (:157-166), case-sensitive, on the raw wire bytes: the domain's last sl bytes must be
     // dnsDomain's wire labels and start at a label boundary ('.' + dnsDomain in the dotted view)
-    const uint32_t sl = E->suffix_len;
+    const uint32_t sl = P.suffix_len;
     if (dl < sl) { r.rcode = RC_REFUSED; return true; }       // (a truncated SRV domain is shorter still)
     {
         const uint32_t t0 = d_end - sl;                                       // where the suffix's first length byte must sit
@@ -453,6 +459,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         }
     }
     h = hash_finish(h, dl);
+    STAMP(4);
     if (refuse) { r.rcode = RC_REFUSED; return true; }
     if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
     r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
@@ -488,6 +495,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
         else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
     }
+    STAMP(5);
     if (!(hit && clean)) {
         // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a
         // label, a character outside [a-z0-9_.-] (:208-215) -> REFUSED; an SRV name with a
@@ -605,6 +613,7 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
     r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
     const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
     if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
+    STAMP(3);
     if (r.sp && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, qidx, fixed)) return;
     const uint8_t* nm = r.p + 12;
     for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
@@ -619,19 +628,25 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
 // ---- mname encode (DESIGN.md "Wire spec: encode") ------------------------------------------
 // OPT echoed when the query carried one: root owner, type 41, udp size 1200, ttl 0, rdlen 0
 __constant__ uint8_t c_opt_rr[11] = { 0, 0, QT_OPT, 0x04, 0xB0, 0, 0, 0, 0, 0, 0 };
+// The response staging buffer is XOR-swizzled: 16-byte chunk index ^ (128-byte row & 7).  With one
+// 64-byte response per lane, word w of every lane would otherwise fall into 2 of the 32 banks (a
+// 16-way conflict on every store); swizzled, a warp's stores spread over 16 banks, and the flush
+// (consecutive 16-byte chunks) still reads each row as a permutation of itself.
+__device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
+
 struct Out {
-    uint8_t* o;
-    __device__ void u8(uint32_t v) { *o++ = (uint8_t)v; }
-    __device__ void u16(uint32_t v) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)v; o += 2; }
-    __device__ void u32(uint32_t v) { o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v; o += 4; }
-    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) o[i] = s[i]; o += n; }
+    uint8_t* base; uint32_t o;           // swizzled staging buffer, logical offset
+    __device__ void u8(uint32_t v) { base[swz(o)] = (uint8_t)v; ++o; }
+    __device__ void u16(uint32_t v) { u8(v >> 8); u8(v); }
+    __device__ void u32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
+    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) u8(s[i]); }
 };
 // the domain part, lower-cased, as wire labels up to `stop` (no terminator)
 __device__ void put_dom_labels(Out& w, const Res& r, uint32_t stop) {
     const uint8_t* nm = r.p + 12;
-    uint8_t* start = w.o;
+    const uint32_t start = w.o;
     for (uint32_t pos = r.d_off; pos < stop; pos++) w.u8(lower8(nm[pos]));    // length bytes (<64) are unaffected
-    if (r.trunc && stop > r.lastlen) start[r.lastlen - r.d_off] = (uint8_t)(r.d_end - r.lastlen - 1);
+    if (r.trunc && stop > r.lastlen) w.base[swz(start + r.lastlen - r.d_off)] = (uint8_t)(r.d_end - r.lastlen - 1);
 }
 __device__ void put_dom_owner(Out& w, const Res& r) {
     if (r.ptr_tgt != NONE16) { put_dom_labels(w, r, r.ptr_tgt); w.u16(0xC000 | (12 + r.ptr_tgt)); }
@@ -639,8 +654,8 @@ __device__ void put_dom_owner(Out& w, const Res& r) {
 }
 __device__ void put_rr_head(Out& w, uint32_t type, uint32_t ttl, uint32_t rdlen) { w.u16(type); w.u16(1); w.u32(ttl); w.u16(rdlen); }
 
-__device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint32_t qidx) {
-    Out w; w.o = dst;
+__device__ void emit_response(const Params& P, const Res& r, uint8_t* stage, uint32_t off, uint32_t qidx) {
+    Out w; w.base = stage; w.o = off;
     const uint8_t* p = r.p;
     uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
     switch (r.rk) {
@@ -703,18 +718,21 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
 // A byte stream into shared memory at an arbitrary byte address, stored as aligned 32-bit words;
 // only the bytes shared with the neighbouring responses (first / last partial word) go out as
 // single bytes, so two threads never write the same word.
-struct Wr {
-    uint32_t wp;         // shared address of the word being filled
+template <bool SWZ>
+struct WrT {
+    uint32_t base;       // shared address of the buffer (SWZ: offsets below are logical and get swizzled)
+    uint32_t wp;         // offset of the word being filled
     uint64_t acc; uint32_t fill, head;
-    __device__ void begin(uint32_t dst) { head = dst & 3u; wp = dst - head; acc = 0; fill = head; }
+    __device__ void begin(uint32_t buf, uint32_t off) { base = buf; head = off & 3u; wp = off - head; acc = 0; fill = head; }
+    __device__ __forceinline__ uint32_t at(uint32_t off) const { return base + (SWZ ? swz(off) : off); }
     __device__ __forceinline__ void flush() {
-        if (head) { for (uint32_t b = head; b < 4; b++) sts8(wp + b, (uint32_t)(acc >> (8 * b)) & 0xFF); head = 0; }
-        else sts32(wp, (uint32_t)acc);
+        if (head) { for (uint32_t b = head; b < 4; b++) sts8(at(wp) + b, (uint32_t)(acc >> (8 * b)) & 0xFF); head = 0; }
+        else sts32(at(wp), (uint32_t)acc);
         wp += 4; acc >>= 32; fill -= 4;
     }
     // v holds n (1..4) bytes in memory order (little-endian integer)
     __device__ __forceinline__ void put(uint32_t v, uint32_t n) { acc |= (uint64_t)v << (8 * fill); fill += n; if (fill >= 4) flush(); }
-    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(wp + b, (uint32_t)(acc >> (8 * b)) & 0xFF); }
+    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(at(wp) + b, (uint32_t)(acc >> (8 * b)) & 0xFF); }
     // n bytes from shared memory
     __device__ void copy(uint32_t src, uint32_t n) {
         uint32_t i = 0;
@@ -725,8 +743,8 @@ struct Wr {
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
 // emit_response() for the two commonest shapes (rcode-only and one A record), word-wise.
-__device__ void emit_fast(const Res& r, uint32_t dst) {
-    Wr w; w.begin(dst);
+__device__ void emit_fast(const Res& r, uint32_t stage, uint32_t off) {
+    WrT<true> w; w.begin(stage, off);
     const uint32_t p = r.sp;
     const uint32_t an = r.rk == RK_A1 ? r.keep_ans : 0;
     const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
@@ -771,10 +789,6 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     return v;
 }
 
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
-#define STAMP(k) do { if (P.stage_log && tid == 0) P.stage_log[(size_t)blockIdx.x * 8 + (k)] = gtime(); } while (0)
-
 #ifndef BB_MIN_BLOCKS
 #define BB_MIN_BLOCKS 8      /* 64 registers, no spills: 8 tiles (1024 threads) resident per SM */
 #endif
@@ -784,7 +798,7 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 template <bool ORDERED>
 __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params P) {
     __shared__ __align__(16) uint8_t s_in[S_IN + 32];
-    __shared__ __align__(16) uint8_t s_out[S_OUT];
+    __shared__ __align__(128) uint8_t s_out[S_OUT];          // XOR-swizzled (swz())
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
     __shared__ uint32_t s_wsum[8];
@@ -850,7 +864,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const uint32_t my_len = r.rlen;
     const uint32_t my_miss = (tid < (int)nq && r.status == ST_MISS) ? 1u : 0u;
 
-    STAMP(3);
+    STAMP(6);
     // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
     uint32_t v = my_len | (my_miss << 24);     // 128 x 1232 < 2^24
     uint32_t inc = v;
@@ -865,7 +879,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     s_scan[tid] = my_o;
     if (tid == 0) s_scan[T] = tile_bytes;
 
-    STAMP(4);
+    STAMP(7);
     // ---- where this tile's responses (and misses) go ------------------------------------------
     if (!ORDERED) {
         if (tid == 0)                                    // one claim per tile: bytes | misses << 40
@@ -908,7 +922,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         if (lane == 0) s_prefix = ex;
     }
     __syncthreads();
-    STAMP(5);
+    STAMP(8);
     const uint64_t ex = s_prefix;
     const uint64_t gbase = ex & ((1ull << D_MISS_SHIFT) - 1);
     const uint32_t mbase = (uint32_t)(ex >> D_MISS_SHIFT);
@@ -931,11 +945,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         const bool mine = my_len && my_o >= w0 && my_o < w0 + CAPW;
         if (mine) {
             if (r.sp && (r.rk == RK_HEADER || r.rk == RK_A1))
-                emit_fast(r, (uint32_t)__cvta_generic_to_shared(s_out) + shift + (my_o - w0));
-            else emit_response(P, r, s_out + shift + (my_o - w0), qidx);
+                emit_fast(r, (uint32_t)__cvta_generic_to_shared(s_out), shift + (my_o - w0));
+            else emit_response(P, r, s_out, shift + (my_o - w0), qidx);
         }
         __syncthreads();
-        if (rd == 0) STAMP(6);
+        if (rd == 0) STAMP(9);
         // bytes of this round: from the first response starting in the window to the end of the last
         uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
         if (nrounds > 1 && rd > 0) {                                                         // skip the previous round's overhang
@@ -952,23 +966,23 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             // zero-length entries at the boundary share the same offset: fine, range is [lo, hi)
         }
         if (hi > lo) {
-            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[shift + x - w0]
-            const uint8_t* s = s_out + shift - w0;
+            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[swz(shift + x - w0)]
+            const uint32_t so = shift - w0;
             uint32_t x0 = lo, x1 = hi;
             // head up to 16-byte alignment of the global address
             uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);
             if (head > x1 - x0) head = x1 - x0;
-            if (tid < (int)head) g[x0 + tid] = s[x0 + tid];
+            if (tid < (int)head) g[x0 + tid] = s_out[swz(so + x0 + tid)];
             x0 += head;
             const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s + x0 + 16 * i);
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(so + x0 + 16 * i));
             x0 += nv << 4;
-            if (x0 + tid < x1) g[x0 + tid] = s[x0 + tid];
+            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(so + x0 + tid)];
         }
         __syncthreads();
     }
 
-    STAMP(7);
+    STAMP(10);
     }   // tile < ntiles
     // ---- self-cleaning: the last block to finish publishes the totals and resets the placement
     // state for the next launch (blocks beyond ntiles only take part in this count) ------------
@@ -1090,7 +1104,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         if (staged) {
             s_moff[s_kstart[r.owner] + k] = gb;
             s_mq[s_kstart[r.owner] + k] = A.qidx_base + q0 + tid;
-            Wr w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted) + s_bstart[r.owner] + boff);
+            WrT<false> w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted), s_bstart[r.owner] + boff);
             w.copy(r.sp, len);
             w.end();
         } else {                                   // oversized tile: plain peer stores from global memory
@@ -1333,7 +1347,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table;
-    P.eng = e->d_const;
+    P.eng = e->d_const; P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion;
     P.ntiles = (n + bbk::T - 1) / bbk::T;
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
@@ -1513,6 +1527,7 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
     bb_engine* e = s->e;
     bbk::PushParams A; memset(&A, 0, sizeof A);
     A.P.pkts = d_pkts; A.P.pkt_off = d_pkt_off; A.P.n = n; A.P.eng = e->d_const; A.P.ready = 1;
+    A.P.suffix_len = e->hconst.suffix_len; A.P.soa_len = e->hconst.soa_len; A.P.recursion = e->hconst.recursion;
     A.P.route = 1; A.P.nranks = s->nranks; A.P.rank = s->rank; A.P.table = e->d_table; A.P.mask = e->mask; A.P.arena = e->d_arena;
     A.epoch = ++s->epoch;
     const size_t set = (size_t)(s->epoch & 1) * s->nranks;
@@ -1546,6 +1561,7 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     P.out = s->d_out; P.out_cap = s->out_cap; P.out_off = (uint32_t*)s->d_out_off; P.out_len = (uint16_t*)s->d_out_len;
     P.status = s->d_status; P.miss_idx = (uint32_t*)s->d_miss; P.totals = (uint32_t*)s->d_totals;
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
+    P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion;
     P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
     P.desc = (unsigned long long*)s->d_desc; P.counter = (uint32_t*)((unsigned long long*)s->d_desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch); P.stage_log = nullptr; P.route = 0; P.nranks = s->nranks; P.rank = s->rank;

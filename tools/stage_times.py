@@ -20,7 +20,8 @@ out = torch.empty(B * 96, dtype=torch.uint8, device=dev); oo = torch.empty(B + 1
 st = torch.empty(B, dtype=torch.uint8, device=dev); ms = torch.empty(B, dtype=torch.int32, device=dev)
 tot = torch.zeros(4, dtype=torch.int32, device=dev); ol = torch.empty(B, dtype=torch.int16, device=dev)
 nt = (B + 127) // 128
-log = torch.zeros(nt * 8, dtype=torch.int64, device=dev)
+NS = 12
+log = torch.zeros(nt * NS, dtype=torch.int64, device=dev)
 s = torch.cuda.current_stream().cuda_stream
 def run(k):
     pk, of = bufs[k % 8]
@@ -31,13 +32,13 @@ lib().bb_engine_set_stage_log(eng._h, log.data_ptr())
 acc = []
 for k in range(10):
     run(5 + k); torch.cuda.synchronize()
-    acc.append(log.cpu().numpy().reshape(nt, 8).copy())
+    acc.append(log.cpu().numpy().reshape(nt, NS)[:, :11].copy())
 print('ordered' if ORDERED else 'arrival', 'packing, batch', B)
-names = ['start', 'offsets', 'staged', 'resolved', 'scan', 'lookback', 'emitted', 'flushed']
+names = ['start', 'offsets', 'staged', 'decoded', 'hashed', 'probed', 'sized', 'scan', 'placed', 'emitted', 'flushed']
 for a in acc[-3:]:
     t0 = a[:, 0].min()
     rel = (a - t0) / 1000.0
-    print('kernel span %.2f us (first start -> last flush); tile starts spread %.2f us' % (rel[:, 7].max(), rel[:, 0].max()))
+    print('kernel span %.2f us (first start -> last flush); tile starts spread %.2f us' % (rel[:, 10].max(), rel[:, 0].max()))
     d = np.diff(a, axis=1) / 1000.0
-    print('  stage durations us (mean / max over tiles): ' + ', '.join('%s %.2f/%.2f' % (names[i + 1], d[:, i].mean(), d[:, i].max()) for i in range(7)))
-    print('  completion time of each stage, max over tiles: ' + ', '.join('%s %.2f' % (names[i], rel[:, i].max()) for i in range(8)))
+    print('  stage durations us (mean / max over tiles): ' + ', '.join('%s %.2f/%.2f' % (names[i + 1], d[:, i].mean(), d[:, i].max()) for i in range(10)))
+    print('  completion time of each stage, max over tiles: ' + ', '.join('%s %.2f' % (names[i], rel[:, i].max()) for i in range(11)))
