@@ -351,7 +351,9 @@ __device__ __forceinline__ uint32_t upper_bytes(uint32_t x) {
 // Decode of a packet staged in shared memory, word-wise (same acceptance as decode()).
 __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
     if (len < 17) return false;                                               // header + root name + type/class at least
-    const uint32_t w0 = ldsu32(sp), w1 = ldsu32(sp + 4), w2 = ldsu32(sp + 8);
+    const uint32_t hb = sp & ~3u, hs = (sp & 3u) * 8;
+    const uint32_t t0 = lds32(hb), t1 = lds32(hb + 4), t2 = lds32(hb + 8), t3 = lds32(hb + 12);
+    const uint32_t w0 = __funnelshift_r(t0, t1, hs), w1 = __funnelshift_r(t1, t2, hs), w2 = __funnelshift_r(t2, t3, hs);
     const uint32_t fl = (w0 >> 16) & 0xFF;                                    // byte 2: QR opcode AA TC RD
     if (fl & 0x80) return false;
     r.opcode = (fl >> 3) & 0xF; r.rd = fl & 1;
@@ -442,11 +444,16 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     uint32_t kw[12];
     uint32_t h = hash_init(NS_FORWARD);
     uint32_t upw = 0, upi = 0;
+    // consecutive unaligned words share their aligned halves: one LDS per word, not two
+    const uint32_t ka = nm + d_off + 1, kb = ka & ~3u, ksh = (ka & 3u) * 8;
+    uint32_t wprev = lds32(kb);
 #pragma unroll
     for (int i = 0; i < 12; i++) {
         kw[i] = 0;
         if ((uint32_t)i < nwords) {
-            const uint32_t x = ldsu32(nm + d_off + 1 + 4 * i);
+            const uint32_t wnext = lds32(kb + 4 * (i + 1));
+            const uint32_t x = __funnelshift_r(wprev, wnext, ksh);
+            wprev = wnext;
             const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
             const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // label-boundary positions
             uint32_t xd = (x & ~m8) | (0x2E2E2E2Eu & m8);
@@ -735,9 +742,10 @@ struct WrT {
     __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(at(wp) + b, (uint32_t)(acc >> (8 * b)) & 0xFF); }
     // n bytes from shared memory
     __device__ void copy(uint32_t src, uint32_t n) {
-        uint32_t i = 0;
-        for (; i + 4 <= n; i += 4) put(ldsu32(src + i), 4);
-        if (i < n) put(ldsu32(src + i) & ((1u << (8 * (n - i))) - 1), n - i);
+        const uint32_t b = src & ~3u, sh = (src & 3u) * 8;
+        uint32_t prev = lds32(b), i = 0, k = 1;
+        for (; i + 4 <= n; i += 4, k++) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh), 4); prev = nx; }
+        if (i < n) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh) & ((1u << (8 * (n - i))) - 1), n - i); }
     }
 };
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
