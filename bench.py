@@ -229,7 +229,7 @@ def main():
     # IN_FLIGHT batches at a time, one stream each (independent batches, as a server runs them and
     # as the e2e path below does); timed on the device: the streams fork from / join into the main
     # stream between two CUDA events.
-    IN_FLIGHT = int(os.environ.get('BB_IN_FLIGHT', '4'))
+    IN_FLIGHT = 4
     side_streams = [torch.cuda.Stream(device=dev) for _ in range(IN_FLIGHT)]
 
     def step_on(k, st):

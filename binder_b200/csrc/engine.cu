@@ -31,12 +31,9 @@ extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
 namespace bbk {
 using namespace bb;
 
-#ifndef BB_T
-#define BB_T 128
-#endif
-constexpr int T = BB_T;                   // queries (= threads) per tile
-constexpr int S_IN = BB_T * 64;           // staged input bytes per tile
-constexpr int CAPW = BB_T * 96;           // output staging window per flush round
+constexpr int T = 128;                    // queries (= threads) per tile
+constexpr int S_IN = 8192;                // staged input bytes per tile
+constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + MAXRESP + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
 constexpr uint32_t NONE16 = 0xFFFF;
@@ -82,9 +79,6 @@ struct Res {
     uint16_t keep_ans, keep_add, n_walk, nk;
     uint8_t status, rk, rcode, tc, opcode, rd, edns, trunc;
     uint8_t owner;           // route mode: rank that owns this query's lookup key
-    uint8_t probe;           // word-wise path: the warp-cooperative probe must look this query up
-    uint8_t l0, l1;          // SRV: lengths of the _service and _proto labels
-    uint32_t ph;             // word-wise path: key hash
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -338,8 +332,6 @@ constexpr int NSTAGE = 12;
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ uint4 lds128(uint32_t a) { uint4 v; asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v; }
-__device__ __forceinline__ void sts128(uint32_t a, uint32_t x, uint32_t y, uint32_t z, uint32_t w) { asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(a), "r"(x), "r"(y), "r"(z), "r"(w) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 // unaligned 32-bit load from shared memory (the staging buffers carry read slack)
 __device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
@@ -407,10 +399,7 @@ __device__ __forceinline__ uint32_t bad_chars(uint32_t lo) {
     return ~ok & 0x80808080u;
 }
 
-// forward declaration: the generic front end (used by fast_post for the SRV line-terminator quirk)
-__device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed);
-
-__device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t rec, uint32_t qidx, uint32_t fixed) {
+__device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
     const EngineConst* E = P.eng;
     if (!P.ready && !P.route) return false;            // not-ready engines: exact ordering of refusals lives in the generic path
     const uint32_t nm = r.sp + 12;
@@ -487,97 +476,53 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t r
         const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
         r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
     }
-    // zk.lookup(domain) is done by the whole warp together (coop_probe): hand over the compare record
-    // — hash, header word (key length, namespace, dot count: a query with a '.' inside a label has
-    // fewer label boundaries than any key that spells the same, so it can never match), 12 key words —
-    // through this lane's 64-byte record in shared memory.  Chunk c sits at c ^ ((lane >> 1) & 3):
-    // conflict-free 16-byte stores here and 16-byte loads there.
+    // zk.lookup(domain): one 64-byte slot per probe, compared as words.  The header compare also
+    // carries the key's dot count: a query with a '.' inside a label has fewer label boundaries than
+    // any key that spells the same, so it can never match here.
     const uint32_t ndots = (uint32_t)__popcll(r.lenmask >> (d_off + 1));
     const uint32_t want = dl | ((NS_FORWARD | (ndots << 1)) << 16);
-    const uint32_t x = (threadIdx.x >> 1) & 3u;
-    sts128(rec + 16 * (0 ^ x), h, want, 0u, 0u);
-    sts128(rec + 16 * (1 ^ x), kw[0], kw[1], kw[2], kw[3]);
-    sts128(rec + 16 * (2 ^ x), kw[4], kw[5], kw[6], kw[7]);
-    sts128(rec + 16 * (3 ^ x), kw[8], kw[9], kw[10], kw[11]);
-    r.probe = 1; r.ph = h; r.l0 = (uint8_t)l0; r.l1 = (uint8_t)l1;
-    return true;
-}
-
-// Warp-cooperative cuckoo probe.  Four lanes fetch one 64-byte slot (16 bytes each), so one LDG.128
-// of the warp covers 8 slots = 8 cache lines instead of 32: the 64 candidate slots of the warp's 32
-// queries cost 8 x 8 = 64 L1 wavefronts instead of 256.  In step t the warp handles queries
-// 4t..4t+3: lane l looks at chunk (l & 3) of candidate ((l >> 2) & 1) of query 4t + (l >> 3) and
-// compares it with the same chunk of that query's record.  A slot matches when its four lanes
-// agree; the lane holding chunk 0 then publishes kind/flags, ttl, val to the query's result cell.
-__device__ __forceinline__ void coop_probe(const Params& P, uint32_t recs, uint32_t ress, uint32_t h) {
-    const uint32_t lane = threadIdx.x & 31u;
-    const uint32_t ia = slot1_of(h, P.mask), ib = slot2_of(h, P.mask);
-    const uint32_t c = lane & 3u, which = (lane >> 2) & 1u, sub = lane >> 3;
-    // two rounds of four steps: 16 data registers in flight instead of 32 (the kernel runs at 64 registers)
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        uint4 v[4];
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint32_t q = 16 * half + 4 * t + sub;
-            const uint32_t sa = __shfl_sync(0xffffffffu, ia, q), sb = __shfl_sync(0xffffffffu, ib, q);
-            v[t] = __ldg((const uint4*)(P.table + (which ? sb : sa)) + c);
-        }
-#pragma unroll
-        for (int t = 0; t < 4; t++) {
-            const uint32_t q = 16 * half + 4 * t + sub;
-            const uint4 e = lds128(recs + 64 * q + 16 * (c ^ ((q >> 1) & 3u)));
-            const bool m = c ? (v[t].x == e.x && v[t].y == e.y && v[t].z == e.z && v[t].w == e.w)
-                             : (v[t].x == e.x && (v[t].y & 0x00FF00FFu) == e.y);
-            const uint32_t bal = __ballot_sync(0xffffffffu, m);
-            if (c == 0 && ((bal >> (lane & ~3u)) & 0xFu) == 0xFu) sts128(ress + 16 * q, v[t].y, v[t].z, v[t].w, 1u);
-        }
+    uint32_t kind = 0, ttl = 0, val = 0;
+    bool hit = false, clean = false;
+    {
+        // 2-choice cuckoo: both candidate slots are fetched together — one DRAM round trip per lookup,
+        // hit or miss, for every lane of the warp
+        const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
+        const uint4* sb = (const uint4*)(P.table + slot2_of(h, P.mask));
+        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
+        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
+        const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |
+                            (kw[0] ^ a1.x) | (kw[1] ^ a1.y) | (kw[2] ^ a1.z) | (kw[3] ^ a1.w) |
+                            (kw[4] ^ a2.x) | (kw[5] ^ a2.y) | (kw[6] ^ a2.z) | (kw[7] ^ a2.w) |
+                            (kw[8] ^ a3.x) | (kw[9] ^ a3.y) | (kw[10] ^ a3.z) | (kw[11] ^ a3.w);
+        const uint32_t db = (b0.x ^ h) | ((b0.y & 0x00FF00FFu) ^ want) |
+                            (kw[0] ^ b1.x) | (kw[1] ^ b1.y) | (kw[2] ^ b1.z) | (kw[3] ^ b1.w) |
+                            (kw[4] ^ b2.x) | (kw[5] ^ b2.y) | (kw[6] ^ b2.z) | (kw[7] ^ b2.w) |
+                            (kw[8] ^ b3.x) | (kw[9] ^ b3.y) | (kw[10] ^ b3.z) | (kw[11] ^ b3.w);
+        // an empty slot has kind 0 and klen 0, so it can never equal `want` (dl >= 1)
+        if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
+        else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
     }
-}
-
-// What fast_forward() leaves to do once the warp has probed: classify on anything but a clean hit,
-// then the shared tail of resolve().
-__device__ void fast_post(const Params& P, Res& r, uint32_t rec, uint32_t res, uint32_t qidx) {
-    const uint4 pay = lds128(res);                       // kind/flags word, ttl, val, hit
-    const bool hit = pay.w != 0;
-    const uint32_t kind = (pay.x >> 8) & 0xFF, ttl = pay.y, val = pay.z;
-    const bool clean = (pay.x >> 24) & SLOT_KEY_CLEAN;
-    const bool srv = r.qtype == QT_SRV;
-    const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
+    STAMP(5);
     if (!(hit && clean)) {
         // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a
         // label, a character outside [a-z0-9_.-] (:208-215) -> REFUSED; an SRV name with a
         // line terminator goes to the generic path (its regex group stops there, :141).
-        const uint32_t dl = (uint32_t)r.d_end - r.d_off - 1;
-        const uint32_t nwords = (dl + 3) >> 2;
-        const uint32_t tailm = (dl & 3) ? ((1u << (8 * (dl & 3))) - 1) : 0xFFFFFFFFu;
-        const uint64_t lm = r.lenmask >> (r.d_off + 1);
-        const uint32_t x = (threadIdx.x >> 1) & 3u;
         uint32_t bad = 0, nlc = 0;
 #pragma unroll
-        for (int ch = 0; ch < 3; ch++) {
-            const uint4 k4 = lds128(rec + 16 * ((ch + 1) ^ x));
-            const uint32_t kws[4] = { k4.x, k4.y, k4.z, k4.w };
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t i = 4 * ch + j;
-                if (i < nwords) {
-                    const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
-                    const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;
-                    const uint32_t tm = (i == nwords - 1) ? tailm : 0xFFFFFFFFu;
-                    bad |= bad_chars(kws[j]) & ~m8 & tm;
-                    nlc |= (zero_bytes(kws[j] ^ 0x0A0A0A0Au) | zero_bytes(kws[j] ^ 0x0D0D0D0Du)) & ~m8 & tm;
-                }
+        for (int i = 0; i < 12; i++) {
+            if ((uint32_t)i < nwords) {
+                const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
+                const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;
+                const uint32_t tm = ((uint32_t)i == nwords - 1) ? tailm : 0xFFFFFFFFu;
+                bad |= bad_chars(kw[i]) & ~m8 & tm;
+                nlc |= (zero_bytes(kw[i] ^ 0x0A0A0A0Au) | zero_bytes(kw[i] ^ 0x0D0D0D0Du)) & ~m8 & tm;
             }
         }
-        if (srv && nlc) {                                // generic path, from scratch
-            r.rk = RK_HEADER; r.rlen = (uint16_t)fixed; r.ptr_tgt = (uint16_t)NONE16;
-            resolve_forward(P, r, qidx, fixed);
-            return;
-        }
-        if (bad) { r.rcode = RC_REFUSED; return; }
+        if (srv && nlc) return false;
+        if (bad) { r.rcode = RC_REFUSED; return true; }
     }
-    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, r.l0, r.l1);
+    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
+    return true;
 }
 
 // ---- resolve (lib/server.js:136-429) -------------------------------------------------------
@@ -666,9 +611,9 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 }
 
 // onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
-__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx, uint32_t rec) {
+__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
     r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
-    r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0; r.probe = 0; r.ph = 0;
+    r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
     if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
     r.maxsz = r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
     const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
@@ -676,7 +621,7 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
     const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
     if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
     STAMP(3);
-    if (r.sp && rec && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, rec, qidx, fixed)) return;
+    if (r.sp && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, qidx, fixed)) return;
     const uint8_t* nm = r.p + 12;
     for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
         uint32_t l = nm[q];
@@ -914,30 +859,16 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     STAMP(2);
     // ---- parse + lookup + size ----------------------------------------------------------------
     Res r;
-    r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE; r.probe = 0; r.ph = 0;
-    // per-warp scratch inside the (still idle) response staging buffer: 32 x 64-byte compare records
-    // + 32 x 16-byte result cells
-    const uint32_t warp_recs = (uint32_t)__cvta_generic_to_shared(s_out) + warp * 2560u, warp_ress = warp_recs + 2048u;
-    const uint32_t my_rec = warp_recs + 64u * lane, my_res = warp_ress + 16u * lane;
-    sts128(my_res, 0u, 0u, 0u, 0u);
+    r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
     const uint32_t qidx = (r_qidx_map && tid < (int)nq) ? r_qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
     if (tid < (int)nq) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
         if (o1 >= o0 && o1 - o0 <= 65535u) {
             r.p = staged ? s_in + (o0 - a0) : r_pkts + o0;
             r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
-            resolve_query(P, r, o1 - o0, qidx, (uint32_t)__cvta_generic_to_shared(s_sfx), my_rec);
+            resolve_query(P, r, o1 - o0, qidx, (uint32_t)__cvta_generic_to_shared(s_sfx));
         }
     }
-    // the warp looks up all of its word-wise queries together (response staging is idle until the
-    // scan's barrier, so it hosts the compare records and the result cells)
-    __syncwarp();
-    if (__any_sync(0xffffffffu, r.probe)) {
-        coop_probe(P, warp_recs, warp_ress, r.ph);
-        __syncwarp();
-        if (r.probe) fast_post(P, r, my_rec, my_res, qidx);
-    }
-    STAMP(5);
     const uint32_t my_len = r.rlen;
     const uint32_t my_miss = (tid < (int)nq && r.status == ST_MISS) ? 1u : 0u;
 
@@ -1149,7 +1080,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             len = o1 - o0;
             r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
             r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
-            resolve_query(P, r, len, 0, (uint32_t)__cvta_generic_to_shared(s_sfx), (uint32_t)__cvta_generic_to_shared(s_sorted) + 64u * tid);
+            resolve_query(P, r, len, 0, (uint32_t)__cvta_generic_to_shared(s_sfx));
             if (r.owner >= P.nranks) r.owner = (uint8_t)P.rank;
         }
         const unsigned long long old = atomicAdd(&s_cur[r.owner], (1ull << PUSH_CNT_SHIFT) | len);
