@@ -360,16 +360,17 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
     if (w1 != 0x00000100u) return false;                                      // QDCOUNT=1, ANCOUNT=0
     if (w2 != 0u && w2 != 0x01000000u) return false;                          // NSCOUNT=0, ARCOUNT<=1
     const uint32_t nm = sp + 12, lim = len - 12;                              // name bytes available
-    uint32_t pos = 0, lo = 0, hi = 0;
-    for (;;) {
-        if (pos >= lim) return false;
-        const uint32_t c = lds8(nm + pos);
-        if (c == 0) break;
-        if (c > 63) return false;
-        if (pos < 32) lo |= 1u << pos; else if (pos < 64) hi |= 1u << (pos - 32);
+    // label hop: one dependent shared-memory byte per label; validity is accumulated, not branched on
+    uint32_t pos = 0, lo = 0, hi = 0, bad = 0, c = lds8(nm);
+#pragma unroll 1
+    while (c != 0) {
+        bad |= c > 63;                                                        // pointers / extended label types
+        lo |= pos < 32 ? 1u << pos : 0u; hi |= (pos >= 32 && pos < 64) ? 1u << (pos - 32) : 0u;
         pos += 1 + c;
-        if (pos > 254) return false;
+        if (pos >= lim || pos > 254) { bad = 1; break; }
+        c = lds8(nm + pos);
     }
+    if (bad) return false;
     if (pos + 1 + 4 > lim) return false;
     r.qn_len = pos + 1;
     r.lenmask = (uint64_t)lo | ((uint64_t)hi << 32);
@@ -728,23 +729,35 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* stage, uin
 template <bool SWZ>
 struct WrT {
     uint32_t base;       // shared address of the buffer (SWZ: offsets below are logical and get swizzled)
-    uint32_t wp;         // offset of the word being filled
-    uint64_t acc; uint32_t fill, head;
+    uint32_t wp;         // offset of the aligned word being filled
+    uint32_t acc, fill;  // its bytes so far (fill = 0..3 of them)
+    uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
     __device__ void begin(uint32_t buf, uint32_t off) { base = buf; head = off & 3u; wp = off - head; acc = 0; fill = head; }
     __device__ __forceinline__ uint32_t at(uint32_t off) const { return base + (SWZ ? swz(off) : off); }
-    __device__ __forceinline__ void flush() {
-        if (head) { for (uint32_t b = head; b < 4; b++) sts8(at(wp) + b, (uint32_t)(acc >> (8 * b)) & 0xFF); head = 0; }
-        else sts32(at(wp), (uint32_t)acc);
-        wp += 4; acc >>= 32; fill -= 4;
+    __device__ __forceinline__ void store(uint32_t v) {
+        if (head) { for (uint32_t b = head; b < 4; b++) sts8(at(wp) + b, (v >> (8 * b)) & 0xFF); head = 0; }
+        else sts32(at(wp), v);
+        wp += 4;
     }
-    // v holds n (1..4) bytes in memory order (little-endian integer)
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) { acc |= (uint64_t)v << (8 * fill); fill += n; if (fill >= 4) flush(); }
-    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(at(wp) + b, (uint32_t)(acc >> (8 * b)) & 0xFF); }
-    // n bytes from shared memory
+    // four bytes in memory order: the word being filled completes, `fill` bytes carry over
+    __device__ __forceinline__ void put4(uint32_t v) {
+        const uint32_t s8 = 8 * fill;
+        store(acc | (v << s8));
+        acc = __funnelshift_l(v, 0u, s8);                // v >> (32 - s8), 0 when s8 == 0
+    }
+    // v holds n (1..4) bytes in memory order (little-endian integer), upper bytes zero
+    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
+        const uint32_t s8 = 8 * fill;
+        const uint32_t w = acc | (v << s8);
+        if (fill + n >= 4) { store(w); acc = __funnelshift_l(v, 0u, s8); fill = fill + n - 4; }
+        else { acc = w; fill += n; }
+    }
+    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(at(wp) + b, (acc >> (8 * b)) & 0xFF); }
+    // n bytes from shared memory (consecutive unaligned words share their aligned halves)
     __device__ void copy(uint32_t src, uint32_t n) {
         const uint32_t b = src & ~3u, sh = (src & 3u) * 8;
         uint32_t prev = lds32(b), i = 0, k = 1;
-        for (; i + 4 <= n; i += 4, k++) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh), 4); prev = nx; }
+        for (; i + 4 <= n; i += 4, k++) { const uint32_t nx = lds32(b + 4 * k); put4(__funnelshift_r(prev, nx, sh)); prev = nx; }
         if (i < n) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh) & ((1u << (8 * (n - i))) - 1), n - i); }
     }
 };
@@ -756,9 +769,9 @@ __device__ void emit_fast(const Res& r, uint32_t stage, uint32_t off) {
     const uint32_t p = r.sp;
     const uint32_t an = r.rk == RK_A1 ? r.keep_ans : 0;
     const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
-    w.put((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24), 4);   // id, QR AA TC RD, rcode
-    w.put(0x00000100u | (an << 24), 4);                                           // QDCOUNT=1, ANCOUNT
-    w.put(r.edns ? 0x01000000u : 0u, 4);                                          // NSCOUNT=0, ARCOUNT
+    w.put4((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24));   // id, QR AA TC RD, rcode
+    w.put4(0x00000100u | (an << 24));                                           // QDCOUNT=1, ANCOUNT
+    w.put4(r.edns ? 0x01000000u : 0u);                                          // NSCOUNT=0, ARCOUNT
     w.copy(p + 12, r.qn_len + 4);                                                 // question, verbatim
     if (an) {
         if (r.ptr_tgt != NONE16) {
@@ -782,12 +795,12 @@ __device__ void emit_fast(const Res& r, uint32_t stage, uint32_t off) {
             }
             w.put(0, 1);
         }
-        w.put(0x01000100u, 4);                      // TYPE A, CLASS IN
-        w.put(bswap32(r.ttl), 4);
+        w.put4(0x01000100u);                        // TYPE A, CLASS IN
+        w.put4(bswap32(r.ttl));
         w.put(0x0400u, 2);                          // RDLENGTH 4
-        w.put(bswap32(r.val), 4);
+        w.put4(bswap32(r.val));
     }
-    if (r.edns) { w.put(0x04290000u, 4); w.put(0x000000B0u, 4); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+    if (r.edns) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
     w.end();
 }
 
