@@ -88,13 +88,18 @@ __device__ __forceinline__ uint32_t ld16a(const uint8_t* p) { return *(const uin
 
 // byte-fed murmur (same result as bb::hash_key over the materialised key)
 struct KeyHash {
-    uint32_t h, acc, n;
-    __device__ void init(uint32_t ns) { h = hash_init(ns); acc = 0; n = 0; }
+    uint32_t h, g, acc, n;
+    __device__ void init(uint32_t ns) { h = hash_init(ns); g = hash2_init(ns); acc = 0; n = 0; }
     __device__ void feed(uint32_t c) {
         acc |= c << (8 * (n & 3)); ++n;
-        if ((n & 3) == 0) { h = hash_word(h, acc); acc = 0; }
+        if ((n & 3) == 0) { h = hash_word(h, acc); g = hash2_word(g, acc); acc = 0; }
     }
-    __device__ uint32_t finish() { if (n & 3) h = hash_word(h, acc); return hash_finish(h, n); }
+    // -> primary hash; h2 = second hash (second cuckoo slot)
+    __device__ uint32_t finish(uint32_t& h2) {
+        if (n & 3) { h = hash_word(h, acc); g = hash2_word(g, acc); }
+        h2 = hash2_finish(g, n);
+        return hash_finish(h, n);
+    }
 };
 
 // ---- mname decode (DESIGN.md "Wire spec: decode") ---------------------------------------
@@ -168,10 +173,11 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
     KeyHash kh; kh.init(ns);
     kg.start();
     for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
-    uint32_t h = kh.finish();
+    uint32_t h2;
+    uint32_t h = kh.finish(h2);
     if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return false; }   // sharding: who would answer
     // 2-choice cuckoo: the key is in slot1_of(h) or slot2_of(h) or nowhere
-    const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, P.mask) };
+    const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, h2, P.mask) };
     for (int c = 0; c < 2; c++) {
         const Slot* s = P.table + cand[c];
         uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,flags | ttl | val
@@ -443,7 +449,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
     const uint32_t nwords = (dl + 3) >> 2;
     const uint32_t tailm = (dl & 3) ? ((1u << (8 * (dl & 3))) - 1) : 0xFFFFFFFFu;
     uint32_t kw[12];
-    uint32_t h = hash_init(NS_FORWARD);
+    uint32_t h = hash_init(NS_FORWARD), g = hash2_init(NS_FORWARD);
     uint32_t upw = 0, upi = 0;
     // consecutive unaligned words share their aligned halves: one LDS per word, not two
     const uint32_t ka = nm + d_off + 1, kb = ka & ~3u, ksh = (ka & 3u) * 8;
@@ -463,10 +469,11 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
             if (up) { upw = up; upi = i; }
             const uint32_t lo = xd | (up >> 2);
             kw[i] = lo;
-            h = hash_word(h, lo);
+            h = hash_word(h, lo); g = hash2_word(g, lo);
         }
     }
     h = hash_finish(h, dl);
+    const uint32_t h2 = hash2_finish(g, dl);
     STAMP(4);
     if (refuse) { r.rcode = RC_REFUSED; return true; }
     if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
@@ -488,7 +495,7 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         // 2-choice cuckoo: both candidate slots are fetched together — one DRAM round trip per lookup,
         // hit or miss, for every lane of the warp
         const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
-        const uint4* sb = (const uint4*)(P.table + slot2_of(h, P.mask));
+        const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
         const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
         const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
         const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |

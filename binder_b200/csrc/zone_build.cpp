@@ -10,6 +10,7 @@
 #include "../../include/binder_b200.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -413,6 +414,7 @@ struct TableBuilder {
     uint32_t nranks = 1, rank = 0;
     bool mine(uint32_t ns, const uint8_t* k, uint32_t len) const { return nranks == 1 || owner_of(hash_key(ns, k, len), nranks) == rank; }
     bool failed = false;         // a cuckoo insertion ran out of kicks: the caller rebuilds with a larger table
+    std::vector<uint32_t> h2s;   // second hash of the key resident in each slot (host-side only: evictions need it)
     void fill(Slot& s, uint32_t h, uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
         memset(&s, 0, sizeof s);
         s.hash = h;
@@ -430,21 +432,27 @@ struct TableBuilder {
     }
     // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo
     bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
-        const uint32_t h = hash_key(ns, k, len);
-        const uint32_t i1 = slot1_of(h, mask), i2 = slot2_of(h, mask);
+        uint32_t h2;
+        const uint32_t h = hash_key2(ns, k, len, &h2);
+        const uint32_t i1 = slot1_of(h, mask), i2 = slot2_of(h, h2, mask);
+        if (h2s.size() != (size_t)mask + 1) h2s.assign((size_t)mask + 1, 0);
         for (uint32_t i : { i1, i2 }) {
             Slot& s = z->slots[i];
             if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; return false; }
         }
         Slot cur; fill(cur, h, ns, k, len, kind, ttl, val);
+        uint32_t cur_h2 = h2;
         uint32_t pos = z->slots[i1].kind == K_EMPTY ? i1 : (z->slots[i2].kind == K_EMPTY ? i2 : i1);
         for (int kick = 0; kick < 2000; kick++) {
             Slot& s = z->slots[pos];
-            if (s.kind == K_EMPTY) { s = cur; return true; }
+            if (s.kind == K_EMPTY) { s = cur; h2s[pos] = cur_h2; return true; }
+            if (getenv("BB_DEBUG") && kick >= 1990) fprintf(stderr, "  kick %d pos=%u resident h=%08x klen=%u ns=%u key=%.*s\n", kick, pos, s.hash, s.klen, s.ns, (int)(s.klen < 49 ? s.klen : 8), (const char*)s.key);
             Slot ev = s; s = cur; cur = ev;                          // evict the resident, move it to its other slot
-            const uint32_t a = slot1_of(cur.hash, mask), b = slot2_of(cur.hash, mask);
+            const uint32_t ev_h2 = h2s[pos]; h2s[pos] = cur_h2; cur_h2 = ev_h2;
+            const uint32_t a = slot1_of(cur.hash, mask), b = slot2_of(cur.hash, cur_h2, mask);
             pos = pos == a ? b : a;
         }
+        if (getenv("BB_DEBUG")) fprintf(stderr, "cuckoo fail: ns=%u len=%u key=%.*s h=%08x i1=%u i2=%u mask=%u\n", ns, len, (int)len, (const char*)k, h, i1, i2, mask);
         failed = true;
         return true;
     }

@@ -1,7 +1,8 @@
 // Zone image: the HBM-resident, flattened form of binder's ZKCache (lib/zk.js:20-119).
 //
 // One 2-choice cuckoo table (power-of-two, load factor < 0.46) of 64-byte slots holds BOTH of
-// ZKCache's maps (a key lives in slot h1 or slot h2, never anywhere else, so a lookup — hit or
+// ZKCache's maps (a key lives in slot hash & mask or slot hash2 & mask — two independent hashes of
+// the key — never anywhere else, so a lookup — hit or
 // miss — is two independent 64-byte reads issued together: one DRAM round trip per warp):
 //   forward  ca_treeNodes[lower-cased fqdn]  (lib/zk.js:62-64, keys written at :84,96)
 //   reverse  ca_revLookup[address string]    (lib/zk.js:65-67, keys written at :187-188)
@@ -95,23 +96,34 @@ BB_HD uint32_t hash_word(uint32_t h, uint32_t w) {
 }
 BB_HD uint32_t hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ len); }
 
-inline uint32_t hash_key(uint32_t ns, const uint8_t* k, uint32_t len) {
-    uint32_t h = hash_init(ns);
+// Second, independent hash over the same words (two ALU ops per word): it picks the key's second
+// cuckoo slot, so two keys whose 32-bit hashes collide do not also share both of their slots.
+BB_HD uint32_t hash2_init(uint32_t ns) { return ns ? 0x7F4A7C15u : 0x2545F491u; }
+BB_HD uint32_t hash2_word(uint32_t g, uint32_t w) { return (g ^ w) * 0x9E3779B1u; }
+BB_HD uint32_t hash2_finish(uint32_t g, uint32_t len) { return fmix32(g ^ (len * 0x85EBCA77u)); }
+
+// -> primary hash; *h2 = second hash
+inline uint32_t hash_key2(uint32_t ns, const uint8_t* k, uint32_t len, uint32_t* h2) {
+    uint32_t h = hash_init(ns), g = hash2_init(ns);
     uint32_t i = 0;
-    for (; i + 4 <= len; i += 4)
-        h = hash_word(h, (uint32_t)k[i] | (uint32_t)k[i + 1] << 8 | (uint32_t)k[i + 2] << 16 | (uint32_t)k[i + 3] << 24);
+    for (; i + 4 <= len; i += 4) {
+        const uint32_t w = (uint32_t)k[i] | (uint32_t)k[i + 1] << 8 | (uint32_t)k[i + 2] << 16 | (uint32_t)k[i + 3] << 24;
+        h = hash_word(h, w); g = hash2_word(g, w);
+    }
     if (i < len) {
         uint32_t w = 0;
         for (uint32_t j = 0; i + j < len; j++) w |= (uint32_t)k[i + j] << (8 * j);
-        h = hash_word(h, w);
+        h = hash_word(h, w); g = hash2_word(g, w);
     }
+    *h2 = hash2_finish(g, len);
     return hash_finish(h, len);
 }
+inline uint32_t hash_key(uint32_t ns, const uint8_t* k, uint32_t len) { uint32_t h2; return hash_key2(ns, k, len, &h2); }
 
 // ---- cuckoo: the two slots a key may live in -------------------------------------------------
 BB_HD uint32_t slot1_of(uint32_t key_hash, uint32_t mask) { return key_hash & mask; }
-BB_HD uint32_t slot2_of(uint32_t key_hash, uint32_t mask) {
-    const uint32_t a = key_hash & mask, b = fmix32(key_hash ^ 0x5BD1E995u) & mask;
+BB_HD uint32_t slot2_of(uint32_t key_hash, uint32_t key_hash2, uint32_t mask) {
+    const uint32_t a = key_hash & mask, b = key_hash2 & mask;
     return b != a ? b : (a ^ 1u) & mask;
 }
 

@@ -51,3 +51,13 @@ def test_no_cpu_fallback():
     with pytest.raises(_lib.BinderError) as ei:
         Engine('foo.com')
     assert ei.value.code == -6
+
+
+def test_zone_build_survives_hash_collisions():
+    """1.5M znodes with services: ~3M keys contain several hundred pairs with identical 32-bit
+    hashes.  With the second cuckoo slot derived from the same hash, two such pairs plus one more
+    key formed an unsatisfiable cycle (zone build failed after growing 4x); the second slot now
+    comes from an independent second hash and the table keeps its intended size."""
+    z = synth.gen_zone(1500000, service_frac=0.15)
+    st = Zone(z.jsonl, z.dns_domain).stat()
+    assert st['slots'] == 8388608 and st['forward_keys'] == st['nodes']
