@@ -770,44 +770,106 @@ struct WrT {
 };
 __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
 
-// emit_response() for the two commonest shapes (rcode-only and one A record), word-wise.
-__device__ void emit_fast(const Res& r, uint32_t stage, uint32_t off) {
+// emit_response() with the word-wise writer, for every response shape of a packet staged in shared
+// memory (everything except the SRV line-terminator quirk, which keeps the byte emitter).
+__device__ __forceinline__ uint32_t bswap16(uint32_t v) { return ((v & 0xFF) << 8) | ((v >> 8) & 0xFF); }
+
+// domain labels [d_off, stop) of the QNAME, lower-cased (length bytes < 64 are unaffected)
+__device__ void put_dom_labels_w(WrT<true>& w, const Res& r, uint32_t stop) {
+    const uint32_t n = stop - r.d_off;
+    const uint32_t src = r.sp + 12 + r.d_off, b = src & ~3u, sh = (src & 3u) * 8;
+    uint32_t prev = lds32(b), i = 0, k = 1;
+    for (; i < n; i += 4, k++) {
+        const uint32_t nx = lds32(b + 4 * k);
+        uint32_t x = __funnelshift_r(prev, nx, sh);
+        prev = nx;
+        x |= upper_bytes(x) >> 2;
+        const uint32_t nb = n - i;
+        if (nb >= 4) w.put4(x); else w.put(x & ((1u << (8 * nb)) - 1), nb);
+    }
+}
+__device__ void put_dom_owner_w(WrT<true>& w, const Res& r) {
+    if (r.ptr_tgt != NONE16) {
+        if (r.ptr_tgt != r.d_off) put_dom_labels_w(w, r, r.ptr_tgt);
+        const uint32_t ptr = 0xC000u | (12u + r.ptr_tgt);
+        w.put(bswap16(ptr), 2);
+    } else { put_dom_labels_w(w, r, r.d_end); w.put(0, 1); }
+}
+__device__ __forceinline__ void put_global_bytes(WrT<true>& w, const uint8_t* s, uint32_t n) {
+    for (uint32_t i = 0; i < n; i++) w.put(__ldg(s + i), 1);
+}
+
+__device__ void emit_fast(const Params& P, const Res& r, uint32_t stage, uint32_t off, uint32_t qidx) {
     WrT<true> w; w.begin(stage, off);
     const uint32_t p = r.sp;
-    const uint32_t an = r.rk == RK_A1 ? r.keep_ans : 0;
+    uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
+    switch (r.rk) {
+    case RK_A1: case RK_PTR: an = r.keep_ans; break;
+    case RK_SOA: ns = r.keep_ans; break;
+    case RK_SVC_A: case RK_SVC_SRV: an = r.keep_ans; ar += r.keep_add; break;
+    }
     const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
     w.put4((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24));   // id, QR AA TC RD, rcode
-    w.put4(0x00000100u | (an << 24));                                           // QDCOUNT=1, ANCOUNT
-    w.put4(r.edns ? 0x01000000u : 0u);                                          // NSCOUNT=0, ARCOUNT
-    w.copy(p + 12, r.qn_len + 4);                                                 // question, verbatim
-    if (an) {
-        if (r.ptr_tgt != NONE16) {
-            // literal labels before the pointer target, lower-cased (length bytes < 64 are unaffected)
-            const uint32_t n = (uint32_t)(r.ptr_tgt - r.d_off);
-            for (uint32_t i = 0; i < n; i += 4) {
-                uint32_t x = ldsu32(p + 12 + r.d_off + i);
-                x |= upper_bytes(x) >> 2;
-                const uint32_t nb = n - i;
-                w.put(nb >= 4 ? x : x & ((1u << (8 * nb)) - 1), nb >= 4 ? 4 : nb);
+    w.put4(0x00000100u | (bswap16(an) << 16));                                  // QDCOUNT=1, ANCOUNT
+    w.put4(bswap16(ns) | (bswap16(ar) << 16));                                  // NSCOUNT, ARCOUNT
+    w.copy(p + 12, r.qn_len + 4);                                               // question, verbatim
+    bool opt_done = !r.edns;
+    if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310
+        put_dom_owner_w(w, r);
+        w.put4(0x01000100u); w.put4(bswap32(r.ttl)); w.put(0x0400u, 2); w.put4(bswap32(r.val));
+    } else if (r.rk == RK_PTR && r.keep_ans) {                                  // :130
+        const uint32_t tl = P.arena[r.val];
+        w.put(0x0CC0u, 2); w.put4(0x01000C00u); w.put4(bswap32(r.ttl)); w.put(bswap16(tl), 2);
+        put_global_bytes(w, P.arena + r.val + 1, tl);
+    } else if (r.rk == RK_SOA && r.keep_ans) {                                  // :286-287
+        const EngineConst* E = P.eng;
+        put_dom_owner_w(w, r);
+        w.put4(0x01000600u); w.put4(bswap32(r.ttl)); w.put(bswap16(P.soa_len + 20), 2);
+        put_global_bytes(w, E->soa, P.soa_len);
+        w.put4(0); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(r.ttl));
+    } else if (r.rk == RK_SVC_A || r.rk == RK_SVC_SRV) {
+        const bool srv = r.rk == RK_SVC_SRV;
+        SvcView sv; sv.open(P.arena, r.val);
+        const uint32_t dwl = dom_wire_len(r);
+        uint32_t left = r.keep_ans;
+        for (uint32_t t = 0; t < r.n_walk && left; t++) {
+            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+            const uint32_t fl = k->flags;
+            if (fl & KID_ADDR_NULL) continue;
+            if (srv) {                                                          // :396-400
+                const uint32_t np = k->nports, wl = k->wire_len;
+                const uint8_t* ports = (const uint8_t*)(k + 1);
+                const uint8_t* kwp = ports + 2 * np;
+                for (uint32_t c = 0; c < np && left; c++, left--) {
+                    w.put(0x0CC0u, 2); w.put4(0x01002100u); w.put4(bswap32(r.ttl)); w.put(bswap16(6 + wl + dwl), 2);
+                    w.put4(0x0A000000u);                                        // priority 0, weight 10
+                    w.put(bswap16(ld16a(ports + 2 * c)), 2);
+                    put_global_bytes(w, kwp, wl);
+                    put_dom_labels_w(w, r, r.d_end); w.put(0, 1);
+                }
+            } else {                                                            // :411-414
+                uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                if (r.ttl < rttl) rttl = r.ttl;
+                put_dom_owner_w(w, r);
+                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
             }
-            const uint32_t ptr = 0xC000u | (12u + r.ptr_tgt);
-            w.put((ptr >> 8) | ((ptr & 0xFF) << 8), 2);
-        } else {
-            const uint32_t n = (uint32_t)(r.d_end - r.d_off);
-            for (uint32_t i = 0; i < n; i += 4) {
-                uint32_t x = ldsu32(p + 12 + r.d_off + i);
-                x |= upper_bytes(x) >> 2;
-                const uint32_t nb = n - i;
-                w.put(nb >= 4 ? x : x & ((1u << (8 * nb)) - 1), nb >= 4 ? 4 : nb);
-            }
-            w.put(0, 1);
         }
-        w.put4(0x01000100u);                        // TYPE A, CLASS IN
-        w.put4(bswap32(r.ttl));
-        w.put(0x0400u, 2);                          // RDLENGTH 4
-        w.put4(bswap32(r.val));
+        if (srv) {
+            if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); opt_done = true; }
+            left = r.keep_add;
+            for (uint32_t t = 0; t < r.n_walk && left; t++) {                   // :401-402
+                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
+                const uint32_t fl = k->flags;
+                if (fl & KID_ADDR_NULL) continue;
+                const uint8_t* kwp = (const uint8_t*)(k + 1) + 2 * k->nports;
+                const uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                put_global_bytes(w, kwp, k->wire_len);
+                put_dom_owner_w(w, r);
+                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
+            }
+        }
     }
-    if (r.edns) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+    if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
     w.end();
 }
 
@@ -972,8 +1034,8 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         const uint32_t shift = (uint32_t)((gbase + w0) & 15);                // same 16B phase in smem and global
         const bool mine = my_len && my_o >= w0 && my_o < w0 + CAPW;
         if (mine) {
-            if (r.sp && (r.rk == RK_HEADER || r.rk == RK_A1))
-                emit_fast(r, (uint32_t)__cvta_generic_to_shared(s_out), shift + (my_o - w0));
+            if (r.sp && !r.trunc)
+                emit_fast(P, r, (uint32_t)__cvta_generic_to_shared(s_out), shift + (my_o - w0), qidx);
             else emit_response(P, r, s_out, shift + (my_o - w0), qidx);
         }
         __syncthreads();
