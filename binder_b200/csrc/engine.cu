@@ -35,7 +35,7 @@ constexpr int T = 128;                    // queries (= threads) per tile
 constexpr int S_IN = 8192;                // staged input bytes per tile
 constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
-constexpr int S_OUT = ((CAPW + MAXRESP + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
+constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -645,23 +645,24 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
 __constant__ uint8_t c_opt_rr[11] = { 0, 0, QT_OPT, 0x04, 0xB0, 0, 0, 0, 0, 0, 0 };
 // The response staging buffer is XOR-swizzled: 16-byte chunk index ^ (128-byte row & 7).  With one
 // 64-byte response per lane, word w of every lane would otherwise fall into 2 of the 32 banks (a
-// 16-way conflict on every store); swizzled, a warp's stores spread over 16 banks, and the flush
+// 16-way conflict on every store); swizzled, a warp's stores spread over more banks, and the flush
 // (consecutive 16-byte chunks) still reads each row as a permutation of itself.
 __device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
 
+// byte emitter of the generic path: writes the response straight to its place in global memory
 struct Out {
-    uint8_t* base; uint32_t o;           // swizzled staging buffer, logical offset
-    __device__ void u8(uint32_t v) { base[swz(o)] = (uint8_t)v; ++o; }
-    __device__ void u16(uint32_t v) { u8(v >> 8); u8(v); }
-    __device__ void u32(uint32_t v) { u8(v >> 24); u8(v >> 16); u8(v >> 8); u8(v); }
-    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) u8(s[i]); }
+    uint8_t* o;
+    __device__ void u8(uint32_t v) { *o++ = (uint8_t)v; }
+    __device__ void u16(uint32_t v) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)v; o += 2; }
+    __device__ void u32(uint32_t v) { o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v; o += 4; }
+    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) o[i] = s[i]; o += n; }
 };
 // the domain part, lower-cased, as wire labels up to `stop` (no terminator)
 __device__ void put_dom_labels(Out& w, const Res& r, uint32_t stop) {
     const uint8_t* nm = r.p + 12;
-    const uint32_t start = w.o;
+    uint8_t* start = w.o;
     for (uint32_t pos = r.d_off; pos < stop; pos++) w.u8(lower8(nm[pos]));    // length bytes (<64) are unaffected
-    if (r.trunc && stop > r.lastlen) w.base[swz(start + r.lastlen - r.d_off)] = (uint8_t)(r.d_end - r.lastlen - 1);
+    if (r.trunc && stop > r.lastlen) start[r.lastlen - r.d_off] = (uint8_t)(r.d_end - r.lastlen - 1);
 }
 __device__ void put_dom_owner(Out& w, const Res& r) {
     if (r.ptr_tgt != NONE16) { put_dom_labels(w, r, r.ptr_tgt); w.u16(0xC000 | (12 + r.ptr_tgt)); }
@@ -669,8 +670,8 @@ __device__ void put_dom_owner(Out& w, const Res& r) {
 }
 __device__ void put_rr_head(Out& w, uint32_t type, uint32_t ttl, uint32_t rdlen) { w.u16(type); w.u16(1); w.u32(ttl); w.u16(rdlen); }
 
-__device__ void emit_response(const Params& P, const Res& r, uint8_t* stage, uint32_t off, uint32_t qidx) {
-    Out w; w.base = stage; w.o = off;
+__device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint32_t qidx) {
+    Out w; w.o = dst;
     const uint8_t* p = r.p;
     uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
     switch (r.rk) {
@@ -733,17 +734,26 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* stage, uin
 // A byte stream into shared memory at an arbitrary byte address, stored as aligned 32-bit words;
 // only the bytes shared with the neighbouring responses (first / last partial word) go out as
 // single bytes, so two threads never write the same word.
-template <bool SWZ>
+// MODE 0: plain shared buffer, 1: XOR-swizzled shared staging, 2: global memory (gbase + offset)
+template <int MODE>
 struct WrT {
-    uint32_t base;       // shared address of the buffer (SWZ: offsets below are logical and get swizzled)
+    uint32_t base;       // shared address of the buffer (modes 0, 1)
+    uint8_t* gbase;      // global destination (mode 2)
     uint32_t wp;         // offset of the aligned word being filled
     uint32_t acc, fill;  // its bytes so far (fill = 0..3 of them)
     uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
-    __device__ void begin(uint32_t buf, uint32_t off) { base = buf; head = off & 3u; wp = off - head; acc = 0; fill = head; }
-    __device__ __forceinline__ uint32_t at(uint32_t off) const { return base + (SWZ ? swz(off) : off); }
+    __device__ void begin(uint32_t buf, uint32_t off) { base = buf; gbase = nullptr; head = off & 3u; wp = off - head; acc = 0; fill = head; }
+    // global: `g` must be 4-byte aligned (the output buffer is 16-byte aligned), off = byte offset in it
+    __device__ void begin_global(uint8_t* g, uint32_t off) { base = 0; gbase = g; head = off & 3u; wp = off - head; acc = 0; fill = head; }
+    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) {
+        if (MODE == 2) *(uint32_t*)(gbase + off) = v; else sts32(base + (MODE == 1 ? swz(off) : off), v);
+    }
+    __device__ __forceinline__ void st8(uint32_t off, uint32_t v) {
+        if (MODE == 2) gbase[off] = (uint8_t)v; else sts8(base + (MODE == 1 ? swz(off) : off), v & 0xFF);
+    }
     __device__ __forceinline__ void store(uint32_t v) {
-        if (head) { for (uint32_t b = head; b < 4; b++) sts8(at(wp) + b, (v >> (8 * b)) & 0xFF); head = 0; }
-        else sts32(at(wp), v);
+        if (head) { for (uint32_t b = head; b < 4; b++) st8(wp + b, (v >> (8 * b)) & 0xFF); head = 0; }
+        else st32(wp, v);
         wp += 4;
     }
     // four bytes in memory order: the word being filled completes, `fill` bytes carry over
@@ -759,7 +769,7 @@ struct WrT {
         if (fill + n >= 4) { store(w); acc = __funnelshift_l(v, 0u, s8); fill = fill + n - 4; }
         else { acc = w; fill += n; }
     }
-    __device__ void end() { for (uint32_t b = head; b < fill; b++) sts8(at(wp) + b, (acc >> (8 * b)) & 0xFF); }
+    __device__ void end() { for (uint32_t b = head; b < fill; b++) st8(wp + b, (acc >> (8 * b)) & 0xFF); }
     // n bytes from shared memory (consecutive unaligned words share their aligned halves)
     __device__ void copy(uint32_t src, uint32_t n) {
         const uint32_t b = src & ~3u, sh = (src & 3u) * 8;
@@ -775,7 +785,8 @@ __device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 
 __device__ __forceinline__ uint32_t bswap16(uint32_t v) { return ((v & 0xFF) << 8) | ((v >> 8) & 0xFF); }
 
 // domain labels [d_off, stop) of the QNAME, lower-cased (length bytes < 64 are unaffected)
-__device__ void put_dom_labels_w(WrT<true>& w, const Res& r, uint32_t stop) {
+template <class W>
+__device__ void put_dom_labels_w(W& w, const Res& r, uint32_t stop) {
     const uint32_t n = stop - r.d_off;
     const uint32_t src = r.sp + 12 + r.d_off, b = src & ~3u, sh = (src & 3u) * 8;
     uint32_t prev = lds32(b), i = 0, k = 1;
@@ -788,19 +799,21 @@ __device__ void put_dom_labels_w(WrT<true>& w, const Res& r, uint32_t stop) {
         if (nb >= 4) w.put4(x); else w.put(x & ((1u << (8 * nb)) - 1), nb);
     }
 }
-__device__ void put_dom_owner_w(WrT<true>& w, const Res& r) {
+template <class W>
+__device__ void put_dom_owner_w(W& w, const Res& r) {
     if (r.ptr_tgt != NONE16) {
         if (r.ptr_tgt != r.d_off) put_dom_labels_w(w, r, r.ptr_tgt);
         const uint32_t ptr = 0xC000u | (12u + r.ptr_tgt);
         w.put(bswap16(ptr), 2);
     } else { put_dom_labels_w(w, r, r.d_end); w.put(0, 1); }
 }
-__device__ __forceinline__ void put_global_bytes(WrT<true>& w, const uint8_t* s, uint32_t n) {
+template <class W>
+__device__ __forceinline__ void put_global_bytes(W& w, const uint8_t* s, uint32_t n) {
     for (uint32_t i = 0; i < n; i++) w.put(__ldg(s + i), 1);
 }
 
-__device__ void emit_fast(const Params& P, const Res& r, uint32_t stage, uint32_t off, uint32_t qidx) {
-    WrT<true> w; w.begin(stage, off);
+template <class W>
+__device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
     const uint32_t p = r.sp;
     uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
     switch (r.rk) {
@@ -890,7 +903,6 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ __align__(16) uint8_t s_in[S_IN + 32];
     __shared__ __align__(128) uint8_t s_out[S_OUT];          // XOR-swizzled (swz())
     __shared__ uint32_t s_off[T + 1];
-    __shared__ uint32_t s_scan[T + 1];       // exclusive scan of response lengths, [T] = tile total
     __shared__ uint32_t s_wsum[8];
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
@@ -966,8 +978,6 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const uint32_t excl = wbase + inc - v;
     const uint32_t my_o = excl & 0xFFFFFF, my_mrank = excl >> 24;
     const uint32_t tile_bytes = tot & 0xFFFFFF, tile_miss = tot >> 24;
-    s_scan[tid] = my_o;
-    if (tid == 0) s_scan[T] = tile_bytes;
 
     STAMP(7);
     // ---- where this tile's responses (and misses) go ------------------------------------------
@@ -1027,49 +1037,35 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     }
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
-    // ---- assemble in shared memory, flush with aligned 16-byte stores ---------------------------
-    const uint32_t nrounds = overflow ? 0 : (tile_bytes + CAPW - 1) / CAPW;
-    for (uint32_t rd = 0; rd < nrounds; rd++) {
-        const uint32_t w0 = rd * CAPW;                                        // window start (tile offset)
-        const uint32_t shift = (uint32_t)((gbase + w0) & 15);                // same 16B phase in smem and global
-        const bool mine = my_len && my_o >= w0 && my_o < w0 + CAPW;
-        if (mine) {
-            if (r.sp && !r.trunc)
-                emit_fast(P, r, (uint32_t)__cvta_generic_to_shared(s_out), shift + (my_o - w0), qidx);
-            else emit_response(P, r, s_out, shift + (my_o - w0), qidx);
+    // ---- emit ---------------------------------------------------------------------------------------
+    // A tile whose responses fit the staging window is assembled in (swizzled) shared memory and
+    // flushed with aligned 16-byte stores.  A larger tile (service answers are ~250 B each), or one
+    // with a query on the generic byte path, writes straight to global memory instead: every thread's
+    // response is one long contiguous run, and L2 merges its 4-byte stores.
+    const bool generic_emit = my_len && !(r.sp && !r.trunc);
+    const bool direct = __syncthreads_or(generic_emit) || tile_bytes > (uint32_t)CAPW;
+    if (!overflow && direct) {
+        if (my_len) {
+            if (generic_emit) emit_response(P, r, r_out + gbase + my_o, qidx);
+            else { WrT<2> w; w.begin_global(r_out, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
         }
+        STAMP(9);
+    } else if (!overflow && tile_bytes) {
+        const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
+        if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
         __syncthreads();
-        if (rd == 0) STAMP(9);
-        // bytes of this round: from the first response starting in the window to the end of the last
-        uint32_t lo = w0, hi = min(tile_bytes, w0 + CAPW);
-        if (nrounds > 1 && rd > 0) {                                                         // skip the previous round's overhang
-            // first response start >= w0: binary search over the scan
-            int a = 0, b = T;
-            while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0) a = m + 1; else b = m; }
-            lo = a < T ? max(s_scan[a], w0) : tile_bytes;
-            lo = min(lo, tile_bytes);
-        }
-        if (nrounds > 1 && hi < tile_bytes) {                                 // extend to the end of the last response that starts in the window
-            int a = 0, b = T;
-            while (a < b) { int m = (a + b) >> 1; if (s_scan[m] < w0 + CAPW) a = m + 1; else b = m; }
-            hi = a < T ? s_scan[a] : tile_bytes;                              // start of the first response of the next round
-            // zero-length entries at the boundary share the same offset: fine, range is [lo, hi)
-        }
-        if (hi > lo) {
-            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[swz(shift + x - w0)]
-            const uint32_t so = shift - w0;
-            uint32_t x0 = lo, x1 = hi;
-            // head up to 16-byte alignment of the global address
-            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);
-            if (head > x1 - x0) head = x1 - x0;
-            if (tid < (int)head) g[x0 + tid] = s_out[swz(so + x0 + tid)];
-            x0 += head;
-            const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(so + x0 + 16 * i));
-            x0 += nv << 4;
-            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(so + x0 + tid)];
-        }
-        __syncthreads();
+        STAMP(9);
+        uint8_t* g = r_out + gbase;                                           // g[x] <-> s_out[swz(shift + x)]
+        uint32_t x0 = 0;
+        const uint32_t x1 = tile_bytes;
+        uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);                 // up to 16-byte alignment of the global address
+        if (head > x1) head = x1;
+        if (tid < (int)head) g[tid] = s_out[swz(shift + tid)];
+        x0 = head;
+        const uint32_t nv = (x1 - x0) >> 4;
+        for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i));
+        x0 += nv << 4;
+        if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid)];
     }
 
     STAMP(10);
@@ -1194,7 +1190,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         if (staged) {
             s_moff[s_kstart[r.owner] + k] = gb;
             s_mq[s_kstart[r.owner] + k] = A.qidx_base + q0 + tid;
-            WrT<false> w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted), s_bstart[r.owner] + boff);
+            WrT<0> w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted), s_bstart[r.owner] + boff);
             w.copy(r.sp, len);
             w.end();
         } else {                                   // oversized tile: plain peer stores from global memory

@@ -8,15 +8,16 @@ from binder_b200._lib import lib
 
 build.build()
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
-zone = synth.gen_zone(1000000)
+WL = os.environ.get('BB_WL', 'config2')
+zone = synth.gen_zone(1000000, service_frac=0.15 if WL == 'config3' else 0.0)
 ORDERED = os.environ.get('BB_ORDERED', '0') == '1'
 eng = Engine(zone.dns_domain, zone.datacenter, device=0, max_batch=B, max_batch_bytes=B * 64, snapshot=zone.jsonl, ordered=ORDERED)
 dev = torch.device('cuda:0')
 bufs = []
 for r in range(8):
-    data, off = synth.batch_host_a_fast(zone, B, seed=r)
+    data, off = synth.batch_host_a_fast(zone, B, seed=r) if WL != 'config3' else synth.pack_batch(synth.batch_service(zone, B, seed=r))
     bufs.append((torch.from_numpy(data).to(dev), torch.from_numpy(off.view(np.int32)).to(dev)))
-out = torch.empty(B * 96, dtype=torch.uint8, device=dev); oo = torch.empty(B + 1, dtype=torch.int32, device=dev)
+out = torch.empty(B * 400, dtype=torch.uint8, device=dev); oo = torch.empty(B + 1, dtype=torch.int32, device=dev)
 st = torch.empty(B, dtype=torch.uint8, device=dev); ms = torch.empty(B, dtype=torch.int32, device=dev)
 tot = torch.zeros(4, dtype=torch.int32, device=dev); ol = torch.empty(B, dtype=torch.int16, device=dev)
 nt = (B + 127) // 128
