@@ -245,6 +245,14 @@ __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_
 // Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
 __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
     SvcView sv; sv.open(P.arena, r.val);
+    {   // The record (header, child offsets, children) is contiguous: touch all of its cache lines now,
+        // with independent loads, so that the dependent walks below (and in the emit pass) hit in
+        // L1/L2 instead of paying a DRAM round trip per child.
+        const uint32_t rl = sv.hdr()->rec_len;
+        const uint8_t* b0 = (const uint8_t*)((uintptr_t)sv.base & ~(uintptr_t)127);
+        const uint8_t* e0 = sv.base + rl;
+        for (const uint8_t* q = b0 + 128; q < e0; q += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
+    }
     uint32_t nk = sv.hdr()->nkids;
     r.nk = (uint16_t)nk;
     r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;

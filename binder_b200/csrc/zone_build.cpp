@@ -10,6 +10,7 @@
 #include "../../include/binder_b200.h"
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -571,7 +572,7 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
                 for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib) if (B.nodes[k].flags & NF_KIDTYPE) kids.push_back(k);
                 if (kids.size() > 65535) { bb_zone_free(zone); return fail(BB_ERR_SNAPSHOT); }
                 std::vector<uint8_t> rec;
-                SvcHdr h; h.ttl = si.ttl; h.nkids = (uint16_t)kids.size();
+                SvcHdr h; h.ttl = si.ttl; h.nkids = (uint16_t)kids.size(); h.rec_len = 0;
                 bool s_ok = si.has_srvce && si.srvce.size() < 255, p_ok = si.has_proto && si.proto.size() < 255;
                 h.srvce_len = s_ok ? (uint8_t)si.srvce.size() : 0xFF;
                 h.proto_len = p_ok ? (uint8_t)si.proto.size() : 0xFF;
@@ -610,6 +611,7 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
                     rec.insert(rec.end(), (uint8_t*)pl.data(), (uint8_t*)pl.data() + 2 * pl.size());
                     rec.insert(rec.end(), kw.begin(), kw.end());
                 }
+                { uint32_t rl = (uint32_t)rec.size(); memcpy(rec.data() + offsetof(SvcHdr, rec_len), &rl, 4); }
                 val = T.arena_put(rec.data(), rec.size());
             }
             uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;

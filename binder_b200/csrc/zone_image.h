@@ -65,6 +65,7 @@ struct SvcHdr {
     uint16_t nkids;          // children that pass the type filter (:352-360), in child order
     uint8_t  srvce_len;      // 0xFF: s.srvce absent or not a string -> never equal (:334-335)
     uint8_t  proto_len;      // same for s.proto
+    uint32_t rec_len;        // bytes of the whole record (header .. last child): one prefetch burst covers it
     // followed by: srvce bytes, proto bytes, pad to 4, uint32_t kid_off[nkids] (arena offsets)
 };
 enum : uint8_t {
