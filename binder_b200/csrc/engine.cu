@@ -59,6 +59,8 @@ struct Params {
     const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
     uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
     uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
+    uint8_t* bounce;         // zero-copy results: device buffer (same offsets as `out`) that direct-emit tiles write to
+                             // before copying their range to the host buffer with coalesced stores
     // multi-region launch (grid.y = regions): every per-batch pointer advances by its stride per region
     uint32_t regions;
     size_t in_stride, out_stride, off_stride, len_stride, status_stride, miss_stride, totals_stride, desc_stride;
@@ -1053,11 +1055,27 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const bool generic_emit = my_len && !(r.sp && !r.trunc);
     const bool direct = __syncthreads_or(generic_emit) || tile_bytes > (uint32_t)CAPW;
     if (!overflow && direct) {
+        // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
+        // so such tiles assemble in the device bounce buffer and then move their contiguous range with
+        // coalesced 16-byte stores (the bytes are still in L2)
+        uint8_t* const dst = P.bounce ? P.bounce : r_out;
         if (my_len) {
-            if (generic_emit) emit_response(P, r, r_out + gbase + my_o, qidx);
-            else { WrT<2> w; w.begin_global(r_out, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
+            if (generic_emit) emit_response(P, r, dst + gbase + my_o, qidx);
+            else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
         }
         STAMP(9);
+        if (P.bounce && tile_bytes) {
+            __syncthreads();
+            const uint8_t* src = P.bounce + gbase;
+            uint8_t* g = r_out + gbase;
+            uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);
+            if (head > tile_bytes) head = tile_bytes;
+            if (tid < (int)head) g[tid] = src[tid];
+            const uint32_t nv = (tile_bytes - head) >> 4;
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + head + 16 * i) = *(const uint4*)(src + head + 16 * i);
+            const uint32_t x0 = head + (nv << 4);
+            if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
+        }
     } else if (!overflow && tile_bytes) {
         const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
         if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
@@ -1438,7 +1456,7 @@ void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log) { if (e) e
 
 static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts, const uint32_t* d_off, uint32_t n,
                   uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint16_t* d_out_len,
-                  uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st) {
+                  uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st, uint8_t* bounce = nullptr) {
     bbk::Params P;
     P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
@@ -1448,7 +1466,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
     P.stage_log = e->stage_log;
-    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0;
+    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0; P.bounce = bounce;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, st>>>(P);
@@ -1502,7 +1520,8 @@ int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_
     }
     s.zero_copy = s.zc_ok && n != 0;
     if (s.zero_copy) {
-        int rc = launch(e, s.d_desc, s.d_pkts, s.d_off, n, seed, qidx_base, out, out_cap, out_off, out_len, status, miss_idx, s.h_totals, s.stream);
+        const uint32_t zcap = out_cap < e->out_dev_cap ? out_cap : e->out_dev_cap;    // the bounce buffer bounds it too
+        int rc = launch(e, s.d_desc, s.d_pkts, s.d_off, n, seed, qidx_base, out, zcap, out_off, out_len, status, miss_idx, s.h_totals, s.stream, s.d_out);
         if (rc != BB_OK) return rc;
         CK(cudaEventRecord(s.ev, s.stream));
         s.busy = true; s.n = n; s.epoch = (uint32_t)e->epoch; s.out = out; s.out_cap = out_cap; s.miss_idx = miss_idx; s.n_miss = n_miss;
