@@ -1100,7 +1100,10 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     // state for the next launch (blocks beyond ntiles only take part in this count) ------------
     if (warp == 0) {
         uint32_t last = 0;
-        if (lane == 0) { __threadfence(); last = atomicAdd(r_counter + 1, 1u) == gridDim.x - 1; }
+        // ORDERED: this tile's descriptor store must be visible before it counts itself done.  Arrival
+        // packing needs no fence here: the claim was an atomic whose return value this thread already
+        // consumed, so it has been performed at L2.
+        if (lane == 0) { if (ORDERED) __threadfence(); last = atomicAdd(r_counter + 1, 1u) == gridDim.x - 1; }
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last) {                                // every tile has finished reading descriptors / claiming
             __threadfence();

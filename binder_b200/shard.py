@@ -62,6 +62,7 @@ class ShardedEngine(object):
         self.dist = dist
         self._flag = None
         self._lanes = []
+        self._fetch_bufs = {}
         for _ in range(lanes):
             err = ctypes.c_int(0)
             h = lib().bb_shard_create(self.engine._h, world, rank, max_batch, bytes_per_query, ctypes.byref(err))
@@ -101,18 +102,32 @@ class ShardedEngine(object):
             self.barrier()
         self.resolve(seed, stream, lane)
 
-    def fetch(self, src, lane=0):
-        """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays."""
-        cap = self.cap_q
-        out = np.empty(cap * 256, np.uint8); out_off = np.zeros(cap + 1, np.uint32); out_len = np.zeros(cap, np.uint16)
-        status = np.zeros(cap, np.uint8); qidx = np.zeros(cap, np.uint32); miss = np.zeros(cap, np.uint32)
+    def _bufs(self, lane, src):
+        """Pinned host buffers for one region's results, allocated once (a fresh pageable array per
+        call costs page faults on every copy)."""
+        key = (lane, src)
+        if key not in self._fetch_bufs:
+            import torch
+            cap = self.cap_q
+            pin = torch.cuda.is_available()
+            mk = lambda n, dt: torch.empty(n, dtype=dt, pin_memory=pin).numpy()
+            self._fetch_bufs[key] = dict(out=mk(cap * 256, torch.uint8), out_off=mk(cap + 1, torch.int32).view(np.uint32),
+                                         out_len=mk(cap, torch.int16).view(np.uint16), status=mk(cap, torch.uint8),
+                                         qidx=mk(cap, torch.int32).view(np.uint32), miss=mk(cap, torch.int32).view(np.uint32))
+        return self._fetch_bufs[key]
+
+    def fetch(self, src, lane=0, copy=True):
+        """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays (views of
+        reused pinned buffers unless copy=True)."""
+        b = self._bufs(lane, src)
         n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
-        check(lib().bb_shard_fetch(self._lanes[lane], src, out.ctypes.data, out.size, out_off.ctypes.data,
-                                   out_len.ctypes.data, status.ctypes.data, qidx.ctypes.data, miss.ctypes.data,
-                                   ctypes.byref(n), ctypes.byref(nm), ctypes.byref(tot)))
+        check(lib().bb_shard_fetch(self._lanes[lane], src, b['out'].ctypes.data, b['out'].size, b['out_off'].ctypes.data,
+                                   b['out_len'].ctypes.data, b['status'].ctypes.data, b['qidx'].ctypes.data,
+                                   b['miss'].ctypes.data, ctypes.byref(n), ctypes.byref(nm), ctypes.byref(tot)))
         n = n.value
-        return dict(n=n, out=out[:tot.value], out_off=out_off[:n + 1], out_len=out_len[:n], status=status[:n],
-                    qidx=qidx[:n], miss=miss[:nm.value])
+        f = (lambda a: a.copy()) if copy else (lambda a: a)
+        return dict(n=n, out=f(b['out'][:tot.value]), out_off=f(b['out_off'][:n + 1]), out_len=f(b['out_len'][:n]),
+                    status=f(b['status'][:n]), qidx=f(b['qidx'][:n]), miss=f(b['miss'][:nm.value]))
 
     def close(self):
         for h in self._lanes:
