@@ -164,7 +164,7 @@ def run_reference(args, zone):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--steps', type=int, default=20000)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--zone-records', type=int, default=ZONE_RECORDS)
@@ -284,13 +284,15 @@ def main():
     # is the kernel's own average duration (what the roofline uses)
     graph_ms = None
     try:
+        gsteps = min(args.steps, 500)                # launches per graph; replayed to cover args.steps
+        reps = max(1, args.steps // gsteps)
         g = torch.cuda.CUDAGraph()
         side = torch.cuda.Stream()
         step_on(0, side)                 # the engine allocates this stream's scratch outside the capture
         torch.cuda.synchronize()
         with torch.cuda.graph(g, stream=side):
             cs = torch.cuda.current_stream().cuda_stream
-            for k in range(args.steps):
+            for k in range(gsteps):
                 b = d[(args.warmup + k) % RING]
                 eng.resolve_device(b['pk'].data_ptr(), b['off'].data_ptr(), B, 0xB1DDE5, 0, b['out'].data_ptr(), out_cap,
                                    b['oo'].data_ptr(), b['ol'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(), cs)
@@ -298,10 +300,11 @@ def main():
         torch.cuda.synchronize()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record()
-        g.replay()
+        for _ in range(reps):
+            g.replay()
         g1.record()
         torch.cuda.synchronize()
-        graph_ms = g0.elapsed_time(g1)
+        graph_ms = g0.elapsed_time(g1) * args.steps / (gsteps * reps)
     except Exception as ex:      # capture is an optimisation of the measurement, not a requirement
         log('[bench] CUDA-graph replay unavailable: %r' % (ex,))
     clocks = sampler.stop()
@@ -352,7 +355,7 @@ def main():
         def submit(slot, h):
             check(L.bb_resolve_submit(eng._h, slot, h['ptr']['pk'], h['ptr']['off'], B, 0xB1DDE5, 0, h['ptr']['out'],
                                       out_cap, h['ptr']['oo'], h['ptr']['ol'], h['ptr']['st'], h['ptr']['ms'], ctypes.byref(h['nm'])))
-        ksteps = max(args.steps, nslots * 4)
+        ksteps = min(max(args.steps, nslots * 4), 4000)
         for phase in ('warm', 'timed'):
             nst = max(args.warmup, nslots) if phase == 'warm' else ksteps
             torch.cuda.synchronize()

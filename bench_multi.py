@@ -97,7 +97,7 @@ def main(args, rank, world, local_rank):
     # ---- e2e: pinned host ingress -> H2D -> route+push -> resolve -> D2H of the owned answers ----
     h_ring = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(o.view(np.int32)).pin_memory()) for x, o in ring[:4]]
     d_pk = torch.empty_like(d[0][0]); d_off = torch.empty_like(d[0][1])
-    ksteps = max(8, min(args.steps, 40))
+    ksteps = max(8, min(args.steps, 200))
 
     def e2e_step(k):
         hp, ho = h_ring[k % len(h_ring)]
@@ -121,6 +121,17 @@ def main(args, rank, world, local_rank):
            'steps': ksteps, 'timing': 'wall clock, max over ranks; one step at a time (not pipelined)',
            'api': 'pinned H2D + bb_shard_route_push + NCCL barrier + bb_shard_resolve + bb_shard_fetch'}
 
+    # step-level roofline per GPU (the kernels of different steps overlap, so there is no per-kernel
+    # duration here): algorithmic HBM bytes of one rank's step = its batch parsed twice (route, then
+    # resolve: 2 x (packet + 4)) + probe + answers, per SURVEY.md section 8d, over the step time
+    peak, peak_src = B1.measured_peaks()
+    in_b = int(ring[0][1][B]) + 4 * B
+    step_bytes = 2 * in_b + B * (30 + 1 + 8) + B * (64 + 8)
+    achieved = step_bytes / (ms / args.steps * 1e-3) / 1e9
+    roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak, 'traffic': None,
+                'peak_source': peak_src, 'kernel': 'route_push_kernel + resolve_kernel (per GPU, per step, steps overlapped)',
+                'algorithmic_bytes_per_launch': step_bytes,
+                'nvlink_bytes_per_step': int((in_b + 8 * B) * (world - 1) / world)}
     if rank == 0:
         line = {'metric': B1.METRIC, 'value': world * B * args.steps / (ms * 1e-3), 'unit': B1.UNIT, 'n_gpus': world,
                 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
@@ -131,7 +142,7 @@ def main(args, rank, world, local_rank):
                            'parallelism': 'shard%d: route+push kernel stores each query into its owner rank over NVLink peer memory; %s; owner resolves; %d steps in flight' % (world, 'per-region epoch flags + device-side wait (no collective)' if sync == 'flags' else '1-element NCCL all-reduce as barrier', LANES),
                            'l2_policy': 'ring of %d distinct batches per rank; shard table %.0f MB' % (RING, se.zone_stat['image_bytes'] / 1e6),
                            'output_packing': 'query order' if args.ordered else 'arrival'},
-                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': None, 'cpu_baseline': None}
+                'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roofline, 'cpu_baseline': None}
         B1.emit(line)
     dist.barrier()
     dist.destroy_process_group()

@@ -245,7 +245,10 @@ __device__ __forceinline__ uint32_t dom_owner_len(const Res& r) {
 __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_t)(r.d_end - r.d_off) + 1; }
 
 // Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
+__device__ __forceinline__ unsigned long long gtime_early() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STAMP_SVC(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * 16 + (k)] = gtime_early(); } while (0)
 __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
+    STAMP_SVC(11);
     SvcView sv; sv.open(P.arena, r.val);
     {   // The record (header, child offsets, children) is contiguous: touch all of its cache lines now,
         // with independent loads, so that the dependent walks below (and in the emit pass) hit in
@@ -257,7 +260,9 @@ __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, u
     }
     uint32_t nk = sv.hdr()->nkids;
     r.nk = (uint16_t)nk;
+    STAMP_SVC(12);
     r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
+    STAMP_SVC(13);
     const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
     uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
     const uint8_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
@@ -272,6 +277,7 @@ __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, u
         } else { ans_b += dol + 14; n_ans++; }
     }
     r.n_walk = (uint16_t)n_walk;
+    STAMP_SVC(14);
     if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = (uint16_t)n_ans; r.keep_add = (uint16_t)n_add; r.rlen = (uint16_t)(fixed + ans_b + add_b); return; }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits
     r.tc = 1;
@@ -338,7 +344,7 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
 
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 // per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
-constexpr int NSTAGE = 12;
+constexpr int NSTAGE = 16;
 #define STAMP(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * NSTAGE + (k)] = gtime(); } while (0)
 
 // ---- word-wise front end of resolve() -----------------------------------------------------

@@ -157,10 +157,11 @@ uint64_t bb_engine_launch_count(const bb_engine* e);
 uint32_t bb_engine_launch_epoch(const bb_engine* e);
 /*
  * Stage timers, the batched analogue of query._stamp() (lib/server.js:479-483): when d_log is
- * a device buffer of ceil(n/128) x 12 uint64, every 128-query tile of later launches stores
+ * a device buffer of ceil(n/128) x 16 uint64, every 128-query tile of later launches stores
  * %globaltimer (ns) at: 0 start, 1 offsets in, 2 packets staged, 3 decoded, 4 normalised+hashed,
  * 5 probed, 6 sized, 7 tile scan, 8 placed (claim / look-back), 9 responses assembled,
- * 10 flushed (thread 0's view of its tile).  NULL turns it off.
+ * 10 flushed; 11-14 service sizing: entered, record opened, permutation built, children walked
+ * (thread 0's view of its tile).  NULL turns it off.
  */
 void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
 

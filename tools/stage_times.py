@@ -21,7 +21,7 @@ out = torch.empty(B * 400, dtype=torch.uint8, device=dev); oo = torch.empty(B + 
 st = torch.empty(B, dtype=torch.uint8, device=dev); ms = torch.empty(B, dtype=torch.int32, device=dev)
 tot = torch.zeros(4, dtype=torch.int32, device=dev); ol = torch.empty(B, dtype=torch.int16, device=dev)
 nt = (B + 127) // 128
-NS = 12
+NS = 16
 log = torch.zeros(nt * NS, dtype=torch.int64, device=dev)
 s = torch.cuda.current_stream().cuda_stream
 def run(k):
@@ -33,7 +33,7 @@ lib().bb_engine_set_stage_log(eng._h, log.data_ptr())
 acc = []
 for k in range(10):
     run(5 + k); torch.cuda.synchronize()
-    acc.append(log.cpu().numpy().reshape(nt, NS)[:, :11].copy())
+    full = log.cpu().numpy().reshape(nt, NS).copy(); acc.append(full[:, :11]); svc = full[:, 11:15]
 print('ordered' if ORDERED else 'arrival', 'packing, batch', B)
 names = ['start', 'offsets', 'staged', 'decoded', 'hashed', 'probed', 'sized', 'scan', 'placed', 'emitted', 'flushed']
 for a in acc[-3:]:
@@ -43,3 +43,8 @@ for a in acc[-3:]:
     d = np.diff(a, axis=1) / 1000.0
     print('  stage durations us (mean / max over tiles): ' + ', '.join('%s %.2f/%.2f' % (names[i + 1], d[:, i].mean(), d[:, i].max()) for i in range(10)))
     print('  completion time of each stage, max over tiles: ' + ', '.join('%s %.2f' % (names[i], rel[:, i].max()) for i in range(11)))
+
+if WL == 'config3':
+    ok = (svc > 0).all(axis=1)
+    d = np.diff(svc[ok], axis=1) / 1000.0
+    print('  service sizing (thread 0 of tiles whose first query is a service): record opened %.2f us, permutation %.2f us, child walk %.2f us' % tuple(d.mean(axis=0)))
