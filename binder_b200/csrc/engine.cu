@@ -360,6 +360,8 @@ __device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
     const uint32_t b = a & ~3u;
     return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) * 8);
 }
+// v << n with PTX semantics: any n > 31 (including a wrapped-around negative) gives 0
+__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
 // 0x80 in every byte of v that is zero
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); }
 // 0x80 in every byte of x7 (7-bit bytes) that is >= k
@@ -387,7 +389,7 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
 #pragma unroll 1
     while (c != 0) {
         bad |= c > 63;                                                        // pointers / extended label types
-        lo |= pos < 32 ? 1u << pos : 0u; hi |= (pos >= 32 && pos < 64) ? 1u << (pos - 32) : 0u;
+        lo |= shl_clamp(1u, pos); hi |= shl_clamp(1u, pos - 32u);             // positions >= 64 fall off (shl.b32 clamps its count)
         pos += 1 + c;
         if (pos >= lim || pos > 254) { bad = 1; break; }
         c = lds8(nm + pos);
@@ -750,27 +752,45 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
 // A byte stream into shared memory at an arbitrary byte address, stored as aligned 32-bit words;
 // only the bytes shared with the neighbouring responses (first / last partial word) go out as
 // single bytes, so two threads never write the same word.
-// MODE 0: plain shared buffer, 1: XOR-swizzled shared staging, 2: global memory (gbase + offset)
-template <int MODE>
+// MODE 0: plain shared buffer, 1: XOR-swizzled shared staging (buffer 1024-byte aligned, so the
+// swizzle applies to the address itself), 2: global memory (gbase + offset).
+// HEADCHK: any put may be the one that completes the first word.  Without it the stream must open
+// with put4_first(), and every later store is a plain aligned word.
+template <int MODE, bool HEADCHK = false>
 struct WrT {
-    uint32_t base;       // shared address of the buffer (modes 0, 1)
+    uint32_t base;       // shared address of the buffer (mode 0)
     uint8_t* gbase;      // global destination (mode 2)
-    uint32_t wp;         // offset of the aligned word being filled
+    uint32_t wp;         // position of the aligned word being filled: offset (modes 0, 2) or shared address (mode 1)
     uint32_t acc, fill;  // its bytes so far (fill = 0..3 of them)
     uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
-    __device__ void begin(uint32_t buf, uint32_t off) { base = buf; gbase = nullptr; head = off & 3u; wp = off - head; acc = 0; fill = head; }
+    __device__ void begin(uint32_t buf, uint32_t off) {
+        gbase = nullptr; head = off & 3u; acc = 0; fill = head;
+        if (MODE == 1) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
+    }
     // global: `g` must be 4-byte aligned (the output buffer is 16-byte aligned), off = byte offset in it
     __device__ void begin_global(uint8_t* g, uint32_t off) { base = 0; gbase = g; head = off & 3u; wp = off - head; acc = 0; fill = head; }
-    __device__ __forceinline__ void st32(uint32_t off, uint32_t v) {
-        if (MODE == 2) *(uint32_t*)(gbase + off) = v; else sts32(base + (MODE == 1 ? swz(off) : off), v);
+    __device__ __forceinline__ void st32(uint32_t pos, uint32_t v) {
+        if (MODE == 2) *(uint32_t*)(gbase + pos) = v;
+        else if (MODE == 1) sts32(pos ^ ((pos >> 3) & 0x70u), v);
+        else sts32(base + pos, v);
     }
-    __device__ __forceinline__ void st8(uint32_t off, uint32_t v) {
-        if (MODE == 2) gbase[off] = (uint8_t)v; else sts8(base + (MODE == 1 ? swz(off) : off), v & 0xFF);
+    __device__ __forceinline__ void st8(uint32_t pos, uint32_t v) {
+        if (MODE == 2) gbase[pos] = (uint8_t)v;
+        else if (MODE == 1) sts8(pos ^ ((pos >> 3) & 0x70u), v & 0xFF);
+        else sts8(base + pos, v & 0xFF);
     }
     __device__ __forceinline__ void store(uint32_t v) {
-        if (head) { for (uint32_t b = head; b < 4; b++) st8(wp + b, (v >> (8 * b)) & 0xFF); head = 0; }
+        if (HEADCHK && head) { for (uint32_t b = head; b < 4; b++) st8(wp + b, (v >> (8 * b)) & 0xFF); head = 0; }
         else st32(wp, v);
         wp += 4;
+    }
+    // the first four bytes of the stream: the only word that may be shared with the previous response
+    __device__ __forceinline__ void put4_first(uint32_t v) {
+        const uint32_t s8 = 8 * head, w = v << s8;
+        if (head == 0) st32(wp, w);
+        else for (uint32_t b = head; b < 4; b++) st8(wp + b, (w >> (8 * b)) & 0xFF);
+        acc = __funnelshift_l(v, 0u, s8);
+        wp += 4; head = 0;
     }
     // four bytes in memory order: the word being filled completes, `fill` bytes carry over
     __device__ __forceinline__ void put4(uint32_t v) {
@@ -838,14 +858,22 @@ __device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
     case RK_SVC_A: case RK_SVC_SRV: an = r.keep_ans; ar += r.keep_add; break;
     }
     const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
-    w.put4((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24));   // id, QR AA TC RD, rcode
+    w.put4_first((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24));   // id, QR AA TC RD, rcode
     w.put4(0x00000100u | (bswap16(an) << 16));                                  // QDCOUNT=1, ANCOUNT
     w.put4(bswap16(ns) | (bswap16(ar) << 16));                                  // NSCOUNT, ARCOUNT
     w.copy(p + 12, r.qn_len + 4);                                               // question, verbatim
     bool opt_done = !r.edns;
     if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310
-        put_dom_owner_w(w, r);
-        w.put4(0x01000100u); w.put4(bswap32(r.ttl)); w.put(0x0400u, 2); w.put4(bswap32(r.val));
+        const uint32_t bt = bswap32(r.ttl);
+        if (r.ptr_tgt == r.d_off) {              // owner is a bare pointer: the 16-byte RR as four whole words
+            w.put4(bswap16(0xC000u | (12u + r.ptr_tgt)) | 0x01000000u);        // ptr | TYPE A ...
+            w.put4(0x00000100u | (bt << 16));                                    // ... CLASS IN | ttl (high half)
+            w.put4((bt >> 16) | 0x04000000u);                                    // ttl (low half) | RDLENGTH 4
+            w.put4(bswap32(r.val));
+        } else {
+            put_dom_owner_w(w, r);
+            w.put4(0x01000100u); w.put4(bt); w.put(0x0400u, 2); w.put4(bswap32(r.val));
+        }
     } else if (r.rk == RK_PTR && r.keep_ans) {                                  // :130
         const uint32_t tl = P.arena[r.val];
         w.put(0x0CC0u, 2); w.put4(0x01000C00u); w.put4(bswap32(r.ttl)); w.put(bswap16(tl), 2);
@@ -914,29 +942,30 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 // ORDERED: responses packed in query order (tile bases from a decoupled look-back; a tile waits
 // for its predecessors' sizes).  !ORDERED ("arrival" packing): a tile claims its output range
 // with one atomicAdd and never waits; response i is still out[out_off[i] .. +out_len[i]).
-template <bool ORDERED>
+// MULTI: one launch over several receive regions (routed batches, grid.y = source rank): every
+// per-batch pointer advances by its stride per region, sizes and shuffle indices come from device memory.
+template <bool ORDERED, bool MULTI>
 __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params P) {
     __shared__ __align__(16) uint8_t s_in[S_IN + 32];
-    __shared__ __align__(128) uint8_t s_out[S_OUT];          // XOR-swizzled (swz())
+    __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // region of a multi-region launch (routed batches: one region per source rank)
-    const size_t ry = P.regions ? blockIdx.y : 0;
-    const uint8_t* const r_pkts = P.pkts + ry * P.in_stride;
-    const uint32_t* const r_pkt_off = (const uint32_t*)((const uint8_t*)P.pkt_off + ry * P.in_stride);
-    const uint32_t* const r_n_dev = P.n_dev ? (const uint32_t*)((const uint8_t*)P.n_dev + ry * P.in_stride) : nullptr;
-    const uint32_t* const r_qidx_map = P.qidx_map ? (const uint32_t*)((const uint8_t*)P.qidx_map + ry * P.in_stride) : nullptr;
-    uint8_t* const r_out = P.out + ry * P.out_stride;
-    uint32_t* const r_out_off = (uint32_t*)((uint8_t*)P.out_off + ry * P.off_stride);
-    uint16_t* const r_out_len = (uint16_t*)((uint8_t*)P.out_len + ry * P.len_stride);
-    uint8_t* const r_status = P.status + ry * P.status_stride;
-    uint32_t* const r_miss_idx = (uint32_t*)((uint8_t*)P.miss_idx + ry * P.miss_stride);
-    uint32_t* const r_totals = (uint32_t*)((uint8_t*)P.totals + ry * P.totals_stride);
-    unsigned long long* const r_desc = (unsigned long long*)((uint8_t*)P.desc + ry * P.desc_stride);
-    uint32_t* const r_counter = (uint32_t*)((uint8_t*)P.counter + ry * P.desc_stride);
+    const size_t ry = MULTI ? blockIdx.y : 0;
+    const uint8_t* const r_pkts = MULTI ? P.pkts + ry * P.in_stride : P.pkts;
+    const uint32_t* const r_pkt_off = MULTI ? (const uint32_t*)((const uint8_t*)P.pkt_off + ry * P.in_stride) : P.pkt_off;
+    const uint32_t* const r_n_dev = (MULTI && P.n_dev) ? (const uint32_t*)((const uint8_t*)P.n_dev + ry * P.in_stride) : nullptr;
+    const uint32_t* const r_qidx_map = (MULTI && P.qidx_map) ? (const uint32_t*)((const uint8_t*)P.qidx_map + ry * P.in_stride) : nullptr;
+    uint8_t* const r_out = MULTI ? P.out + ry * P.out_stride : P.out;
+    uint32_t* const r_out_off = MULTI ? (uint32_t*)((uint8_t*)P.out_off + ry * P.off_stride) : P.out_off;
+    uint16_t* const r_out_len = MULTI ? (uint16_t*)((uint8_t*)P.out_len + ry * P.len_stride) : P.out_len;
+    uint8_t* const r_status = MULTI ? P.status + ry * P.status_stride : P.status;
+    uint32_t* const r_miss_idx = MULTI ? (uint32_t*)((uint8_t*)P.miss_idx + ry * P.miss_stride) : P.miss_idx;
+    uint32_t* const r_totals = MULTI ? (uint32_t*)((uint8_t*)P.totals + ry * P.totals_stride) : P.totals;
+    unsigned long long* const r_desc = MULTI ? (unsigned long long*)((uint8_t*)P.desc + ry * P.desc_stride) : P.desc;
+    uint32_t* const r_counter = MULTI ? (uint32_t*)((uint8_t*)P.counter + ry * P.desc_stride) : P.counter;
 
     // Tiles are taken in blockIdx order: like CUB's single-pass scan, the look-back below relies on
     // thread blocks being dispatched in increasing blockIdx order (a block only ever waits for
@@ -1225,7 +1254,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         if (staged) {
             s_moff[s_kstart[r.owner] + k] = gb;
             s_mq[s_kstart[r.owner] + k] = A.qidx_base + q0 + tid;
-            WrT<0> w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted), s_bstart[r.owner] + boff);
+            WrT<0, true> w; w.begin((uint32_t)__cvta_generic_to_shared(s_sorted), s_bstart[r.owner] + boff);
             w.copy(r.sp, len);
             w.end();
         } else {                                   // oversized tile: plain peer stores from global memory
@@ -1478,8 +1507,8 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0; P.bounce = bounce;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
-    if (e->ordered) bbk::resolve_kernel<true><<<P.ntiles, bbk::T, 0, st>>>(P);
-    else bbk::resolve_kernel<false><<<P.ntiles, bbk::T, 0, st>>>(P);
+    if (e->ordered) bbk::resolve_kernel<true, false><<<P.ntiles, bbk::T, 0, st>>>(P);
+    else bbk::resolve_kernel<false, false><<<P.ntiles, bbk::T, 0, st>>>(P);
     CK(cudaGetLastError());
     e->launches++;
     return BB_OK;
@@ -1714,8 +1743,8 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     P.regions = 1; P.in_stride = s->reg_size; P.out_stride = s->out_stride; P.off_stride = s->off_stride; P.len_stride = s->len_stride;
     P.status_stride = s->status_stride; P.miss_stride = s->miss_stride; P.totals_stride = s->totals_stride; P.desc_stride = s->desc_stride;
     const dim3 grid(P.ntiles, s->nranks);
-    if (e->ordered) bbk::resolve_kernel<true><<<grid, bbk::T, 0, main>>>(P);
-    else bbk::resolve_kernel<false><<<grid, bbk::T, 0, main>>>(P);
+    if (e->ordered) bbk::resolve_kernel<true, true><<<grid, bbk::T, 0, main>>>(P);
+    else bbk::resolve_kernel<false, true><<<grid, bbk::T, 0, main>>>(P);
     CK(cudaGetLastError());
     e->launches++;
     return BB_OK;
