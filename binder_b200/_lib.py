@@ -45,6 +45,8 @@ SYMBOLS = {
     'bb_shard_resolve': (_c.c_int, [_c.c_void_p, _c.c_uint64, _c.c_int, _c.c_void_p]),
     'bb_shard_fetch': (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                   _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'bb_shard_host_results': (_c.c_int, [_c.c_void_p, _c.c_int]),
+    'bb_shard_results': (_c.c_int, [_c.c_void_p, _c.c_uint32] + [_c.c_void_p] * 9),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),
     'bb_host_free': (None, [_c.c_void_p]),
 }

@@ -59,6 +59,8 @@ struct Params {
     const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
     uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
     uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
+    uint32_t* qidx_out;      // multi-region: each result's ingress index is also written here (host result mirrors)
+    const uint32_t* err_in;  // multi-region: the shard's wait-timeout word, copied into totals[6]
     uint8_t* bounce;         // zero-copy results: device buffer (same offsets as `out`) that direct-emit tiles write to
                              // before copying their range to the host buffer with coalesced stores
     // multi-region launch (grid.y = regions): every per-batch pointer advances by its stride per region
@@ -966,6 +968,8 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     uint32_t* const r_totals = MULTI ? (uint32_t*)((uint8_t*)P.totals + ry * P.totals_stride) : P.totals;
     unsigned long long* const r_desc = MULTI ? (unsigned long long*)((uint8_t*)P.desc + ry * P.desc_stride) : P.desc;
     uint32_t* const r_counter = MULTI ? (uint32_t*)((uint8_t*)P.counter + ry * P.desc_stride) : P.counter;
+    uint32_t* const r_qidx_out = (MULTI && P.qidx_out) ? (uint32_t*)((uint8_t*)P.qidx_out + ry * P.off_stride) : nullptr;
+    uint8_t* const r_bounce = (MULTI && P.bounce) ? P.bounce + ry * P.out_stride : P.bounce;
 
     // Tiles are taken in blockIdx order: like CUB's single-pass scan, the look-back below relies on
     // thread blocks being dispatched in increasing blockIdx order (a block only ever waits for
@@ -1079,6 +1083,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         r_out_len[q0 + tid] = (uint16_t)my_len;
         r_status[q0 + tid] = r.status;
         if (my_miss) r_miss_idx[mbase + my_mrank] = q0 + tid;
+        if (MULTI && r_qidx_out) r_qidx_out[q0 + tid] = qidx;
     }
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
@@ -1093,15 +1098,15 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
         // coalesced 16-byte stores (the bytes are still in L2)
-        uint8_t* const dst = P.bounce ? P.bounce : r_out;
+        uint8_t* const dst = r_bounce ? r_bounce : r_out;
         if (my_len) {
             if (generic_emit) emit_response(P, r, dst + gbase + my_o, qidx);
             else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
         }
         STAMP(9);
-        if (P.bounce && tile_bytes) {
+        if (r_bounce && tile_bytes) {
             __syncthreads();
-            const uint8_t* src = P.bounce + gbase;
+            const uint8_t* src = r_bounce + gbase;
             uint8_t* g = r_out + gbase;
             uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);
             if (head > tile_bytes) head = tile_bytes;
@@ -1149,6 +1154,9 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             if (lane == 0) {
                 const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
                 r_out_off[n] = tb; r_totals[0] = tb; r_totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); r_totals[3] = P.epoch;
+                if (MULTI) {                   // what a host reading only the totals needs to know about the region
+                    r_totals[4] = n; r_totals[5] = r_n_dev ? r_n_dev[3] : 0u; r_totals[6] = P.err_in ? *(volatile const uint32_t*)P.err_in : 0u;
+                }
             }
             __syncwarp();
             if (ORDERED) { for (uint32_t i = lane; i < ntiles; i += 32) r_desc[i] = 0; }
@@ -1504,7 +1512,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
     P.stage_log = e->stage_log;
-    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0; P.bounce = bounce;
+    P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0; P.bounce = bounce; P.qidx_out = nullptr; P.err_in = nullptr;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (e->ordered) bbk::resolve_kernel<true, false><<<P.ntiles, bbk::T, 0, st>>>(P);
@@ -1622,8 +1630,12 @@ struct bb_shard {
     // all regions resolve in ONE launch (grid.y = region)
     uint8_t* d_out = nullptr; uint8_t* d_out_off = nullptr; uint8_t* d_out_len = nullptr; uint8_t* d_status = nullptr;
     uint8_t* d_miss = nullptr; uint8_t* d_totals = nullptr; uint8_t* d_desc = nullptr;
-    size_t out_stride = 0, off_stride = 0, len_stride = 0, status_stride = 0, miss_stride = 0, totals_stride = 16, desc_stride = 0;
+    size_t out_stride = 0, off_stride = 0, len_stride = 0, status_stride = 0, miss_stride = 0, totals_stride = 32, desc_stride = 0;
     uint32_t out_cap = 0;
+    // optional pinned host mirrors of the result set (same strides): the resolve kernel writes them directly
+    uint8_t* h_out = nullptr; uint8_t* h_out_off = nullptr; uint8_t* h_out_len = nullptr; uint8_t* h_status = nullptr;
+    uint8_t* h_miss = nullptr; uint8_t* h_totals = nullptr; uint8_t* h_qidx = nullptr;
+    bool host = false; uint32_t resolve_epoch = 0;
 };
 
 extern "C" {
@@ -1665,6 +1677,8 @@ void bb_shard_destroy(bb_shard* s) {
     cudaFree(s->d_out); cudaFree(s->d_out_off); cudaFree(s->d_out_len); cudaFree(s->d_status); cudaFree(s->d_miss);
     cudaFree(s->d_totals); cudaFree(s->d_desc);
     cudaFree(s->recv); cudaFree(s->cursor); cudaFree(s->done);
+    cudaFreeHost(s->h_out); cudaFreeHost(s->h_out_off); cudaFreeHost(s->h_out_len); cudaFreeHost(s->h_status);
+    cudaFreeHost(s->h_miss); cudaFreeHost(s->h_totals); cudaFreeHost(s->h_qidx);
     delete s;
 }
 
@@ -1735,6 +1749,12 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     P.seed = seed; P.qidx_base = 0;
     P.out = s->d_out; P.out_cap = s->out_cap; P.out_off = (uint32_t*)s->d_out_off; P.out_len = (uint16_t*)s->d_out_len;
     P.status = s->d_status; P.miss_idx = (uint32_t*)s->d_miss; P.totals = (uint32_t*)s->d_totals;
+    P.err_in = s->err;
+    if (s->host) {                                   // results straight into the pinned mirrors (zero-copy)
+        P.out = s->h_out; P.out_off = (uint32_t*)s->h_out_off; P.out_len = (uint16_t*)s->h_out_len; P.status = s->h_status;
+        P.miss_idx = (uint32_t*)s->h_miss; P.totals = (uint32_t*)s->h_totals; P.qidx_out = (uint32_t*)s->h_qidx;
+        P.bounce = s->d_out;                         // tiles too large to stage assemble on the device first
+    }
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
     P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion;
     P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
@@ -1746,7 +1766,47 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     if (e->ordered) bbk::resolve_kernel<true, true><<<grid, bbk::T, 0, main>>>(P);
     else bbk::resolve_kernel<false, true><<<grid, bbk::T, 0, main>>>(P);
     CK(cudaGetLastError());
+    s->resolve_epoch = P.epoch;
     e->launches++;
+    return BB_OK;
+}
+
+// Pinned host mirrors of the per-region result set: from now on bb_shard_resolve writes responses,
+// offsets, lengths, statuses, ingress indices, miss lists and totals straight into host memory
+// (no copies, no size round trip), and bb_shard_results hands out pointers into them.
+int bb_shard_host_results(bb_shard* s, int enable) {
+    if (!s) return BB_ERR_ARG;
+    CK(cudaSetDevice(s->e->device));
+    if (enable && !s->h_out) {
+        const unsigned fl = cudaHostAllocPortable | cudaHostAllocMapped;
+        const size_t R = s->nranks;
+        CK(cudaHostAlloc((void**)&s->h_out, s->out_stride * R, fl)); CK(cudaHostAlloc((void**)&s->h_out_off, s->off_stride * R, fl));
+        CK(cudaHostAlloc((void**)&s->h_out_len, s->len_stride * R, fl)); CK(cudaHostAlloc((void**)&s->h_status, s->status_stride * R, fl));
+        CK(cudaHostAlloc((void**)&s->h_miss, s->miss_stride * R, fl)); CK(cudaHostAlloc((void**)&s->h_totals, s->totals_stride * R, fl));
+        CK(cudaHostAlloc((void**)&s->h_qidx, s->off_stride * R, fl));
+        memset(s->h_totals, 0, s->totals_stride * R);
+    }
+    CK(cudaDeviceSynchronize());                     // resolves in flight finish with the old destination
+    s->host = enable != 0;
+    return BB_OK;
+}
+
+// Region `src` of the last bb_shard_resolve, in the host mirrors.  The caller has waited for the work
+// it enqueued on the resolve's stream (event or stream synchronize); BB_ERR_ARG if that resolve has
+// not finished writing this region.  The pointers stay valid until the next resolve on this shard.
+int bb_shard_results(bb_shard* s, uint32_t src, const uint8_t** out, const uint32_t** out_off, const uint16_t** out_len,
+                     const uint8_t** status, const uint32_t** qidx, const uint32_t** miss_idx,
+                     uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out) {
+    if (!s || src >= s->nranks || !s->host || !s->resolve_epoch) return BB_ERR_ARG;
+    const volatile uint32_t* tot = (const volatile uint32_t*)(s->h_totals + src * s->totals_stride);
+    if (tot[3] != s->resolve_epoch) return BB_ERR_ARG;
+    if (tot[6] == 2) { g_cuda_err = "timed out waiting for a peer rank's push"; return BB_ERR_CUDA; }
+    if (tot[5] || tot[2] == s->resolve_epoch) return BB_ERR_CAPACITY;      // a sender overflowed the region / responses overflowed out
+    const uint32_t n = tot[4];
+    *n_out = n; *n_miss = n ? tot[1] : 0; *total_out = n ? tot[0] : 0;
+    *out = s->h_out + src * s->out_stride; *out_off = (const uint32_t*)(s->h_out_off + src * s->off_stride);
+    *out_len = (const uint16_t*)(s->h_out_len + src * s->len_stride); *status = s->h_status + src * s->status_stride;
+    *qidx = (const uint32_t*)(s->h_qidx + src * s->off_stride); *miss_idx = (const uint32_t*)(s->h_miss + src * s->miss_stride);
     return BB_OK;
 }
 
@@ -1754,7 +1814,7 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
 // rank src's ingress numbering (qidx_base + position).  Returns the region's query count in *n_out.
 int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
                    uint8_t* status, uint32_t* qidx, uint32_t* miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out) {
-    if (!s || src >= s->nranks) return BB_ERR_ARG;
+    if (!s || src >= s->nranks || s->host) return BB_ERR_ARG;       // host mirrors on: use bb_shard_results
     CK(cudaSetDevice(s->e->device));
     uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + src) * s->reg_size;
     uint32_t hdr[4], tot[4];

@@ -54,8 +54,8 @@ class ShardedEngine(object):
     double-buffered receive regions) let several steps be in flight on different streams."""
 
     def __init__(self, dns_domain, datacenter, snapshot, rank, world, device, max_batch, recursion=False,
-                 ordered=False, bytes_per_query=64, dist=None, lanes=1, sync='flags'):
-        self.rank, self.world, self.sync = rank, world, sync
+                 ordered=False, bytes_per_query=64, dist=None, lanes=1, sync='flags', host_results=False):
+        self.rank, self.world, self.sync, self.host_results = rank, world, sync, host_results
         self.engine = Engine(dns_domain, datacenter, recursion=recursion, device=device, max_batch=max_batch,
                              max_batch_bytes=max_batch * bytes_per_query, ordered=ordered)
         self.zone_stat = self.engine.load_snapshot(snapshot, world, rank)
@@ -69,6 +69,8 @@ class ShardedEngine(object):
             if not h:
                 raise _lib.BinderError(err.value)
             self._lanes.append(h)
+            if host_results:            # results land in the shard's pinned host mirrors (zero-copy)
+                check(lib().bb_shard_host_results(h, 1))
         self._h = self._lanes[0]
         self.cap_q = lib().bb_shard_region_capacity(self._h)
         if world > 1:
@@ -80,6 +82,13 @@ class ShardedEngine(object):
                 dist.all_gather_object(gathered, bytes(mine))
                 check(lib().bb_shard_open_peers(h, b''.join(gathered)))
             dist.barrier()
+
+    def set_host_results(self, on):
+        """Switch every lane between device result buffers (+ fetch copies) and pinned host mirrors
+        the resolve kernel writes directly (bb_shard_host_results).  Synchronises the device."""
+        for h in self._lanes:
+            check(lib().bb_shard_host_results(h, 1 if on else 0))
+        self.host_results = bool(on)
 
     def route_push(self, d_pkts, d_off, n, qidx_base, stream, lane=0):
         check(lib().bb_shard_route_push(self._lanes[lane], d_pkts, d_off, n, qidx_base, stream))
@@ -118,7 +127,10 @@ class ShardedEngine(object):
 
     def fetch(self, src, lane=0, copy=True):
         """Region `src` -> dict(out, out_off, out_len, status, qidx, miss) as numpy arrays (views of
-        reused pinned buffers unless copy=True)."""
+        reused pinned buffers unless copy=True).  With host_results the arrays are views of the
+        shard's own mirrors: the caller must have waited for the resolve's stream."""
+        if self.host_results:
+            return self._results(src, lane, copy)
         b = self._bufs(lane, src)
         n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
         check(lib().bb_shard_fetch(self._lanes[lane], src, b['out'].ctypes.data, b['out'].size, b['out_off'].ctypes.data,
@@ -128,6 +140,30 @@ class ShardedEngine(object):
         f = (lambda a: a.copy()) if copy else (lambda a: a)
         return dict(n=n, out=f(b['out'][:tot.value]), out_off=f(b['out_off'][:n + 1]), out_len=f(b['out_len'][:n]),
                     status=f(b['status'][:n]), qidx=f(b['qidx'][:n]), miss=f(b['miss'][:nm.value]))
+
+    def _results(self, src, lane, copy):
+        P = ctypes.POINTER
+        out, status = P(ctypes.c_uint8)(), P(ctypes.c_uint8)()
+        out_off, qidx, miss = P(ctypes.c_uint32)(), P(ctypes.c_uint32)(), P(ctypes.c_uint32)()
+        out_len = P(ctypes.c_uint16)()
+        n, nm, tot = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        check(lib().bb_shard_results(self._lanes[lane], src, ctypes.byref(out), ctypes.byref(out_off), ctypes.byref(out_len),
+                                     ctypes.byref(status), ctypes.byref(qidx), ctypes.byref(miss),
+                                     ctypes.byref(n), ctypes.byref(nm), ctypes.byref(tot)))
+        n = n.value
+
+        def view(ptr, count):
+            if count == 0:
+                return np.zeros(0, dtype=np.dtype(ptr._type_))
+            a = np.ctypeslib.as_array(ptr, shape=(count,))
+            return a.copy() if copy else a
+        return dict(n=n, out=view(out, tot.value), out_off=view(out_off, n + 1), out_len=view(out_len, n),
+                    status=view(status, n), qidx=view(qidx, n), miss=view(miss, nm.value))
+
+    def totals(self, src, lane=0):
+        """(queries, misses, response bytes) of region `src` after a finished resolve (host_results only)."""
+        r = self._results(src, lane, False)
+        return r['n'], len(r['miss']), len(r['out'])
 
     def close(self):
         for h in self._lanes:

@@ -187,6 +187,13 @@ void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
  *   bb_shard_fetch         one region's results to host memory; qidx[] = ingress index of each
  *                          query on the source rank (qidx_base + position), which also keys the
  *                          service shuffle, so answers are identical to the unsharded engine's.
+ *   bb_shard_host_results  enable=1: the shard keeps pinned host mirrors of its result set and every
+ *                          later bb_shard_resolve writes responses, offsets, lengths, statuses, ingress
+ *                          indices, miss lists and totals straight into them (zero-copy: no device-to-
+ *                          host copies, no size round trip).  bb_shard_fetch is then unavailable.
+ *   bb_shard_results       pointers into the mirrors for region `src` of the last bb_shard_resolve,
+ *                          once the caller has waited for the work it enqueued on that stream.  Valid
+ *                          until the next bb_shard_resolve on this shard.
  */
 typedef struct bb_shard bb_shard;
 bb_shard* bb_shard_create(bb_engine* e, uint32_t nranks, uint32_t rank, uint32_t max_batch,
@@ -202,6 +209,11 @@ int bb_shard_resolve(bb_shard* s, uint64_t shuffle_seed, int wait_for_peers, voi
 int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, uint32_t* out_off,
                    uint16_t* out_len, uint8_t* status, uint32_t* qidx, uint32_t* miss_idx,
                    uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
+
+int bb_shard_host_results(bb_shard* s, int enable);
+int bb_shard_results(bb_shard* s, uint32_t src, const uint8_t** out, const uint32_t** out_off,
+                     const uint16_t** out_len, const uint8_t** status, const uint32_t** qidx,
+                     const uint32_t** miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);

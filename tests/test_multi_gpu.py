@@ -10,13 +10,26 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('ordered', ['0', '1'])
-def test_sharded_two_ranks(ordered):
+@pytest.mark.parametrize('ordered,host_results', [('0', '0'), ('1', '0'), ('0', '1')])
+def test_sharded_two_ranks(ordered, host_results):
+    """host_results=1: the owner writes its answers straight into pinned host mirrors (bb_shard_host_results)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip('needs 2 GPUs')
-    env = dict(os.environ, BB_ORDERED=ordered, BB_BATCH='20000', BB_ZONE='100000')
+    env = dict(os.environ, BB_ORDERED=ordered, BB_HOST_RESULTS=host_results, BB_BATCH='20000', BB_ZONE='100000')
     p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
                         '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'tools', 'multi_check.py')],
                        env=env, capture_output=True, text=True, timeout=600)
     assert 'MULTI_CHECK_OK world=2' in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('host_results', ['0', '1'])
+def test_sharded_single_rank(host_results):
+    """world=1 on one GPU: the same route+push -> region resolve path (multi-region kernel instantiation,
+    device-side batch size and shuffle indices), with device result buffers and with host mirrors."""
+    env = dict(os.environ, BB_ORDERED='0', BB_HOST_RESULTS=host_results, BB_BATCH='20000', BB_ZONE='100000')
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '1',
+                        '--master-addr', '127.0.0.1', '--master-port', '29534', os.path.join(ROOT, 'tools', 'multi_check.py')],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert 'MULTI_CHECK_OK world=1' in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

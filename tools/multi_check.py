@@ -22,7 +22,8 @@ def main():
     B = int(os.environ.get('BB_BATCH', '20000'))
     zone = synth.gen_zone(int(os.environ.get('BB_ZONE', '200000')), service_frac=0.15)
     se = ShardedEngine(zone.dns_domain, zone.datacenter, zone.jsonl, rank, world, lr, max_batch=B, recursion=True,
-                       ordered=bool(int(os.environ.get('BB_ORDERED', '0'))), dist=dist, sync=os.environ.get('BB_SYNC', 'flags'))
+                       ordered=bool(int(os.environ.get('BB_ORDERED', '0'))), dist=dist, sync=os.environ.get('BB_SYNC', 'flags'),
+                       host_results=bool(int(os.environ.get('BB_HOST_RESULTS', '0'))))
     orc = Oracle(zone.dns_domain, zone.datacenter, True, snapshot=zone.jsonl)
 
     def ingress(r, rnd):      # rank r's batch in round rnd (any rank can regenerate it)
