@@ -26,7 +26,7 @@ def main(args, rank, world, local_rank):
     dist.barrier()
     B = args.batch
     zone = synth.gen_zone(args.zone_records)
-    LANES = 4
+    LANES = int(os.environ.get('BB_LANES', '8'))
     sync = os.environ.get('BB_SYNC', 'flags')
     se = ShardedEngine(zone.dns_domain, zone.datacenter, zone.jsonl, rank, world, local_rank, max_batch=B,
                        ordered=args.ordered, dist=dist, lanes=LANES, sync=sync)

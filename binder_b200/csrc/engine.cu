@@ -1197,7 +1197,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     __shared__ __align__(16) uint8_t s_sorted[S_IN + 16 * MAX_RANKS + 32];     // the tile's packets grouped by owner
     __shared__ uint32_t s_moff[T], s_mq[T];                                    // per-owner-grouped offsets / query indices
     __shared__ uint32_t s_off[T + 1];
-    __shared__ unsigned long long s_cur[MAX_RANKS], s_base[MAX_RANKS];
+    // per (tile, owner): queries << 24 | packet bytes.  One 32-bit word so that the claim is a native shared-memory
+    // add (a 64-bit one is a compare-and-swap loop, and the whole tile contends on nranks words).
+    // <= 128 queries of <= 65535 bytes each: the byte field stays below 2^24.
+    __shared__ uint32_t s_cur[MAX_RANKS];
+    __shared__ unsigned long long s_base[MAX_RANKS];
     __shared__ uint32_t s_kstart[MAX_RANKS + 1], s_bstart[MAX_RANKS];
     __shared__ uint32_t s_ovf;
     __shared__ __align__(16) uint8_t s_sfx[256];
@@ -1205,10 +1209,12 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     for (int i = tid; i < 64; i += T) ((uint32_t*)s_sfx)[i] = __ldg((const uint32_t*)P.eng->wire_tail + i);
     if (tid < MAX_RANKS) s_cur[tid] = 0;
     if (tid == 0) s_ovf = 0;
+    STAMP(0);
     const uint32_t q0 = blockIdx.x * T;
     const uint32_t nq = min((uint32_t)T, P.n - q0);
     for (int i = tid; i <= (int)nq; i += T) s_off[i] = P.pkt_off[q0 + i];
     __syncthreads();
+    STAMP(1);
     const uint32_t b0 = s_off[0], b1 = s_off[nq];
     const uint32_t a0 = b0 & ~15u;
     const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
@@ -1219,6 +1225,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         for (uint32_t i = tid; i < nv; i += T) dst[i] = __ldg(src + i);
     }
     __syncthreads();
+    STAMP(2);
     Res r;
     r.owner = (uint8_t)P.rank;                     // queries that need no lookup are answered where they arrived
     r.sp = 0; r.p = nullptr;
@@ -1233,18 +1240,22 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             resolve_query(P, r, len, 0, (uint32_t)__cvta_generic_to_shared(s_sfx));
             if (r.owner >= P.nranks) r.owner = (uint8_t)P.rank;
         }
-        const unsigned long long old = atomicAdd(&s_cur[r.owner], (1ull << PUSH_CNT_SHIFT) | len);
-        k = (uint32_t)(old >> PUSH_CNT_SHIFT); boff = (uint32_t)(old & ((1ull << PUSH_CNT_SHIFT) - 1));
+        const uint32_t old = atomicAdd(&s_cur[r.owner], (1u << 24) | len);
+        k = old >> 24; boff = old & 0xFFFFFFu;
     }
     __syncthreads();
+    STAMP(6);
     // one claim per (tile, owner) in the sender-local cursor of region (this rank -> owner)
-    if (tid < (int)P.nranks) { const unsigned long long t = s_cur[tid]; s_base[tid] = t ? atomicAdd(A.cursor + tid, t) : 0ull; }
+    if (tid < (int)P.nranks) {
+        const uint32_t t = s_cur[tid];
+        s_base[tid] = t ? atomicAdd(A.cursor + tid, ((unsigned long long)(t >> 24) << PUSH_CNT_SHIFT) | (t & 0xFFFFFFu)) : 0ull;
+    }
     __syncthreads();
     if (tid == 0) {
         uint32_t kk = 0, bb = 0;
         for (uint32_t d = 0; d < P.nranks; d++) {
-            const unsigned long long t = s_cur[d], base = s_base[d];
-            const uint32_t cnt = (uint32_t)(t >> PUSH_CNT_SHIFT), nb = (uint32_t)(t & ((1ull << PUSH_CNT_SHIFT) - 1));
+            const uint32_t t = s_cur[d]; const unsigned long long base = s_base[d];
+            const uint32_t cnt = t >> 24, nb = t & 0xFFFFFFu;
             const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT);
             const unsigned long long gb = base & ((1ull << PUSH_CNT_SHIFT) - 1);
             if (cnt && (gk + cnt > A.cap_q || gb + nb > A.cap_b)) { s_ovf = 1; *A.err = 1; }
@@ -1256,6 +1267,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     }
     __syncthreads();
     const bool ovf = s_ovf != 0;
+    STAMP(7);
     if (have && !ovf) {
         const unsigned long long base = s_base[r.owner];
         const uint32_t gb = (uint32_t)(base & ((1ull << PUSH_CNT_SHIFT) - 1)) + boff;
@@ -1276,11 +1288,12 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         }
     }
     __syncthreads();
+    STAMP(8);
     if (staged && !ovf) {
         // per owner: one contiguous chunk of packets and of metadata, pushed with coalesced peer stores
         for (uint32_t d = 0; d < P.nranks; d++) {
-            const unsigned long long t = s_cur[d], base = s_base[d];
-            const uint32_t cnt = (uint32_t)(t >> PUSH_CNT_SHIFT), nb = (uint32_t)(t & ((1ull << PUSH_CNT_SHIFT) - 1));
+            const uint32_t t = s_cur[d]; const unsigned long long base = s_base[d];
+            const uint32_t cnt = t >> 24, nb = t & 0xFFFFFFu;
             if (!cnt) continue;
             uint8_t* reg = A.region[d];
             const uint32_t gk = (uint32_t)(base >> PUSH_CNT_SHIFT);
@@ -1301,14 +1314,19 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             if (x0 + tid < nb) g[x0 + tid] = sm[x0 + tid];
         }
     }
-    __threadfence_system();                        // this block's peer stores are performed before it counts itself done
     // The last block publishes the region headers (count, bytes, end-of-offsets sentinel) and then,
     // after a system-scope fence, the epoch flag the owner's wait kernel spins on: the exchange
     // needs no collective, only this ordered pair of peer stores per (source, owner).
+    // A block orders its peer stores before its done count with a device-scope fence only (the barrier
+    // orders every thread's stores before thread 0's fence; fences are cumulative).  The system-scope
+    // fence is the last block's alone: it has observed every other block's count, so by causality
+    // order all their stores precede its flag store for whoever acquires the flag at system scope.
     __syncthreads();
+    STAMP(9);
     if (warp == 0) {
         uint32_t last = 0;
         if (lane == 0) { __threadfence(); last = atomicAdd(A.done, 1u) == gridDim.x - 1; }
+        STAMP(10);
         last = __shfl_sync(0xffffffffu, last, 0);
         if (last && lane < (int)P.nranks) {
             __threadfence();
@@ -1321,6 +1339,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             hdr[0] = cnt; hdr[1] = nb; hdr[3] = *A.err;
             __threadfence_system();
             hdr[2] = A.epoch;                      // the flag: everything above is visible to whoever sees it
+            if (P.stage_log && lane == 0) P.stage_log[(size_t)gridDim.x * NSTAGE] = gtime();   // one extra row: flag published
             A.cursor[lane] = 0;
         }
         if (last && lane == 0) *A.done = 0;
@@ -1722,7 +1741,7 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
     const size_t set = (size_t)(s->epoch & 1) * s->nranks;
     for (uint32_t r = 0; r < s->nranks; r++) A.region[r] = s->peer_recv[r] + (set + s->rank) * s->reg_size;
     A.cap_q = s->cap_q; A.cap_b = s->cap_b; A.cursor = s->cursor; A.done = s->done; A.err = s->err;
-    A.qidx_base = qidx_base;
+    A.qidx_base = qidx_base; A.P.stage_log = e->stage_log;
     // n == 0 still publishes empty region headers (one block, no queries)
     const uint32_t grid = n ? (n + bbk::T - 1) / bbk::T : 1;
     bbk::route_push_kernel<<<grid, bbk::T, 0, (cudaStream_t)stream>>>(A);

@@ -161,7 +161,10 @@ uint32_t bb_engine_launch_epoch(const bb_engine* e);
  * %globaltimer (ns) at: 0 start, 1 offsets in, 2 packets staged, 3 decoded, 4 normalised+hashed,
  * 5 probed, 6 sized, 7 tile scan, 8 placed (claim / look-back), 9 responses assembled,
  * 10 flushed; 11-14 service sizing: entered, record opened, permutation built, children walked
- * (thread 0's view of its tile).  NULL turns it off.
+ * (thread 0's view of its tile).  NULL turns it off.  bb_shard_route_push stamps the same log (which
+ * then needs one more row): 0 start, 1 offsets in, 2 packets staged, 3-4 decoded/hashed, 6 routed,
+ * 7 space claimed, 8 grouped by owner, 9 peer stores issued, 10 system fence done + block counted;
+ * row ntiles, slot 0: epoch flags published.
  */
 void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log);
 
