@@ -16,6 +16,9 @@ SYMBOLS = {
     'bb_zone_build_shard': (_c.c_void_p, [_c.c_char_p, _c.c_size_t, _c.c_char_p, _c.c_uint32, _c.c_uint32,
                                           _c.POINTER(_c.c_int)]),
     'bb_zone_free': (None, [_c.c_void_p]),
+    'bb_zone_apply': (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_size_t]),
+    'bb_zone_probe': (_c.c_int, [_c.c_void_p, _c.c_uint32, _c.c_char_p, _c.c_uint32] + [_c.c_void_p] * 4 + [_c.c_uint32, _c.c_void_p]),
+    'bb_engine_apply_update': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'bb_zone_stat': (_c.c_uint64, [_c.c_void_p, _c.c_int]),
     'bb_engine_create': (_c.c_void_p, [_c.c_void_p, _c.POINTER(_c.c_int)]),
     'bb_engine_destroy': (None, [_c.c_void_p]),

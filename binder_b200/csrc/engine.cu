@@ -27,6 +27,9 @@
 #include <vector>
 
 extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
+extern "C" int bb_zone_pending(const bb_zone* z, const uint32_t** slots, uint32_t* n_slots, uint64_t* arena_from, int* relaid);
+extern "C" void bb_zone_mark_synced(bb_zone* z);
+extern "C" uint64_t bb_zone_sync_gen(const bb_zone* z);
 
 namespace bbk {
 using namespace bb;
@@ -1360,6 +1363,13 @@ __global__ void wait_regions_kernel(const uint8_t* recv_set, size_t reg_size, ui
     __threadfence_system();
 }
 
+// Incremental zone update: overwrite the listed slots (one thread per 16-byte chunk).  Runs with no
+// batch in flight (bb_engine_apply_update synchronises first), so a reader never sees half a slot.
+__global__ void patch_slots_kernel(Slot* table, const uint32_t* idx, const uint4* data, uint32_t n) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < 4u * n) ((uint4*)(table + idx[t >> 2]))[t & 3u] = data[t];
+}
+
 }  // namespace bbk
 
 // =================================================================================================
@@ -1394,6 +1404,8 @@ struct bb_engine {
     void* dev_stream[MAX_DEV_STREAMS] = {}; unsigned long long* dev_desc[MAX_DEV_STREAMS] = {}; int n_dev_streams = 0;
     uint64_t launches = 0, epoch = 0;
     unsigned long long* stage_log = nullptr;
+    // the zone this engine last synchronised with (incremental updates only continue from that state)
+    const bb_zone* zone = nullptr; uint64_t zone_gen = 0; uint64_t arena_cap = 0;
 };
 
 static bool name_to_wire(const std::string& s, std::string& out) {
@@ -1503,14 +1515,56 @@ int bb_engine_swap_zone(bb_engine* e, const bb_zone* z) {
     const bb::ZoneImage* img = bb_zone_image(z);
     CK(cudaSetDevice(e->device));
     bb::Slot* nt = nullptr; uint8_t* na = nullptr;
+    // head room in the arena: updates append re-derived records (bb_engine_apply_update)
+    const uint64_t cap = img->arena_len + (img->arena_len / 2 > (4u << 20) ? img->arena_len / 2 : (4u << 20));
     CK(cudaMalloc(&nt, (size_t)img->nslots * sizeof(bb::Slot)));
-    CK(cudaMalloc(&na, (size_t)img->arena_len + 64));
+    CK(cudaMalloc(&na, (size_t)cap + 64));
     CK(cudaMemcpy(nt, img->slots, (size_t)img->nslots * sizeof(bb::Slot), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(na, img->arena, (size_t)img->arena_len, cudaMemcpyHostToDevice));
     CK(cudaDeviceSynchronize());                 // batches in flight finish on the old epoch
     bb::Slot* ot = e->d_table; uint8_t* oa = e->d_arena;
-    e->d_table = nt; e->d_arena = na; e->mask = img->nslots - 1; e->ready = img->ready;
+    e->d_table = nt; e->d_arena = na; e->mask = img->nslots - 1; e->ready = img->ready; e->arena_cap = cap;
     cudaFree(ot); cudaFree(oa);
+    // the zone's pending-change list restarts here (a zone feeds one engine incrementally)
+    bb_zone_mark_synced(const_cast<bb_zone*>(z));
+    e->zone = z; e->zone_gen = bb_zone_sync_gen(z);
+    return BB_OK;
+}
+
+// After bb_zone_apply: ship what changed — the touched 64-byte slots and the arena tail — instead of the
+// whole image.  Falls back to a full swap when the table was laid out again, the arena outgrew its
+// device allocation, or this engine is not the one that took the zone's previous changes.
+int bb_engine_apply_update(bb_engine* e, bb_zone* z) {
+    if (!e || !z) return BB_ERR_ARG;
+    const bb::ZoneImage* img = bb_zone_image(z);
+    const uint32_t* slots = nullptr; uint32_t n = 0; uint64_t from = 0; int relaid = 0;
+    if (bb_zone_pending(z, &slots, &n, &from, &relaid) != BB_OK) return BB_ERR_ARG;
+    if (relaid || !e->d_table || e->zone != z || e->zone_gen != bb_zone_sync_gen(z) || e->mask != img->nslots - 1 ||
+        img->arena_len > e->arena_cap)
+        return bb_engine_swap_zone(e, z);
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());                 // batches in flight finish on the old state
+    if (img->arena_len > from)
+        CK(cudaMemcpy(e->d_arena + from, img->arena + from, (size_t)(img->arena_len - from), cudaMemcpyHostToDevice));
+    if (n) {
+        std::vector<bb::Slot> data(n);
+        for (uint32_t i = 0; i < n; i++) data[i] = img->slots[slots[i]];
+        uint32_t* d_idx = nullptr; uint4* d_data = nullptr;
+        CK(cudaMalloc(&d_idx, (size_t)n * 4)); 
+        if (cudaMalloc(&d_data, (size_t)n * sizeof(bb::Slot)) != cudaSuccess) { cudaFree(d_idx); g_cuda_err = "cudaMalloc (slot patch)"; return BB_ERR_CUDA; }
+        cudaError_t c1 = cudaMemcpy(d_idx, slots, (size_t)n * 4, cudaMemcpyHostToDevice);
+        cudaError_t c2 = cudaMemcpy(d_data, data.data(), (size_t)n * sizeof(bb::Slot), cudaMemcpyHostToDevice);
+        if (c1 == cudaSuccess && c2 == cudaSuccess) {
+            bbk::patch_slots_kernel<<<(4 * n + 255) / 256, 256>>>(e->d_table, d_idx, d_data, n);
+            c1 = cudaGetLastError(); c2 = cudaDeviceSynchronize();
+        }
+        cudaFree(d_idx); cudaFree(d_data);
+        if (c1 != cudaSuccess || c2 != cudaSuccess) { g_cuda_err = cudaGetErrorString(c1 != cudaSuccess ? c1 : c2); return BB_ERR_CUDA; }
+        e->launches++;
+    }
+    e->ready = img->ready;
+    bb_zone_mark_synced(z);
+    e->zone_gen = bb_zone_sync_gen(z);
     return BB_OK;
 }
 int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }

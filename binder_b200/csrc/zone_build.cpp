@@ -13,8 +13,10 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <string>
+#include <utility>
 #include <vector>
 
 namespace {
@@ -228,12 +230,15 @@ enum : uint16_t {
     NF_PORTS_BAD = 128,  // ports present but unusable
     NF_REV = 256,        // registers in ca_revLookup
     NF_HOSTLIKE = 512,
+    NF_DEAD = 1024,      // unbound (lib/zk.js:195-208): out of the tree, but a reverse entry may still name it
+    NF_REV_LOST = 2048,  // another node's address change deleted this node's reverse entry (tn_ip itself stays, :183-185)
 };
 struct Node {
     uint32_t parent, name_off, name_len;
     uint32_t first_kid = 0, last_kid = 0, next_sib = 0;      // 0 = none (node 0 is the root)
     uint32_t ttl = 30, addr = 0, extra = 0xFFFFFFFFu;        // extra: index into svcs / ports
     uint32_t rev_off = 0, rev_len = 0;                        // address string in pool (reverse key)
+    uint32_t rev_seq = 0;                                     // when this node last wrote its reverse entry (event order)
     uint16_t flags = 0; uint8_t kind = K_INVALID; uint8_t pad = 0;
 };
 struct SvcInfo { std::string srvce, proto; bool has_srvce = false, has_proto = false, port_ok = false; uint32_t port = 0; uint32_t ttl = 30; };
@@ -270,7 +275,7 @@ struct Builder {
         uint32_t i = (uint32_t)child_hash(parent, s, n) & child_mask;
         while (child_tab[i]) {
             const Node& nd = nodes[child_tab[i] - 1];
-            if (nd.parent == parent && nd.name_len == n && memcmp(pool.data() + nd.name_off, s, n) == 0) return (int)(child_tab[i] - 1);
+            if (nd.parent == parent && nd.name_len == n && !(nd.flags & NF_DEAD) && memcmp(pool.data() + nd.name_off, s, n) == 0) return (int)(child_tab[i] - 1);
             i = (i + 1) & child_mask;
         }
         return -1;
@@ -292,15 +297,35 @@ struct Builder {
         return id;
     }
 
+    // what the last ingest() did to the node's tn_ip (lib/zk.js:176-189)
+    bool ip_event = false, old_ip_valid = false; uint32_t old_ip_off = 0, old_ip_len = 0;
+    uint32_t rev_clock = 0;                 // orders reverse-map writes across nodes
+
     // lib/zk.js:139-194 + the query-independent half of lib/server.js:249-274,296-332
     void ingest(uint32_t id, int v) {
         Node& nd = nodes[id];
-        nd.kind = K_INVALID; nd.flags = 0; nd.ttl = 30;
+        const uint16_t keep = nd.flags & (NF_REV | NF_REV_LOST);   // tn_ip outlives data that never reaches the address branch
+        ip_event = false;
+        nd.kind = K_INVALID; nd.flags = keep; nd.ttl = 30;
+        // ttl of whatever is stored — record.ttl, then record[type].ttl (:270-274; resolvePtr reads it the
+        // same way at :123-128, whatever the record's shape); kept even when unusable so that a service
+        // child can tell "has its own ttl" from "inherits" (:389-393)
+        int type = -1, sub = -1, tv = -1; const char* ts = nullptr; size_t tl = 0;
+        if (v >= 0 && J.t[v].type == J_OBJ) {
+            int a = J.get(v, "ttl");
+            if (a >= 0) tv = a;
+            type = J.get(v, "type");
+            if (type >= 0 && J.t[type].type == J_STR) {
+                ts = J.pool.data() + J.t[type].a; tl = J.t[type].b;
+                sub = J.get(v, ts, tl);
+                if (J.is_obj(sub)) { int b = J.get(sub, "ttl"); if (b >= 0) tv = b; }
+            }
+        }
+        bool ttl_ok = true;
+        if (tv >= 0) { nd.flags |= NF_HAS_TTL; ttl_ok = uint_ok(J, tv, 2147483648.0, nd.ttl); }
+        if (ttl_ok) nd.flags |= NF_TTL_OK;
         if (v < 0 || J.t[v].type != J_OBJ) return;           // null, array (no .type), or nothing stored
-        int type = J.get(v, "type");
         if (type < 0 || J.t[type].type != J_STR) return;
-        const char* ts = J.pool.data() + J.t[type].a; size_t tl = J.t[type].b;
-        int sub = J.get(v, ts, tl);
         bool hostlike = false, kidtype = false;
         for (auto h : kHostLike) if (strlen(h) == tl && !memcmp(h, ts, tl)) hostlike = true;
         for (auto h : kSvcKid) if (strlen(h) == tl && !memcmp(h, ts, tl)) kidtype = true;
@@ -308,24 +333,19 @@ struct Builder {
         if (hostlike) nd.flags |= NF_HOSTLIKE;
         if (!J.is_obj(sub)) return;                           // :251-253 / :366-368
         nd.flags |= NF_SUB_OBJ;
-        // ttl: record.ttl then record[type].ttl (:270-274); kept even when unusable so that a
-        // service child can tell "has its own ttl" from "inherits" (:389-393)
-        int tv = -1, a = J.get(v, "ttl"), b = J.get(sub, "ttl");
-        if (a >= 0) tv = a;
-        if (b >= 0) tv = b;
-        bool ttl_ok = true;
-        if (tv >= 0) { nd.flags |= NF_HAS_TTL; ttl_ok = uint_ok(J, tv, 2147483648.0, nd.ttl); }
-        if (ttl_ok) nd.flags |= NF_TTL_OK;
         bool is_service = tl == 7 && !memcmp(ts, "service", 7);
         bool is_db = tl == 8 && !memcmp(ts, "database", 8);
         if (hostlike) {
+            // the old address leaves the reverse map, the new one enters it (lib/zk.js:183-188; strings only)
+            ip_event = true; old_ip_valid = (keep & NF_REV) != 0; old_ip_off = nd.rev_off; old_ip_len = nd.rev_len;
+            nd.flags &= ~(NF_REV | NF_REV_LOST);
             int ad = J.get(sub, "address");
             if (ad >= 0 && J.t[ad].type == J_NULL) nd.flags |= NF_ADDR_NULL;
             if (ad >= 0 && J.t[ad].type == J_STR) {
                 const char* as = J.pool.data() + J.t[ad].a; size_t al = J.t[ad].b;
                 if (ipv4_ok(as, al, nd.addr)) nd.flags |= NF_ADDR_OK;
                 if (al > 0) {                                  // lib/zk.js:183-188 (strings only)
-                    nd.flags |= NF_REV; nd.rev_off = (uint32_t)pool.size(); nd.rev_len = (uint32_t)al;
+                    nd.flags |= NF_REV; nd.rev_off = (uint32_t)pool.size(); nd.rev_len = (uint32_t)al; nd.rev_seq = ++rev_clock;
                     pool.append(as, al);
                 }
             }
@@ -396,9 +416,9 @@ bool to_wire(const char* s, size_t n, std::string& out) {
 }
 
 struct TableBuilder {
-    ZoneImage* z;
+    ZoneImage* z = nullptr;
     std::vector<uint8_t> arena;
-    uint32_t mask;
+    uint32_t mask = 0;
     uint32_t arena_put(const void* p, size_t n) {
         while (arena.size() & 3) arena.push_back(0);
         uint32_t off = (uint32_t)arena.size();
@@ -415,7 +435,18 @@ struct TableBuilder {
     uint32_t nranks = 1, rank = 0;
     bool mine(uint32_t ns, const uint8_t* k, uint32_t len) const { return nranks == 1 || owner_of(hash_key(ns, k, len), nranks) == rank; }
     bool failed = false;         // a cuckoo insertion ran out of kicks: the caller rebuilds with a larger table
-    std::vector<uint32_t> h2s;   // second hash of the key resident in each slot (host-side only: evictions need it)
+    // host-side only, per slot: second hash of the resident key (evictions need it) and the node that wrote it
+    std::vector<uint32_t> h2s, own;
+    uint64_t count = 0;          // resident keys
+    // slots changed since the device last saw the table (bb_zone_apply -> bb_engine_apply_update)
+    bool track = false; std::vector<uint32_t> dirty; std::vector<uint8_t> dirty_mark;
+    void touch(uint32_t pos) { if (track && !dirty_mark[pos]) { dirty_mark[pos] = 1; dirty.push_back(pos); } }
+    void reset(ZoneImage* img, uint32_t nslots) {
+        z = img; mask = nslots - 1; failed = false; count = 0;
+        h2s.assign(nslots, 0); own.assign(nslots, 0);
+        dirty.clear(); dirty_mark.assign(nslots, 0);
+        arena.assign(4, 0);                                   // offset 0 is never a valid record
+    }
     void fill(Slot& s, uint32_t h, uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
         memset(&s, 0, sizeof s);
         s.hash = h;
@@ -431,30 +462,44 @@ struct TableBuilder {
         else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); }
         s.kind = kind; s.ttl = ttl; s.val = val;
     }
-    // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo
-    bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
+    // slot holding the key, or -1
+    int64_t find(uint32_t ns, const uint8_t* k, uint32_t len) const {
+        uint32_t h2;
+        const uint32_t h = hash_key2(ns, k, len, &h2);
+        for (uint32_t i : { slot1_of(h, mask), slot2_of(h, h2, mask) }) {
+            const Slot& s = z->slots[i];
+            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) return i;
+        }
+        return -1;
+    }
+    // a cuckoo table needs no tombstones: a lookup only ever reads the key's two slots
+    void erase(uint32_t pos) { memset(&z->slots[pos], 0, sizeof(Slot)); h2s[pos] = 0; own[pos] = 0; --count; touch(pos); }
+    // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo.
+    // Returns true when the key is new.
+    bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val, uint32_t owner) {
         uint32_t h2;
         const uint32_t h = hash_key2(ns, k, len, &h2);
         const uint32_t i1 = slot1_of(h, mask), i2 = slot2_of(h, h2, mask);
-        if (h2s.size() != (size_t)mask + 1) h2s.assign((size_t)mask + 1, 0);
         for (uint32_t i : { i1, i2 }) {
             Slot& s = z->slots[i];
-            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; return false; }
+            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; own[i] = owner; touch(i); return false; }
         }
         Slot cur; fill(cur, h, ns, k, len, kind, ttl, val);
-        uint32_t cur_h2 = h2;
+        uint32_t cur_h2 = h2, cur_own = owner;
         uint32_t pos = z->slots[i1].kind == K_EMPTY ? i1 : (z->slots[i2].kind == K_EMPTY ? i2 : i1);
+        ++count;
         for (int kick = 0; kick < 2000; kick++) {
             Slot& s = z->slots[pos];
-            if (s.kind == K_EMPTY) { s = cur; h2s[pos] = cur_h2; return true; }
-            if (getenv("BB_DEBUG") && kick >= 1990) fprintf(stderr, "  kick %d pos=%u resident h=%08x klen=%u ns=%u key=%.*s\n", kick, pos, s.hash, s.klen, s.ns, (int)(s.klen < 49 ? s.klen : 8), (const char*)s.key);
+            touch(pos);
+            if (s.kind == K_EMPTY) { s = cur; h2s[pos] = cur_h2; own[pos] = cur_own; return true; }
             Slot ev = s; s = cur; cur = ev;                          // evict the resident, move it to its other slot
             const uint32_t ev_h2 = h2s[pos]; h2s[pos] = cur_h2; cur_h2 = ev_h2;
+            const uint32_t ev_own = own[pos]; own[pos] = cur_own; cur_own = ev_own;
             const uint32_t a = slot1_of(cur.hash, mask), b = slot2_of(cur.hash, cur_h2, mask);
             pos = pos == a ? b : a;
         }
         if (getenv("BB_DEBUG")) fprintf(stderr, "cuckoo fail: ns=%u len=%u key=%.*s h=%08x i1=%u i2=%u mask=%u\n", ns, len, (int)len, (const char*)k, h, i1, i2, mask);
-        failed = true;
+        failed = true;                                           // one key fell out: the caller lays the table out again
         return true;
     }
 };
@@ -462,33 +507,208 @@ struct TableBuilder {
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// C ABI
+// a zone: the flattened tree (kept, so that deltas can be applied) + its table image
 // ---------------------------------------------------------------------------------------
-struct bb_zone { bb::ZoneImage img; };
+struct bb_zone {
+    bb::ZoneImage img;
+    Builder B; TableBuilder T;
+    std::string root_path;
+    uint32_t nranks = 1, rank = 0;
+    bool relaid = false;             // the table was laid out again since the device last saw it: full upload
+    uint64_t arena_synced = 0;       // arena bytes the device already has
+    uint64_t arena_garbage = 0;      // bytes of superseded service / PTR records
+    uint64_t sync_gen = 0;           // bumped whenever an engine takes the pending changes
+};
 
-extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char* dns_domain, uint32_t nranks,
-                                        uint32_t rank, int* err) {
-    auto fail = [&](int e) -> bb_zone* { if (err) *err = e; return nullptr; };
-    if (err) *err = BB_OK;
-    if ((!buf && len) || !dns_domain || nranks == 0 || rank >= nranks) return fail(BB_ERR_ARG);
-    Builder B;
-    B.dns_domain = dns_domain;
-    // ZKCache.isReady() compares with options.domain verbatim (lib/zk.js:55-58) while keys are
-    // lower-cased (:84): an upper-case domain is never ready.  We require lower case instead.
-    for (char c : B.dns_domain) if (c >= 'A' && c <= 'Z') return fail(BB_ERR_DOMAIN);
-    std::string w;
-    if (B.dns_domain.empty() || !to_wire(B.dns_domain.data(), B.dns_domain.size(), w) || w.size() + 1 > 244) return fail(BB_ERR_DOMAIN);
-    // root node (lib/zk.js:68-76): exists as soon as the cache is built, data null
-    size_t dot = B.dns_domain.find('.');
-    std::string first = B.dns_domain.substr(0, dot);
-    B.add_node(0, first.data(), first.size());
-    std::string root_path;                                     // lib/zk.js:225-228
-    {
-        std::vector<std::string> parts; size_t s = 0;
-        for (;;) { size_t d = B.dns_domain.find('.', s); parts.push_back(B.dns_domain.substr(s, d == std::string::npos ? d : d - s)); if (d == std::string::npos) break; s = d + 1; }
-        for (size_t i = parts.size(); i-- > 0;) { root_path += "/"; root_path += parts[i]; }
+namespace {
+
+// ---- one node's forward key (lib/zk.js:96) and its payload ------------------------------------
+// Returns false only for a snapshot the image cannot express (> 65535 children in a service).
+bool emit_forward(bb_zone& zn, uint32_t id) {
+    Builder& B = zn.B; TableBuilder& T = zn.T;
+    const Node& nd = B.nodes[id];
+    std::string dom, dom_wire, kw;
+    B.domain_of(id, dom);
+    const bool dom_ok = to_wire(dom.data(), dom.size(), dom_wire) && dom_wire.size() + 1 <= 255;
+    // unspellable names are unreachable; other ranks own the rest
+    if (!dom_ok || !T.mine(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size())) return true;
+    uint32_t val = nd.addr;
+    if (nd.kind == K_SERVICE) {
+        const SvcInfo& si = B.svcs[nd.extra];
+        std::vector<uint32_t> kids;
+        for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib)
+            if ((B.nodes[k].flags & (NF_KIDTYPE | NF_DEAD)) == NF_KIDTYPE) kids.push_back(k);
+        if (kids.size() > 65535) return false;
+        std::vector<uint8_t> rec;
+        SvcHdr h; h.ttl = si.ttl; h.nkids = (uint16_t)kids.size(); h.rec_len = 0;
+        bool s_ok = si.has_srvce && si.srvce.size() < 255, p_ok = si.has_proto && si.proto.size() < 255;
+        h.srvce_len = s_ok ? (uint8_t)si.srvce.size() : 0xFF;
+        h.proto_len = p_ok ? (uint8_t)si.proto.size() : 0xFF;
+        rec.insert(rec.end(), (uint8_t*)&h, (uint8_t*)&h + sizeof h);
+        if (s_ok) rec.insert(rec.end(), si.srvce.begin(), si.srvce.end());
+        if (p_ok) rec.insert(rec.end(), si.proto.begin(), si.proto.end());
+        while (rec.size() & 3) rec.push_back(0);
+        size_t tab = rec.size();
+        rec.resize(tab + 4 * kids.size());
+        while (T.arena.size() & 3) T.arena.push_back(0);
+        uint32_t base = (uint32_t)T.arena.size();
+        for (size_t ki = 0; ki < kids.size(); ki++) {
+            const Node& kn = B.nodes[kids[ki]];
+            while (rec.size() & 3) rec.push_back(0);
+            uint32_t koff = base + (uint32_t)rec.size();
+            memcpy(rec.data() + tab + 4 * ki, &koff, 4);
+            KidRec kr; memset(&kr, 0, sizeof kr);
+            std::vector<uint16_t> pl;
+            bool name_ok = to_wire(B.pool.data() + kn.name_off, kn.name_len, kw) && kw.size() + dom_wire.size() + 1 <= 255;
+            if (!(kn.flags & NF_SUB_OBJ)) kr.flags = KID_BAD_A | KID_BAD_SRV;            // :366-376
+            else if (kn.flags & NF_ADDR_NULL) kr.flags = KID_ADDR_NULL;                    // :378-381
+            else {
+                bool bad = !(kn.flags & NF_ADDR_OK) || !(kn.flags & NF_TTL_OK);
+                bool bad_srv = bad || !name_ok || (kn.flags & NF_PORTS_BAD);
+                if (kn.flags & NF_PORTS_LIST) pl = B.ports[kn.extra];
+                else if (si.port_ok) pl.push_back((uint16_t)si.port);                     // :383-385
+                else bad_srv = true;
+                kr.flags = (bad ? KID_BAD_A : 0) | (bad_srv ? KID_BAD_SRV : 0);
+                if (kn.flags & NF_HAS_TTL) kr.flags |= KID_HAS_RTTL;
+                kr.addr = kn.addr; kr.rttl = kn.ttl;
+                if (bad_srv) pl.clear();
+            }
+            if (!name_ok) kw.clear();
+            kr.wire_len = (uint8_t)kw.size(); kr.nports = (uint8_t)pl.size();
+            rec.insert(rec.end(), (uint8_t*)&kr, (uint8_t*)&kr + sizeof kr);
+            rec.insert(rec.end(), (uint8_t*)pl.data(), (uint8_t*)pl.data() + 2 * pl.size());
+            rec.insert(rec.end(), kw.begin(), kw.end());
+        }
+        { uint32_t rl = (uint32_t)rec.size(); memcpy(rec.data() + offsetof(SvcHdr, rec_len), &rl, 4); }
+        val = T.arena_put(rec.data(), rec.size());
     }
-    std::vector<uint8_t> seen_data(1, 0);
+    uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;
+    if (T.put(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size(), nd.kind, ttl, val, id)) zn.img.n_fwd++;
+    return true;
+}
+
+// ---- the reverse key a node registered (lib/zk.js:183-188), answered as lib/server.js:123-130 ----
+void emit_reverse(bb_zone& zn, uint32_t id) {
+    Builder& B = zn.B; TableBuilder& T = zn.T;
+    const Node nd = B.nodes[id];
+    if ((nd.flags & (NF_REV | NF_REV_LOST)) != NF_REV || nd.rev_len > 253) return;
+    const uint8_t* key = (const uint8_t*)B.pool.data() + nd.rev_off;
+    if (!T.mine(NS_REVERSE, key, nd.rev_len)) return;
+    std::string dom, dom_wire;
+    B.domain_of(id, dom);
+    const bool dom_ok = to_wire(dom.data(), dom.size(), dom_wire) && dom_wire.size() + 1 <= 255;
+    uint8_t kind = K_PTR_BAD; uint32_t val = 0;
+    if ((nd.flags & NF_TTL_OK) && dom_ok) {
+        std::string t; t.push_back((char)(dom_wire.size() + 1)); t += dom_wire; t.push_back(0);
+        val = T.arena_put(t.data(), t.size()); kind = K_PTR;
+    }
+    // assignment into ca_revLookup replaces whoever was there: that node's entry is gone for good, even if
+    // this one later moves to another address (:183-188)
+    const int64_t prev = T.find(NS_REVERSE, key, nd.rev_len);
+    if (prev >= 0 && T.own[prev] != id) B.nodes[T.own[prev]].flags |= NF_REV_LOST;
+    if (T.put(NS_REVERSE, key, nd.rev_len, kind, nd.ttl, val, id)) zn.img.n_rev++;
+}
+
+// ---- (re)build the whole table from the tree -----------------------------------------------------
+int layout(bb_zone& zn) {
+    Builder& B = zn.B; TableBuilder& T = zn.T; ZoneImage& Z = zn.img;
+    for (uint32_t grow = 0;; grow++) {      // cuckoo insertion can (rarely) fail: rebuild one size up
+        uint64_t nkeys = 0;
+        for (auto& nd : B.nodes) nkeys += ((nd.flags & NF_DEAD) ? 0 : 1) + ((nd.flags & NF_REV) ? 1 : 0);
+        // 2-choice cuckoo needs a load factor below 0.5: size for <= 0.45 (a shard holds ~1/nranks of the keys)
+        uint64_t want = (nkeys * 22 / 10) / zn.nranks + (zn.nranks > 1 ? nkeys / (4 * zn.nranks) : 0) + 64; uint32_t ns = 64;
+        while (ns < want) { ns <<= 1; if (ns == 0) return BB_ERR_NOMEM; }
+        ns <<= grow;
+        if (ns == 0) return BB_ERR_NOMEM;
+        free(Z.slots); Z.slots = nullptr; Z.n_fwd = Z.n_rev = 0;
+        Z.nslots = ns;
+        Z.slots = (Slot*)aligned_alloc(64, (size_t)ns * sizeof(Slot));
+        if (!Z.slots) return BB_ERR_NOMEM;
+        memset(Z.slots, 0, (size_t)ns * sizeof(Slot));
+        const bool track = T.track;
+        T.track = false;
+        T.reset(&Z, ns); T.nranks = zn.nranks; T.rank = zn.rank;
+        Z.n_nodes = B.nodes.size();
+        // Forward keys in creation order: the TreeNode constructor takes the key from an earlier node
+        // that spells it the same (:96); an unbound node that held it took it along (:205-207).
+        std::string dom;
+        for (uint32_t id = 0; id < B.nodes.size(); id++) {
+            if (!(B.nodes[id].flags & NF_DEAD)) { if (!emit_forward(zn, id)) return BB_ERR_SNAPSHOT; continue; }
+            B.domain_of(id, dom);
+            const int64_t pos = T.find(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size());
+            if (pos >= 0) { T.erase((uint32_t)pos); Z.n_fwd--; }
+        }
+        // Reverse keys in the order they were written (last writer wins, :187-188); an unbound node
+        // keeps its entry (unbind never removes it).
+        std::vector<std::pair<uint32_t, uint32_t>> rev;
+        for (uint32_t id = 0; id < B.nodes.size(); id++) if (B.nodes[id].flags & NF_REV) rev.emplace_back(B.nodes[id].rev_seq, id);
+        std::sort(rev.begin(), rev.end());
+        for (auto& e : rev) emit_reverse(zn, e.second);
+        T.track = track;
+        if (!T.failed) break;
+        if (grow > 3) return BB_ERR_NOMEM;
+    }
+    while (T.arena.size() & 15) T.arena.push_back(0);
+    Z.arena = T.arena.data(); Z.arena_len = T.arena.size();
+    Z.ready = 1;                                              // the root TreeNode exists (lib/zk.js:55-58)
+    zn.relaid = true; zn.arena_synced = 0; zn.arena_garbage = 0;
+    T.dirty.clear(); std::fill(T.dirty_mark.begin(), T.dirty_mark.end(), 0);
+    return BB_OK;
+}
+
+// ---- one snapshot / delta line ---------------------------------------------------------------------
+enum { LINE_SKIP = 0, LINE_DATA = 1, LINE_DELETE = 2, LINE_BAD = -1 };
+// Parses the line into B.J and resolves its path.  LINE_DATA: *id = the node (created when its parent is
+// mirrored and `create` allows), *v = tape index of the accepted value or -1 when the content is ignored
+// (lib/zk.js:141-155: unparsable, or neither null nor an object).  *created reports a new node.
+int read_line(bb_zone& zn, const char* a, const char* b, uint32_t* id, int* v, bool* created) {
+    Builder& B = zn.B;
+    B.J.clear();
+    *created = false; *v = -1;
+    int ent = B.J.parse(a, b);
+    if (ent < 0 || B.J.t[ent].type != J_OBJ) return LINE_BAD;
+    int path = B.J.get(ent, "path");
+    if (path < 0 || B.J.t[path].type != J_STR) return LINE_BAD;
+    const int del = B.J.get(ent, "deleted");
+    const bool deleting = del >= 0 && B.J.t[del].type == J_TRUE;
+    const char* ps = B.J.pool.data() + B.J.t[path].a; size_t pl = B.J.t[path].b;
+    const std::string& root_path = zn.root_path;
+    if (pl == root_path.size() && !memcmp(ps, root_path.data(), pl)) *id = 0;
+    else {
+        if (pl <= root_path.size() + 1 || memcmp(ps, root_path.data(), root_path.size()) || ps[root_path.size()] != '/') return LINE_SKIP;
+        size_t i = root_path.size() + 1; uint32_t cur = 0; int found = -1;
+        for (;;) {
+            size_t j = i; while (j < pl && ps[j] != '/') ++j;
+            if (j == i) return LINE_SKIP;                          // empty component
+            found = B.find_child(cur, ps + i, j - i);
+            if (j == pl) {                                         // last component: the znode itself
+                if (found < 0) {
+                    if (deleting) return LINE_SKIP;
+                    found = (int)B.add_node(cur, ps + i, j - i); *created = true;
+                }
+                break;
+            }
+            if (found < 0) return LINE_SKIP;                       // parent not mirrored
+            cur = (uint32_t)found; i = j + 1;
+            if (i >= pl) return LINE_SKIP;                         // trailing '/'
+        }
+        *id = (uint32_t)found;
+    }
+    if (deleting) return LINE_DELETE;
+    int raw = B.J.get(ent, "raw"), data = B.J.get(ent, "data");
+    if (raw >= 0 && B.J.t[raw].type == J_STR) {
+        // the znode's bytes: JSON.parse them (lib/zk.js:141-148); failure = ignored
+        std::string rs(B.J.pool.data() + B.J.t[raw].a, B.J.t[raw].b);
+        int pv = B.J.parse(rs.data(), rs.data() + rs.size());
+        if (pv >= 0 && (B.J.t[pv].type == J_NULL || B.J.is_obj(pv))) *v = pv;      // :149-155
+    } else if (data >= 0) {
+        if (B.J.t[data].type == J_NULL || B.J.is_obj(data)) *v = data;
+    }
+    return LINE_DATA;
+}
+
+template <class F>
+int for_each_line(const char* buf, size_t len, F&& f) {
     const char* p = buf; const char* end = buf + len;
     while (p < end) {
         const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
@@ -497,145 +717,60 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
         while (a < b && (*a == ' ' || *a == '\t' || *a == '\r')) ++a;
         while (b > a && (b[-1] == ' ' || b[-1] == '\t' || b[-1] == '\r')) --b;
         if (a == b) continue;
-        B.J.clear();
-        int ent = B.J.parse(a, b);
-        if (ent < 0 || B.J.t[ent].type != J_OBJ) return fail(BB_ERR_SNAPSHOT);
-        int path = B.J.get(ent, "path");
-        if (path < 0 || B.J.t[path].type != J_STR) return fail(BB_ERR_SNAPSHOT);
-        const char* ps = B.J.pool.data() + B.J.t[path].a; size_t pl = B.J.t[path].b;
-        uint32_t id;
-        if (pl == root_path.size() && !memcmp(ps, root_path.data(), pl)) id = 0;
-        else {
-            if (pl <= root_path.size() + 1 || memcmp(ps, root_path.data(), root_path.size()) || ps[root_path.size()] != '/') continue;
-            size_t i = root_path.size() + 1; uint32_t cur = 0; bool skip = false; int found = -1;
-            for (;;) {
-                size_t j = i; while (j < pl && ps[j] != '/') ++j;
-                if (j == i) { skip = true; break; }               // empty component
-                found = B.find_child(cur, ps + i, j - i);
-                if (j == pl) {                                     // last component: the znode itself
-                    if (found < 0) found = (int)B.add_node(cur, ps + i, j - i);
-                    break;
-                }
-                if (found < 0) { skip = true; break; }            // parent not mirrored
-                cur = (uint32_t)found; i = j + 1;
-                if (i >= pl) { skip = true; break; }              // trailing '/'
-            }
-            if (skip) continue;
-            id = (uint32_t)found;
-        }
-        if (seen_data.size() < B.nodes.size()) seen_data.resize(B.nodes.size(), 0);
-        if (seen_data[id]) return fail(BB_ERR_SNAPSHOT);           // one line per znode
-        seen_data[id] = 1;
-        int raw = B.J.get(ent, "raw"), data = B.J.get(ent, "data");
-        if (raw >= 0 && B.J.t[raw].type == J_STR) {
-            // the znode's bytes: JSON.parse them (lib/zk.js:141-148); failure = ignored
-            std::string rs(B.J.pool.data() + B.J.t[raw].a, B.J.t[raw].b);
-            int v = B.J.parse(rs.data(), rs.data() + rs.size());
-            if (v >= 0 && (B.J.t[v].type == J_NULL || B.J.is_obj(v))) B.ingest(id, v);     // :149-155
-        } else if (data >= 0) {
-            if (B.J.t[data].type == J_NULL || B.J.is_obj(data)) B.ingest(id, data);
-        }
+        int rc = f(a, b);
+        if (rc != BB_OK) return rc;
     }
+    return BB_OK;
+}
 
-    // ---- lay out the table ------------------------------------------------------------
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------
+extern "C" void bb_zone_free(bb_zone* z);
+
+extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char* dns_domain, uint32_t nranks,
+                                        uint32_t rank, int* err) {
+    auto fail = [&](int e) -> bb_zone* { if (err) *err = e; return nullptr; };
+    if (err) *err = BB_OK;
+    if ((!buf && len) || !dns_domain || nranks == 0 || rank >= nranks) return fail(BB_ERR_ARG);
     bb_zone* zone = new bb_zone();
-    ZoneImage& Z = zone->img;
-    memset(&Z, 0, sizeof Z);
-    TableBuilder T;
-    for (uint32_t grow = 0;; grow++) {      // cuckoo insertion can (rarely) fail: rebuild one size up
-    uint64_t nkeys = 0;
-    for (auto& nd : B.nodes) nkeys += 1 + ((nd.flags & NF_REV) ? 1 : 0);
-    // 2-choice cuckoo needs a load factor below 0.5: size for <= 0.45 (a shard holds ~1/nranks of the keys)
-    uint64_t want = (nkeys * 22 / 10) / nranks + (nranks > 1 ? nkeys / (4 * nranks) : 0) + 64; uint32_t ns = 64;
-    while (ns < want) { ns <<= 1; if (ns == 0) { delete zone; return fail(BB_ERR_NOMEM); } }
-    ns <<= grow;
-    free(Z.slots); Z.slots = nullptr; Z.n_fwd = Z.n_rev = 0;
-    Z.nslots = ns;
-    Z.slots = (Slot*)aligned_alloc(64, (size_t)ns * sizeof(Slot));
-    if (!Z.slots) { delete zone; return fail(BB_ERR_NOMEM); }
-    memset(Z.slots, 0, (size_t)ns * sizeof(Slot));
-    T = TableBuilder(); T.z = &Z; T.mask = ns - 1; T.nranks = nranks; T.rank = rank;
-    T.arena.assign(4, 0);                                     // offset 0 is never a valid record
-    Z.n_nodes = B.nodes.size();
-    std::string dom, kw, tmp;
-    for (uint32_t id = 0; id < B.nodes.size(); id++) {
-        const Node& nd = B.nodes[id];
-        B.domain_of(id, dom);
-        bool dom_ok = to_wire(dom.data(), dom.size(), tmp) && tmp.size() + 1 <= 255;
-        std::string dom_wire = tmp;
-        // ---- forward key (lib/zk.js:96) -------------------------------------------------
-        if (dom_ok && T.mine(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size())) {   // unspellable names are unreachable; other ranks own the rest
-            uint32_t val = nd.addr;
-            if (nd.kind == K_SERVICE) {
-                const SvcInfo& si = B.svcs[nd.extra];
-                std::vector<uint32_t> kids;
-                for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib) if (B.nodes[k].flags & NF_KIDTYPE) kids.push_back(k);
-                if (kids.size() > 65535) { bb_zone_free(zone); return fail(BB_ERR_SNAPSHOT); }
-                std::vector<uint8_t> rec;
-                SvcHdr h; h.ttl = si.ttl; h.nkids = (uint16_t)kids.size(); h.rec_len = 0;
-                bool s_ok = si.has_srvce && si.srvce.size() < 255, p_ok = si.has_proto && si.proto.size() < 255;
-                h.srvce_len = s_ok ? (uint8_t)si.srvce.size() : 0xFF;
-                h.proto_len = p_ok ? (uint8_t)si.proto.size() : 0xFF;
-                rec.insert(rec.end(), (uint8_t*)&h, (uint8_t*)&h + sizeof h);
-                if (s_ok) rec.insert(rec.end(), si.srvce.begin(), si.srvce.end());
-                if (p_ok) rec.insert(rec.end(), si.proto.begin(), si.proto.end());
-                while (rec.size() & 3) rec.push_back(0);
-                size_t tab = rec.size();
-                rec.resize(tab + 4 * kids.size());
-                while (T.arena.size() & 3) T.arena.push_back(0);
-                uint32_t base = (uint32_t)T.arena.size();
-                for (size_t ki = 0; ki < kids.size(); ki++) {
-                    const Node& kn = B.nodes[kids[ki]];
-                    while (rec.size() & 3) rec.push_back(0);
-                    uint32_t koff = base + (uint32_t)rec.size();
-                    memcpy(rec.data() + tab + 4 * ki, &koff, 4);
-                    KidRec kr; memset(&kr, 0, sizeof kr);
-                    std::vector<uint16_t> pl;
-                    bool name_ok = to_wire(B.pool.data() + kn.name_off, kn.name_len, kw) && kw.size() + dom_wire.size() + 1 <= 255;
-                    if (!(kn.flags & NF_SUB_OBJ)) kr.flags = KID_BAD_A | KID_BAD_SRV;            // :366-376
-                    else if (kn.flags & NF_ADDR_NULL) kr.flags = KID_ADDR_NULL;                    // :378-381
-                    else {
-                        bool bad = !(kn.flags & NF_ADDR_OK) || !(kn.flags & NF_TTL_OK);
-                        bool bad_srv = bad || !name_ok || (kn.flags & NF_PORTS_BAD);
-                        if (kn.flags & NF_PORTS_LIST) pl = B.ports[kn.extra];
-                        else if (si.port_ok) pl.push_back((uint16_t)si.port);                     // :383-385
-                        else bad_srv = true;
-                        kr.flags = (bad ? KID_BAD_A : 0) | (bad_srv ? KID_BAD_SRV : 0);
-                        if (kn.flags & NF_HAS_TTL) kr.flags |= KID_HAS_RTTL;
-                        kr.addr = kn.addr; kr.rttl = kn.ttl;
-                        if (bad_srv) pl.clear();
-                    }
-                    if (!name_ok) kw.clear();
-                    kr.wire_len = (uint8_t)kw.size(); kr.nports = (uint8_t)pl.size();
-                    rec.insert(rec.end(), (uint8_t*)&kr, (uint8_t*)&kr + sizeof kr);
-                    rec.insert(rec.end(), (uint8_t*)pl.data(), (uint8_t*)pl.data() + 2 * pl.size());
-                    rec.insert(rec.end(), kw.begin(), kw.end());
-                }
-                { uint32_t rl = (uint32_t)rec.size(); memcpy(rec.data() + offsetof(SvcHdr, rec_len), &rl, 4); }
-                val = T.arena_put(rec.data(), rec.size());
-            }
-            uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;
-            if (T.put(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size(), nd.kind, ttl, val)) Z.n_fwd++;
-        }
-        // ---- reverse key (lib/zk.js:183-188) ---------------------------------------------
-        if ((nd.flags & NF_REV) && nd.rev_len <= 253 && T.mine(NS_REVERSE, (const uint8_t*)B.pool.data() + nd.rev_off, nd.rev_len)) {
-            uint8_t kind = K_PTR_BAD; uint32_t val = 0;
-            if ((nd.flags & NF_TTL_OK) && dom_ok) {          // lib/server.js:123-130
-                std::string t; t.push_back((char)(dom_wire.size() + 1)); t += dom_wire; t.push_back(0);
-                val = T.arena_put(t.data(), t.size()); kind = K_PTR;
-            }
-            if (T.put(NS_REVERSE, (const uint8_t*)B.pool.data() + nd.rev_off, nd.rev_len, kind, nd.ttl, val)) Z.n_rev++;
-        }
+    memset(&zone->img, 0, sizeof zone->img);
+    zone->nranks = nranks; zone->rank = rank;
+    Builder& B = zone->B;
+    auto bail = [&](int e) -> bb_zone* { bb_zone_free(zone); return fail(e); };
+    B.dns_domain = dns_domain;
+    // ZKCache.isReady() compares with options.domain verbatim (lib/zk.js:55-58) while keys are
+    // lower-cased (:84): an upper-case domain is never ready.  We require lower case instead.
+    for (char c : B.dns_domain) if (c >= 'A' && c <= 'Z') return bail(BB_ERR_DOMAIN);
+    std::string w;
+    if (B.dns_domain.empty() || !to_wire(B.dns_domain.data(), B.dns_domain.size(), w) || w.size() + 1 > 244) return bail(BB_ERR_DOMAIN);
+    // root node (lib/zk.js:68-76): exists as soon as the cache is built, data null
+    size_t dot = B.dns_domain.find('.');
+    std::string first = B.dns_domain.substr(0, dot);
+    B.add_node(0, first.data(), first.size());
+    {                                                              // lib/zk.js:225-228
+        std::vector<std::string> parts; size_t s = 0;
+        for (;;) { size_t d = B.dns_domain.find('.', s); parts.push_back(B.dns_domain.substr(s, d == std::string::npos ? d : d - s)); if (d == std::string::npos) break; s = d + 1; }
+        for (size_t i = parts.size(); i-- > 0;) { zone->root_path += "/"; zone->root_path += parts[i]; }
     }
-    if (!T.failed) break;
-    if (grow > 3) { bb_zone_free(zone); return fail(BB_ERR_NOMEM); }
-    }   // grow
-    while (T.arena.size() & 15) T.arena.push_back(0);
-    Z.arena_len = T.arena.size();
-    Z.arena = (uint8_t*)aligned_alloc(64, (Z.arena_len + 63) & ~(uint64_t)63);
-    if (!Z.arena) { bb_zone_free(zone); return fail(BB_ERR_NOMEM); }
-    memcpy(Z.arena, T.arena.data(), Z.arena_len);
-    Z.ready = 1;                                              // the root TreeNode exists (lib/zk.js:55-58)
+    std::vector<uint8_t> seen_data(1, 0);
+    int rc = for_each_line(buf, len, [&](const char* a, const char* b) -> int {
+        uint32_t id; int v; bool created;
+        const int what = read_line(*zone, a, b, &id, &v, &created);
+        if (what == LINE_BAD || what == LINE_DELETE) return BB_ERR_SNAPSHOT;   // a snapshot states what exists
+        if (what == LINE_SKIP) return BB_OK;
+        if (seen_data.size() < B.nodes.size()) seen_data.resize(B.nodes.size(), 0);
+        if (seen_data[id]) return BB_ERR_SNAPSHOT;                 // one line per znode
+        seen_data[id] = 1;
+        if (v >= 0) B.ingest(id, v);
+        return BB_OK;
+    });
+    if (rc != BB_OK) return bail(rc);
+    rc = layout(*zone);
+    if (rc != BB_OK) return bail(rc);
+    zone->T.track = true;
     return zone;
 }
 
@@ -643,9 +778,105 @@ extern "C" bb_zone* bb_zone_build(const char* buf, size_t len, const char* dns_d
     return bb_zone_build_shard(buf, len, dns_domain, 1, 0, err);
 }
 
+// Apply a delta — the batched analogue of the ZooKeeper watch events lib/zk.js handles — to a built zone:
+//   {"path": P, "data": D} / {"path": P, "raw": "<znode bytes>"}   the znode now holds this content
+//       (dataChanged, :139-194); a path not seen before is a new child appended to its parent's child
+//       list (childrenChanged, :120-130) — its parent must already be mirrored
+//   {"path": P, "deleted": true}                                       the znode and its subtree are gone
+//       (childrenChanged -> unbind, :131-133,195-208)
+// Only the keys that depend on the touched nodes are re-derived: the node's own key, the reverse-map
+// entry of its address, and its parent's service record.  The changed slots and the arena tail are
+// what bb_engine_apply_update ships to the device.
+extern "C" int bb_zone_apply(bb_zone* zone, const char* buf, size_t len) {
+    if (!zone || (!buf && len)) return BB_ERR_ARG;
+    Builder& B = zone->B; TableBuilder& T = zone->T;
+    std::vector<uint32_t> stack;
+    auto refresh_parent = [&](uint32_t id) -> bool {               // the parent's answer lists its children (:352-417)
+        if (id == 0) return true;
+        const uint32_t p = B.nodes[id].parent;
+        const Node& pn = B.nodes[p];
+        if ((pn.flags & NF_DEAD) || pn.kind != K_SERVICE) return true;
+        std::string dom; B.domain_of(p, dom);
+        const int64_t pos = T.find(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size());
+        if (pos < 0 || T.own[pos] != p) return true;               // the key belongs to a case-twin (or another rank)
+        return emit_forward(*zone, p);
+    };
+    int rc = for_each_line(buf, len, [&](const char* a, const char* b) -> int {
+        uint32_t id; int v; bool created;
+        const int what = read_line(*zone, a, b, &id, &v, &created);
+        if (what == LINE_BAD) return BB_ERR_SNAPSHOT;
+        if (what == LINE_SKIP) return BB_OK;
+        if (what == LINE_DELETE) {
+            if (id == 0) return BB_ERR_SNAPSHOT;                   // the root of the mirrored subtree stays
+            stack.assign(1, id);
+            while (!stack.empty()) {                               // unbind(): the node and everything below it
+                const uint32_t cur = stack.back(); stack.pop_back();
+                for (uint32_t k = B.nodes[cur].first_kid; k; k = B.nodes[k].next_sib) if (!(B.nodes[k].flags & NF_DEAD)) stack.push_back(k);
+                std::string dom; B.domain_of(cur, dom);
+                const int64_t pos = T.find(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size());
+                if (pos >= 0 && T.own[pos] == cur) { T.erase((uint32_t)pos); zone->img.n_fwd--; }   // `=== this` (:205-207)
+                B.nodes[cur].flags |= NF_DEAD;                     // its reverse entry, if any, stays (never removed)
+            }
+            return refresh_parent(id) ? BB_OK : BB_ERR_SNAPSHOT;
+        }
+        // LINE_DATA
+        const bool had_rev = (B.nodes[id].flags & NF_REV) != 0;
+        if (v >= 0) {
+            B.ingest(id, v);
+            if (B.ip_event) {
+                if (B.old_ip_valid && B.old_ip_len <= 253) {       // `delete ca_revLookup[this.tn_ip]`, whoever wrote it last
+                    const uint8_t* ok = (const uint8_t*)B.pool.data() + B.old_ip_off;
+                    const int64_t pos = T.find(NS_REVERSE, ok, B.old_ip_len);
+                    if (pos >= 0) {
+                        if (T.own[pos] != id) B.nodes[T.own[pos]].flags |= NF_REV_LOST;   // that node's tn_ip stays, its entry is gone
+                        T.erase((uint32_t)pos); zone->img.n_rev--;
+                    }
+                }
+                emit_reverse(*zone, id);                           // `ca_revLookup[addr] = this`
+            } else if (had_rev) {                                  // the entry (if still ours) answers with the new ttl
+                const Node& nd = B.nodes[id];
+                const int64_t pos = nd.rev_len <= 253 ? T.find(NS_REVERSE, (const uint8_t*)B.pool.data() + nd.rev_off, nd.rev_len) : -1;
+                if (pos >= 0 && T.own[pos] == id) emit_reverse(*zone, id);
+            }
+        }
+        if (created) {                                             // the TreeNode constructor takes the key (:96)
+            if (!emit_forward(*zone, id)) return BB_ERR_SNAPSHOT;
+        } else if (v >= 0) {                                       // data changed: only the node that holds the key answers
+            std::string dom; B.domain_of(id, dom);
+            const int64_t pos = T.find(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size());
+            if (pos >= 0 && T.own[pos] == id && !emit_forward(*zone, id)) return BB_ERR_SNAPSHOT;
+        }
+        if ((created || v >= 0) && !refresh_parent(id)) return BB_ERR_SNAPSHOT;
+        return BB_OK;
+    });
+    if (rc != BB_OK) return rc;
+    // a cuckoo insertion that failed, or a table filling past what two choices sustain: lay it out again
+    if (T.failed || T.count * 100 > (uint64_t)zone->img.nslots * 47) {
+        rc = layout(*zone);
+        if (rc != BB_OK) return rc;
+    }
+    while (T.arena.size() & 15) T.arena.push_back(0);
+    zone->img.arena = T.arena.data(); zone->img.arena_len = T.arena.size();
+    zone->img.n_nodes = B.nodes.size();
+    return BB_OK;
+}
+
+// What the device has not seen yet (used by bb_engine_apply_update in engine.cu).
+extern "C" int bb_zone_pending(const bb_zone* z, const uint32_t** slots, uint32_t* n_slots, uint64_t* arena_from, int* relaid) {
+    if (!z) return BB_ERR_ARG;
+    *slots = z->T.dirty.data(); *n_slots = (uint32_t)z->T.dirty.size(); *arena_from = z->arena_synced; *relaid = z->relaid ? 1 : 0;
+    return BB_OK;
+}
+extern "C" void bb_zone_mark_synced(bb_zone* z) {
+    if (!z) return;
+    for (uint32_t pos : z->T.dirty) z->T.dirty_mark[pos] = 0;
+    z->T.dirty.clear(); z->relaid = false; z->arena_synced = z->img.arena_len; z->sync_gen++;
+}
+extern "C" uint64_t bb_zone_sync_gen(const bb_zone* z) { return z ? z->sync_gen : 0; }
+
 extern "C" void bb_zone_free(bb_zone* z) {
     if (!z) return;
-    free(z->img.slots); free(z->img.arena);
+    free(z->img.slots);                                        // img.arena is the table builder's vector
     delete z;
 }
 
@@ -658,8 +889,44 @@ extern "C" uint64_t bb_zone_stat(const bb_zone* z, int what) {
     case 3: return z->img.nslots;
     case 4: return (uint64_t)z->img.nslots * sizeof(bb::Slot) + z->img.arena_len;
     case 5: return z->img.arena_len;
+    case 6: return z->T.dirty.size();                          // slots changed since the device last saw the table
+    case 7: return z->relaid ? 1 : 0;
     }
     return 0;
+}
+
+// Diagnostics: what the image holds for a key (host side; the tests compare an updated zone with a fresh
+// build through it).  rec = the payload in a position-independent form: service header + srvce + proto
+// + every child (KidRec, ports, name); PTR target wire bytes.  Returns 1 when the key is present.
+extern "C" int bb_zone_probe(const bb_zone* z, uint32_t ns, const uint8_t* key, uint32_t len, uint8_t* kind, uint32_t* ttl,
+                             uint32_t* val, uint8_t* rec, uint32_t rec_cap, uint32_t* rec_len) {
+    if (!z || !key) return 0;
+    const int64_t pos = z->T.find(ns, key, len);
+    if (pos < 0) return 0;
+    const bb::Slot& s = z->img.slots[pos];
+    if (kind) *kind = s.kind;
+    if (ttl) *ttl = s.ttl;
+    if (val) *val = (s.kind == bb::K_SERVICE || s.kind == bb::K_PTR) ? 0 : s.val;
+    std::string out;
+    const uint8_t* A = z->T.arena.data();
+    if (s.kind == bb::K_SERVICE) {
+        const bb::SvcHdr* h = (const bb::SvcHdr*)(A + s.val);
+        out.append((const char*)&h->ttl, 4); out.append((const char*)&h->nkids, 2);
+        out.push_back((char)h->srvce_len); out.push_back((char)h->proto_len);
+        const uint32_t sl = h->srvce_len == 0xFF ? 0 : h->srvce_len, pl = h->proto_len == 0xFF ? 0 : h->proto_len;
+        const uint8_t* q = A + s.val + sizeof(bb::SvcHdr);
+        out.append((const char*)q, sl + pl);
+        const uint32_t* tab = (const uint32_t*)(A + s.val + ((sizeof(bb::SvcHdr) + sl + pl + 3) & ~3u));
+        for (uint32_t k = 0; k < h->nkids; k++) {
+            const bb::KidRec* kr = (const bb::KidRec*)(A + tab[k]);
+            out.append((const char*)kr, sizeof *kr + 2u * kr->nports + kr->wire_len);
+        }
+    } else if (s.kind == bb::K_PTR) {
+        out.append((const char*)(A + s.val + 1), A[s.val]);
+    }
+    if (rec_len) *rec_len = (uint32_t)out.size();
+    if (rec && out.size() <= rec_cap) memcpy(rec, out.data(), out.size());
+    return 1;
 }
 
 // used by engine.cu

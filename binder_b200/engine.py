@@ -46,6 +46,27 @@ class Zone(object):
         keys = ('nodes', 'forward_keys', 'reverse_keys', 'slots', 'image_bytes', 'arena_bytes')
         return {k: int(L.bb_zone_stat(self._h, i)) for i, k in enumerate(keys)}
 
+    def apply(self, delta_jsonl):
+        """Watch events (dataChanged / childrenChanged, lib/zk.js:120-208) as JSON lines; see bb_zone_apply."""
+        if isinstance(delta_jsonl, str):
+            delta_jsonl = delta_jsonl.encode('utf-8')
+        check(lib().bb_zone_apply(self._h, delta_jsonl, len(delta_jsonl)))
+
+    def pending(self):
+        """(slots changed since the device last saw the table, table laid out again?)"""
+        return int(lib().bb_zone_stat(self._h, 6)), bool(lib().bb_zone_stat(self._h, 7))
+
+    def probe(self, key, reverse=False):
+        """Diagnostics: (kind, ttl, val, payload bytes) the image holds for a key, or None."""
+        if isinstance(key, str):
+            key = key.encode('latin-1')
+        kind, ttl, val, rl = ctypes.c_uint8(0), ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_uint32(0)
+        buf = ctypes.create_string_buffer(1 << 16)
+        if not lib().bb_zone_probe(self._h, 1 if reverse else 0, key, len(key), ctypes.byref(kind), ctypes.byref(ttl),
+                                   ctypes.byref(val), buf, len(buf), ctypes.byref(rl)):
+            return None
+        return kind.value, ttl.value, val.value, buf.raw[:rl.value]
+
     def close(self):
         if getattr(self, '_h', None):
             lib().bb_zone_free(self._h)
@@ -87,6 +108,10 @@ class Engine(object):
 
     def swap_zone(self, zone):
         check(lib().bb_engine_swap_zone(self._h, zone._h))
+
+    def apply_update(self, zone):
+        """After zone.apply(): upload only the changed slots and the arena tail (bb_engine_apply_update)."""
+        check(lib().bb_engine_apply_update(self._h, zone._h))
 
     def is_ready(self):
         return bool(lib().bb_engine_is_ready(self._h))

@@ -65,7 +65,27 @@ bb_zone* bb_zone_build_shard(const char* snapshot_jsonl, size_t len, const char*
                              uint32_t nranks, uint32_t rank, int* err);
 void     bb_zone_free(bb_zone* z);
 /* introspection: znodes mirrored (root included), forward keys, reverse keys, table bytes */
-uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 rev 3 slots 4 image bytes 5 arena bytes */
+uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 rev 3 slots 4 image bytes 5 arena bytes
+                                                         6 slots changed since the device last saw the table 7 table laid out again */
+/*
+ * Watch events on a built zone (lib/zk.js:120-208), batched as JSON lines:
+ *   {"path": P, "data": D} | {"path": P, "raw": "<znode bytes>"}   the znode now holds this content (dataChanged,
+ *        :139-194: unparsable or non-object content is ignored and the previous data kept); a path not seen before is
+ *        a new child appended to its parent's child list (childrenChanged, :120-130) — the parent must be mirrored
+ *   {"path": P, "deleted": true}    the znode and its subtree are gone (childrenChanged -> unbind, :131-133,195-208;
+ *        like the reference, a reverse-map entry the node registered is NOT removed)
+ * Only what depends on the touched znodes is re-derived: the node's own key, the reverse entry of its address, its
+ * parent's service record.  Superseded arena records become garbage until the next full build.  Deviation: the
+ * reference re-orders a node's children to ZooKeeper's list on every childrenChanged; here a new child goes last.
+ * Returns BB_OK, or BB_ERR_SNAPSHOT for a line that is not a JSON object with a string "path" (earlier lines of
+ * the delta stay applied).
+ */
+int bb_zone_apply(bb_zone* z, const char* delta_jsonl, size_t len);
+/* Diagnostics (host side): what the image holds for a key.  ns 0 = forward (lower-cased fqdn), 1 = reverse (address
+ * string).  rec = the payload in a position-independent form (service header, srvce, proto, every child record;
+ * PTR target as wire labels).  Returns 1 when the key is present. */
+int bb_zone_probe(const bb_zone* z, uint32_t ns, const uint8_t* key, uint32_t len, uint8_t* kind, uint32_t* ttl,
+                  uint32_t* val, uint8_t* rec, uint32_t rec_cap, uint32_t* rec_len);
 
 /* ---- engine: replaces lib/server.js createServer()'s query handler ----------------- */
 /*
@@ -100,6 +120,11 @@ void       bb_engine_destroy(bb_engine* e);
  * The engine keeps its own device copy; the caller may free `z` afterwards.
  */
 int bb_engine_swap_zone(bb_engine* e, const bb_zone* z);
+/* After bb_zone_apply: ship only what changed (the touched 64-byte slots, scattered by a small kernel, and the arena
+ * tail) instead of the whole image; batches in flight finish on the old state first.  Falls back to a full swap when
+ * the table had to be laid out again, the arena outgrew its device allocation, or another engine took the zone's
+ * previous changes (a zone feeds ONE engine incrementally). */
+int bb_engine_apply_update(bb_engine* e, bb_zone* z);
 int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/zk.js:55-58 */
 
 /*

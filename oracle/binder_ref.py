@@ -218,14 +218,37 @@ class ZKCache(object):
         self.ca_domain = domain
         self.by_path = {}
 
+    def unbind(self, node):
+        """lib/zk.js:195-208: the subtree leaves ca_treeNodes (a key only if it is still the node's
+        own); ca_revLookup is never touched."""
+        for kid in node.tn_kids.values():
+            self.unbind(kid)
+        if self.ca_treeNodes.get(node.tn_domain) is node:
+            del self.ca_treeNodes[node.tn_domain]
+
+    def _forget_paths(self, node, path):
+        for name, kid in node.tn_kids.items():
+            self._forget_paths(kid, path + '/' + name)
+        self.by_path.pop(path, None)
+
+    def apply_delta(self, lines):
+        """Watch events on a loaded cache, as JSON lines: a known path = dataChanged (:139-194), a new
+        path = a child appended by childrenChanged (:120-130) plus its data, {"path": P, "deleted":
+        true} = the child vanishing from its parent's list (:131-133 -> unbind)."""
+        return self._apply(lines, True)
+
     def load_snapshot(self, lines):
         """Snapshot = JSON lines {"path": "/com/foo/x", "data": <value>} (or "raw":
         "<znode bytes>"), parents before children, children in ZK child-list order.
         Mirrors rebuildCache (:68-76) + the watcher callbacks."""
         parts = self.ca_domain.split('.')
         root = TreeNode(self, '.'.join(parts[1:]), parts[0])
+        self.by_path[domain_to_path(self.ca_domain)] = root
+        return self._apply(lines, False)
+
+    def _apply(self, lines, allow_delete):
         root_path = domain_to_path(self.ca_domain)
-        self.by_path[root_path] = root
+        root = self.by_path[root_path]
         for line in lines:
             if isinstance(line, (bytes, bytearray)):
                 line = line.decode('utf-8')
@@ -234,7 +257,12 @@ class ZKCache(object):
                 continue
             ent = json.loads(line)
             path = ent['path']
+            deleting = ent.get('deleted') is True
+            if deleting and not allow_delete:
+                raise ValueError('a snapshot states what exists')
             if path == root_path:
+                if deleting:
+                    raise ValueError('the root of the mirrored subtree stays')
                 node = root
             else:
                 ppath, _, name = path.rpartition('/')
@@ -242,6 +270,12 @@ class ZKCache(object):
                 if parent is None or name == '':
                     continue                        # outside the watched subtree
                 node = parent.tn_kids.get(name)
+                if deleting:
+                    if node is not None:
+                        self.unbind(node)
+                        self._forget_paths(node, path)
+                        del parent.tn_kids[name]
+                    continue
                 if node is None:
                     node = TreeNode(self, parent.tn_domain, name)
                     parent.tn_kids[name] = node

@@ -244,14 +244,35 @@ struct ZKCache {
         for (size_t i = parts.size(); i-- > 0;) { o += "/"; o += parts[i]; }
         return o;
     }
+    // lib/zk.js:195-208: the node and its subtree leave ca_treeNodes (each only if the key is still its
+    // own); ca_revLookup is never touched.
+    void unbind(int id) {
+        TreeNode& n = *nodes[id];
+        for (int k : n.tn_kids) unbind(k);
+        auto it = ca_treeNodes.find(n.tn_domain);
+        if (it != ca_treeNodes.end() && it->second == id) ca_treeNodes.erase(it);
+    }
+    void forget_paths(int id, const std::string& path) {
+        for (int k : nodes[id]->tn_kids) forget_paths(k, path + "/" + nodes[k]->tn_name);
+        by_path.erase(path);
+    }
     // Snapshot = JSON lines {"path":..., "data":<value>} | {"path":..., "raw":"<znode bytes>"}.
     int load(const char* buf, size_t len) {
         size_t dot = ca_domain.find('.');
         std::string first = ca_domain.substr(0, dot);
         std::string rest = dot == std::string::npos ? "" : ca_domain.substr(dot + 1);
         int root = new_node(rest, first);                                 // lib/zk.js:68-76
+        by_path[domain_to_path(ca_domain)] = root;
+        if (apply(buf, len, false) != 0) return -1;
+        loaded = true;
+        return 0;
+    }
+    // The same lines as watch events on a live cache: a known path = dataChanged (:139-194), a new
+    // path = a child appended by childrenChanged (:120-130) followed by its data, and
+    // {"path":..., "deleted":true} = the child vanishing from its parent's list (:131-133).
+    int apply(const char* buf, size_t len, bool allow_delete) {
         std::string root_path = domain_to_path(ca_domain);
-        by_path[root_path] = root;
+        int root = by_path[root_path];
         const char* p = buf; const char* end = buf + len;
         while (p < end) {
             const char* nl = (const char*)memchr(p, '\n', end - p);
@@ -265,8 +286,11 @@ struct ZKCache {
             if (!jp.document(ent) || ent.t != JVal::OBJ) return -1;
             const JVal& path = ent.get("path");
             if (path.t != JVal::STR) return -1;
+            const JVal& dv = ent.get("deleted");
+            const bool deleting = dv.t == JVal::BOOL && dv.b;
+            if (deleting && !allow_delete) return -1;
             int id;
-            if (path.str == root_path) id = root;
+            if (path.str == root_path) { if (deleting) return -1; id = root; }
             else {
                 size_t sl = path.str.rfind('/');
                 if (sl == std::string::npos) continue;
@@ -275,6 +299,15 @@ struct ZKCache {
                 if (it == by_path.end() || name.empty()) continue;         // not under the watched root
                 int parent = it->second;
                 auto self = by_path.find(path.str);
+                if (deleting) {
+                    if (self == by_path.end()) continue;
+                    id = self->second;
+                    unbind(id);
+                    forget_paths(id, path.str);
+                    auto& kids = nodes[parent]->tn_kids;
+                    kids.erase(std::find(kids.begin(), kids.end(), id));
+                    continue;
+                }
                 if (self != by_path.end()) id = self->second;
                 else {
                     std::string pdom = nodes[parent]->tn_domain;
@@ -293,7 +326,6 @@ struct ZKCache {
                 on_data_changed(id, std::move(*data));
             }
         }
-        loaded = true;
         return 0;
     }
     bool isReady() const { return loaded && ca_treeNodes.count(ca_domain) != 0; }   // lib/zk.js:55-58
@@ -731,6 +763,12 @@ int orc_load_snapshot(void* h, const char* buf, size_t len) {
     e->zk = std::move(zk);
     e->opt.zkCache = e->zk.get();
     return 0;
+}
+// Watch events on the loaded cache (see ZKCache::apply).
+int orc_apply_delta(void* h, const char* buf, size_t len) {
+    Engine* e = (Engine*)h;
+    if (!e->zk) return -1;
+    return e->zk->apply(buf, len, true);
 }
 long orc_node_count(void* h) { Engine* e = (Engine*)h; return e->zk ? (long)e->zk->nodes.size() : 0; }
 

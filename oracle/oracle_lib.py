@@ -34,6 +34,7 @@ def lib():
         L.orc_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
         L.orc_destroy.argtypes = [ctypes.c_void_p]
         L.orc_load_snapshot.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_apply_delta.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
         L.orc_node_count.restype = ctypes.c_long
         L.orc_node_count.argtypes = [ctypes.c_void_p]
         L.orc_resolve_batch.argtypes = [
@@ -56,6 +57,14 @@ class Oracle(object):
         rc = lib().orc_load_snapshot(self._h, jsonl, len(jsonl))
         if rc != 0:
             raise ValueError('oracle: bad snapshot (%d)' % rc)
+
+    def apply_delta(self, jsonl):
+        """Watch events on the loaded cache (JSON lines; see ZKCache::apply in oracle.cpp)."""
+        if isinstance(jsonl, str):
+            jsonl = jsonl.encode('utf-8')
+        rc = lib().orc_apply_delta(self._h, jsonl, len(jsonl))
+        if rc != 0:
+            raise ValueError('oracle: bad delta (%d)' % rc)
 
     def node_count(self):
         return lib().orc_node_count(self._h)

@@ -266,3 +266,69 @@ def tolerated_packets():
         synth.make_query('', 'A'), synth.make_query('', 'PTR'), synth.make_query('', 'SRV'),
         struct.pack('>HHHHHH', 1, 0x0100, 1, 0, 0, 0) + b'\x00' + struct.pack('>HH', 1, 1),
     ]
+
+
+# ---------------------------------------------------------------------------------------
+# deltas: the watch events of lib/zk.js:120-208 as JSON lines (bb_zone_apply / orc_apply_delta)
+# ---------------------------------------------------------------------------------------
+def snapshot_paths(snap):
+    """Paths of a snapshot's lines, in order."""
+    return [json.loads(l)['path'] for l in snap.decode('utf-8').split('\n') if l.strip()]
+
+
+def gen_delta(seed, paths, info, n_ops=40):
+    """A batch of watch events around the zone's znodes -> (jsonl bytes, paths after it).  Updates `info`
+    (names / addrs / services) so that gen_queries also asks about what the delta touched.
+
+    Covers: data changes of every record shape (type changes included), address changes that reuse another
+    node's address (the reverse map's last-writer / stale-entry behaviour), new children (case twins of
+    existing ones included), deletions of leaves and subtrees, re-creation of deleted paths, events outside
+    the mirrored subtree, unparsable content (ignored: previous data stays)."""
+    rng = random.Random(seed ^ 0xDE17A)
+    dom = info['dns_domain']
+    root = '/' + '/'.join(reversed(dom.split('.')))
+    live = [p for p in paths if p == root or p.startswith(root + '/')]
+    lines = []
+
+    def dom_of(path):
+        return '.'.join(reversed(path[len(root) + 1:].split('/'))) + '.' + dom if path != root else dom
+
+    def note(path, kind, val):
+        if kind == 'data' and isinstance(val, dict):
+            t = val.get('type')
+            if isinstance(t, str) and isinstance(val.get(t), dict) and isinstance(val[t].get('address'), str):
+                info['addrs'].append(val[t]['address'])
+            if t == 'service':
+                info['services'].append(dom_of(path))
+        info['names'].append(dom_of(path))
+
+    for _ in range(n_ops):
+        r = rng.random()
+        if r < 0.40 and live:                           # dataChanged: any shape
+            p = rng.choice(live)
+            kind, val = _record(rng)
+            lines.append(json.dumps({'path': p, kind: val})); note(p, kind, val)
+        elif r < 0.58 and live:                         # address change, often onto an address in use
+            p = rng.choice(live)
+            val = _hostlike(rng, ['host', 'load_balancer', 'rr_host', 'redis_host'])
+            t = val['type']
+            if isinstance(val.get(t), dict) and info['addrs'] and rng.random() < 0.6:
+                val[t]['address'] = rng.choice(info['addrs'])
+            lines.append(json.dumps({'path': p, 'data': val})); note(p, 'data', val)
+        elif r < 0.76 and live:                         # childrenChanged: a new child (maybe a case twin)
+            parent = rng.choice(live)
+            p = parent + '/' + rng.choice(LABELS)
+            kind, val = _record(rng) if rng.random() < 0.5 else ('data', _hostlike(rng, ['load_balancer', 'rr_host', 'moray_host', 'host']))
+            lines.append(json.dumps({'path': p, kind: val})); note(p, kind, val)
+            if p not in live:
+                live.append(p)
+        elif r < 0.93 and len(live) > 1:                # childrenChanged: a child (and its subtree) is gone
+            p = rng.choice([x for x in live if x != root])
+            lines.append(json.dumps({'path': p, 'deleted': True}))
+            live = [x for x in live if x != p and not x.startswith(p + '/')]
+        elif r < 0.96:
+            lines.append(json.dumps({'path': '/other/zone/x', 'data': {'type': 'host', 'host': {'address': '8.8.8.8'}}}))
+        else:                                           # deleting what is not there; content for a child of nothing
+            lines.append(json.dumps({'path': root + '/ghost/child', 'data': None}))
+            lines.append(json.dumps({'path': root + '/ghost', 'deleted': True}))
+    return ('\n'.join(lines) + '\n').encode('utf-8'), live

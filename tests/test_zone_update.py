@@ -1,0 +1,150 @@
+"""Incremental zone updates (lib/zk.js:120-208 watch events as deltas).
+CPU side: the two oracles agree on what a delta does; the product's zone builder re-derives exactly what a
+fresh build of the resulting tree holds (bb_zone_probe), including across a forced re-layout."""
+import json
+
+import pytest
+
+import fuzzgen
+import helpers as H
+from test_oracle_cross import check_against_ref
+
+
+class RefAfterDelta(object):
+    """H.ref_options, with deltas applied to its cache."""
+    def __init__(self, snap, info, recursion):
+        self.opts = H.ref_options(snap, info['dns_domain'], recursion=recursion)
+
+    def apply(self, delta):
+        self.opts.zkCache.apply_delta(delta.decode('utf-8').split('\n'))
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_oracles_agree_after_deltas(seed, monkeypatch):
+    snap, info = fuzzgen.gen_zone(seed, n_top=25)
+    recursion = seed % 3 == 0
+    impl = H.make_impl('oracle', info['dns_domain'], snap, recursion=recursion)
+    ref = RefAfterDelta(snap, info, recursion)
+    monkeypatch.setattr(H, 'ref_options', lambda *a, **k: ref.opts)
+    paths = fuzzgen.snapshot_paths(snap)
+    for rnd in range(4):
+        delta, paths = fuzzgen.gen_delta(seed * 100 + rnd, paths, info, n_ops=30)
+        impl.apply_delta(delta)
+        ref.apply(delta)
+        pkts = fuzzgen.gen_queries(seed * 31 + rnd, info, n=300)
+        check_against_ref(impl, snap, info, pkts, recursion, seed=seed * 7919 + rnd)
+
+
+ZONE0 = [
+    ('/com/foo', None),
+    ('/com/foo/hosta', {'type': 'host', 'host': {'address': '192.168.0.1'}}),
+    ('/com/foo/hostb', {'type': 'host', 'host': {'address': '192.168.0.2'}, 'ttl': 60}),
+    ('/com/foo/svc', {'type': 'service', 'service': {'srvce': '_http', 'proto': '_tcp', 'port': 80}}),
+    ('/com/foo/svc/lb0', {'type': 'load_balancer', 'load_balancer': {'address': '10.0.0.1'}}),
+    ('/com/foo/svc/lb1', {'type': 'load_balancer', 'load_balancer': {'address': '10.0.0.2'}}),
+    ('/com/foo/grp', None),
+    ('/com/foo/grp/x', {'type': 'host', 'host': {'address': '172.16.0.1'}}),
+    ('/com/foo/grp/y', {'type': 'host', 'host': {'address': '172.16.0.2'}}),
+]
+DELTA = [
+    {'path': '/com/foo/hosta', 'data': {'type': 'host', 'host': {'address': '192.168.0.9'}}},        # address change
+    {'path': '/com/foo/hostb', 'data': {'type': 'host', 'host': {'address': '192.168.0.2', 'ttl': 5}}},  # ttl change
+    {'path': '/com/foo/svc/lb2', 'data': {'type': 'rr_host', 'rr_host': {'address': '10.0.0.3', 'ports': [8080, 8081]}}},
+    {'path': '/com/foo/svc/lb0', 'deleted': True},
+    {'path': '/com/foo/newhost', 'data': {'type': 'host', 'host': {'address': '192.168.0.77'}}},
+    {'path': '/com/foo/grp', 'deleted': True},
+    {'path': '/com/foo/hosta', 'raw': 'not json'},                                                      # ignored
+]
+ZONE1 = [
+    ('/com/foo', None),
+    ('/com/foo/hosta', {'type': 'host', 'host': {'address': '192.168.0.9'}}),
+    ('/com/foo/hostb', {'type': 'host', 'host': {'address': '192.168.0.2', 'ttl': 5}}),
+    ('/com/foo/svc', {'type': 'service', 'service': {'srvce': '_http', 'proto': '_tcp', 'port': 80}}),
+    ('/com/foo/svc/lb1', {'type': 'load_balancer', 'load_balancer': {'address': '10.0.0.2'}}),
+    ('/com/foo/svc/lb2', {'type': 'rr_host', 'rr_host': {'address': '10.0.0.3', 'ports': [8080, 8081]}}),
+    ('/com/foo/newhost', {'type': 'host', 'host': {'address': '192.168.0.77'}}),
+]
+FWD = ['foo.com', 'hosta.foo.com', 'hostb.foo.com', 'svc.foo.com', 'lb0.svc.foo.com', 'lb1.svc.foo.com', 'lb2.svc.foo.com',
+       'grp.foo.com', 'x.grp.foo.com', 'y.grp.foo.com', 'newhost.foo.com', 'nope.foo.com']
+# an unbound node keeps its reverse entry (lib/zk.js never removes it), so the deleted znodes' addresses are
+# compared separately below
+REV = ['192.168.0.1', '192.168.0.9', '192.168.0.2', '10.0.0.2', '10.0.0.3', '192.168.0.77', '1.2.3.4']
+REV_OF_DELETED = {'10.0.0.1': 'lb0.svc.foo.com', '172.16.0.1': 'x.grp.foo.com', '172.16.0.2': 'y.grp.foo.com'}
+
+
+def wire(name):
+    return b''.join(bytes([len(l)]) + l.encode() for l in name.split('.')) + b'\0'
+
+
+def test_incremental_equals_fresh_build():
+    from binder_b200.engine import Zone
+    z = Zone(H.snapshot(ZONE0), 'foo.com')
+    assert z.pending() == (0, True)            # a fresh build has never been uploaded: full upload pending
+    z.apply('\n'.join(json.dumps(d) for d in DELTA))
+    fresh = Zone(H.snapshot(ZONE1), 'foo.com')
+    for k in FWD:
+        assert z.probe(k) == fresh.probe(k), k
+    for k in REV:
+        assert z.probe(k, reverse=True) == fresh.probe(k, reverse=True), k
+    for addr, dom in REV_OF_DELETED.items():
+        kind, ttl, _, rec = z.probe(addr, reverse=True)
+        assert (kind, ttl, rec) == (6, 30, wire(dom)), addr       # K_PTR, still answering
+        assert fresh.probe(addr, reverse=True) is None
+    assert z.probe('lb0.svc.foo.com') is None and z.probe('grp.foo.com') is None and z.probe('x.grp.foo.com') is None
+    st, fs = z.stat(), fresh.stat()
+    assert st['forward_keys'] == fs['forward_keys'] and st['reverse_keys'] == fs['reverse_keys'] + 3
+
+
+def test_growth_forces_relayout_and_keeps_every_key():
+    from binder_b200.engine import Zone
+    z = Zone(H.snapshot(ZONE0), 'foo.com')
+    slots0 = z.stat()['slots']
+    new = [{'path': '/com/foo/n%04d' % i, 'data': {'type': 'host', 'host': {'address': '10.9.%d.%d' % (i >> 8, i & 255)}}}
+           for i in range(600)]
+    z.apply('\n'.join(json.dumps(d) for d in new))
+    assert z.stat()['slots'] > slots0 and z.pending()[1]
+    fresh = Zone(H.snapshot(ZONE0 + [(d['path'], d['data']) for d in new]), 'foo.com')
+    for i in range(600):
+        assert z.probe('n%04d.foo.com' % i) == fresh.probe('n%04d.foo.com' % i)
+        a = '10.9.%d.%d' % (i >> 8, i & 255)
+        assert z.probe(a, reverse=True) == fresh.probe(a, reverse=True)
+    for k in FWD:
+        assert z.probe(k) == fresh.probe(k), k
+
+
+def test_bad_delta_line_is_an_error():
+    from binder_b200.engine import Zone
+    from binder_b200._lib import BinderError
+    z = Zone(H.snapshot(ZONE0), 'foo.com')
+    with pytest.raises(BinderError):
+        z.apply('{"data": null}\n')
+    with pytest.raises(BinderError):
+        z.apply('{"path": "/com/foo", "deleted": true}\n')
+    with pytest.raises(BinderError):
+        Zone(H.snapshot(ZONE0) + b'{"path": "/com/foo/hosta", "deleted": true}\n', 'foo.com')
+
+
+@pytest.mark.parametrize('seed', range(10))
+def test_incremental_state_survives_a_relayout(seed):
+    """What a sequence of deltas left in the table (incrementally maintained) must equal what a full
+    re-derivation from the tree produces: forcing a re-layout must not change any existing key's answer."""
+    from binder_b200.engine import Zone
+    snap, info = fuzzgen.gen_zone(seed + 50, n_top=25)
+    z = Zone(snap, info['dns_domain'])
+    paths = fuzzgen.snapshot_paths(snap)
+    for rnd in range(5):
+        delta, paths = fuzzgen.gen_delta(seed * 100 + rnd, paths, info, n_ops=40)
+        z.apply(delta)
+    lower = lambda s: ''.join(chr(ord(c) + 32) if 'A' <= c <= 'Z' else c for c in s)
+    fkeys = sorted({lower(n).encode('utf-8') for n in info['names']})
+    rkeys = sorted({a.encode('utf-8') for a in info['addrs'] if a})
+    before = [z.probe(k) for k in fkeys] + [z.probe(k, reverse=True) for k in rkeys]
+    assert any(b is not None for b in before)
+    slots0 = z.stat()['slots']
+    root = '/' + '/'.join(reversed(info['dns_domain'].split('.')))
+    grow = [{'path': '%s/grow%05d' % (root, i), 'data': {'type': 'host', 'host': {'address': '203.0.%d.%d' % (i >> 8, i & 255)}}}
+            for i in range(max(400, slots0 // 3))]
+    z.apply('\n'.join(json.dumps(d) for d in grow))
+    assert z.stat()['slots'] > slots0
+    after = [z.probe(k) for k in fkeys] + [z.probe(k, reverse=True) for k in rkeys]
+    assert before == after
