@@ -65,6 +65,27 @@ static napi_value EngineSwapZone(napi_env env, napi_callback_info info) {
     return nullptr;
 }
 
+// zoneApply(zone, delta: Buffer): watch events as JSON lines (bb_zone_apply)
+static napi_value ZoneApply(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    void* z; NAPI_OK(napi_get_value_external(env, argv[0], &z));
+    void* data; size_t len; NAPI_OK(napi_get_buffer_info(env, argv[1], &data, &len));
+    int rc = bb_zone_apply((bb_zone*)z, (const char*)data, len);
+    if (rc != BB_OK) return Throw(env, rc);
+    return nullptr;
+}
+
+// engineApplyUpdate(engine, zone): ship what the deltas changed (bb_engine_apply_update)
+static napi_value EngineApplyUpdate(napi_env env, napi_callback_info info) {
+    size_t argc = 2; napi_value argv[2];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    void *e, *z; NAPI_OK(napi_get_value_external(env, argv[0], &e)); NAPI_OK(napi_get_value_external(env, argv[1], &z));
+    int rc = bb_engine_apply_update((bb_engine*)e, (bb_zone*)z);
+    if (rc != BB_OK) return Throw(env, rc);
+    return nullptr;
+}
+
 // resolveBatch(engine, pkts: Buffer, pktOff: Uint32Array(n+1), seed: BigInt) -> result object
 static napi_value ResolveBatch(napi_env env, napi_callback_info info) {
     size_t argc = 4; napi_value argv[4];
@@ -99,6 +120,8 @@ static napi_value Init(napi_env env, napi_value exports) {
         { "zoneBuild", nullptr, ZoneBuild, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "engineCreate", nullptr, EngineCreate, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "engineSwapZone", nullptr, EngineSwapZone, nullptr, nullptr, nullptr, napi_default, nullptr },
+        { "zoneApply", nullptr, ZoneApply, nullptr, nullptr, nullptr, napi_default, nullptr },
+        { "engineApplyUpdate", nullptr, EngineApplyUpdate, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "resolveBatch", nullptr, ResolveBatch, nullptr, nullptr, nullptr, napi_default, nullptr },
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);
