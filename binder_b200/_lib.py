@@ -24,6 +24,7 @@ SYMBOLS = {
     'bb_engine_destroy': (None, [_c.c_void_p]),
     'bb_engine_swap_zone': (_c.c_int, [_c.c_void_p, _c.c_void_p]),
     'bb_engine_is_ready': (_c.c_int, [_c.c_void_p]),
+    'bb_engine_set_recursion_filter': (_c.c_int, [_c.c_void_p, _c.c_char_p, _c.c_void_p, _c.c_uint32, _c.c_int]),
     'bb_resolve_batch': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_uint32,
                                     _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                     _c.c_void_p]),

@@ -309,6 +309,42 @@ __device__ __forceinline__ void size_single(Res& r, uint32_t fixed, uint32_t rr)
     else { r.rlen = (uint16_t)fixed; r.keep_ans = 0; r.tc = 1; }
 }
 
+// Recursion.resolve()'s quick rejects (lib/recursion.js:329-344), for a miss that would otherwise be handed
+// to the host: would it be forwarded anywhere?  nm = QNAME wire bytes — query.name() in its original case,
+// SRV prefix included — W = its length without the terminator.  In the dotted string every label boundary
+// is a '.', so the string operations map one to one onto wire positions:
+//   domain.indexOf(dnsDomain, domain.length - dnsDomain.length) === -1            -> not ours   (:330-333)
+//   p = domain minus the suffix and the one character before it; dc = p after its last '.';
+//   self.dcs[dc] === undefined (or every upstream of dc is this host)              -> nowhere to ask (:338-343,377-379)
+// Kept out of line: it runs for misses only and must not cost the hit path registers.
+__device__ __noinline__ bool recursion_forwardable(const EngineConst* E, const uint8_t* nm, uint32_t W) {
+    const uint32_t L = E->rf_dom_len;
+    if (W < 1 + L) return false;                       // name shorter than the suffix
+    const uint32_t s0 = W - L;                         // wire index where the suffix must start
+    if (s0 < 2) return false;                          // nothing before it: dc = ''
+    const uint32_t cw = s0 - 1;                        // the character substring() drops (normally the '.')
+    uint32_t nlp = 1u + nm[0], last_b = 0;             // next length byte; last boundary before cw
+    bool ok = true;
+    for (uint32_t w = 1; w < W; w++) {
+        const bool boundary = w == nlp;
+        if (boundary) { nlp = w + 1u + nm[w]; if (w < cw) last_b = w; }
+        if (w >= s0) {
+            const uint32_t e = E->rf_dom[w - s0];
+            ok &= boundary ? e == '.' : (e != '.' && e == nm[w]);
+        }
+    }
+    if (!ok) return false;
+    const uint32_t d0 = last_b + 1, dl = cw - d0;      // dc = dotted[d0 .. cw)
+    if (dl == 0 || dl > 63) return false;
+    for (uint32_t k = 0; k < E->rf_ndc; k++) {
+        if (E->rf_dc_len[k] != dl) continue;
+        bool eq = true;
+        for (uint32_t i = 0; i < dl; i++) eq &= E->rf_dc[k][i] == nm[d0 + i];
+        if (eq) return true;
+    }
+    return false;
+}
+
 // What resolve() does once zk.lookup() has answered (lib/server.js:219-424); shared by the
 // generic and the word-wise front ends.
 __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed, bool srv, bool hit,
@@ -316,7 +352,11 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     const uint8_t* nm = r.p + 12;
     const EngineConst* E = P.eng;
     if (!hit) {                                                               // :219-247
-        if (P.recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        if (P.recursion && r.rd) {
+            // pre-filter: a miss recursion.js would refuse without asking anyone is refused here (same bytes)
+            if (P.recursion == 2 && !recursion_forwardable(E, nm, r.qn_len - 1)) { r.rcode = RC_REFUSED; return; }
+            r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return;
+        }
         r.rcode = RC_REFUSED; return;
     }
     r.ttl = ttl; r.val = val;
@@ -633,7 +673,10 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
     uint32_t kind = 0, ttl = 0, val = 0;
     bool hit = kg.length() > 0 && probe(P, r, NS_REVERSE, kg, kind, ttl, val);
     if (!hit) {                                                               // :107-121
-        if (P.eng->recursion && r.rd) { r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return; }
+        if (P.recursion && r.rd) {                                            // a PTR miss asks every datacenter (:346-354)
+            if (P.recursion == 2 && !P.eng->rf_ptr) { r.rcode = RC_REFUSED; return; }
+            r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return;
+        }
         r.rcode = RC_REFUSED; return;
     }
     if (kind != K_PTR) { r.rcode = RC_SERVFAIL; return; }                     // contract
@@ -1565,6 +1608,33 @@ int bb_engine_apply_update(bb_engine* e, bb_zone* z) {
     e->ready = img->ready;
     bb_zone_mark_synced(z);
     e->zone_gen = bb_zone_sync_gen(z);
+    return BB_OK;
+}
+// Recursion pre-filter (lib/recursion.js:329-344).  region_domain =
+// Recursion's opts.dnsDomain; dc_names = the keys of self.dcs that still have an upstream after the
+// "not one of my own addresses" filter (:360-379); ptr_forwardable = any such upstream exists at all.
+// With a filter set, a miss Recursion.resolve() would answer REFUSED without asking anyone is answered
+// REFUSED by the kernel and never enters miss_idx.  NULL region_domain removes the filter.
+int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, const char* const* dc_names, uint32_t n_dc,
+                                   int ptr_forwardable) {
+    if (!e || (n_dc && !dc_names) || n_dc > bb::RF_MAX_DC) return BB_ERR_ARG;
+    bb::EngineConst& C = e->hconst;
+    if (!region_domain) {
+        if (C.recursion) C.recursion = 1;
+    } else {
+        if (!C.recursion) return BB_ERR_ARG;                       // the engine was created without recursion
+        const size_t L = strlen(region_domain);
+        if (L > 255) return BB_ERR_ARG;
+        for (uint32_t k = 0; k < n_dc; k++) { const size_t l = dc_names[k] ? strlen(dc_names[k]) : 0; if (l < 1 || l > 63) return BB_ERR_ARG; }
+        C.rf_dom_len = (uint32_t)L; memset(C.rf_dom, 0, sizeof C.rf_dom); memcpy(C.rf_dom, region_domain, L);
+        C.rf_ndc = n_dc; memset(C.rf_dc, 0, sizeof C.rf_dc); memset(C.rf_dc_len, 0, sizeof C.rf_dc_len);
+        for (uint32_t k = 0; k < n_dc; k++) { C.rf_dc_len[k] = (uint8_t)strlen(dc_names[k]); memcpy(C.rf_dc[k], dc_names[k], C.rf_dc_len[k]); }
+        C.rf_ptr = ptr_forwardable ? 1 : 0;
+        C.recursion = 2;
+    }
+    CK(cudaSetDevice(e->device));
+    CK(cudaDeviceSynchronize());                                   // batches in flight finish with the old filter
+    CK(cudaMemcpy(e->d_const, &e->hconst, sizeof(bb::EngineConst), cudaMemcpyHostToDevice));
     return BB_OK;
 }
 int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }

@@ -150,7 +150,17 @@ struct EngineConst {
     uint8_t  suffix[256];        // '.' + dnsDomain, as query.name() would spell it
     uint8_t  soa[528];           // mname wire + rname wire of SOARecord(dnsDomain) (:286-287)
     uint8_t  wire_tail[256];     // dnsDomain as wire labels (no terminator), right-aligned: ends at wire_tail[256]
+    // recursion pre-filter (lib/recursion.js:329-344; engaged when `recursion` == 2): which misses
+    // Recursion.resolve() would forward at all
+    uint32_t rf_dom_len;         // strlen(recursion's dnsDomain), compared case-sensitively as a string suffix
+    uint32_t rf_ndc;             // datacenters with at least one upstream resolver that is not this host
+    uint32_t rf_ptr;             // a PTR miss has somewhere to go (any such upstream in any datacenter)
+    uint32_t rf_pad;
+    uint8_t  rf_dom[256];        // that domain, dotted
+    uint8_t  rf_dc_len[16];
+    uint8_t  rf_dc[16][64];      // datacenter names (self.dcs keys), case-sensitive
 };
+constexpr uint32_t RF_MAX_DC = 16;
 
 // host-side container of a built zone
 struct ZoneImage {

@@ -113,6 +113,15 @@ class Engine(object):
         """After zone.apply(): upload only the changed slots and the arena tail (bb_engine_apply_update)."""
         check(lib().bb_engine_apply_update(self._h, zone._h))
 
+    def set_recursion_filter(self, region_domain, dcs=(), ptr=False):
+        """Misses lib/recursion.js:329-344 would refuse without asking anyone are answered REFUSED on the
+        device instead of entering the miss list (bb_engine_set_recursion_filter).  None removes it."""
+        if region_domain is None:
+            check(lib().bb_engine_set_recursion_filter(self._h, None, None, 0, 0))
+            return
+        arr = (ctypes.c_char_p * max(len(dcs), 1))(*[d.encode('latin-1') for d in dcs])
+        check(lib().bb_engine_set_recursion_filter(self._h, region_domain.encode('latin-1'), arr, len(dcs), int(ptr)))
+
     def is_ready(self):
         return bool(lib().bb_engine_is_ready(self._h))
 

@@ -125,6 +125,20 @@ int bb_engine_swap_zone(bb_engine* e, const bb_zone* z);
  * the table had to be laid out again, the arena outgrew its device allocation, or another engine took the zone's
  * previous changes (a zone feeds ONE engine incrementally). */
 int bb_engine_apply_update(bb_engine* e, bb_zone* z);
+/*
+ * Recursion pre-filter.  Recursion.resolve() (lib/recursion.js:285-388) refuses a
+ * handed-off miss without asking anyone when the name is outside its dnsDomain (:330-333), when the label in front
+ * of that suffix is not a datacenter it knows (:338-343), or when every upstream of that datacenter is this host
+ * itself (:360-379).  With a filter set, the kernel evaluates those string operations on query.name() exactly as
+ * the reference does and answers such misses REFUSED itself (the same bytes recursion.js would send); only misses
+ * that have somewhere to go enter miss_idx.
+ *   region_domain     Recursion's opts.dnsDomain (case-sensitive string suffix; NULL removes the filter)
+ *   dc_names[n_dc]    keys of self.dcs that keep at least one upstream after the own-address filter (n_dc <= 16)
+ *   ptr_forwardable   any such upstream exists (a PTR miss asks every datacenter, :346-354)
+ * The host refreshes it whenever lib/recursion.js refreshes self.dcs (:205-240).  Requires opts.recursion.
+ */
+int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, const char* const* dc_names,
+                                   uint32_t n_dc, int ptr_forwardable);
 int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/zk.js:55-58 */
 
 /*

@@ -332,6 +332,20 @@ class Options(object):
         self.dnsDomain = dnsDomain
         self.datacenterName = datacenterName
         self.recursion = recursion
+        self.recursion_filter = None        # (region dnsDomain, forwardable dc names, ptr forwardable) or None
+
+
+def recursion_forwards(flt, domain, is_ptr):
+    """lib/recursion.js:329-344,377-379: would Recursion.resolve() forward this miss anywhere?  `domain` is
+    query.name() as received."""
+    dns_domain, dcs, ptr = flt
+    if is_ptr:
+        return bool(ptr)                                        # :346-354: every datacenter's resolvers
+    if domain.find(dns_domain, max(len(domain) - len(dns_domain), 0)) == -1:
+        return False                                            # :330-333
+    p = domain[:max(len(domain) - len(dns_domain) - 1, 0)]     # :338-339
+    dc = p[p.rfind('.') + 1:]                                   # :340
+    return dc in dcs                                            # :341-343
 
 
 def encodable(name):
@@ -374,6 +388,9 @@ def resolve_ptr(options, name, rd, resp):
     node = zk.reverseLookup(ip)
     if not node:
         if options.recursion and rd:
+            if options.recursion_filter and not recursion_forwards(options.recursion_filter, name, True):
+                resp.setError('refused')
+                return resp
             resp.status = MISS_RECURSE
             return resp
         resp.setError('refused')
@@ -422,6 +439,9 @@ def resolve(options, name, qtype, rd, resp, seed, qidx):
     node = zk.lookup(domain)
     if not node:
         if options.recursion and rd:
+            if options.recursion_filter and not recursion_forwards(options.recursion_filter, name, False):
+                resp.setError('refused')
+                return resp
             resp.status = MISS_RECURSE
             return resp
         resp.setError('refused')

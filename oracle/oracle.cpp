@@ -554,10 +554,29 @@ struct Responder {
 // ---------------------------------------------------------------------------------------
 // lib/server.js restated
 // ---------------------------------------------------------------------------------------
+// Recursion.resolve()'s quick rejects (lib/recursion.js:329-344,377-379) as a pre-filter on misses: would
+// the miss be forwarded anywhere?  dcs = the keys of self.dcs that keep an upstream after the own-address
+// filter (:360-379); ptr = any such upstream exists (PTR asks every datacenter, :346-354).
+struct RecursionFilter {
+    bool enabled = false, ptr = false;
+    std::string dnsDomain;
+    std::vector<std::string> dcs;
+    bool forwards(const std::string& domain, bool is_ptr) const {
+        if (is_ptr) return ptr;
+        long from = (long)domain.size() - (long)dnsDomain.size();             // indexOf clamps a negative start to 0
+        if (domain.find(dnsDomain, (size_t)(from < 0 ? 0 : from)) == std::string::npos) return false;   // :330-333
+        long end = (long)domain.size() - (long)dnsDomain.size() - 1;           // substring clamps it too
+        std::string p = domain.substr(0, (size_t)(end < 0 ? 0 : end));         // :338-339
+        size_t dot = p.rfind('.');
+        std::string dc = p.substr(dot == std::string::npos ? 0 : dot + 1);     // :340
+        return std::find(dcs.begin(), dcs.end(), dc) != dcs.end();             // :341-343
+    }
+};
 struct Options {
     ZKCache* zkCache = nullptr;
     std::string dnsDomain, datacenterName;
     bool recursion = false;
+    RecursionFilter rf;
 };
 
 uint32_t fmix32(uint32_t x) { x ^= x >> 16; x *= 0x85EBCA6Bu; x ^= x >> 13; x *= 0xC2B2AE35u; x ^= x >> 16; return x; }
@@ -599,7 +618,10 @@ void resolvePtr(const Options& o, const Query& q, Responder& r) {               
     if (!o.zkCache || !o.zkCache->isReady()) { r.setError(RC_SERVFAIL); return; }
     const TreeNode* node = o.zkCache->reverseLookup(ip);
     if (!node) {
-        if (o.recursion && q.rd) { r.status = ST_MISS_RECURSE; return; }
+        if (o.recursion && q.rd) {
+            if (o.rf.enabled && !o.rf.forwards(q.name, true)) { r.setError(RC_REFUSED); return; }   // recursion.js would refuse
+            r.status = ST_MISS_RECURSE; return;
+        }
         r.setError(RC_REFUSED); return;
     }
     uint32_t ttl;
@@ -648,7 +670,10 @@ void resolve(const Options& o, const Query& q, Responder& r, uint64_t seed, uint
         if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '.' || c == '-')) { r.setError(RC_REFUSED); return; }
     const TreeNode* node = o.zkCache->lookup(domain);
     if (!node) {
-        if (o.recursion && q.rd) { r.status = ST_MISS_RECURSE; return; }
+        if (o.recursion && q.rd) {
+            if (o.rf.enabled && !o.rf.forwards(q.name, false)) { r.setError(RC_REFUSED); return; }  // recursion.js would refuse
+            r.status = ST_MISS_RECURSE; return;
+        }
         r.setError(RC_REFUSED); return;
     }
     const JVal& record = node->tn_data;
@@ -762,6 +787,15 @@ int orc_load_snapshot(void* h, const char* buf, size_t len) {
     if (zk->load(buf, len) != 0) return -1;
     e->zk = std::move(zk);
     e->opt.zkCache = e->zk.get();
+    return 0;
+}
+// Recursion pre-filter (see RecursionFilter); region_domain NULL removes it.
+int orc_set_recursion_filter(void* h, const char* region_domain, const char* const* dcs, uint32_t n, int ptr) {
+    Engine* e = (Engine*)h;
+    e->opt.rf = RecursionFilter();
+    if (!region_domain) return 0;
+    e->opt.rf.enabled = true; e->opt.rf.ptr = ptr != 0; e->opt.rf.dnsDomain = region_domain;
+    for (uint32_t i = 0; i < n; i++) e->opt.rf.dcs.push_back(dcs[i]);
     return 0;
 }
 // Watch events on the loaded cache (see ZKCache::apply).

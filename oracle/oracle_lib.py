@@ -34,6 +34,7 @@ def lib():
         L.orc_create.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
         L.orc_destroy.argtypes = [ctypes.c_void_p]
         L.orc_load_snapshot.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.orc_set_recursion_filter.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_int]
         L.orc_apply_delta.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
         L.orc_node_count.restype = ctypes.c_long
         L.orc_node_count.argtypes = [ctypes.c_void_p]
@@ -57,6 +58,14 @@ class Oracle(object):
         rc = lib().orc_load_snapshot(self._h, jsonl, len(jsonl))
         if rc != 0:
             raise ValueError('oracle: bad snapshot (%d)' % rc)
+
+    def set_recursion_filter(self, region_domain, dcs=(), ptr=False):
+        """Misses lib/recursion.js:329-344 would refuse without asking anyone are answered REFUSED."""
+        if region_domain is None:
+            lib().orc_set_recursion_filter(self._h, None, None, 0, 0)
+            return
+        arr = (ctypes.c_char_p * max(len(dcs), 1))(*[d.encode('latin-1') for d in dcs])
+        lib().orc_set_recursion_filter(self._h, region_domain.encode('latin-1'), arr, len(dcs), int(ptr))
 
     def apply_delta(self, jsonl):
         """Watch events on the loaded cache (JSON lines; see ZKCache::apply in oracle.cpp)."""
