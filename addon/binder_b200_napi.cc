@@ -86,6 +86,27 @@ static napi_value EngineApplyUpdate(napi_env env, napi_callback_info info) {
     return nullptr;
 }
 
+// engineSetRecursionFilter(engine, regionDomain: string | null, dcNames: string[], ptrForwardable: boolean)
+static napi_value EngineSetRecursionFilter(napi_env env, napi_callback_info info) {
+    size_t argc = 4; napi_value argv[4];
+    NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    void* e; NAPI_OK(napi_get_value_external(env, argv[0], &e));
+    napi_valuetype t; NAPI_OK(napi_typeof(env, argv[1], &t));
+    if (t != napi_string) { int rc0 = bb_engine_set_recursion_filter((bb_engine*)e, nullptr, nullptr, 0, 0); return rc0 == BB_OK ? nullptr : Throw(env, rc0); }
+    char dom[256]; size_t dl; NAPI_OK(napi_get_value_string_utf8(env, argv[1], dom, sizeof dom, &dl));
+    uint32_t n = 0; NAPI_OK(napi_get_array_length(env, argv[2], &n));
+    if (n > 16) return Throw(env, BB_ERR_ARG);
+    char names[16][64]; const char* ptrs[16];
+    for (uint32_t i = 0; i < n; i++) {
+        napi_value v; size_t l; NAPI_OK(napi_get_element(env, argv[2], i, &v));
+        NAPI_OK(napi_get_value_string_utf8(env, v, names[i], sizeof names[i], &l)); ptrs[i] = names[i];
+    }
+    bool ptr = false; napi_get_value_bool(env, argv[3], &ptr);
+    int rc = bb_engine_set_recursion_filter((bb_engine*)e, dom, ptrs, n, ptr ? 1 : 0);
+    if (rc != BB_OK) return Throw(env, rc);
+    return nullptr;
+}
+
 // resolveBatch(engine, pkts: Buffer, pktOff: Uint32Array(n+1), seed: BigInt) -> result object
 static napi_value ResolveBatch(napi_env env, napi_callback_info info) {
     size_t argc = 4; napi_value argv[4];
@@ -122,6 +143,7 @@ static napi_value Init(napi_env env, napi_value exports) {
         { "engineSwapZone", nullptr, EngineSwapZone, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "zoneApply", nullptr, ZoneApply, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "engineApplyUpdate", nullptr, EngineApplyUpdate, nullptr, nullptr, nullptr, napi_default, nullptr },
+        { "engineSetRecursionFilter", nullptr, EngineSetRecursionFilter, nullptr, nullptr, nullptr, napi_default, nullptr },
         { "resolveBatch", nullptr, ResolveBatch, nullptr, nullptr, nullptr, napi_default, nullptr },
     };
     napi_define_properties(env, exports, sizeof d / sizeof d[0], d);

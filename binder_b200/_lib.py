@@ -33,6 +33,12 @@ SYMBOLS = {
                                      _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                      _c.c_void_p, _c.c_void_p]),
     'bb_resolve_wait': (_c.c_int, [_c.c_void_p, _c.c_int]),
+    'bb_resolve_batch_ex': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64, _c.c_uint32,
+                                       _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                       _c.c_void_p, _c.c_uint32]),
+    'bb_resolve_submit_ex': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,
+                                        _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                        _c.c_void_p, _c.c_void_p, _c.c_uint32]),
     'bb_resolve_batch_device': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,
                                            _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p,
                                            _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),

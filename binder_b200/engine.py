@@ -129,24 +129,25 @@ class Engine(object):
         return int(lib().bb_engine_launch_count(self._h))
 
     # -- host-buffer path (bb_resolve_batch) -------------------------------------------------
-    def resolve_batch(self, data, off, seed=0, qidx_base=0, out_cap=None):
+    def resolve_batch(self, data, off, seed=0, qidx_base=0, out_cap=None, tcp=False):
         """data: uint8[...] packed packets, off: uint32[n+1] ->
         (out uint8[total], out_off uint32[n+1], out_len uint16[n], status uint8[n], miss uint32[m]);
-        response i = out[out_off[i] : out_off[i] + out_len[i]]"""
+        response i = out[out_off[i] : out_off[i] + out_len[i]].  tcp: the batch arrived over TCP
+        (BB_BATCH_TCP: no UDP size limit)."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n = len(off) - 1
         if out_cap is None:
-            out_cap = max(4096, min(n * 1232, 0xFFFFFF00))
+            out_cap = max(4096, min(n * (16384 if tcp else 1232), 0xFFFFFF00))
         out = np.empty(out_cap, dtype=np.uint8)
         out_off = np.zeros(n + 1, dtype=np.uint32)
         out_len = np.zeros(max(n, 1), dtype=np.uint16)
         status = np.zeros(max(n, 1), dtype=np.uint8)
         miss = np.zeros(max(n, 1), dtype=np.uint32)
         n_miss = ctypes.c_uint32(0)
-        check(lib().bb_resolve_batch(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
-                                     out.ctypes.data, out_cap, out_off.ctypes.data, out_len.ctypes.data,
-                                     status.ctypes.data, miss.ctypes.data, ctypes.byref(n_miss)))
+        check(lib().bb_resolve_batch_ex(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
+                                        out.ctypes.data, out_cap, out_off.ctypes.data, out_len.ctypes.data,
+                                        status.ctypes.data, miss.ctypes.data, ctypes.byref(n_miss), 1 if tcp else 0))
         return out[:out_off[n]].copy(), out_off, out_len[:n], status[:n], miss[:n_miss.value].copy()
 
     # -- device-buffer path (bb_resolve_batch_device); pointers are raw device addresses ------

@@ -176,6 +176,23 @@ int bb_resolve_submit(bb_engine* e, int slot, const uint8_t* pkts, const uint32_
 int bb_resolve_wait(bb_engine* e, int slot);
 
 /*
+ * Batches that arrived over TCP (mname's listenTcp, lib/server.js:643-652; RFC 1035 4.2.2 two-byte length framing is
+ * the host's job — binder_b200/server.py mirrors it): flags = BB_BATCH_TCP lifts the 512-byte / EDNS size limit, a
+ * response may be up to 65,535 bytes and is truncated (TC) only beyond that.  flags = 0 is bb_resolve_batch/submit.
+ * out_cap must allow for the larger answers (BB_ERR_CAPACITY otherwise; the engine's own staging holds 512 bytes
+ * per query of max_batch on average).
+ */
+#define BB_BATCH_TCP 1u
+int bb_resolve_batch_ex(bb_engine* e, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
+                        uint64_t shuffle_seed, uint32_t qidx_base,
+                        uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
+                        uint32_t* miss_idx, uint32_t* n_miss, uint32_t flags);
+int bb_resolve_submit_ex(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
+                         uint64_t shuffle_seed, uint32_t qidx_base,
+                         uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len, uint8_t* status,
+                         uint32_t* miss_idx, uint32_t* n_miss, uint32_t flags);
+
+/*
  * Device-resident form (inputs and outputs already in HBM; used for kernel-only timing and
  * by the multi-GPU router).  All pointers are device pointers; d_pkts must be 16-byte
  * aligned and readable up to the next multiple of 16 past pkt_off[n]; d_out must be 16-byte

@@ -406,6 +406,7 @@ struct Query {
     uint16_t qtype, qclass;
     uint32_t q_end;                     // end of question section
     bool edns; uint16_t adv;
+    bool tcp = false;                   // arrived over TCP: no UDP size limit (RFC 1035 4.2.2)
     bool label_dot;
     std::string name;                   // query.name(): labels joined by '.', latin-1 bytes
 };
@@ -510,6 +511,7 @@ struct Responder {
         int rc = rcode >= 0 ? rcode : (n_answers ? RC_NOERROR : RC_NOTIMP);
         size_t maxsz = 512;
         if (q.edns) maxsz = std::min<size_t>(std::max<size_t>(q.adv, 512), 1200);
+        if (q.tcp) maxsz = 65535;
         std::vector<uint8_t> fixed(12, 0);
         fixed.insert(fixed.end(), q.pkt + 12, q.pkt + q.q_end);         // question echoed verbatim
         std::vector<uint8_t> opt;
@@ -807,10 +809,12 @@ int orc_apply_delta(void* h, const char* buf, size_t len) {
 long orc_node_count(void* h) { Engine* e = (Engine*)h; return e->zk ? (long)e->zk->nodes.size() : 0; }
 
 // Same batch container as bb_resolve_batch (include/binder_b200.h).  nthreads<=1: scalar.
-int orc_resolve_batch(void* h, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
-                      uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
-                      uint32_t* miss_idx, uint32_t* n_miss, int nthreads) {
+// flags: 1 = the batch arrived over TCP
+int orc_resolve_batch_ex(void* h, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
+                         uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                         uint32_t* miss_idx, uint32_t* n_miss, int nthreads, uint32_t flags) {
     Engine* e = (Engine*)h;
+    const bool tcp = (flags & 1u) != 0;
     if (nthreads < 1) nthreads = 1;
     if ((uint32_t)nthreads > n) nthreads = n ? (int)n : 1;
     struct Part { std::vector<uint8_t> bytes; std::vector<uint32_t> lens; };
@@ -818,15 +822,17 @@ int orc_resolve_batch(void* h, const uint8_t* pkts, const uint32_t* pkt_off, uin
     auto work = [&](int t) {
         uint32_t lo = (uint32_t)((uint64_t)n * t / nthreads), hi = (uint32_t)((uint64_t)n * (t + 1) / nthreads);
         Part& P = parts[t]; P.lens.resize(hi - lo);
-        uint8_t tmp[1300];
+        std::vector<uint8_t> tmpv(tcp ? 65536 : 1300);
+        uint8_t* const tmp = tmpv.data();
         for (uint32_t i = lo; i < hi; i++) {
             Query q; size_t w = 0;
             if (!decode(pkts + pkt_off[i], pkt_off[i + 1] - pkt_off[i], q)) status[i] = ST_DROPPED;
             else {
+                q.tcp = tcp;
                 Responder r(q);
                 onQuery(e->opt, q, r, seed, qidx_base + i);
                 status[i] = (uint8_t)r.status;
-                if (r.status == ST_ANSWERED) w = r.encode(tmp, sizeof tmp);
+                if (r.status == ST_ANSWERED) w = r.encode(tmp, tmpv.size());
             }
             P.lens[i - lo] = (uint32_t)w;
             P.bytes.insert(P.bytes.end(), tmp, tmp + w);
@@ -844,6 +850,11 @@ int orc_resolve_batch(void* h, const uint8_t* pkts, const uint32_t* pkt_off, uin
     out_off[n] = (uint32_t)pos;
     *n_miss = nm;
     return 0;
+}
+int orc_resolve_batch(void* h, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
+                      uint32_t qidx_base, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint8_t* status,
+                      uint32_t* miss_idx, uint32_t* n_miss, int nthreads) {
+    return orc_resolve_batch_ex(h, pkts, pkt_off, n, seed, qidx_base, out, out_cap, out_off, status, miss_idx, n_miss, nthreads, 0);
 }
 
 }  // extern "C"

@@ -42,6 +42,7 @@ def lib():
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64,
             ctypes.c_uint32, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        L.orc_resolve_batch_ex.argtypes = L.orc_resolve_batch.argtypes + [ctypes.c_uint32]
         _lib = L
     return _lib
 
@@ -78,23 +79,23 @@ class Oracle(object):
     def node_count(self):
         return lib().orc_node_count(self._h)
 
-    def resolve_batch(self, data, off, seed=0, qidx_base=0, nthreads=1, out_cap=None):
+    def resolve_batch(self, data, off, seed=0, qidx_base=0, nthreads=1, out_cap=None, tcp=False):
         """data: uint8 array of packed packets, off: uint32[n+1].
         Returns (out uint8[total], out_off uint32[n+1], out_len uint16[n], status uint8[n], miss uint32[m])."""
         data = np.ascontiguousarray(data, dtype=np.uint8)
         off = np.ascontiguousarray(off, dtype=np.uint32)
         n = len(off) - 1
         if out_cap is None:
-            out_cap = max(1, min(n * 1232, 0xFFFFFFF0))
+            out_cap = max(1, min(n * (65536 if tcp else 1232), 0xFFFFFFF0))
         out = np.empty(out_cap, dtype=np.uint8)
         out_off = np.zeros(n + 1, dtype=np.uint32)
         status = np.zeros(max(n, 1), dtype=np.uint8)
         miss = np.zeros(max(n, 1), dtype=np.uint32)
         n_miss = ctypes.c_uint32(0)
-        rc = lib().orc_resolve_batch(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
-                                     out.ctypes.data, out_cap, out_off.ctypes.data,
-                                     status.ctypes.data, miss.ctypes.data, ctypes.byref(n_miss),
-                                     nthreads)
+        rc = lib().orc_resolve_batch_ex(self._h, data.ctypes.data, off.ctypes.data, n, seed, qidx_base,
+                                        out.ctypes.data, out_cap, out_off.ctypes.data,
+                                        status.ctypes.data, miss.ctypes.data, ctypes.byref(n_miss),
+                                        nthreads, 1 if tcp else 0)
         if rc != 0:
             raise RuntimeError('oracle resolve failed (%d)' % rc)
         lens = np.diff(out_off.astype(np.int64)).astype(np.uint16)

@@ -13,11 +13,11 @@ pytestmark = pytest.mark.gpu
 from binder_b200.engine import repack
 
 
-def assert_same(gpu, orc, data, off, seed=0, qidx_base=0):
+def assert_same(gpu, orc, data, off, seed=0, qidx_base=0, **kw):
     """GPU result == oracle result: status, every response's bytes, the miss set — and in
     ordered mode also the exact layout (offsets, packed bytes, ascending miss list)."""
-    out, ooff, olen, status, miss = gpu.resolve_batch(data, off, seed=seed, qidx_base=qidx_base)
-    o_out, o_off, o_len, o_status, o_miss = orc.resolve_batch(data, off, seed=seed, qidx_base=qidx_base)
+    out, ooff, olen, status, miss = gpu.resolve_batch(data, off, seed=seed, qidx_base=qidx_base, **kw)
+    o_out, o_off, o_len, o_status, o_miss = orc.resolve_batch(data, off, seed=seed, qidx_base=qidx_base, **kw)
     n = len(off) - 1
     bad = np.nonzero(status != o_status)[0]
     assert bad.size == 0, ('status differs at', bad[:5], status[bad[:5]], o_status[bad[:5]])
