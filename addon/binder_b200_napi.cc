@@ -107,17 +107,19 @@ static napi_value EngineSetRecursionFilter(napi_env env, napi_callback_info info
     return nullptr;
 }
 
-// resolveBatch(engine, pkts: Buffer, pktOff: Uint32Array(n+1), seed: BigInt) -> result object
+// resolveBatch(engine, pkts: Buffer, pktOff: Uint32Array(n+1), seed: BigInt[, tcp: boolean]) -> result object
 static napi_value ResolveBatch(napi_env env, napi_callback_info info) {
-    size_t argc = 4; napi_value argv[4];
+    size_t argc = 5; napi_value argv[5];
     NAPI_OK(napi_get_cb_info(env, info, &argc, argv, nullptr, nullptr));
+    bool tcp = false;                              // optional 5th argument: the batch arrived over TCP
+    if (argc > 4) napi_get_value_bool(env, argv[4], &tcp);
     void* e; NAPI_OK(napi_get_value_external(env, argv[0], &e));
     void* pk; size_t pklen; NAPI_OK(napi_get_buffer_info(env, argv[1], &pk, &pklen));
     napi_typedarray_type tt; size_t offn; void* offp; napi_value ab; size_t bo;
     NAPI_OK(napi_get_typedarray_info(env, argv[2], &tt, &offn, &offp, &ab, &bo));
     uint64_t seed = 0; bool lossless; napi_get_value_bigint_uint64(env, argv[3], &seed, &lossless);
     const uint32_t n = (uint32_t)offn - 1;
-    const uint32_t cap = n * 1232u;
+    const uint32_t cap = n * (tcp ? 16384u : 1232u);
     void *out, *oo, *ol, *st, *ms; napi_value o_out, a_oo, a_ol, a_st, a_ms, t_oo, t_ol, t_st, t_ms;
     NAPI_OK(napi_create_buffer(env, cap, &out, &o_out));
     NAPI_OK(napi_create_arraybuffer(env, (n + 1) * 4, &oo, &a_oo)); NAPI_OK(napi_create_typedarray(env, napi_uint32_array, n + 1, a_oo, 0, &t_oo));
@@ -125,8 +127,8 @@ static napi_value ResolveBatch(napi_env env, napi_callback_info info) {
     NAPI_OK(napi_create_arraybuffer(env, n, &st, &a_st));           NAPI_OK(napi_create_typedarray(env, napi_uint8_array, n, a_st, 0, &t_st));
     NAPI_OK(napi_create_arraybuffer(env, n * 4, &ms, &a_ms));
     uint32_t nmiss = 0;
-    int rc = bb_resolve_batch((bb_engine*)e, (const uint8_t*)pk, (const uint32_t*)offp, n, seed, 0, (uint8_t*)out, cap,
-                              (uint32_t*)oo, (uint16_t*)ol, (uint8_t*)st, (uint32_t*)ms, &nmiss);
+    int rc = bb_resolve_batch_ex((bb_engine*)e, (const uint8_t*)pk, (const uint32_t*)offp, n, seed, 0, (uint8_t*)out, cap,
+                                 (uint32_t*)oo, (uint16_t*)ol, (uint8_t*)st, (uint32_t*)ms, &nmiss, tcp ? BB_BATCH_TCP : 0u);
     if (rc != BB_OK) return Throw(env, rc);
     NAPI_OK(napi_create_typedarray(env, napi_uint32_array, nmiss, a_ms, 0, &t_ms));
     napi_value res; NAPI_OK(napi_create_object(env, &res));
