@@ -57,6 +57,14 @@ SYMBOLS = {
                                   _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     'bb_shard_host_results': (_c.c_int, [_c.c_void_p, _c.c_int]),
     'bb_shard_results': (_c.c_int, [_c.c_void_p, _c.c_uint32] + [_c.c_void_p] * 9),
+    'bb_frames_parse': (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
+                                   _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p]),
+    'bb_frames_build': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_uint32,
+                                   _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    'bb_backend_create': (_c.c_void_p, [_c.c_void_p, _c.c_uint32, _c.POINTER(_c.c_int)]),
+    'bb_backend_destroy': (None, [_c.c_void_p]),
+    'bb_backend_feed': (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_uint64, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
+    'bb_backend_stat': (_c.c_uint64, [_c.c_void_p, _c.c_int]),
     'bb_host_alloc': (_c.c_void_p, [_c.c_size_t]),
     'bb_host_free': (None, [_c.c_void_p]),
 }

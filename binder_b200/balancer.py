@@ -107,3 +107,84 @@ class Backend(object):
                 i = int(i)
                 self.recursion.resolve(bytes(data[off[i]:off[i + 1]]), (int(ips[i]), int(ports[i])))
         return build_frames(out, out_off, out_len, status, ips, ports, control)
+
+
+# ---- the same protocol, natively (csrc/balancer_frames.cpp) ---------------------------------------------
+def parse_frames_native(buf, cap_n=1 << 16, cap_bytes=1 << 22, cap_ctrl=64):
+    """bb_frames_parse -> (data u8, off u32[n+1], src_ip, src_port, control list, consumed, rc)"""
+    import ctypes
+    from ._lib import lib
+    buf = bytes(buf)
+    data = np.zeros(cap_bytes + 32, dtype=np.uint8); off = np.zeros(cap_n + 1, dtype=np.uint32)
+    ips = np.zeros(max(cap_n, 1), dtype=np.uint32); ports = np.zeros(max(cap_n, 1), dtype=np.uint32)
+    ctrl = np.zeros(max(cap_ctrl, 1), dtype=np.uint32)
+    n, nc, used = ctypes.c_uint32(0), ctypes.c_uint32(0), ctypes.c_size_t(0)
+    rc = lib().bb_frames_parse(buf, len(buf), data.ctypes.data, cap_bytes, off.ctypes.data, ips.ctypes.data, ports.ctypes.data,
+                               cap_n, ctypes.byref(n), ctrl.ctypes.data, cap_ctrl, ctypes.byref(nc), ctypes.byref(used))
+    n = n.value
+    return data[:(int(off[n]) + 15) // 16 * 16 + 16], off[:n + 1], ips[:n], ports[:n], [int(x) for x in ctrl[:nc.value]], used.value, rc
+
+
+def build_frames_native(out, out_off, out_len, status, dst_ip, dst_port, control=()):
+    """bb_frames_build -> bytes"""
+    import ctypes
+    from ._lib import check, lib
+    n = len(status)
+    a = lambda x, dt: np.ascontiguousarray(x, dtype=dt)
+    out, out_off, out_len, status = a(out, np.uint8), a(out_off, np.uint32), a(out_len, np.uint16), a(status, np.uint8)
+    dst_ip, dst_port, control = a(dst_ip, np.uint32), a(dst_port, np.uint32), a(list(control), np.uint32)
+    need = ctypes.c_size_t(0)
+    p = lambda x: x.ctypes.data if x.size else None
+    args = (p(out), p(out_off), p(out_len), p(status), p(dst_ip), p(dst_port), n, p(control), len(control))
+    rc = lib().bb_frames_build(*args, None, 0, ctypes.byref(need))
+    if need.value == 0:
+        return b''
+    buf = np.zeros(need.value, dtype=np.uint8)
+    check(lib().bb_frames_build(*args, buf.ctypes.data, buf.size, ctypes.byref(need)))
+    return buf.tobytes()
+
+
+class NativeBackend(object):
+    """bb_backend: one balancer session in the C library (frames in -> bb_resolve_batch -> frames out)."""
+
+    def __init__(self, engine, max_batch=1 << 14):
+        import ctypes
+        from ._lib import BinderError, lib
+        err = ctypes.c_int(0)
+        self._h = lib().bb_backend_create(engine._h, max_batch, ctypes.byref(err))
+        if not self._h:
+            raise BinderError(err.value)
+        self._engine = engine
+
+    def feed(self, chunk, seed):
+        """-> (bytes to write back, [(packet, src_ip, src_port)] handed to recursion)"""
+        import ctypes
+        from ._lib import check, lib
+
+        class Misses(ctypes.Structure):
+            _fields_ = [('n', ctypes.c_uint32), ('pkts', ctypes.POINTER(ctypes.c_uint8)), ('pkt_off', ctypes.POINTER(ctypes.c_uint32)),
+                        ('src_ip', ctypes.POINTER(ctypes.c_uint32)), ('src_port', ctypes.POINTER(ctypes.c_uint32))]
+        chunk = bytes(chunk)
+        out, out_len, m = ctypes.POINTER(ctypes.c_uint8)(), ctypes.c_size_t(0), Misses()
+        check(lib().bb_backend_feed(self._h, chunk, len(chunk), seed, ctypes.byref(out), ctypes.byref(out_len), ctypes.byref(m)))
+        data = ctypes.string_at(out, out_len.value) if out_len.value else b''
+        misses = [(ctypes.string_at(ctypes.addressof(m.pkts.contents) + m.pkt_off[i], m.pkt_off[i + 1] - m.pkt_off[i]),
+                   int(m.src_ip[i]), int(m.src_port[i])) for i in range(m.n)]
+        return data, misses
+
+    def stats(self):
+        from ._lib import lib
+        keys = ('udp', 'answered', 'missed', 'dropped', 'pending_bytes')
+        return {k: int(lib().bb_backend_stat(self._h, i)) for i, k in enumerate(keys)}
+
+    def close(self):
+        from ._lib import lib
+        if getattr(self, '_h', None):
+            lib().bb_backend_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

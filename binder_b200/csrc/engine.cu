@@ -1474,6 +1474,7 @@ const char* bb_strerror(int err) {
     case BB_ERR_CAPACITY: return "output capacity too small for this batch";
     case BB_ERR_NO_DEVICE: return "no CUDA device (binder_b200 has no CPU fallback)";
     case BB_ERR_DOMAIN: return "dns_domain must be a lower-case, encodable DNS name";
+    case BB_ERR_PROTOCOL: return "balancer frame stream: unknown frame type, INBOUND_TCP, or oversized packet";
     }
     return "unknown error";
 }

@@ -31,7 +31,8 @@ enum {
     BB_ERR_NOMEM = -4,      /* host or device allocation failed                          */
     BB_ERR_CAPACITY = -5,   /* out_cap too small for this batch's responses              */
     BB_ERR_NO_DEVICE = -6,  /* no CUDA device: there is NO CPU fallback                   */
-    BB_ERR_DOMAIN = -7      /* dns_domain is not an encodable DNS name                   */
+    BB_ERR_DOMAIN = -7,     /* dns_domain is not an encodable DNS name                   */
+    BB_ERR_PROTOCOL = -8    /* balancer frame stream: unknown type, INBOUND_TCP, oversized packet */
 };
 const char* bb_strerror(int err);
 const char* bb_last_cuda_error(void);
@@ -273,6 +274,42 @@ int bb_shard_host_results(bb_shard* s, int enable);
 int bb_shard_results(bb_shard* s, uint32_t src, const uint8_t** out, const uint32_t** out_off,
                      const uint16_t** out_len, const uint8_t** status, const uint32_t** qidx,
                      const uint32_t** miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
+
+/* ---- mname-balancer backend frames -------------------------------------
+ * The balancer relays UDP packets to a backend over an AF_UNIX stream as frames of little-endian u32 words
+ * (deps/mname-balancer/backend.c:22-113, bbal.h:80-87): INBOUND_UDP {2, src ip, src port, len, bytes} in,
+ * OUTBOUND_UDP {1002, dst ip, dst port, len, bytes} out, HELLO 1 -> 1001, HEARTBEAT 4 -> 1004.
+ *   bb_frames_parse   byte stream -> batch container (+ source addresses, control frames in order).  Only whole
+ *                     frames are consumed (*consumed); stops early when the batch or the control list is full.
+ *                     BB_ERR_PROTOCOL on an unknown type, INBOUND_TCP (which turns the session into a TCP proxy,
+ *                     backend.c:60-75) or a packet over 1500 bytes (udp_proxy.c:159-170) — what was parsed before
+ *                     it is still returned.
+ *   bb_frames_build   results -> one SERVER_HELLO/HEARTBEAT per control frame, then an OUTBOUND_UDP frame per answered
+ *                     query (misses and drops produce no frame).  *out_len = bytes needed; BB_ERR_CAPACITY if out_cap
+ *                     is smaller (call with out = NULL to size).
+ *   bb_backend_*      a session: feed() the bytes read from the socket, get the bytes to write back; every complete
+ *                     INBOUND_UDP frame fed so far is resolved in batches of up to max_batch through bb_resolve_batch,
+ *                     a partial trailing frame is kept for the next call.  *out and the miss arrays point into the
+ *                     session and stay valid until the next feed.  Handed-off misses (lib/server.js:110-113,222-225)
+ *                     come back as packets + source addresses for the host's recursion.
+ */
+enum { BB_FRAME_CLIENT_HELLO = 1, BB_FRAME_INBOUND_UDP = 2, BB_FRAME_INBOUND_TCP = 3, BB_FRAME_CLIENT_HEARTBEAT = 4,
+       BB_FRAME_SERVER_HELLO = 1001, BB_FRAME_OUTBOUND_UDP = 1002, BB_FRAME_INBOUND_TCP_OK = 1003, BB_FRAME_SERVER_HEARTBEAT = 1004 };
+int bb_frames_parse(const uint8_t* in, size_t in_len, uint8_t* pkts, uint32_t cap_bytes, uint32_t* pkt_off,
+                    uint32_t* src_ip, uint32_t* src_port, uint32_t cap_n, uint32_t* n,
+                    uint32_t* control, uint32_t cap_ctrl, uint32_t* n_ctrl, size_t* consumed);
+int bb_frames_build(const uint8_t* resp, const uint32_t* resp_off, const uint16_t* resp_len, const uint8_t* status,
+                    const uint32_t* dst_ip, const uint32_t* dst_port, uint32_t n, const uint32_t* control, uint32_t n_ctrl,
+                    uint8_t* out, size_t out_cap, size_t* out_len);
+typedef struct bb_backend bb_backend;
+typedef struct bb_backend_misses {
+    uint32_t n; const uint8_t* pkts; const uint32_t* pkt_off /* n+1 */; const uint32_t* src_ip; const uint32_t* src_port;
+} bb_backend_misses;
+bb_backend* bb_backend_create(bb_engine* e, uint32_t max_batch, int* err);
+void        bb_backend_destroy(bb_backend* b);
+int         bb_backend_feed(bb_backend* b, const uint8_t* in, size_t in_len, uint64_t shuffle_seed,
+                            const uint8_t** out, size_t* out_len, bb_backend_misses* misses);
+uint64_t    bb_backend_stat(const bb_backend* b, int what);   /* 0 udp frames 1 answered 2 missed 3 dropped 4 pending bytes */
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);
