@@ -516,7 +516,7 @@ struct bb_zone {
     uint32_t nranks = 1, rank = 0;
     bool relaid = false;             // the table was laid out again since the device last saw it: full upload
     uint64_t arena_synced = 0;       // arena bytes the device already has
-    uint64_t arena_garbage = 0;      // bytes of superseded service / PTR records
+    uint64_t arena_base = 0;         // arena bytes right after the last full layout (no garbage yet)
     uint64_t sync_gen = 0;           // bumped whenever an engine takes the pending changes
 };
 
@@ -651,7 +651,7 @@ int layout(bb_zone& zn) {
     while (T.arena.size() & 15) T.arena.push_back(0);
     Z.arena = T.arena.data(); Z.arena_len = T.arena.size();
     Z.ready = 1;                                              // the root TreeNode exists (lib/zk.js:55-58)
-    zn.relaid = true; zn.arena_synced = 0; zn.arena_garbage = 0;
+    zn.relaid = true; zn.arena_synced = 0; zn.arena_base = Z.arena_len;
     T.dirty.clear(); std::fill(T.dirty_mark.begin(), T.dirty_mark.end(), 0);
     return BB_OK;
 }
@@ -850,8 +850,9 @@ extern "C" int bb_zone_apply(bb_zone* zone, const char* buf, size_t len) {
         return BB_OK;
     });
     if (rc != BB_OK) return rc;
-    // a cuckoo insertion that failed, or a table filling past what two choices sustain: lay it out again
-    if (T.failed || T.count * 100 > (uint64_t)zone->img.nslots * 47) {
+    // a cuckoo insertion that failed, a table filling past what two choices sustain, or an arena that is
+    // mostly superseded records (every re-derived service / PTR record is appended): lay it out again
+    if (T.failed || T.count * 100 > (uint64_t)zone->img.nslots * 47 || T.arena.size() > 2 * zone->arena_base + (16u << 20)) {
         rc = layout(*zone);
         if (rc != BB_OK) return rc;
     }

@@ -76,7 +76,8 @@ uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 re
  *   {"path": P, "deleted": true}    the znode and its subtree are gone (childrenChanged -> unbind, :131-133,195-208;
  *        like the reference, a reverse-map entry the node registered is NOT removed)
  * Only what depends on the touched znodes is re-derived: the node's own key, the reverse entry of its address, its
- * parent's service record.  Superseded arena records become garbage until the next full build.  Deviation: the
+ * parent's service record.  Superseded arena records are garbage until the table is laid out again (which happens
+ * when they outweigh the live records, when the table fills past its load limit, or on a cuckoo failure).  Deviation: the
  * reference re-orders a node's children to ZooKeeper's list on every childrenChanged; here a new child goes last.
  * Returns BB_OK, or BB_ERR_SNAPSHOT for a line that is not a JSON object with a string "path" (earlier lines of
  * the delta stay applied).

@@ -148,3 +148,20 @@ def test_incremental_state_survives_a_relayout(seed):
     assert z.stat()['slots'] > slots0
     after = [z.probe(k) for k in fkeys] + [z.probe(k, reverse=True) for k in rkeys]
     assert before == after
+
+
+def test_arena_garbage_triggers_compaction():
+    """Re-deriving a service record appends to the arena; churn on one service must not grow it without bound."""
+    from binder_b200.engine import Zone
+    kids = [('/com/foo/svc/k%03d' % i, {'type': 'load_balancer', 'load_balancer': {'address': '10.5.0.%d' % i}}) for i in range(200)]
+    z = Zone(H.snapshot(ZONE0 + kids), 'foo.com')
+    a0 = z.stat()['arena_bytes']
+    relaid = 0
+    for rnd in range(6000):                       # each event re-emits the ~7 KB record of /com/foo/svc
+        z.apply(json.dumps({'path': '/com/foo/svc/k%03d' % (rnd % 200), 'data': {'type': 'load_balancer', 'load_balancer': {'address': '10.6.%d.%d' % (rnd >> 8, rnd & 255)}}}))
+        relaid += z.pending()[1]
+    assert z.stat()['arena_bytes'] < 2 * a0 + (17 << 20) and relaid > 0
+    kind, ttl, _, rec = z.probe('svc.foo.com')
+    fresh = Zone(H.snapshot(ZONE0 + [(p, {'type': 'load_balancer', 'load_balancer': {'address': '10.6.%d.%d' % ((5800 + i) >> 8, (5800 + i) & 255)}})
+                                     for i, (p, _) in enumerate(kids)]), 'foo.com')
+    assert (kind, ttl, rec) == (fresh.probe('svc.foo.com')[0], fresh.probe('svc.foo.com')[1], fresh.probe('svc.foo.com')[3])
