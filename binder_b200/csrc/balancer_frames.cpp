@@ -56,7 +56,7 @@ int bb_frames_parse(const uint8_t* in, size_t in_len, uint8_t* pkts, uint32_t ca
 int bb_frames_build(const uint8_t* resp, const uint32_t* resp_off, const uint16_t* resp_len, const uint8_t* status,
                     const uint32_t* dst_ip, const uint32_t* dst_port, uint32_t n, const uint32_t* control, uint32_t n_ctrl,
                     uint8_t* out, size_t out_cap, size_t* out_len) {
-    if (!out_len || (n && (!resp || !resp_off || !resp_len || !status || !dst_ip || !dst_port)) || (n_ctrl && !control)) return BB_ERR_ARG;
+    if (!out_len || (n && (!resp_off || !resp_len || !status || !dst_ip || !dst_port)) || (n_ctrl && !control)) return BB_ERR_ARG;
     size_t need = 4 * (size_t)n_ctrl;
     for (uint32_t i = 0; i < n; i++) if (status[i] == BB_ANSWERED) need += 16 + (size_t)resp_len[i];
     *out_len = need;
@@ -66,7 +66,7 @@ int bb_frames_build(const uint8_t* resp, const uint32_t* resp_off, const uint16_
     for (uint32_t i = 0; i < n; i++) {
         if (status[i] != BB_ANSWERED) continue;                     // misses go to recursion, drops get no answer
         wr32(w, BB_FRAME_OUTBOUND_UDP); wr32(w + 4, dst_ip[i]); wr32(w + 8, dst_port[i]); wr32(w + 12, resp_len[i]);
-        memcpy(w + 16, resp + resp_off[i], resp_len[i]);
+        if (resp_len[i]) { if (!resp) return BB_ERR_ARG; memcpy(w + 16, resp + resp_off[i], resp_len[i]); }
         w += 16 + (size_t)resp_len[i];
     }
     return BB_OK;
