@@ -9,7 +9,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, 'libbinder_b200.so')
 SRCS = [os.path.join(HERE, 'csrc', f) for f in ('engine.cu', 'zone_build.cpp', 'balancer_frames.cpp')]
-DEPS = SRCS + [os.path.join(HERE, 'csrc', 'zone_image.h'),
+DEPS = SRCS + [os.path.join(HERE, 'csrc', 'zone_image.h'), os.path.join(HERE, 'csrc', 'resolve_device.cuh'),
                os.path.join(os.path.dirname(HERE), 'include', 'binder_b200.h')]
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',

@@ -31,954 +31,9 @@ extern "C" int bb_zone_pending(const bb_zone* z, const uint32_t** slots, uint32_
 extern "C" void bb_zone_mark_synced(bb_zone* z);
 extern "C" uint64_t bb_zone_sync_gen(const bb_zone* z);
 
+#include "resolve_device.cuh"
+
 namespace bbk {
-using namespace bb;
-
-constexpr int T = 128;                    // queries (= threads) per tile
-constexpr int S_IN = 8192;                // staged input bytes per tile
-constexpr int CAPW = 12288;               // output staging window per flush round
-constexpr int MAXRESP = 1232;             // >= the largest response (1200)
-constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
-constexpr uint32_t NONE16 = 0xFFFF;
-
-constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
-constexpr int D_MISS_SHIFT = 40;
-
-enum { ST_ANSWERED = 0, ST_MISS = 1, ST_DROPPED = 2 };
-enum { RC_NOERROR = 0, RC_SERVFAIL = 2, RC_NXDOMAIN = 3, RC_NOTIMP = 4, RC_REFUSED = 5 };
-enum { QT_A = 1, QT_SOA = 6, QT_PTR = 12, QT_SRV = 33, QT_OPT = 41 };
-enum { RK_NONE = 0, RK_HEADER = 1, RK_A1 = 2, RK_PTR = 3, RK_SOA = 4, RK_SVC_A = 5, RK_SVC_SRV = 6 };
-
-struct Params {
-    const uint8_t* pkts; const uint32_t* pkt_off; uint32_t n;
-    uint64_t seed; uint32_t qidx_base;
-    uint8_t* out; uint32_t out_cap; uint32_t* out_off; uint16_t* out_len; uint8_t* status; uint32_t* miss_idx; uint32_t* totals;
-    const Slot* table; uint32_t mask; const uint8_t* arena; int ready;
-    const EngineConst* eng;
-    unsigned long long* desc; uint32_t* counter; uint32_t ntiles, ntiles_cap;   // desc[ntiles_cap] = arrival cursor
-    uint32_t epoch;          // launch number: marks totals[2] (overflow) / totals[3] (done) of THIS launch
-    unsigned long long* stage_log;   // optional [ntiles][8] globaltimer stamps (bb_engine_set_stage_log)
-    const uint32_t* n_dev;           // when set, the batch size is read from device memory (routed batches)
-    const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
-    uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
-    uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
-    uint32_t tcp;            // the batch arrived over TCP: no 512-byte / EDNS size limit (RFC 1035 4.2.2)
-    uint32_t* qidx_out;      // multi-region: each result's ingress index is also written here (host result mirrors)
-    const uint32_t* err_in;  // multi-region: the shard's wait-timeout word, copied into totals[6]
-    uint8_t* bounce;         // zero-copy results: device buffer (same offsets as `out`) that direct-emit tiles write to
-                             // before copying their range to the host buffer with coalesced stores
-    // multi-region launch (grid.y = regions): every per-batch pointer advances by its stride per region
-    uint32_t regions;
-    size_t in_stride, out_stride, off_stride, len_stride, status_stride, miss_stride, totals_stride, desc_stride;
-};
-
-// per-thread state carried from the sizing pass to the emit pass
-struct Res {
-    const uint8_t* p;        // packet bytes (shared memory, or global when the tile did not fit)
-    uint64_t lenmask;        // bit i set: QNAME byte i is a label-length byte (names <= 64 bytes)
-    uint32_t sp;             // shared-memory address of the packet (0 when not staged)
-    uint32_t qn_len;         // QNAME wire length incl. terminator
-    uint32_t ttl, val;
-    uint64_t perm;           // shuffled child order, 4 bits each (nk <= 16)
-    uint16_t rlen, maxsz, qtype, adv;
-    uint16_t d_off, d_end;   // domain part [d_off, d_end) in QNAME wire coordinates
-    uint16_t ptr_tgt;        // label boundary the owner's compression pointer targets, or NONE16
-    uint16_t lastlen;        // position of the domain's last length byte
-    uint16_t keep_ans, keep_add, n_walk, nk;
-    uint8_t status, rk, rcode, tc, opcode, rd, edns, trunc;
-    uint8_t owner;           // route mode: rank that owns this query's lookup key
-};
-
-__device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
-__device__ __forceinline__ uint32_t be16(const uint8_t* p) { return (uint32_t)p[0] << 8 | p[1]; }
-__device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }    // 4-byte aligned
-__device__ __forceinline__ uint32_t ld16a(const uint8_t* p) { return *(const uint16_t*)p; }   // 2-byte aligned
-
-// byte-fed murmur (same result as bb::hash_key over the materialised key)
-struct KeyHash {
-    uint32_t h, g, acc, n;
-    __device__ void init(uint32_t ns) { h = hash_init(ns); g = hash2_init(ns); acc = 0; n = 0; }
-    __device__ void feed(uint32_t c) {
-        acc |= c << (8 * (n & 3)); ++n;
-        if ((n & 3) == 0) { h = hash_word(h, acc); g = hash2_word(g, acc); acc = 0; }
-    }
-    // -> primary hash; h2 = second hash (second cuckoo slot)
-    __device__ uint32_t finish(uint32_t& h2) {
-        if (n & 3) { h = hash_word(h, acc); g = hash2_word(g, acc); }
-        h2 = hash2_finish(g, n);
-        return hash_finish(h, n);
-    }
-};
-
-// ---- mname decode (DESIGN.md "Wire spec: decode") ---------------------------------------
-__device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
-    if (len < 12) return false;
-    if (p[2] & 0x80) return false;
-    r.opcode = (p[2] >> 3) & 0xF; r.rd = p[2] & 1;
-    uint32_t qd = be16(p + 4), an = be16(p + 6), ns = be16(p + 8), ar = be16(p + 10);
-    if (qd != 1 || an != 0 || ns != 0 || ar > 1) return false;
-    uint32_t pos = 12;
-    uint64_t lm = 0;
-    for (;;) {
-        if (pos >= len) return false;
-        uint32_t c = p[pos];
-        if (c == 0) { ++pos; break; }
-        if (c > 63 || pos + 1 + c > len) return false;
-        if (pos - 12 < 64) lm |= 1ull << (pos - 12);
-        pos += 1 + c;
-        if (pos - 12 + 1 > 255) return false;
-    }
-    r.lenmask = lm;
-    r.qn_len = pos - 12;
-    if (pos + 4 > len) return false;
-    r.qtype = (uint16_t)be16(p + pos);
-    if (be16(p + pos + 2) != 1) return false;
-    pos += 4;
-    r.edns = 0; r.adv = 0;
-    if (ar == 1) {
-        if (pos + 11 > len || p[pos] != 0 || be16(p + pos + 1) != QT_OPT) return false;
-        r.adv = (uint16_t)be16(p + pos + 3);
-        if (pos + 11 + be16(p + pos + 9) > len) return false;
-        r.edns = 1;
-    }
-    return true;
-}
-
-// ---- zkCache.lookup / reverseLookup ------------------------------------------------------
-// The key is produced twice (hash, then compare) by the same generator so that nothing is
-// materialised.  Forward keys: the domain part in dotted lower case.  Reverse keys: the
-// labels before "in-addr.arpa", reversed, joined by '.'.
-struct FwdKey {
-    const uint8_t* nm; uint32_t d_off, d_end;
-    uint32_t pos, nlp;
-    __device__ uint32_t length() const { return d_end - d_off - 1; }
-    __device__ void start() { pos = d_off + 1; nlp = d_off + 1 + nm[d_off]; }
-    __device__ uint32_t next() {
-        uint32_t c;
-        if (pos == nlp) { c = '.'; nlp = pos + 1 + nm[pos]; } else c = lower8(nm[pos]);
-        ++pos; return c;
-    }
-};
-struct RevKey {
-    const uint8_t* nm; uint32_t nlab;       // labels before in-addr.arpa
-    uint32_t len_;
-    int k; uint32_t pos, rem; bool dot;
-    __device__ uint32_t label_pos(int idx) const { uint32_t q = 0; for (int i = 0; i < idx; i++) q += 1 + nm[q]; return q; }
-    __device__ void measure() { len_ = 0; uint32_t q = 0; for (uint32_t i = 0; i < nlab; i++) { len_ += nm[q] + (i ? 1 : 0); q += 1 + nm[q]; } }
-    __device__ uint32_t length() const { return len_; }
-    __device__ void start() { k = (int)nlab - 1; dot = false; if (k >= 0) { pos = label_pos(k); rem = nm[pos]; ++pos; } }
-    __device__ uint32_t next() {
-        if (dot) { dot = false; return '.'; }
-        uint32_t c = nm[pos++]; --rem;
-        if (rem == 0 && k > 0) { --k; pos = label_pos(k); rem = nm[pos]; ++pos; dot = true; }
-        return c;
-    }
-};
-
-template <class KG>
-__device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& kind, uint32_t& ttl, uint32_t& val) {
-    uint32_t klen = kg.length();
-    KeyHash kh; kh.init(ns);
-    kg.start();
-    for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
-    uint32_t h2;
-    uint32_t h = kh.finish(h2);
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return false; }   // sharding: who would answer
-    // 2-choice cuckoo: the key is in slot1_of(h) or slot2_of(h) or nowhere
-    const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, h2, P.mask) };
-    for (int c = 0; c < 2; c++) {
-        const Slot* s = P.table + cand[c];
-        uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,flags | ttl | val
-        uint32_t sk = (hd.y >> 8) & 0xFF;
-        if (sk == K_EMPTY) continue;
-        if (hd.x == h && ((hd.y >> 16) & 1) == ns) {
-            uint32_t sl = hd.y & 0xFF;
-            const uint8_t* kb = nullptr;
-            if (sl == KLEN_OVERFLOW) {
-                uint32_t off = __ldg((const uint32_t*)s->key), l = __ldg((const uint32_t*)(s->key + 4));
-                if (l == klen) kb = P.arena + off;
-            } else if (sl == klen) kb = s->key;
-            if (kb) {
-                kg.start();
-                bool eq = true;
-                for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
-                if (eq) { kind = sk; ttl = hd.z; val = hd.w; return true; }
-            }
-        }
-    }
-    return false;
-}
-
-// ---- shuffle (lib/server.js:40-53) --------------------------------------------------------
-__device__ uint64_t make_perm(uint32_t n, uint64_t seed, uint32_t qidx) {     // n <= 16
-    uint64_t perm = 0xFEDCBA9876543210ull;
-    for (uint32_t i = n; i-- > 1;) {
-        uint32_t j = shuffle_rand(seed, qidx, i);
-        uint64_t x = ((perm >> (4 * i)) ^ (perm >> (4 * j))) & 15;
-        perm ^= (x << (4 * i)) | (x << (4 * j));
-    }
-    return perm;
-}
-// element that ends up at position `p`, for any n: undo the swaps in reverse order
-__device__ uint32_t perm_at_slow(uint32_t p, uint32_t n, uint64_t seed, uint32_t qidx) {
-    uint32_t pos = p;
-    for (uint32_t i = 1; i < n; i++) {
-        uint32_t j = shuffle_rand(seed, qidx, i);
-        if (pos == i) pos = j; else if (pos == j) pos = i;
-    }
-    return pos;
-}
-__device__ __forceinline__ uint32_t perm_at(const Res& r, uint32_t t, uint64_t seed, uint32_t qidx) {
-    return r.nk <= 16 ? (uint32_t)(r.perm >> (4 * t)) & 15 : perm_at_slow(t, r.nk, seed, qidx);
-}
-
-struct SvcView {
-    const uint8_t* base; const uint8_t* arena; const uint32_t* kid_off;
-    __device__ void open(const uint8_t* arena_, uint32_t off) {
-        arena = arena_; base = arena_ + off;
-        const SvcHdr* h = (const SvcHdr*)base;
-        uint32_t sl = h->srvce_len == 0xFF ? 0 : h->srvce_len, pl = h->proto_len == 0xFF ? 0 : h->proto_len;
-        kid_off = (const uint32_t*)(base + ((sizeof(SvcHdr) + sl + pl + 3) & ~3u));
-    }
-    __device__ const SvcHdr* hdr() const { return (const SvcHdr*)base; }
-    __device__ const KidRec* kid(uint32_t i) const { return (const KidRec*)(arena + kid_off[i]); }
-};
-
-// owner-name sizes for this query's domain part (DESIGN.md "Wire spec: compression")
-__device__ __forceinline__ uint32_t dom_owner_len(const Res& r) {
-    return r.ptr_tgt != NONE16 ? (uint32_t)(r.ptr_tgt - r.d_off) + 2 : (uint32_t)(r.d_end - r.d_off) + 1;
-}
-__device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_t)(r.d_end - r.d_off) + 1; }
-
-// Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
-__device__ __forceinline__ unsigned long long gtime_early() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#define STAMP_SVC(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * 16 + (k)] = gtime_early(); } while (0)
-__device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
-    STAMP_SVC(11);
-    SvcView sv; sv.open(P.arena, r.val);
-    {   // The record (header, child offsets, children) is contiguous: touch all of its cache lines now,
-        // with independent loads, so that the dependent walks below (and in the emit pass) hit in
-        // L1/L2 instead of paying a DRAM round trip per child.
-        const uint32_t rl = sv.hdr()->rec_len;
-        const uint8_t* b0 = (const uint8_t*)((uintptr_t)sv.base & ~(uintptr_t)127);
-        const uint8_t* e0 = sv.base + rl;
-        for (const uint8_t* q = b0 + 128; q < e0; q += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
-    }
-    uint32_t nk = sv.hdr()->nkids;
-    r.nk = (uint16_t)nk;
-    STAMP_SVC(12);
-    r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
-    STAMP_SVC(13);
-    const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
-    uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
-    const uint8_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
-    for (uint32_t t = 0; t < nk; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        uint32_t fl = k->flags;
-        if (fl & badbit) { r.rcode = RC_SERVFAIL; n_walk = t; break; }       // :366-376
-        if (fl & KID_ADDR_NULL) continue;                                     // :378-381
-        if (srv) {
-            ans_b += (uint32_t)k->nports * (18 + k->wire_len + dwl); n_ans += k->nports;
-            add_b += k->wire_len + dol + 14; n_add++;
-        } else { ans_b += dol + 14; n_ans++; }
-    }
-    r.n_walk = (uint16_t)n_walk;
-    STAMP_SVC(14);
-    if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = (uint16_t)n_ans; r.keep_add = (uint16_t)n_add; r.rlen = (uint16_t)(fixed + ans_b + add_b); return; }
-    // truncation: keep the longest prefix of [answers..., additionals...] that fits
-    r.tc = 1;
-    uint32_t total = fixed, ka = 0, kd = 0; bool full = false;
-    for (uint32_t t = 0; t < n_walk && !full; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        if (k->flags & KID_ADDR_NULL) continue;
-        uint32_t each = srv ? 18 + k->wire_len + dwl : dol + 14, cnt = srv ? k->nports : 1;
-        for (uint32_t c = 0; c < cnt; c++) { if (total + each > r.maxsz) { full = true; break; } total += each; ++ka; }
-    }
-    if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        if (k->flags & KID_ADDR_NULL) continue;
-        uint32_t each = k->wire_len + dol + 14;
-        if (total + each > r.maxsz) break;
-        total += each; ++kd;
-    }
-    r.keep_ans = (uint16_t)ka; r.keep_add = (uint16_t)kd; r.rlen = (uint16_t)total;
-}
-
-// one RR that either fits or is dropped (TC)
-__device__ __forceinline__ void size_single(Res& r, uint32_t fixed, uint32_t rr) {
-    if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
-    else { r.rlen = (uint16_t)fixed; r.keep_ans = 0; r.tc = 1; }
-}
-
-// Recursion.resolve()'s quick rejects (lib/recursion.js:329-344), for a miss that would otherwise be handed
-// to the host: would it be forwarded anywhere?  nm = QNAME wire bytes — query.name() in its original case,
-// SRV prefix included — W = its length without the terminator.  In the dotted string every label boundary
-// is a '.', so the string operations map one to one onto wire positions:
-//   domain.indexOf(dnsDomain, domain.length - dnsDomain.length) === -1            -> not ours   (:330-333)
-//   p = domain minus the suffix and the one character before it; dc = p after its last '.';
-//   self.dcs[dc] === undefined (or every upstream of dc is this host)              -> nowhere to ask (:338-343,377-379)
-// Kept out of line: it runs for misses only and must not cost the hit path registers.
-__device__ __noinline__ bool recursion_forwardable(const EngineConst* E, const uint8_t* nm, uint32_t W) {
-    const uint32_t L = E->rf_dom_len;
-    if (W < 1 + L) return false;                       // name shorter than the suffix
-    const uint32_t s0 = W - L;                         // wire index where the suffix must start
-    if (s0 < 2) return false;                          // nothing before it: dc = ''
-    const uint32_t cw = s0 - 1;                        // the character substring() drops (normally the '.')
-    uint32_t nlp = 1u + nm[0], last_b = 0;             // next length byte; last boundary before cw
-    bool ok = true;
-    for (uint32_t w = 1; w < W; w++) {
-        const bool boundary = w == nlp;
-        if (boundary) { nlp = w + 1u + nm[w]; if (w < cw) last_b = w; }
-        if (w >= s0) {
-            const uint32_t e = E->rf_dom[w - s0];
-            ok &= boundary ? e == '.' : (e != '.' && e == nm[w]);
-        }
-    }
-    if (!ok) return false;
-    const uint32_t d0 = last_b + 1, dl = cw - d0;      // dc = dotted[d0 .. cw)
-    if (dl == 0 || dl > 63) return false;
-    for (uint32_t k = 0; k < E->rf_ndc; k++) {
-        if (E->rf_dc_len[k] != dl) continue;
-        bool eq = true;
-        for (uint32_t i = 0; i < dl; i++) eq &= E->rf_dc[k][i] == nm[d0 + i];
-        if (eq) return true;
-    }
-    return false;
-}
-
-// What resolve() does once zk.lookup() has answered (lib/server.js:219-424); shared by the
-// generic and the word-wise front ends.
-__device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed, bool srv, bool hit,
-                               uint32_t kind, uint32_t ttl, uint32_t val, uint32_t l0, uint32_t l1) {
-    const uint8_t* nm = r.p + 12;
-    const EngineConst* E = P.eng;
-    if (!hit) {                                                               // :219-247
-        if (P.recursion && r.rd) {
-            // pre-filter: a miss recursion.js would refuse without asking anyone is refused here (same bytes)
-            if (P.recursion == 2 && !recursion_forwardable(E, nm, r.qn_len - 1)) { r.rcode = RC_REFUSED; return; }
-            r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return;
-        }
-        r.rcode = RC_REFUSED; return;
-    }
-    r.ttl = ttl; r.val = val;
-    if (kind == K_INVALID) { r.rcode = RC_SERVFAIL; return; }                 // :251-260
-    if (srv && kind != K_SERVICE) {                                           // :276-292 NODATA + SOA
-        r.rcode = RC_NOERROR; r.rk = RK_SOA;
-        uint32_t rr = dom_owner_len(r) + 10 + E->soa_len + 20;
-        if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
-        else { r.keep_ans = 0; r.tc = 1; }
-        return;
-    }
-    if (kind == K_ADDR) { r.rcode = RC_NOERROR; r.rk = RK_A1; size_single(r, fixed, dom_owner_len(r) + 14); return; }
-    if (kind == K_ADDR_BAD) { r.rcode = RC_SERVFAIL; return; }                // contract
-    if (kind == K_UNKNOWN) { r.rcode = RC_NOTIMP; return; }                   // :419-424 + :346-350
-    // K_SERVICE (:313-417)
-    SvcView sv; sv.open(P.arena, val);
-    const SvcHdr* h = sv.hdr();
-    r.ttl = h->ttl;
-    if (srv) {
-        const uint8_t* sb = sv.base + sizeof(SvcHdr);
-        bool match = h->srvce_len == l0 && h->proto_len == l1;
-        for (uint32_t i = 0; match && i < l0; i++) if (sb[i] != nm[1 + i]) match = false;
-        for (uint32_t i = 0; match && i < l1; i++) if (sb[l0 + i] != nm[2 + l0 + i]) match = false;
-        if (!match) { r.rcode = RC_NXDOMAIN; return; }                        // :334-345
-    }
-    r.rcode = RC_NOERROR;                                                     // :351
-    r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
-    size_service(P, r, qidx, srv, fixed);
-}
-
-__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-// per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
-constexpr int NSTAGE = 16;
-#define STAMP(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * NSTAGE + (k)] = gtime(); } while (0)
-
-// ---- word-wise front end of resolve() -----------------------------------------------------
-// Same decisions as resolve_forward() below, four name bytes per step, for the common case:
-// packet staged in shared memory, QNAME <= 64 wire bytes, lookup key <= 48 bytes (inline slot
-// keys).  Anything else returns false and takes the generic path.
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-// unaligned 32-bit load from shared memory (the staging buffers carry read slack)
-__device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
-    const uint32_t b = a & ~3u;
-    return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) * 8);
-}
-// v << n with PTX semantics: any n > 31 (including a wrapped-around negative) gives 0
-__device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
-// 0x80 in every byte of v that is zero
-__device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); }
-// 0x80 in every byte of x7 (7-bit bytes) that is >= k
-__device__ __forceinline__ uint32_t ge7(uint32_t x7, uint32_t k) { return (x7 + (0x80u - k) * 0x01010101u) & 0x80808080u; }
-// 0x80 in every byte that is 'A'..'Z'
-__device__ __forceinline__ uint32_t upper_bytes(uint32_t x) {
-    const uint32_t x7 = x & 0x7F7F7F7Fu;
-    return ge7(x7, 0x41) & ~ge7(x7, 0x5B) & ~x;
-}
-
-// Decode of a packet staged in shared memory, word-wise (same acceptance as decode()).
-__device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
-    if (len < 17) return false;                                               // header + root name + type/class at least
-    const uint32_t hb = sp & ~3u, hs = (sp & 3u) * 8;
-    const uint32_t t0 = lds32(hb), t1 = lds32(hb + 4), t2 = lds32(hb + 8), t3 = lds32(hb + 12);
-    const uint32_t w0 = __funnelshift_r(t0, t1, hs), w1 = __funnelshift_r(t1, t2, hs), w2 = __funnelshift_r(t2, t3, hs);
-    const uint32_t fl = (w0 >> 16) & 0xFF;                                    // byte 2: QR opcode AA TC RD
-    if (fl & 0x80) return false;
-    r.opcode = (fl >> 3) & 0xF; r.rd = fl & 1;
-    if (w1 != 0x00000100u) return false;                                      // QDCOUNT=1, ANCOUNT=0
-    if (w2 != 0u && w2 != 0x01000000u) return false;                          // NSCOUNT=0, ARCOUNT<=1
-    const uint32_t nm = sp + 12, lim = len - 12;                              // name bytes available
-    // label hop: one dependent shared-memory byte per label; validity is accumulated, not branched on
-    uint32_t pos = 0, lo = 0, hi = 0, bad = 0, c = lds8(nm);
-#pragma unroll 1
-    while (c != 0) {
-        bad |= c > 63;                                                        // pointers / extended label types
-        lo |= shl_clamp(1u, pos); hi |= shl_clamp(1u, pos - 32u);             // positions >= 64 fall off (shl.b32 clamps its count)
-        pos += 1 + c;
-        if (pos >= lim || pos > 254) { bad = 1; break; }
-        c = lds8(nm + pos);
-    }
-    if (bad) return false;
-    if (pos + 1 + 4 > lim) return false;
-    r.qn_len = pos + 1;
-    r.lenmask = (uint64_t)lo | ((uint64_t)hi << 32);
-    const uint32_t tc = ldsu32(nm + pos + 1);                                 // QTYPE, QCLASS (big-endian)
-    r.qtype = (uint16_t)(((tc & 0xFF) << 8) | ((tc >> 8) & 0xFF));
-    if ((tc >> 16) != 0x0100u) return false;                                  // class IN
-    r.edns = 0; r.adv = 0;
-    if (w2) {
-        const uint32_t q = nm + pos + 5;                                      // the one additional RR
-        if (pos + 5 + 11 > lim) return false;
-        const uint32_t a = ldsu32(q), b = ldsu32(q + 4), c2 = ldsu32(q + 8);
-        if ((a & 0xFFFFFF) != 0x290000u) return false;                        // root owner, TYPE 41
-        r.adv = (uint16_t)(((a >> 24) << 8) | (b & 0xFF));
-        const uint32_t rdlen = (((c2 >> 8) & 0xFF) << 8) | ((c2 >> 16) & 0xFF);
-        if (pos + 5 + 11 + rdlen > lim) return false;
-        r.edns = 1;
-    }
-    return true;
-}
-
-// 0x80 in every byte of the lower-cased dotted word `lo` that is NOT in [a-z0-9_-] ('.' counts as bad:
-// the caller masks out the label-boundary positions)
-__device__ __forceinline__ uint32_t bad_chars(uint32_t lo) {
-    const uint32_t y7 = lo & 0x7F7F7F7Fu;
-    const uint32_t ok = ((ge7(y7, 0x61) & ~ge7(y7, 0x7B)) | (ge7(y7, 0x30) & ~ge7(y7, 0x3A)) |
-                         zero_bytes(lo ^ 0x2D2D2D2Du) | zero_bytes(lo ^ 0x5F5F5F5Fu)) & ~lo;
-    return ~ok & 0x80808080u;
-}
-
-__device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
-    const EngineConst* E = P.eng;
-    if (!P.ready && !P.route) return false;            // not-ready engines: exact ordering of refusals lives in the generic path
-    const uint32_t nm = r.sp + 12;
-    const bool srv = r.qtype == QT_SRV;
-    const uint32_t d_end = r.qn_len - 1;
-    uint32_t d_off = 0, l0 = 0, l1 = 0;
-    bool refuse = false;
-    if (srv) {                                                                // :141-154
-        l0 = lds8(nm);
-        if (l0 == 0) { r.rcode = RC_REFUSED; return true; }
-        const uint32_t p1 = 1 + l0; l1 = lds8(nm + p1);
-        if (l1 == 0) { r.rcode = RC_REFUSED; return true; }
-        for (uint32_t i = 1; i <= l0; i++) { const uint32_t c = lds8(nm + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
-        for (uint32_t i = 1; i <= l1; i++) { const uint32_t c = lds8(nm + p1 + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
-        d_off = p1 + 1 + l1;
-        if (lds8(nm + d_off) == 0) { r.rcode = RC_REFUSED; return true; }
-    }
-    if (d_end <= d_off + 1) { r.rcode = RC_REFUSED; return true; }            // root name
-    const uint32_t dl = d_end - d_off - 1;
-    if (dl > KEY_INLINE_MAX) return false;
-    // suffix gate (:157-166), case-sensitive, on the raw wire bytes: the domain's last sl bytes must be
-    // dnsDomain's wire labels and start at a label boundary ('.' + dnsDomain in the dotted view)
-    const uint32_t sl = P.suffix_len;
-    if (dl < sl) { r.rcode = RC_REFUSED; return true; }       // (a truncated SRV domain is shorter still)
-    {
-        const uint32_t t0 = d_end - sl;                                       // where the suffix's first length byte must sit
-        uint32_t bad = ((r.lenmask >> t0) & 1ull) ? 0u : 1u;
-        const uint32_t nw = (sl + 3) >> 2;
-        for (uint32_t j = 0; j < nw; j++) {                                   // words right-aligned to the end of the name
-            const uint32_t x = ldsu32(nm + d_end - 4 * (j + 1));
-            const uint32_t e = lds32(s_sfx + 256 - 4 * (j + 1));
-            const uint32_t rem = sl - 4 * j;                                  // bytes of this word that belong to the suffix
-            const uint32_t cm = rem >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - rem)));
-            bad |= (x ^ e) & cm;
-        }
-        if (bad) { if (srv) return false; r.rcode = RC_REFUSED; return true; }   // SRV: the regex group may stop at a line terminator (:141) -> generic path
-    }
-    // normalise (dotted view, toLowerCase :207) + hash, four bytes per step
-    const uint64_t lm = r.lenmask >> (d_off + 1);
-    const uint32_t nwords = (dl + 3) >> 2;
-    const uint32_t tailm = (dl & 3) ? ((1u << (8 * (dl & 3))) - 1) : 0xFFFFFFFFu;
-    uint32_t kw[12];
-    uint32_t h = hash_init(NS_FORWARD), g = hash2_init(NS_FORWARD);
-    uint32_t upw = 0, upi = 0;
-    // consecutive unaligned words share their aligned halves: one LDS per word, not two
-    const uint32_t ka = nm + d_off + 1, kb = ka & ~3u, ksh = (ka & 3u) * 8;
-    uint32_t wprev = lds32(kb);
-#pragma unroll
-    for (int i = 0; i < 12; i++) {
-        kw[i] = 0;
-        if ((uint32_t)i < nwords) {
-            const uint32_t wnext = lds32(kb + 4 * (i + 1));
-            const uint32_t x = __funnelshift_r(wprev, wnext, ksh);
-            wprev = wnext;
-            const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
-            const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // label-boundary positions
-            uint32_t xd = (x & ~m8) | (0x2E2E2E2Eu & m8);
-            if ((uint32_t)i == nwords - 1) xd &= tailm;
-            const uint32_t up = upper_bytes(xd);
-            if (up) { upw = up; upi = i; }
-            const uint32_t lo = xd | (up >> 2);
-            kw[i] = lo;
-            h = hash_word(h, lo); g = hash2_word(g, lo);
-        }
-    }
-    h = hash_finish(h, dl);
-    const uint32_t h2 = hash2_finish(g, dl);
-    STAMP(4);
-    if (refuse) { r.rcode = RC_REFUSED; return true; }
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
-    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
-    if (!upw) r.ptr_tgt = (uint16_t)d_off;
-    else {
-        const uint32_t pu = d_off + 1 + 4 * upi + ((31 - __clz(upw)) >> 3);  // wire position of the last upper-case byte
-        const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
-        r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
-    }
-    // zk.lookup(domain): one 64-byte slot per probe, compared as words.  The header compare also
-    // carries the key's dot count: a query with a '.' inside a label has fewer label boundaries than
-    // any key that spells the same, so it can never match here.
-    const uint32_t ndots = (uint32_t)__popcll(r.lenmask >> (d_off + 1));
-    const uint32_t want = dl | ((NS_FORWARD | (ndots << 1)) << 16);
-    uint32_t kind = 0, ttl = 0, val = 0;
-    bool hit = false, clean = false;
-    {
-        // 2-choice cuckoo: both candidate slots are fetched together — one DRAM round trip per lookup,
-        // hit or miss, for every lane of the warp
-        const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
-        const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
-        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
-        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
-        const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |
-                            (kw[0] ^ a1.x) | (kw[1] ^ a1.y) | (kw[2] ^ a1.z) | (kw[3] ^ a1.w) |
-                            (kw[4] ^ a2.x) | (kw[5] ^ a2.y) | (kw[6] ^ a2.z) | (kw[7] ^ a2.w) |
-                            (kw[8] ^ a3.x) | (kw[9] ^ a3.y) | (kw[10] ^ a3.z) | (kw[11] ^ a3.w);
-        const uint32_t db = (b0.x ^ h) | ((b0.y & 0x00FF00FFu) ^ want) |
-                            (kw[0] ^ b1.x) | (kw[1] ^ b1.y) | (kw[2] ^ b1.z) | (kw[3] ^ b1.w) |
-                            (kw[4] ^ b2.x) | (kw[5] ^ b2.y) | (kw[6] ^ b2.z) | (kw[7] ^ b2.w) |
-                            (kw[8] ^ b3.x) | (kw[9] ^ b3.y) | (kw[10] ^ b3.z) | (kw[11] ^ b3.w);
-        // an empty slot has kind 0 and klen 0, so it can never equal `want` (dl >= 1)
-        if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
-        else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
-    }
-    STAMP(5);
-    if (!(hit && clean)) {
-        // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a
-        // label, a character outside [a-z0-9_.-] (:208-215) -> REFUSED; an SRV name with a
-        // line terminator goes to the generic path (its regex group stops there, :141).
-        uint32_t bad = 0, nlc = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            if ((uint32_t)i < nwords) {
-                const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
-                const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;
-                const uint32_t tm = ((uint32_t)i == nwords - 1) ? tailm : 0xFFFFFFFFu;
-                bad |= bad_chars(kw[i]) & ~m8 & tm;
-                nlc |= (zero_bytes(kw[i] ^ 0x0A0A0A0Au) | zero_bytes(kw[i] ^ 0x0D0D0D0Du)) & ~m8 & tm;
-            }
-        }
-        if (srv && nlc) return false;
-        if (bad) { r.rcode = RC_REFUSED; return true; }
-    }
-    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
-    return true;
-}
-
-// ---- resolve (lib/server.js:136-429) -------------------------------------------------------
-__device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t fixed) {
-    const uint8_t* nm = r.p + 12;
-    const EngineConst* E = P.eng;
-    const bool srv = r.qtype == QT_SRV;
-    uint32_t d_off = 0, d_end = r.qn_len - 1;
-    uint32_t l0 = 0, l1 = 0;
-    r.trunc = 0;
-    if (srv) {
-        // /^(_[^_.]*)[.](_[^_.]*)[.](.*)/ on query.name() (:141-154); labels hold no '.' here
-        l0 = nm[0];
-        if (l0 == 0 || nm[1] != '_') { r.rcode = RC_REFUSED; return; }
-        for (uint32_t i = 2; i <= l0; i++) if (nm[i] == '_') { r.rcode = RC_REFUSED; return; }
-        uint32_t p1 = 1 + l0; l1 = nm[p1];
-        if (l1 == 0 || nm[p1 + 1] != '_') { r.rcode = RC_REFUSED; return; }
-        for (uint32_t i = 2; i <= l1; i++) if (nm[p1 + i] == '_') { r.rcode = RC_REFUSED; return; }
-        d_off = p1 + 1 + l1;
-        if (nm[d_off] == 0) { r.rcode = RC_REFUSED; return; }                 // no third part
-        // group 3 stops at the first \n or \r (JS '.' excludes line terminators, no '$')
-        uint32_t nlp = d_off;
-        for (uint32_t pos = d_off; pos < d_end; pos++) {
-            if (pos == nlp) { nlp = pos + 1 + nm[pos]; continue; }
-            if (nm[pos] == '\n' || nm[pos] == '\r') { d_end = pos; r.trunc = 1; break; }
-        }
-        if (d_end - d_off - 1 < 1 || d_end <= d_off + 1) { r.rcode = RC_REFUSED; return; }   // :144
-    }
-    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end;
-    if (d_end <= d_off + 1 && !srv) {                                         // root name: ''
-        // isSuffix('.dom', '') is false -> refused; with no dnsDomain: length < 1 -> refused (:198)
-        r.rcode = P.ready || E->suffix_len ? RC_REFUSED : RC_SERVFAIL; return;
-    }
-    // one pass over the domain in dotted view: suffix gate (:157-166, case-sensitive), charset
-    // after toLowerCase (:207-215), and where an owner-name pointer may land
-    const uint32_t dl = d_end - d_off - 1;
-    const uint32_t sl = E->suffix_len;
-    bool suffix_ok = sl == 0 || dl >= sl, charset_ok = true, need_b = false;
-    uint32_t pos0 = d_end - sl, ptr_tgt = d_off, lastlen = d_off;
-    {
-        uint32_t nlp = d_off + 1 + nm[d_off];
-        for (uint32_t pos = d_off + 1; pos < d_end; pos++) {
-            uint32_t c, raw;
-            if (pos == nlp) { raw = c = '.'; nlp = pos + 1 + nm[pos]; lastlen = pos; if (need_b) { ptr_tgt = pos; need_b = false; } }
-            else {
-                raw = nm[pos]; c = lower8(raw);
-                if (raw != c) need_b = true;
-                if (!((c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-')) charset_ok = false;
-            }
-            if (suffix_ok && sl && pos >= pos0 && raw != E->suffix[pos - pos0]) suffix_ok = false;
-        }
-    }
-    if (!suffix_ok) { r.rcode = RC_REFUSED; return; }
-    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return; }             // :186-192
-    if (!charset_ok) { r.rcode = RC_REFUSED; return; }
-    r.ptr_tgt = (need_b || r.trunc) ? (uint16_t)NONE16 : (uint16_t)ptr_tgt;
-    r.lastlen = (uint16_t)lastlen;
-
-    FwdKey kg; kg.nm = nm; kg.d_off = d_off; kg.d_end = d_end;
-    uint32_t kind = 0, ttl = 0, val = 0;
-    const bool hit = probe(P, r, NS_FORWARD, kg, kind, ttl, val);
-    finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
-}
-
-// ---- resolvePtr (lib/server.js:67-134) -----------------------------------------------------
-__device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
-    const uint8_t* nm = r.p + 12;
-    uint32_t nlab = 0, last = 0, prev = 0;
-    for (uint32_t q = 0; nm[q]; q += 1 + nm[q]) { prev = last; last = q; ++nlab; }
-    // parts.reverse(): [0] must be 'arpa', [1] 'in-addr' — case-sensitive (:71-78)
-    bool ok = nlab >= 2 && nm[last] == 4 && nm[last + 1] == 'a' && nm[last + 2] == 'r' && nm[last + 3] == 'p' && nm[last + 4] == 'a' &&
-              nm[prev] == 7 && nm[prev + 1] == 'i' && nm[prev + 2] == 'n' && nm[prev + 3] == '-' && nm[prev + 4] == 'a' &&
-              nm[prev + 5] == 'd' && nm[prev + 6] == 'd' && nm[prev + 7] == 'r';
-    if (!ok) { r.rcode = RC_REFUSED; return; }
-    if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return; }              // :86-92
-    RevKey kg; kg.nm = nm; kg.nlab = nlab - 2; kg.measure();
-    uint32_t kind = 0, ttl = 0, val = 0;
-    bool hit = kg.length() > 0 && probe(P, r, NS_REVERSE, kg, kind, ttl, val);
-    if (!hit) {                                                               // :107-121
-        if (P.recursion && r.rd) {                                            // a PTR miss asks every datacenter (:346-354)
-            if (P.recursion == 2 && !P.eng->rf_ptr) { r.rcode = RC_REFUSED; return; }
-            r.status = ST_MISS; r.rk = RK_NONE; r.rlen = 0; return;
-        }
-        r.rcode = RC_REFUSED; return;
-    }
-    if (kind != K_PTR) { r.rcode = RC_SERVFAIL; return; }                     // contract
-    r.ttl = ttl; r.val = val; r.rcode = RC_NOERROR; r.rk = RK_PTR;
-    size_single(r, fixed, 2 + 10 + P.arena[val]);
-}
-
-// onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
-__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
-    r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
-    r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
-    if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
-    r.maxsz = P.tcp ? (uint16_t)65535 : r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
-    const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
-    r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
-    const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
-    if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
-    STAMP(3);
-    if (r.sp && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, qidx, fixed)) return;
-    const uint8_t* nm = r.p + 12;
-    for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
-        uint32_t l = nm[q];
-        for (uint32_t i = 1; i <= l; i++) if (nm[q + i] == '.') { r.rcode = RC_REFUSED; return; }
-        q += 1 + l;
-    }
-    if (r.qtype == QT_PTR) resolve_ptr(P, r, fixed);
-    else resolve_forward(P, r, qidx, fixed);
-}
-
-// ---- mname encode (DESIGN.md "Wire spec: encode") ------------------------------------------
-// OPT echoed when the query carried one: root owner, type 41, udp size 1200, ttl 0, rdlen 0
-__constant__ uint8_t c_opt_rr[11] = { 0, 0, QT_OPT, 0x04, 0xB0, 0, 0, 0, 0, 0, 0 };
-// The response staging buffer is XOR-swizzled: 16-byte chunk index ^ (128-byte row & 7).  With one
-// 64-byte response per lane, word w of every lane would otherwise fall into 2 of the 32 banks (a
-// 16-way conflict on every store); swizzled, a warp's stores spread over more banks, and the flush
-// (consecutive 16-byte chunks) still reads each row as a permutation of itself.
-__device__ __forceinline__ uint32_t swz(uint32_t off) { return off ^ (((off >> 7) & 7u) << 4); }
-
-// byte emitter of the generic path: writes the response straight to its place in global memory
-struct Out {
-    uint8_t* o;
-    __device__ void u8(uint32_t v) { *o++ = (uint8_t)v; }
-    __device__ void u16(uint32_t v) { o[0] = (uint8_t)(v >> 8); o[1] = (uint8_t)v; o += 2; }
-    __device__ void u32(uint32_t v) { o[0] = (uint8_t)(v >> 24); o[1] = (uint8_t)(v >> 16); o[2] = (uint8_t)(v >> 8); o[3] = (uint8_t)v; o += 4; }
-    __device__ void copy(const uint8_t* s, uint32_t n) { for (uint32_t i = 0; i < n; i++) o[i] = s[i]; o += n; }
-};
-// the domain part, lower-cased, as wire labels up to `stop` (no terminator)
-__device__ void put_dom_labels(Out& w, const Res& r, uint32_t stop) {
-    const uint8_t* nm = r.p + 12;
-    uint8_t* start = w.o;
-    for (uint32_t pos = r.d_off; pos < stop; pos++) w.u8(lower8(nm[pos]));    // length bytes (<64) are unaffected
-    if (r.trunc && stop > r.lastlen) start[r.lastlen - r.d_off] = (uint8_t)(r.d_end - r.lastlen - 1);
-}
-__device__ void put_dom_owner(Out& w, const Res& r) {
-    if (r.ptr_tgt != NONE16) { put_dom_labels(w, r, r.ptr_tgt); w.u16(0xC000 | (12 + r.ptr_tgt)); }
-    else { put_dom_labels(w, r, r.d_end); w.u8(0); }
-}
-__device__ void put_rr_head(Out& w, uint32_t type, uint32_t ttl, uint32_t rdlen) { w.u16(type); w.u16(1); w.u32(ttl); w.u16(rdlen); }
-
-__device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint32_t qidx) {
-    Out w; w.o = dst;
-    const uint8_t* p = r.p;
-    uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
-    switch (r.rk) {
-    case RK_A1: case RK_PTR: an = r.keep_ans; break;
-    case RK_SOA: ns = r.keep_ans; break;
-    case RK_SVC_A: case RK_SVC_SRV: an = r.keep_ans; ar += r.keep_add; break;
-    }
-    w.u8(p[0]); w.u8(p[1]);
-    w.u8(0x80 | (r.opcode << 3) | 0x04 | (r.tc ? 0x02 : 0) | r.rd);          // QR AA TC RD
-    w.u8(r.rcode);                                                            // RA=0 Z=0
-    w.u16(1); w.u16(an); w.u16(ns); w.u16(ar);
-    w.copy(p + 12, r.qn_len + 4);                                             // question, verbatim
-    const uint8_t* opt = c_opt_rr;
-    bool opt_done = !r.edns;
-    if (r.rk == RK_A1 && r.keep_ans) {                                        // :299,310
-        put_dom_owner(w, r); put_rr_head(w, QT_A, r.ttl, 4); w.u32(r.val);
-    } else if (r.rk == RK_PTR && r.keep_ans) {                                // :130
-        w.u16(0xC00C); uint32_t tl = P.arena[r.val]; put_rr_head(w, QT_PTR, r.ttl, tl); w.copy(P.arena + r.val + 1, tl);
-    } else if (r.rk == RK_SOA && r.keep_ans) {                                // :286-287
-        const EngineConst* E = P.eng;
-        put_dom_owner(w, r); put_rr_head(w, QT_SOA, r.ttl, E->soa_len + 20);
-        w.copy(E->soa, E->soa_len); w.u32(0); w.u32(10); w.u32(10); w.u32(10); w.u32(r.ttl);
-    } else if (r.rk == RK_SVC_A || r.rk == RK_SVC_SRV) {
-        const bool srv = r.rk == RK_SVC_SRV;
-        SvcView sv; sv.open(P.arena, r.val);
-        uint32_t left = r.keep_ans;
-        for (uint32_t t = 0; t < r.n_walk && left; t++) {
-            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-            if (k->flags & KID_ADDR_NULL) continue;
-            if (srv) {                                                        // :396-400
-                const uint8_t* ports = (const uint8_t*)(k + 1);
-                const uint8_t* kw = ports + 2 * k->nports;
-                for (uint32_t c = 0; c < k->nports && left; c++, left--) {
-                    w.u16(0xC00C); put_rr_head(w, QT_SRV, r.ttl, 6 + k->wire_len + dom_wire_len(r));
-                    w.u16(0); w.u16(10); w.u16(ld16a(ports + 2 * c));
-                    w.copy(kw, k->wire_len); put_dom_labels(w, r, r.d_end); w.u8(0);
-                }
-            } else {                                                          // :411-414
-                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                if (r.ttl < rttl) rttl = r.ttl;
-                put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
-            }
-        }
-        if (srv) {
-            if (!opt_done) { w.copy(opt, 11); opt_done = true; }
-            left = r.keep_add;
-            for (uint32_t t = 0; t < r.n_walk && left; t++) {                 // :401-402
-                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-                if (k->flags & KID_ADDR_NULL) continue;
-                const uint8_t* kw = (const uint8_t*)(k + 1) + 2 * k->nports;
-                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                w.copy(kw, k->wire_len); put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
-            }
-        }
-    }
-    if (!opt_done) w.copy(opt, 11);
-}
-
-// ---- word-wise response writer -------------------------------------------------------------
-// A byte stream into shared memory at an arbitrary byte address, stored as aligned 32-bit words;
-// only the bytes shared with the neighbouring responses (first / last partial word) go out as
-// single bytes, so two threads never write the same word.
-// MODE 0: plain shared buffer, 1: XOR-swizzled shared staging (buffer 1024-byte aligned, so the
-// swizzle applies to the address itself), 2: global memory (gbase + offset).
-// HEADCHK: any put may be the one that completes the first word.  Without it the stream must open
-// with put4_first(), and every later store is a plain aligned word.
-template <int MODE, bool HEADCHK = false>
-struct WrT {
-    uint32_t base;       // shared address of the buffer (mode 0)
-    uint8_t* gbase;      // global destination (mode 2)
-    uint32_t wp;         // position of the aligned word being filled: offset (modes 0, 2) or shared address (mode 1)
-    uint32_t acc, fill;  // its bytes so far (fill = 0..3 of them)
-    uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
-    __device__ void begin(uint32_t buf, uint32_t off) {
-        gbase = nullptr; head = off & 3u; acc = 0; fill = head;
-        if (MODE == 1) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
-    }
-    // global: `g` must be 4-byte aligned (the output buffer is 16-byte aligned), off = byte offset in it
-    __device__ void begin_global(uint8_t* g, uint32_t off) { base = 0; gbase = g; head = off & 3u; wp = off - head; acc = 0; fill = head; }
-    __device__ __forceinline__ void st32(uint32_t pos, uint32_t v) {
-        if (MODE == 2) *(uint32_t*)(gbase + pos) = v;
-        else if (MODE == 1) sts32(pos ^ ((pos >> 3) & 0x70u), v);
-        else sts32(base + pos, v);
-    }
-    __device__ __forceinline__ void st8(uint32_t pos, uint32_t v) {
-        if (MODE == 2) gbase[pos] = (uint8_t)v;
-        else if (MODE == 1) sts8(pos ^ ((pos >> 3) & 0x70u), v & 0xFF);
-        else sts8(base + pos, v & 0xFF);
-    }
-    __device__ __forceinline__ void store(uint32_t v) {
-        if (HEADCHK && head) { for (uint32_t b = head; b < 4; b++) st8(wp + b, (v >> (8 * b)) & 0xFF); head = 0; }
-        else st32(wp, v);
-        wp += 4;
-    }
-    // the first four bytes of the stream: the only word that may be shared with the previous response
-    __device__ __forceinline__ void put4_first(uint32_t v) {
-        const uint32_t s8 = 8 * head, w = v << s8;
-        if (head == 0) st32(wp, w);
-        else for (uint32_t b = head; b < 4; b++) st8(wp + b, (w >> (8 * b)) & 0xFF);
-        acc = __funnelshift_l(v, 0u, s8);
-        wp += 4; head = 0;
-    }
-    // four bytes in memory order: the word being filled completes, `fill` bytes carry over
-    __device__ __forceinline__ void put4(uint32_t v) {
-        const uint32_t s8 = 8 * fill;
-        store(acc | (v << s8));
-        acc = __funnelshift_l(v, 0u, s8);                // v >> (32 - s8), 0 when s8 == 0
-    }
-    // v holds n (1..4) bytes in memory order (little-endian integer), upper bytes zero
-    __device__ __forceinline__ void put(uint32_t v, uint32_t n) {
-        const uint32_t s8 = 8 * fill;
-        const uint32_t w = acc | (v << s8);
-        if (fill + n >= 4) { store(w); acc = __funnelshift_l(v, 0u, s8); fill = fill + n - 4; }
-        else { acc = w; fill += n; }
-    }
-    __device__ void end() { for (uint32_t b = head; b < fill; b++) st8(wp + b, (acc >> (8 * b)) & 0xFF); }
-    // n bytes from shared memory (consecutive unaligned words share their aligned halves)
-    __device__ void copy(uint32_t src, uint32_t n) {
-        const uint32_t b = src & ~3u, sh = (src & 3u) * 8;
-        uint32_t prev = lds32(b), i = 0, k = 1;
-        for (; i + 4 <= n; i += 4, k++) { const uint32_t nx = lds32(b + 4 * k); put4(__funnelshift_r(prev, nx, sh)); prev = nx; }
-        if (i < n) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh) & ((1u << (8 * (n - i))) - 1), n - i); }
-    }
-};
-__device__ __forceinline__ uint32_t bswap32(uint32_t v) { return __byte_perm(v, 0, 0x0123); }
-
-// emit_response() with the word-wise writer, for every response shape of a packet staged in shared
-// memory (everything except the SRV line-terminator quirk, which keeps the byte emitter).
-__device__ __forceinline__ uint32_t bswap16(uint32_t v) { return ((v & 0xFF) << 8) | ((v >> 8) & 0xFF); }
-
-// domain labels [d_off, stop) of the QNAME, lower-cased (length bytes < 64 are unaffected)
-template <class W>
-__device__ void put_dom_labels_w(W& w, const Res& r, uint32_t stop) {
-    const uint32_t n = stop - r.d_off;
-    const uint32_t src = r.sp + 12 + r.d_off, b = src & ~3u, sh = (src & 3u) * 8;
-    uint32_t prev = lds32(b), i = 0, k = 1;
-    for (; i < n; i += 4, k++) {
-        const uint32_t nx = lds32(b + 4 * k);
-        uint32_t x = __funnelshift_r(prev, nx, sh);
-        prev = nx;
-        x |= upper_bytes(x) >> 2;
-        const uint32_t nb = n - i;
-        if (nb >= 4) w.put4(x); else w.put(x & ((1u << (8 * nb)) - 1), nb);
-    }
-}
-template <class W>
-__device__ void put_dom_owner_w(W& w, const Res& r) {
-    if (r.ptr_tgt != NONE16) {
-        if (r.ptr_tgt != r.d_off) put_dom_labels_w(w, r, r.ptr_tgt);
-        const uint32_t ptr = 0xC000u | (12u + r.ptr_tgt);
-        w.put(bswap16(ptr), 2);
-    } else { put_dom_labels_w(w, r, r.d_end); w.put(0, 1); }
-}
-template <class W>
-__device__ __forceinline__ void put_global_bytes(W& w, const uint8_t* s, uint32_t n) {
-    for (uint32_t i = 0; i < n; i++) w.put(__ldg(s + i), 1);
-}
-
-template <class W>
-__device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
-    const uint32_t p = r.sp;
-    uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
-    switch (r.rk) {
-    case RK_A1: case RK_PTR: an = r.keep_ans; break;
-    case RK_SOA: ns = r.keep_ans; break;
-    case RK_SVC_A: case RK_SVC_SRV: an = r.keep_ans; ar += r.keep_add; break;
-    }
-    const uint32_t flags = 0x80u | ((uint32_t)r.opcode << 3) | 0x04u | (r.tc ? 0x02u : 0u) | r.rd;
-    w.put4_first((ldsu32(p) & 0xFFFFu) | (flags << 16) | ((uint32_t)r.rcode << 24));   // id, QR AA TC RD, rcode
-    w.put4(0x00000100u | (bswap16(an) << 16));                                  // QDCOUNT=1, ANCOUNT
-    w.put4(bswap16(ns) | (bswap16(ar) << 16));                                  // NSCOUNT, ARCOUNT
-    w.copy(p + 12, r.qn_len + 4);                                               // question, verbatim
-    bool opt_done = !r.edns;
-    if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310
-        const uint32_t bt = bswap32(r.ttl);
-        if (r.ptr_tgt == r.d_off) {              // owner is a bare pointer: the 16-byte RR as four whole words
-            w.put4(bswap16(0xC000u | (12u + r.ptr_tgt)) | 0x01000000u);        // ptr | TYPE A ...
-            w.put4(0x00000100u | (bt << 16));                                    // ... CLASS IN | ttl (high half)
-            w.put4((bt >> 16) | 0x04000000u);                                    // ttl (low half) | RDLENGTH 4
-            w.put4(bswap32(r.val));
-        } else {
-            put_dom_owner_w(w, r);
-            w.put4(0x01000100u); w.put4(bt); w.put(0x0400u, 2); w.put4(bswap32(r.val));
-        }
-    } else if (r.rk == RK_PTR && r.keep_ans) {                                  // :130
-        const uint32_t tl = P.arena[r.val];
-        w.put(0x0CC0u, 2); w.put4(0x01000C00u); w.put4(bswap32(r.ttl)); w.put(bswap16(tl), 2);
-        put_global_bytes(w, P.arena + r.val + 1, tl);
-    } else if (r.rk == RK_SOA && r.keep_ans) {                                  // :286-287
-        const EngineConst* E = P.eng;
-        put_dom_owner_w(w, r);
-        w.put4(0x01000600u); w.put4(bswap32(r.ttl)); w.put(bswap16(P.soa_len + 20), 2);
-        put_global_bytes(w, E->soa, P.soa_len);
-        w.put4(0); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(r.ttl));
-    } else if (r.rk == RK_SVC_A || r.rk == RK_SVC_SRV) {
-        const bool srv = r.rk == RK_SVC_SRV;
-        SvcView sv; sv.open(P.arena, r.val);
-        const uint32_t dwl = dom_wire_len(r);
-        uint32_t left = r.keep_ans;
-        for (uint32_t t = 0; t < r.n_walk && left; t++) {
-            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-            const uint32_t fl = k->flags;
-            if (fl & KID_ADDR_NULL) continue;
-            if (srv) {                                                          // :396-400
-                const uint32_t np = k->nports, wl = k->wire_len;
-                const uint8_t* ports = (const uint8_t*)(k + 1);
-                const uint8_t* kwp = ports + 2 * np;
-                for (uint32_t c = 0; c < np && left; c++, left--) {
-                    w.put(0x0CC0u, 2); w.put4(0x01002100u); w.put4(bswap32(r.ttl)); w.put(bswap16(6 + wl + dwl), 2);
-                    w.put4(0x0A000000u);                                        // priority 0, weight 10
-                    w.put(bswap16(ld16a(ports + 2 * c)), 2);
-                    put_global_bytes(w, kwp, wl);
-                    put_dom_labels_w(w, r, r.d_end); w.put(0, 1);
-                }
-            } else {                                                            // :411-414
-                uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                if (r.ttl < rttl) rttl = r.ttl;
-                put_dom_owner_w(w, r);
-                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
-            }
-        }
-        if (srv) {
-            if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); opt_done = true; }
-            left = r.keep_add;
-            for (uint32_t t = 0; t < r.n_walk && left; t++) {                   // :401-402
-                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-                const uint32_t fl = k->flags;
-                if (fl & KID_ADDR_NULL) continue;
-                const uint8_t* kwp = (const uint8_t*)(k + 1) + 2 * k->nports;
-                const uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                put_global_bytes(w, kwp, k->wire_len);
-                put_dom_owner_w(w, r);
-                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
-            }
-        }
-    }
-    if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-    w.end();
-}
-
 // ---- the kernel ------------------------------------------------------------------------------
 __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
