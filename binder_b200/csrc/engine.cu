@@ -507,16 +507,6 @@ struct bb_engine {
     const bb_zone* zone = nullptr; uint64_t zone_gen = 0; uint64_t arena_cap = 0;
 };
 
-static bool name_to_wire(const std::string& s, std::string& out) {
-    out.clear(); size_t st = 0;
-    if (s.empty()) return false;
-    for (size_t i = 0; i <= s.size(); i++) if (i == s.size() || s[i] == '.') {
-        size_t l = i - st; if (l < 1 || l > 63) return false;
-        out.push_back((char)l); out.append(s, st, l); st = i + 1;
-    }
-    return true;
-}
-
 extern "C" {
 
 const char* bb_strerror(int err) {
@@ -574,19 +564,8 @@ bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) return fail(BB_ERR_NO_DEVICE);
     if (o->device < 0 || o->device >= ndev) return fail(BB_ERR_ARG);
-    std::string dom = o->dns_domain, w, hw;
-    for (char c : dom) if (c >= 'A' && c <= 'Z') return fail(BB_ERR_DOMAIN);
-    if (!name_to_wire(dom, w) || !name_to_wire("hostmaster." + dom, hw) || hw.size() + 1 > 255) return fail(BB_ERR_DOMAIN);
     bb_engine* e = new bb_engine();
-    memset(&e->hconst, 0, sizeof e->hconst);
-    e->hconst.suffix_len = (uint32_t)dom.size() + 1;
-    e->hconst.suffix[0] = '.'; memcpy(e->hconst.suffix + 1, dom.data(), dom.size());
-    // SOARecord(dnsDomain): mname = dnsDomain, rname = hostmaster.<dnsDomain>, both uncompressed
-    memcpy(e->hconst.soa, w.data(), w.size()); e->hconst.soa[w.size()] = 0;
-    memcpy(e->hconst.soa + w.size() + 1, hw.data(), hw.size()); e->hconst.soa[w.size() + 1 + hw.size()] = 0;
-    e->hconst.soa_len = (uint32_t)(w.size() + 1 + hw.size() + 1);
-    memcpy(e->hconst.wire_tail + 256 - w.size(), w.data(), w.size());   // word-wise suffix gate compares the name's tail with this
-    e->hconst.recursion = o->recursion ? 1 : 0;
+    if (!bb::make_engine_const(o->dns_domain, o->recursion != 0, e->hconst)) { delete e; return fail(BB_ERR_DOMAIN); }
     e->device = o->device; e->ordered = o->ordered_output ? 1 : 0;
     e->max_batch = o->max_batch ? o->max_batch : (1u << 20);
     if (e->max_batch > (1u << 22)) { delete e; return fail(BB_ERR_ARG); }
@@ -675,20 +654,7 @@ int bb_engine_apply_update(bb_engine* e, bb_zone* z) {
 int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, const char* const* dc_names, uint32_t n_dc,
                                    int ptr_forwardable) {
     if (!e || (n_dc && !dc_names) || n_dc > bb::RF_MAX_DC) return BB_ERR_ARG;
-    bb::EngineConst& C = e->hconst;
-    if (!region_domain) {
-        if (C.recursion) C.recursion = 1;
-    } else {
-        if (!C.recursion) return BB_ERR_ARG;                       // the engine was created without recursion
-        const size_t L = strlen(region_domain);
-        if (L > 255) return BB_ERR_ARG;
-        for (uint32_t k = 0; k < n_dc; k++) { const size_t l = dc_names[k] ? strlen(dc_names[k]) : 0; if (l < 1 || l > 63) return BB_ERR_ARG; }
-        C.rf_dom_len = (uint32_t)L; memset(C.rf_dom, 0, sizeof C.rf_dom); memcpy(C.rf_dom, region_domain, L);
-        C.rf_ndc = n_dc; memset(C.rf_dc, 0, sizeof C.rf_dc); memset(C.rf_dc_len, 0, sizeof C.rf_dc_len);
-        for (uint32_t k = 0; k < n_dc; k++) { C.rf_dc_len[k] = (uint8_t)strlen(dc_names[k]); memcpy(C.rf_dc[k], dc_names[k], C.rf_dc_len[k]); }
-        C.rf_ptr = ptr_forwardable ? 1 : 0;
-        C.recursion = 2;
-    }
+    if (!bb::set_recursion_filter_const(e->hconst, region_domain, dc_names, n_dc, ptr_forwardable != 0)) return BB_ERR_ARG;
     CK(cudaSetDevice(e->device));
     CK(cudaDeviceSynchronize());                                   // batches in flight finish with the old filter
     CK(cudaMemcpy(e->d_const, &e->hconst, sizeof(bb::EngineConst), cudaMemcpyHostToDevice));

@@ -224,7 +224,9 @@ __device__ __forceinline__ uint32_t dom_owner_len(const Res& r) {
 __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_t)(r.d_end - r.d_off) + 1; }
 
 // Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
+#ifndef BB_HOST_EMU
 __device__ __forceinline__ unsigned long long gtime_early() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 #define STAMP_SVC(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * 16 + (k)] = gtime_early(); } while (0)
 __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
     STAMP_SVC(11);
@@ -235,7 +237,9 @@ __device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, u
         const uint32_t rl = sv.hdr()->rec_len;
         const uint8_t* b0 = (const uint8_t*)((uintptr_t)sv.base & ~(uintptr_t)127);
         const uint8_t* e0 = sv.base + rl;
+#ifndef BB_HOST_EMU
         for (const uint8_t* q = b0 + 128; q < e0; q += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
+#endif
     }
     uint32_t nk = sv.hdr()->nkids;
     r.nk = (uint16_t)nk;
@@ -361,7 +365,9 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     size_service(P, r, qidx, srv, fixed);
 }
 
+#ifndef BB_HOST_EMU
 __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#endif
 // per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
 constexpr int NSTAGE = 16;
 #define STAMP(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * NSTAGE + (k)] = gtime(); } while (0)
@@ -370,17 +376,21 @@ constexpr int NSTAGE = 16;
 // Same decisions as resolve_forward() below, four name bytes per step, for the common case:
 // packet staged in shared memory, QNAME <= 64 wire bytes, lookup key <= 48 bytes (inline slot
 // keys).  Anything else returns false and takes the generic path.
+#ifndef BB_HOST_EMU        /* the host emulation (tests/native/cuda_shim.h) supplies these over an emulated shared memory */
 __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+#endif
 // unaligned 32-bit load from shared memory (the staging buffers carry read slack)
 __device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
     const uint32_t b = a & ~3u;
     return __funnelshift_r(lds32(b), lds32(b + 4), (a & 3u) * 8);
 }
 // v << n with PTX semantics: any n > 31 (including a wrapped-around negative) gives 0
+#ifndef BB_HOST_EMU
 __device__ __forceinline__ uint32_t shl_clamp(uint32_t v, uint32_t n) { uint32_t r; asm("shl.b32 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(n)); return r; }
+#endif
 // 0x80 in every byte of v that is zero
 __device__ __forceinline__ uint32_t zero_bytes(uint32_t v) { return ~(((v & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | v | 0x7F7F7F7Fu); }
 // 0x80 in every byte of x7 (7-bit bytes) that is >= k

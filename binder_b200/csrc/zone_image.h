@@ -17,6 +17,7 @@
 #ifndef BB_ZONE_IMAGE_H
 #define BB_ZONE_IMAGE_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #if defined(__CUDACC__)
@@ -142,6 +143,7 @@ BB_HD uint32_t shuffle_rand(uint64_t seed, uint32_t qidx, uint32_t i) {
 }
 
 // ---- per-engine constants (createServer options, lib/server.js:435-441) ----------------
+constexpr uint32_t RF_MAX_DC = 16;
 struct EngineConst {
     uint32_t suffix_len;         // strlen('.' + dnsDomain); 0 when dnsDomain === '' (:157)
     uint32_t soa_len;            // SOA rdata up to (not including) the trailing 5 x u32
@@ -160,7 +162,66 @@ struct EngineConst {
     uint8_t  rf_dc_len[16];
     uint8_t  rf_dc[16][64];      // datacenter names (self.dcs keys), case-sensitive
 };
-constexpr uint32_t RF_MAX_DC = 16;
+
+// ---- building the per-engine constants (host side; shared by the engine and the CPU emulation harness) ----
+// dotted name -> wire labels without terminator; false if a label is empty or longer than 63 bytes
+inline bool name_to_wire_labels(const char* s, size_t n, uint8_t* out, size_t cap, size_t* len) {
+    size_t st = 0, w = 0;
+    if (n == 0) return false;
+    for (size_t i = 0; i <= n; i++) if (i == n || s[i] == '.') {
+        const size_t l = i - st;
+        if (l < 1 || l > 63 || w + 1 + l > cap) return false;
+        out[w++] = (uint8_t)l;
+        for (size_t k = 0; k < l; k++) out[w++] = (uint8_t)s[st + k];
+        st = i + 1;
+    }
+    *len = w;
+    return true;
+}
+// createServer options -> EngineConst (lib/server.js:435-441; SOARecord(dnsDomain) of :286-287: mname = dnsDomain,
+// rname = hostmaster.<dnsDomain>, both uncompressed).  false: dns_domain is not a lower-case, encodable name.
+inline bool make_engine_const(const char* dns_domain, bool recursion, EngineConst& C) {
+    size_t n = 0; while (dns_domain[n]) ++n;
+    for (size_t i = 0; i < n; i++) if (dns_domain[i] >= 'A' && dns_domain[i] <= 'Z') return false;
+    uint8_t w[256], hw[300]; size_t wl = 0, hl = 0;
+    char hm[300]; const char pre[] = "hostmaster.";
+    if (n + sizeof pre > sizeof hm) return false;
+    for (size_t i = 0; i < sizeof pre - 1; i++) hm[i] = pre[i];
+    for (size_t i = 0; i < n; i++) hm[sizeof pre - 1 + i] = dns_domain[i];
+    if (!name_to_wire_labels(dns_domain, n, w, sizeof w, &wl) || !name_to_wire_labels(hm, sizeof pre - 1 + n, hw, sizeof hw, &hl) || hl + 1 > 255)
+        return false;
+    C = EngineConst();
+    unsigned char* z = (unsigned char*)&C; for (size_t i = 0; i < sizeof C; i++) z[i] = 0;
+    C.suffix_len = (uint32_t)n + 1;
+    C.suffix[0] = '.'; for (size_t i = 0; i < n; i++) C.suffix[1 + i] = (uint8_t)dns_domain[i];
+    for (size_t i = 0; i < wl; i++) C.soa[i] = w[i];
+    C.soa[wl] = 0;
+    for (size_t i = 0; i < hl; i++) C.soa[wl + 1 + i] = hw[i];
+    C.soa[wl + 1 + hl] = 0;
+    C.soa_len = (uint32_t)(wl + 1 + hl + 1);
+    for (size_t i = 0; i < wl; i++) C.wire_tail[256 - wl + i] = w[i];     // word-wise suffix gate compares the name's tail with this
+    C.recursion = recursion ? 1 : 0;
+    return true;
+}
+// lib/recursion.js:329-344 pre-filter fields (see bb_engine_set_recursion_filter).  false: bad arguments.
+inline bool set_recursion_filter_const(EngineConst& C, const char* region_domain, const char* const* dc_names, uint32_t n_dc, bool ptr) {
+    if (!region_domain) { if (C.recursion) C.recursion = 1; return true; }
+    if (!C.recursion || n_dc > RF_MAX_DC || (n_dc && !dc_names)) return false;
+    size_t L = 0; while (region_domain[L]) ++L;
+    if (L > 255) return false;
+    for (uint32_t k = 0; k < n_dc; k++) { size_t l = 0; if (dc_names[k]) while (dc_names[k][l]) ++l; if (l < 1 || l > 63) return false; }
+    C.rf_dom_len = (uint32_t)L;
+    for (size_t i = 0; i < sizeof C.rf_dom; i++) C.rf_dom[i] = i < L ? (uint8_t)region_domain[i] : 0;
+    C.rf_ndc = n_dc;
+    for (uint32_t k = 0; k < RF_MAX_DC; k++) {
+        size_t l = 0; if (k < n_dc) while (dc_names[k][l]) ++l;
+        C.rf_dc_len[k] = (uint8_t)l;
+        for (size_t i = 0; i < 64; i++) C.rf_dc[k][i] = i < l ? (uint8_t)dc_names[k][i] : 0;
+    }
+    C.rf_ptr = ptr ? 1 : 0;
+    C.recursion = 2;
+    return true;
+}
 
 // host-side container of a built zone
 struct ZoneImage {

@@ -1,0 +1,98 @@
+// CPU emulation of the resolve kernel: the SAME per-query device source (binder_b200/csrc/resolve_device.cuh:
+// decode, lookup, resolve()/resolvePtr() decisions, sizing, both response writers) compiled for the host through
+// tests/native/cuda_shim.h, driven tile by tile the way bbk::resolve_kernel drives it (staging into an emulated
+// shared memory, CTA scan, placement, staged + swizzled or direct emit, flush).  The tile driver below is a
+// sequential restatement of the kernel body; the per-query functions are the device code itself.  Lets kernel logic
+// be checked against the oracle without a GPU (tests/test_host_emulation.py).  Test infrastructure, not product.
+#include "cuda_shim.h"
+#include "../../binder_b200/csrc/zone_image.h"
+#include "../../include/binder_b200.h"
+#include "../../binder_b200/csrc/resolve_device.cuh"
+
+#include <vector>
+
+uint8_t* bb_emu_smem = nullptr;
+extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
+
+namespace {
+using namespace bbk;
+constexpr size_t OFF_IN = 0;                               // s_in  [S_IN + 32]
+constexpr size_t OFF_OUT = 9216;                           // s_out [S_OUT], 1024-aligned like the kernel's
+constexpr size_t OFF_SFX = OFF_OUT + ((S_OUT + 1023) / 1024) * 1024;
+constexpr size_t SMEM_BYTES = OFF_SFX + 256 + 64;
+static_assert(OFF_OUT >= S_IN + 32 && OFF_OUT % 1024 == 0, "layout");
+}
+
+extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain, int recursion,
+                                    const char* rf_region, const char* const* rf_dcs, uint32_t rf_n, int rf_ptr,
+                                    const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed, uint32_t qidx_base,
+                                    int ordered, int tcp, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
+                                    uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss) {
+    static thread_local std::vector<uint8_t> smem(SMEM_BYTES + 1024);
+    bb_emu_smem = (uint8_t*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);     // offsets == emulated shared addresses
+    bb::EngineConst C;
+    if (!bb::make_engine_const(dns_domain, recursion != 0, C)) return BB_ERR_DOMAIN;
+    if (rf_region && !bb::set_recursion_filter_const(C, rf_region, rf_dcs, rf_n, rf_ptr != 0)) return BB_ERR_ARG;
+    const bb::ZoneImage* img = zone ? bb_zone_image(zone) : nullptr;
+    Params P; memset(&P, 0, sizeof P);
+    P.pkts = pkts; P.pkt_off = pkt_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
+    P.out = out; P.out_cap = out_cap; P.out_off = out_off; P.out_len = out_len; P.status = status; P.miss_idx = miss_idx;
+    P.table = img ? img->slots : nullptr; P.mask = img ? img->nslots - 1 : 0; P.arena = img ? img->arena : nullptr;
+    P.ready = img && img->ready; P.eng = &C; P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion;
+    P.nranks = 1; P.tcp = tcp ? 1u : 0u;
+    (void)ordered;                                          // one tile at a time: arrival order IS query order here
+    uint8_t* s_in = bb_emu_smem + OFF_IN; uint8_t* s_out = bb_emu_smem + OFF_OUT; uint8_t* s_sfx = bb_emu_smem + OFF_SFX;
+    memcpy(s_sfx, C.wire_tail, 256);
+    uint64_t gbase = 0; uint32_t mbase = 0;
+    for (uint32_t q0 = 0; q0 < n; q0 += T) {
+        const uint32_t nq = std::min<uint32_t>(T, n - q0);
+        blockIdx.x = q0 / T;
+        const uint32_t* s_off = pkt_off + q0;
+        const uint32_t b0 = s_off[0], b1 = s_off[nq], a0 = b0 & ~15u;
+        const bool staged = b1 >= b0 && b1 - a0 <= (uint32_t)S_IN;
+        if (staged) memcpy(s_in, pkts + a0, ((b1 - a0 + 15) >> 4) << 4);            // the batch container is padded for this
+        Res r[T]; uint32_t qidx[T];
+        uint32_t tile_bytes = 0, tile_miss = 0, my_o[T], my_m[T];
+        for (uint32_t t = 0; t < nq; t++) {
+            threadIdx.x = t;
+            r[t].status = ST_DROPPED; r[t].rlen = 0; r[t].rk = RK_NONE; r[t].trunc = 0; r[t].sp = 0;
+            qidx[t] = qidx_base + q0 + t;
+            const uint32_t o0 = s_off[t], o1 = s_off[t + 1];
+            if (o1 >= o0 && o1 - o0 <= 65535u) {
+                r[t].p = staged ? s_in + (o0 - a0) : pkts + o0;
+                r[t].sp = staged ? (uint32_t)(OFF_IN + (o0 - a0)) : 0u;
+                resolve_query(P, r[t], o1 - o0, qidx[t], (uint32_t)OFF_SFX);
+            }
+            my_o[t] = tile_bytes; my_m[t] = tile_miss;
+            tile_bytes += r[t].rlen; tile_miss += r[t].status == ST_MISS;
+        }
+        if (gbase + tile_bytes > out_cap) return BB_ERR_CAPACITY;
+        bool any_generic = false;
+        for (uint32_t t = 0; t < nq; t++) {
+            out_off[q0 + t] = (uint32_t)(gbase + my_o[t]); out_len[q0 + t] = r[t].rlen; status[q0 + t] = r[t].status;
+            if (r[t].status == ST_MISS) miss_idx[mbase + my_m[t]] = q0 + t;
+            any_generic |= r[t].rlen && !(r[t].sp && !r[t].trunc);
+        }
+        const bool direct = any_generic || tile_bytes > (uint32_t)CAPW;
+        if (direct) {
+            for (uint32_t t = 0; t < nq; t++) {
+                if (!r[t].rlen) continue;
+                threadIdx.x = t;
+                if (!(r[t].sp && !r[t].trunc)) emit_response(P, r[t], out + gbase + my_o[t], qidx[t]);
+                else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
+            }
+        } else if (tile_bytes) {
+            const uint32_t shift = (uint32_t)(gbase & 15);
+            for (uint32_t t = 0; t < nq; t++) {
+                if (!r[t].rlen) continue;
+                threadIdx.x = t;
+                WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t]); emit_fast(P, r[t], w, qidx[t]);
+            }
+            for (uint32_t x = 0; x < tile_bytes; x++) out[gbase + x] = s_out[swz(shift + x)];     // the flush: g[x] <-> s_out[swz(shift + x)]
+        }
+        gbase += tile_bytes; mbase += tile_miss;
+    }
+    out_off[n] = (uint32_t)gbase;
+    *n_miss = mbase;
+    return BB_OK;
+}

@@ -1,0 +1,134 @@
+"""The per-query device code (binder_b200/csrc/resolve_device.cuh) compiled for the host and run on the CPU by
+tests/native/emu_resolve.cpp, against the oracle: the same source the GPU runs, checked without a GPU.  What this
+does NOT cover is the CUDA kernel body itself (cooperative staging, scan, claims, flush) — the `-m gpu` tests do."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+import fuzzgen
+import helpers as H
+from binder_b200 import synth
+from test_gpu_parity import assert_same
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_EMU = {}
+
+
+def emu_lib(tmp):
+    if 'lib' not in _EMU:
+        cxx = shutil.which('g++')
+        if not cxx:
+            pytest.skip('no g++')
+        so = os.path.join(str(tmp), 'libbbemu.so')
+        srcs = [os.path.join(ROOT, 'tests', 'native', 'emu_resolve.cpp'), os.path.join(ROOT, 'binder_b200', 'csrc', 'zone_build.cpp')]
+        subprocess.check_call([cxx, '-std=c++17', '-O1', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-I', os.path.join(ROOT, 'include'),
+                               '-I', os.path.join(ROOT, 'binder_b200', 'csrc'), '-o', so] + srcs)
+        L = ctypes.CDLL(so)
+        L.bb_zone_build.restype = ctypes.c_void_p
+        L.bb_zone_build.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.POINTER(ctypes.c_int)]
+        L.bb_zone_free.argtypes = [ctypes.c_void_p]
+        L.bb_zone_apply.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]
+        L.bb_emu_resolve_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint32,
+                                           ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
+                                           ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        _EMU['lib'] = L
+    return _EMU['lib']
+
+
+class EmuEngine(object):
+    """Engine look-alike over bb_emu_resolve_batch (query-order packing, like ordered_output=1)."""
+    ordered = True
+
+    def __init__(self, L, dns_domain, snap, recursion=False):
+        self.L, self.dom, self.recursion, self.rf = L, dns_domain.encode(), recursion, None
+        self.zone = None
+        if snap is not None:
+            err = ctypes.c_int(0)
+            self.zone = L.bb_zone_build(snap, len(snap), self.dom, ctypes.byref(err))
+            assert self.zone, err.value
+
+    def apply(self, delta):
+        assert self.L.bb_zone_apply(self.zone, delta, len(delta)) == 0
+
+    def set_recursion_filter(self, region, dcs=(), ptr=False):
+        self.rf = None if region is None else (region.encode('latin-1'), [d.encode('latin-1') for d in dcs], ptr)
+
+    def resolve_batch(self, data, off, seed=0, qidx_base=0, tcp=False):
+        data = np.ascontiguousarray(data, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.uint32)
+        n = len(off) - 1
+        cap = max(4096, min(n * (65536 if tcp else 1232), 0xFFFFFF00))
+        out = np.zeros(cap, dtype=np.uint8); ooff = np.zeros(n + 1, dtype=np.uint32); olen = np.zeros(max(n, 1), dtype=np.uint16)
+        st = np.zeros(max(n, 1), dtype=np.uint8); miss = np.zeros(max(n, 1), dtype=np.uint32); nm = ctypes.c_uint32(0)
+        region, arr, ndc, ptr = None, None, 0, 0
+        if self.rf:
+            region, dcs, ptr = self.rf
+            arr = (ctypes.c_char_p * max(len(dcs), 1))(*dcs); ndc = len(dcs)
+        rc = self.L.bb_emu_resolve_batch(self.zone, self.dom, int(self.recursion), region, arr, ndc, int(ptr), data.ctypes.data, off.ctypes.data, n,
+                                         seed, qidx_base, 1, int(tcp), out.ctypes.data, cap, ooff.ctypes.data, olen.ctypes.data,
+                                         st.ctypes.data, miss.ctypes.data, ctypes.byref(nm))
+        assert rc == 0, rc
+        return out[:ooff[n]].copy(), ooff, olen[:n], st[:n], miss[:nm.value].copy()
+
+
+@pytest.fixture(scope='module')
+def L(tmp_path_factory):
+    return emu_lib(tmp_path_factory.mktemp('emu'))
+
+
+@pytest.mark.parametrize('seed', range(12))
+def test_device_source_on_cpu_matches_oracle(L, seed):
+    snap, info = fuzzgen.gen_zone(seed, n_top=40)
+    recursion = seed % 3 == 0
+    emu = EmuEngine(L, info['dns_domain'], snap, recursion)
+    orc = H.make_impl('oracle', info['dns_domain'], snap, recursion=recursion)
+    pkts = fuzzgen.gen_queries(seed, info, n=3000) + fuzzgen.malformed_packets() + fuzzgen.tolerated_packets()
+    data, off = synth.pack_batch(pkts)
+    assert_same(emu, orc, data, off, seed=seed * 1315423911 + 3, qidx_base=seed * 1000)
+    assert_same(emu, orc, data, off, seed=seed + 1, tcp=True)
+
+
+def test_emulated_not_ready_and_edges(L):
+    emu = EmuEngine(L, 'foo.com', None)
+    orc = H.make_impl('oracle', 'foo.com', None)
+    pkts = fuzzgen.malformed_packets() + fuzzgen.tolerated_packets() + [
+        synth.make_query('hosta.foo.com', 'A'), synth.make_query('1.0.0.10.in-addr.arpa', 'PTR'),
+        synth.make_query('hosta.bar.org', 'A'), synth.make_query('_http._tcp.s.foo.com', 'SRV'), synth.make_query('x.foo.com', 'TXT')]
+    data, off = synth.pack_batch(pkts)
+    assert_same(emu, orc, data, off)
+    for n in (0, 1, 127, 128, 129):
+        d, o = synth.pack_batch(pkts[:n] if n <= len(pkts) else (pkts * 8)[:n])
+        assert_same(emu, orc, d, o, seed=n)
+
+
+@pytest.mark.parametrize('seed', range(4))
+def test_emulated_updates_filter(L, seed):
+    """Deltas (bb_zone_apply) and the recursion pre-filter through the emulated device code."""
+    snap, info = fuzzgen.gen_zone(seed + 300, n_top=30)
+    emu = EmuEngine(L, info['dns_domain'], snap, recursion=True)
+    orc = H.make_impl('oracle', info['dns_domain'], snap, recursion=True)
+    paths = fuzzgen.snapshot_paths(snap)
+    for rnd in range(3):
+        delta, paths = fuzzgen.gen_delta(seed * 100 + rnd, paths, info, n_ops=50)
+        emu.apply(delta); orc.apply_delta(delta)
+        data, off = synth.pack_batch(fuzzgen.gen_queries(seed * 17 + rnd, info, n=1500))
+        assert_same(emu, orc, data, off, seed=rnd)
+    for region, dcs, ptr in (('foo.com', ['web', 'h1', 'nope', 'c'], True), ('oo.com', ['web'], False), ('com', ['foo'], True)):
+        emu.set_recursion_filter(region, dcs, ptr); orc.set_recursion_filter(region, dcs, ptr)
+        assert_same(emu, orc, data, off, seed=9)
+
+
+def test_emulated_large_answers_over_tcp(L):
+    from test_tcp import big_zone
+    snap = big_zone()
+    emu = EmuEngine(L, 'foo.com', snap)
+    orc = H.make_impl('oracle', 'foo.com', snap)
+    pk = [synth.make_query('_http._tcp.big.foo.com', 'SRV'), synth.make_query('big.foo.com', 'A'), synth.make_query('_http._tcp.huge.foo.com', 'SRV'),
+          synth.make_query('huge.foo.com', 'A'), synth.make_query('hosta.foo.com', 'A', edns=4096)] * 30
+    data, off = synth.pack_batch(pk)
+    assert_same(emu, orc, data, off, seed=3, tcp=True)
+    assert_same(emu, orc, data, off, seed=3)
