@@ -25,7 +25,8 @@ def emu_lib(tmp):
             pytest.skip('no g++')
         so = os.path.join(str(tmp), 'libbbemu.so')
         srcs = [os.path.join(ROOT, 'tests', 'native', 'emu_resolve.cpp'), os.path.join(ROOT, 'binder_b200', 'csrc', 'zone_build.cpp')]
-        subprocess.check_call([cxx, '-std=c++17', '-O1', '-fPIC', '-shared', '-Wno-unknown-pragmas', '-I', os.path.join(ROOT, 'include'),
+        san = ['-g', '-fsanitize=address,undefined', '-fno-omit-frame-pointer'] if os.environ.get('BB_EMU_SANITIZE') else []   # run under LD_PRELOAD=libasan
+        subprocess.check_call([cxx, '-std=c++17', '-O1', '-fPIC', '-shared', '-Wno-unknown-pragmas'] + san + ['-I', os.path.join(ROOT, 'include'),
                                '-I', os.path.join(ROOT, 'binder_b200', 'csrc'), '-o', so] + srcs)
         L = ctypes.CDLL(so)
         L.bb_zone_build.restype = ctypes.c_void_p
