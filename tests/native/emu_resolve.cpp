@@ -27,7 +27,7 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                                     const char* rf_region, const char* const* rf_dcs, uint32_t rf_n, int rf_ptr,
                                     const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed, uint32_t qidx_base,
                                     int ordered, int tcp, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
-                                    uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss) {
+                                    uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss, const uint32_t* qidx_map) {
     static thread_local std::vector<uint8_t> smem(SMEM_BYTES + 1024);
     bb_emu_smem = (uint8_t*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);     // offsets == emulated shared addresses
     bb::EngineConst C;
@@ -56,7 +56,7 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
         for (uint32_t t = 0; t < nq; t++) {
             threadIdx.x = t;
             r[t].status = ST_DROPPED; r[t].rlen = 0; r[t].rk = RK_NONE; r[t].trunc = 0; r[t].sp = 0;
-            qidx[t] = qidx_base + q0 + t;
+            qidx[t] = qidx_map ? qidx_map[q0 + t] : qidx_base + q0 + t;     // routed batches carry their ingress index
             const uint32_t o0 = s_off[t], o1 = s_off[t + 1];
             if (o1 >= o0 && o1 - o0 <= 65535u) {
                 r[t].p = staged ? s_in + (o0 - a0) : pkts + o0;
@@ -94,5 +94,40 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
     }
     out_off[n] = (uint32_t)gbase;
     *n_miss = mbase;
+    return BB_OK;
+}
+
+// Route mode (the ingress half of the sharded path, route_push_kernel's per-query step): which rank owns each
+// query's lookup key; queries that need no lookup stay on `rank`.
+extern "C" int bb_emu_route_batch(const char* dns_domain, int recursion, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
+                                  uint32_t nranks, uint32_t rank, uint8_t* owner) {
+    static thread_local std::vector<uint8_t> smem(SMEM_BYTES + 1024);
+    bb_emu_smem = (uint8_t*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);
+    bb::EngineConst C;
+    if (!bb::make_engine_const(dns_domain, recursion != 0, C)) return BB_ERR_DOMAIN;
+    Params P; memset(&P, 0, sizeof P);
+    P.pkts = pkts; P.pkt_off = pkt_off; P.n = n; P.eng = &C; P.ready = 1;
+    P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion;
+    P.route = 1; P.nranks = nranks; P.rank = rank;
+    uint8_t* s_in = bb_emu_smem + OFF_IN;
+    memcpy(bb_emu_smem + OFF_SFX, C.wire_tail, 256);
+    for (uint32_t q0 = 0; q0 < n; q0 += T) {
+        const uint32_t nq = std::min<uint32_t>(T, n - q0);
+        const uint32_t* s_off = pkt_off + q0;
+        const uint32_t b0 = s_off[0], b1 = s_off[nq], a0 = b0 & ~15u;
+        const bool staged = b1 >= b0 && b1 - a0 <= (uint32_t)S_IN;
+        if (staged) memcpy(s_in, pkts + a0, ((b1 - a0 + 15) >> 4) << 4);
+        for (uint32_t t = 0; t < nq; t++) {
+            Res r; r.owner = (uint8_t)rank; r.sp = 0; r.p = nullptr;
+            const uint32_t o0 = s_off[t], o1 = s_off[t + 1];
+            if (o1 >= o0 && o1 - o0 <= 65535u) {
+                r.p = staged ? s_in + (o0 - a0) : pkts + o0;
+                r.sp = staged ? (uint32_t)(OFF_IN + (o0 - a0)) : 0u;
+                resolve_query(P, r, o1 - o0, 0, (uint32_t)OFF_SFX);
+                if (r.owner >= nranks) r.owner = (uint8_t)rank;
+            }
+            owner[q0 + t] = r.owner;
+        }
+    }
     return BB_OK;
 }

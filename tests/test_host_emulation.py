@@ -36,7 +36,11 @@ def emu_lib(tmp):
         L.bb_emu_resolve_batch.argtypes = [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_void_p, ctypes.c_uint32,
                                            ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_uint32,
                                            ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p,
-                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+                                           ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+        L.bb_zone_build_shard.restype = ctypes.c_void_p
+        L.bb_zone_build_shard.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_char_p, ctypes.c_uint32, ctypes.c_uint32, ctypes.POINTER(ctypes.c_int)]
+        L.bb_emu_route_batch.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint32, ctypes.c_uint32,
+                                         ctypes.c_uint32, ctypes.c_void_p]
         _EMU['lib'] = L
     return _EMU['lib']
 
@@ -45,12 +49,12 @@ class EmuEngine(object):
     """Engine look-alike over bb_emu_resolve_batch (query-order packing, like ordered_output=1)."""
     ordered = True
 
-    def __init__(self, L, dns_domain, snap, recursion=False):
+    def __init__(self, L, dns_domain, snap, recursion=False, nranks=1, rank=0):
         self.L, self.dom, self.recursion, self.rf = L, dns_domain.encode(), recursion, None
         self.zone = None
         if snap is not None:
             err = ctypes.c_int(0)
-            self.zone = L.bb_zone_build(snap, len(snap), self.dom, ctypes.byref(err))
+            self.zone = L.bb_zone_build_shard(snap, len(snap), self.dom, nranks, rank, ctypes.byref(err))
             assert self.zone, err.value
 
     def apply(self, delta):
@@ -59,7 +63,7 @@ class EmuEngine(object):
     def set_recursion_filter(self, region, dcs=(), ptr=False):
         self.rf = None if region is None else (region.encode('latin-1'), [d.encode('latin-1') for d in dcs], ptr)
 
-    def resolve_batch(self, data, off, seed=0, qidx_base=0, tcp=False):
+    def resolve_batch(self, data, off, seed=0, qidx_base=0, tcp=False, qidx_map=None):
         data = np.ascontiguousarray(data, dtype=np.uint8); off = np.ascontiguousarray(off, dtype=np.uint32)
         n = len(off) - 1
         cap = max(4096, min(n * (65536 if tcp else 1232), 0xFFFFFF00))
@@ -71,7 +75,8 @@ class EmuEngine(object):
             arr = (ctypes.c_char_p * max(len(dcs), 1))(*dcs); ndc = len(dcs)
         rc = self.L.bb_emu_resolve_batch(self.zone, self.dom, int(self.recursion), region, arr, ndc, int(ptr), data.ctypes.data, off.ctypes.data, n,
                                          seed, qidx_base, 1, int(tcp), out.ctypes.data, cap, ooff.ctypes.data, olen.ctypes.data,
-                                         st.ctypes.data, miss.ctypes.data, ctypes.byref(nm))
+                                         st.ctypes.data, miss.ctypes.data, ctypes.byref(nm),
+                                         None if qidx_map is None else np.ascontiguousarray(qidx_map, dtype=np.uint32).ctypes.data)
         assert rc == 0, rc
         return out[:ooff[n]].copy(), ooff, olen[:n], st[:n], miss[:nm.value].copy()
 
@@ -133,3 +138,35 @@ def test_emulated_large_answers_over_tcp(L):
     data, off = synth.pack_batch(pk)
     assert_same(emu, orc, data, off, seed=3, tcp=True)
     assert_same(emu, orc, data, off, seed=3)
+
+
+@pytest.mark.parametrize('seed,world', [(0, 2), (1, 3), (2, 8), (3, 5)])
+def test_emulated_sharded_pipeline(L, seed, world):
+    """The whole sharded path on the CPU: route mode of the device code picks each query's owner, the owner's shard
+    (bb_zone_build_shard) resolves it with the query's ingress index — every answer must equal the unsharded oracle's."""
+    snap, info = fuzzgen.gen_zone(seed + 600, n_top=35)
+    dom = info['dns_domain']
+    orc = H.make_impl('oracle', dom, snap, recursion=True)
+    shards = [EmuEngine(L, dom, snap, recursion=True, nranks=world, rank=r) for r in range(world)]
+    pkts = fuzzgen.gen_queries(seed, info, n=2500) + fuzzgen.malformed_packets()
+    data, off = synth.pack_batch(pkts)
+    n = len(pkts)
+    ingress = 1 % world                                        # the rank these queries arrive at
+    owner = np.zeros(n, dtype=np.uint8)
+    assert L.bb_emu_route_batch(dom.encode(), 1, data.ctypes.data, off.ctypes.data, n, world, ingress, owner.ctypes.data) == 0
+    o_out, o_off, o_len, o_st, o_miss = orc.resolve_batch(data, off, seed=77, qidx_base=4000)
+    assert len(set(owner.tolist())) > 1 or world == 1
+    seen = 0
+    for r in range(world):
+        idx = np.nonzero(owner == r)[0]
+        if idx.size == 0:
+            continue
+        sub = [pkts[i] for i in idx]
+        d, o = synth.pack_batch(sub)
+        out, ooff, olen, st, miss = shards[r].resolve_batch(d, o, seed=77, qidx_map=(4000 + idx).astype(np.uint32))
+        assert np.array_equal(st, o_st[idx]) and np.array_equal(olen, o_len[idx]), (r, 'status/lengths')
+        for k, i in enumerate(idx):
+            assert bytes(out[ooff[k]:ooff[k] + olen[k]]) == bytes(o_out[o_off[i]:o_off[i + 1]]), (r, int(i), pkts[i])
+        assert sorted(int(idx[m]) for m in miss) == [int(i) for i in o_miss if owner[i] == r]
+        seen += idx.size
+    assert seen == n
