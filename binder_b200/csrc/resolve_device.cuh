@@ -453,6 +453,19 @@ __device__ __forceinline__ uint32_t bad_chars(uint32_t lo) {
     return ~ok & 0x80808080u;
 }
 
+#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
+// The same 32-byte half (32-byte aligned) of BOTH candidate slots through the read-only path, two 256-bit loads in
+// ONE asm statement: the compiler cannot make the second slot's load conditional on the first slot's compare
+// (it does that to separate statements, turning one memory round trip into two).
+__device__ __forceinline__ void ldg256_pair(const uint4* pa, const uint4* pb, uint4& a_lo, uint4& a_hi, uint4& b_lo, uint4& b_hi) {
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
+                 "ld.global.nc.v8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];"
+                 : "=r"(a_lo.x), "=r"(a_lo.y), "=r"(a_lo.z), "=r"(a_lo.w), "=r"(a_hi.x), "=r"(a_hi.y), "=r"(a_hi.z), "=r"(a_hi.w),
+                   "=r"(b_lo.x), "=r"(b_lo.y), "=r"(b_lo.z), "=r"(b_lo.w), "=r"(b_hi.x), "=r"(b_hi.y), "=r"(b_hi.z), "=r"(b_hi.w)
+                 : "l"(pa), "l"(pb));
+}
+#endif
+
 __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
     const EngineConst* E = P.eng;
     if (!P.ready && !P.route) return false;            // not-ready engines: exact ordering of refusals lives in the generic path
@@ -543,8 +556,19 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         // hit or miss, for every lane of the warp
         const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
         const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
+#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
+        // Experiment for the next round (off by default, not yet measured): sm_100 has 256-bit global loads
+        // (LDG.E.256), so a 64-byte slot is two load instructions instead of four — half the passes through the
+        // load/store pipe for the same bytes and the same 32 registers.  Seen in the SASS so far: ptxas sinks the
+        // second slot's loads behind the first slot's compare (a lazy second probe: two round trips for keys in
+        // their second slot and for misses), even with both slots' loads in one asm statement — the compare has to
+        // be made unconditionally dependent on both slots before this is worth a GPU run.
+        uint4 a0, a1, a2, a3, b0, b1, b2, b3;
+        ldg256_pair(sa, sb, a0, a1, b0, b1); ldg256_pair(sa + 2, sb + 2, a2, a3, b2, b3);
+#else
         const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
         const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
+#endif
         const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |
                             (kw[0] ^ a1.x) | (kw[1] ^ a1.y) | (kw[2] ^ a1.z) | (kw[3] ^ a1.w) |
                             (kw[4] ^ a2.x) | (kw[5] ^ a2.y) | (kw[6] ^ a2.z) | (kw[7] ^ a2.w) |
