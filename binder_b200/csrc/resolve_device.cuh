@@ -561,8 +561,10 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
         // (LDG.E.256), so a 64-byte slot is two load instructions instead of four — half the passes through the
         // load/store pipe for the same bytes and the same 32 registers.  Seen in the SASS so far: ptxas sinks the
         // second slot's loads behind the first slot's compare (a lazy second probe: two round trips for keys in
-        // their second slot and for misses), even with both slots' loads in one asm statement — the compare has to
-        // be made unconditionally dependent on both slots before this is worth a GPU run.
+        // their second slot and for misses), even with both slots' loads in one asm statement; with the branch-free
+        // selection below it issues all four loads unconditionally but still waits for the first slot's data before
+        // the second slot's loads (8-register-aligned destinations under the 64-register cap).  Needs the key out of
+        // registers (shared memory) before it is worth a GPU run.
         uint4 a0, a1, a2, a3, b0, b1, b2, b3;
         ldg256_pair(sa, sb, a0, a1, b0, b1); ldg256_pair(sa + 2, sb + 2, a2, a3, b2, b3);
 #else
@@ -578,8 +580,17 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
                             (kw[4] ^ b2.x) | (kw[5] ^ b2.y) | (kw[6] ^ b2.z) | (kw[7] ^ b2.w) |
                             (kw[8] ^ b3.x) | (kw[9] ^ b3.y) | (kw[10] ^ b3.z) | (kw[11] ^ b3.w);
         // an empty slot has kind 0 and klen 0, so it can never equal `want` (dl >= 1)
+#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
+        {   // branch-free selection: both compares feed the result, so neither slot's loads can be made conditional
+            const uint32_t ma = da == 0 ? 0xFFFFFFFFu : 0u, mb = (db == 0 ? 0xFFFFFFFFu : 0u) & ~ma;
+            const uint32_t hy = (a0.y & ma) | (b0.y & mb);
+            hit = (ma | mb) != 0; kind = (hy >> 8) & 0xFF; ttl = (a0.z & ma) | (b0.z & mb); val = (a0.w & ma) | (b0.w & mb);
+            clean = (hy >> 24) & SLOT_KEY_CLEAN;
+        }
+#else
         if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
         else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
+#endif
     }
     STAMP(5);
     if (!(hit && clean)) {
