@@ -233,3 +233,102 @@ def batch_host_a_fast(zone, n, seed, miss_frac=0.0, rd=True):
     data[:n * 48] = pk.reshape(-1)
     off = (np.arange(n + 1, dtype=np.uint64) * 48).astype(np.uint32)
     return data, off
+
+
+# ---------------------------------------------------------------------------------------
+# vectorised workload generators (BASELINE.json configs 2-5 at full size) + SURVEY.md §8(d) byte model
+# ---------------------------------------------------------------------------------------
+K_HOST_A, K_HOST_AAAA, K_SVC_A, K_SVC_SRV = 0, 1, 2, 3
+
+
+def _put_digits(pk, col_last, ndig, v):
+    v = v.copy()
+    for k in range(ndig):
+        pk[:, col_last - k] = 48 + v % 10
+        v //= 10
+
+
+def gen_batch(zone, n, seed, mix, miss_frac=0.0, rd=True):
+    """n packets drawn from `mix` = {K_*: share}; -> (data uint8 padded to 16, off uint32[n+1], meta).
+    meta = dict(kind int8[n], idx int64[n] (host or service index; >= n_hosts: absent name)).
+    K_HOST_A/K_HOST_AAAA: h%07d.g%04d.<dom>;  K_SVC_A: svc%06d.<dom>;  K_SVC_SRV: _http._tcp.svc%06d.<dom>."""
+    rng = np.random.default_rng(seed)
+    kinds = np.array(sorted(mix), dtype=np.int8)
+    shares = np.array([mix[k] for k in kinds], dtype=np.float64)
+    kind = kinds[np.searchsorted(np.cumsum(shares / shares.sum()), rng.random(n), side='right').clip(0, len(kinds) - 1)]
+    is_host = kind <= K_HOST_AAAA
+    idx = np.where(is_host, rng.integers(0, max(zone.n_hosts, 1), size=n), rng.integers(0, max(zone.n_services, 1), size=n))
+    if miss_frac > 0:
+        miss = (rng.random(n) < miss_frac) & is_host
+        idx = np.where(miss, idx + zone.n_hosts + 7, idx)
+    ids = rng.integers(0, 65536, size=n)
+    tm = {K_HOST_A: make_query(host_name(0), 1, 0, rd=rd), K_HOST_AAAA: make_query(host_name(0), 28, 0, rd=rd),
+          K_SVC_A: make_query(svc_name(0), 1, 0, rd=rd), K_SVC_SRV: make_query('_http._tcp.' + svc_name(0), 33, 0, rd=rd)}
+    W = max(len(t) for t in tm.values())
+    pk = np.zeros((n, W), dtype=np.uint8)
+    lens = np.zeros(n, dtype=np.int64)
+    for k, t in tm.items():
+        m = kind == k
+        if not m.any():
+            continue
+        sub = np.tile(np.frombuffer(t, dtype=np.uint8), (int(m.sum()), 1))
+        v = idx[m]
+        if k <= K_HOST_AAAA:
+            _put_digits(sub, 20, 7, v)
+            _put_digits(sub, 26, 4, v % N_GROUPS)
+        else:
+            _put_digits(sub, (21 if k == K_SVC_A else 32), 6, v)
+        pk[m, :len(t)] = sub
+        lens[m] = len(t)
+    pk[:, 0] = ids >> 8
+    pk[:, 1] = ids & 255
+    off = np.zeros(n + 1, dtype=np.uint32)
+    np.cumsum(lens, out=off[1:])
+    keep = np.arange(W)[None, :] < lens[:, None]
+    flat = pk[keep]
+    data = np.zeros((flat.size + 15) // 16 * 16, dtype=np.uint8)
+    data[:flat.size] = flat
+    return data, off, dict(kind=kind, idx=idx)
+
+
+WORKLOADS = {
+    # name: (description, zone service_frac, mix, miss_frac, recursion)
+    'config2': ('config2: 1M-record zone, 65536-query A-record batches (100% hit, RD=1, no OPT)', 0.0, {K_HOST_A: 1.0}, 0.0, False),
+    'config3': ('config3: 10M-record zone, 262144-query batches, 50% SRV _http._tcp.svcN / 50% A on service names', 0.15,
+                {K_SVC_SRV: 0.5, K_SVC_A: 0.5}, 0.0, False),
+    'config4': ('config4: 10M-record zone, 1048576-query global batch, 60% A(host) / 20% SRV(service) / 20% AAAA(->NOTIMP)', 0.15,
+                {K_HOST_A: 0.6, K_SVC_SRV: 0.2, K_HOST_AAAA: 0.2}, 0.0, False),
+    'config5': ('config5: 10M-record zone, A(host) lookups, 90% of names absent, RD=1, recursion on (misses -> compacted miss list)', 0.15,
+                {K_HOST_A: 1.0}, 0.9, True),
+}
+
+
+def service_payload_bytes(zone):
+    """SURVEY.md §8(d) payload(service j) = 16 + sum over member children (len(label)+1 + 4 addr + 4 ttl + 2*nports),
+    for every generated service (children typed `host` are not members, lib/server.js:352-360)."""
+    j = np.arange(max(zone.n_services, 1), dtype=np.int64)
+    k = 1 + (j * 2654435761 >> 7) % 8
+    pay = np.full(j.shape, 16, dtype=np.int64)
+    for c in range(8):
+        sel = (j * 31 + c * 7) % 10
+        has = c < k
+        pay += np.where(has & (sel < 8), 4 + 1 + 4 + 4 + 2, 0) + np.where(has & (sel == 8), 4 + 1 + 4 + 4 + 4, 0)
+    return pay
+
+
+def algorithmic_bytes(zone, off, meta, out_len):
+    """B(q) = len(query)+4 + probe(q) + len(response)+8 summed over a batch -> (read, write).
+    probe: hit = len(key)+1 + payload(node) (host 8; service 16 + members); miss = 8; no lookup (AAAA -> NOTIMP) = 0."""
+    n = len(off) - 1
+    kind, idx = meta['kind'], meta['idx']
+    host_key = len(host_name(0)) + 1
+    svc_key = len(svc_name(0)) + 1
+    probe = np.zeros(n, dtype=np.int64)
+    hostq = kind == K_HOST_A
+    probe[hostq] = np.where(idx[hostq] < zone.n_hosts, host_key + 8, 8)
+    svcq = kind >= K_SVC_A
+    if svcq.any():
+        probe[svcq] = svc_key + service_payload_bytes(zone)[idx[svcq]]
+    read = int(off[n]) + 4 * n + int(probe.sum())
+    write = int(np.asarray(out_len, dtype=np.int64).sum()) + 8 * n
+    return read, write

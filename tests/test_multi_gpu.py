@@ -10,17 +10,20 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 4, 8])
 @pytest.mark.parametrize('ordered,host_results', [('0', '0'), ('1', '0'), ('0', '1')])
-def test_sharded_two_ranks(ordered, host_results):
-    """host_results=1: the owner writes its answers straight into pinned host mirrors (bb_shard_host_results)."""
+def test_sharded_ranks(world, ordered, host_results):
+    """world ranks, one per GPU (skipped when the box has fewer): every routed query answered exactly once, by its
+    owner, with the oracle's bytes.  host_results=1: the owner writes its answers straight into pinned host
+    mirrors (bb_shard_host_results)."""
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip('needs 2 GPUs')
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
     env = dict(os.environ, BB_ORDERED=ordered, BB_HOST_RESULTS=host_results, BB_BATCH='20000', BB_ZONE='100000')
-    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
-                        '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(ROOT, 'tools', 'multi_check.py')],
-                       env=env, capture_output=True, text=True, timeout=600)
-    assert 'MULTI_CHECK_OK world=2' in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+                        '--master-addr', '127.0.0.1', '--master-port', str(29533 + world), os.path.join(ROOT, 'tools', 'multi_check.py')],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert 'MULTI_CHECK_OK world=%d' % world in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
 
 
 @pytest.mark.gpu
