@@ -50,7 +50,9 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 // per-batch pointer advances by its stride per region, sizes and shuffle indices come from device memory.
 template <bool ORDERED, bool MULTI>
 __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params P) {
-    __shared__ __align__(16) uint8_t s_in[S_IN + 32];
+    // the packets start 16 bytes in: a staged packet's shared address is never 0 (Res::sp == 0 means "not staged")
+    __shared__ __align__(16) uint8_t s_inbuf[16 + S_IN + 32];
+    uint8_t* const s_in = s_inbuf + 16;
     __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
@@ -295,7 +297,9 @@ __host__ __device__ inline size_t region_size(uint32_t cap_q, uint32_t cap_b) { 
 
 __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const PushParams A) {
     const Params& P = A.P;
-    __shared__ __align__(16) uint8_t s_in[S_IN + 32];
+    // the packets start 16 bytes in: a staged packet's shared address is never 0 (Res::sp == 0 means "not staged")
+    __shared__ __align__(16) uint8_t s_inbuf[16 + S_IN + 32];
+    uint8_t* const s_in = s_inbuf + 16;
     __shared__ __align__(16) uint8_t s_sorted[S_IN + 16 * MAX_RANKS + 32];     // the tile's packets grouped by owner
     __shared__ uint32_t s_moff[T], s_mq[T];                                    // per-owner-grouped offsets / query indices
     __shared__ uint32_t s_off[T + 1];
@@ -462,11 +466,11 @@ __global__ void wait_regions_kernel(const uint8_t* recv_set, size_t reg_size, ui
     __threadfence_system();
 }
 
-// Incremental zone update: overwrite the listed slots (one thread per 16-byte chunk).  Runs with no
+// Incremental zone update: overwrite the listed 32-byte slots (one thread per 16-byte chunk).  Runs with no
 // batch in flight (bb_engine_apply_update synchronises first), so a reader never sees half a slot.
 __global__ void patch_slots_kernel(Slot* table, const uint32_t* idx, const uint4* data, uint32_t n) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < 4u * n) ((uint4*)(table + idx[t >> 2]))[t & 3u] = data[t];
+    if (t < 2u * n) ((uint4*)(table + idx[t >> 1]))[t & 1u] = data[t];
 }
 
 }  // namespace bbk
@@ -634,7 +638,7 @@ int bb_engine_apply_update(bb_engine* e, bb_zone* z) {
         cudaError_t c1 = cudaMemcpy(d_idx, slots, (size_t)n * 4, cudaMemcpyHostToDevice);
         cudaError_t c2 = cudaMemcpy(d_data, data.data(), (size_t)n * sizeof(bb::Slot), cudaMemcpyHostToDevice);
         if (c1 == cudaSuccess && c2 == cudaSuccess) {
-            bbk::patch_slots_kernel<<<(4 * n + 255) / 256, 256>>>(e->d_table, d_idx, d_data, n);
+            bbk::patch_slots_kernel<<<(2 * n + 255) / 256, 256>>>(e->d_table, d_idx, d_data, n);
             c1 = cudaGetLastError(); c2 = cudaDeviceSynchronize();
         }
         cudaFree(d_idx); cudaFree(d_data);
@@ -673,7 +677,7 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table;
-    P.eng = e->d_const; P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion;
+    P.eng = e->d_const; P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion; P.lean_ok = e->hconst.lean_ok;
     P.ntiles = (n + bbk::T - 1) / bbk::T;
     P.desc = desc; P.ntiles_cap = e->max_tiles; P.counter = (uint32_t*)(desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch);
@@ -893,7 +897,7 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
     bb_engine* e = s->e;
     bbk::PushParams A; memset(&A, 0, sizeof A);
     A.P.pkts = d_pkts; A.P.pkt_off = d_pkt_off; A.P.n = n; A.P.eng = e->d_const; A.P.ready = 1;
-    A.P.suffix_len = e->hconst.suffix_len; A.P.soa_len = e->hconst.soa_len; A.P.recursion = e->hconst.recursion;
+    A.P.suffix_len = e->hconst.suffix_len; A.P.soa_len = e->hconst.soa_len; A.P.recursion = e->hconst.recursion; A.P.lean_ok = e->hconst.lean_ok;
     A.P.route = 1; A.P.nranks = s->nranks; A.P.rank = s->rank; A.P.table = e->d_table; A.P.mask = e->mask; A.P.arena = e->d_arena;
     A.epoch = ++s->epoch;
     const size_t set = (size_t)(s->epoch & 1) * s->nranks;
@@ -933,7 +937,7 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
         P.bounce = s->d_out;                         // tiles too large to stage assemble on the device first
     }
     P.table = e->d_table; P.mask = e->mask; P.arena = e->d_arena; P.ready = e->ready && e->d_table; P.eng = e->d_const;
-    P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion;
+    P.suffix_len = e->hconst.suffix_len; P.soa_len = e->hconst.soa_len; P.recursion = e->hconst.recursion; P.lean_ok = e->hconst.lean_ok;
     P.ntiles = (s->cap_q + bbk::T - 1) / bbk::T; P.ntiles_cap = e->max_tiles;
     P.desc = (unsigned long long*)s->d_desc; P.counter = (uint32_t*)((unsigned long long*)s->d_desc + e->max_tiles + 1);
     P.epoch = (uint32_t)(++e->epoch); P.stage_log = nullptr; P.route = 0; P.nranks = s->nranks; P.rank = s->rank;

@@ -35,6 +35,7 @@ struct Params {
     const uint32_t* qidx_map;        // when set, query i's shuffle index is qidx_map[i] (routed batches)
     uint32_t route, nranks, rank;    // route != 0: compute the owner rank of each query instead of probing
     uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
+    uint32_t lean_ok;        // dnsDomain is made of [a-z0-9_.-] only: a clean key hit proves the whole name passes lib/server.js:208
     uint32_t tcp;            // the batch arrived over TCP: no 512-byte / EDNS size limit (RFC 1035 4.2.2)
     uint32_t* qidx_out;      // multi-region: each result's ingress index is also written here (host result mirrors)
     const uint32_t* err_in;  // multi-region: the shard's wait-timeout word, copied into totals[6]
@@ -48,7 +49,6 @@ struct Params {
 // per-thread state carried from the sizing pass to the emit pass
 struct Res {
     const uint8_t* p;        // packet bytes (shared memory, or global when the tile did not fit)
-    uint64_t lenmask;        // bit i set: QNAME byte i is a label-length byte (names <= 64 bytes)
     uint32_t sp;             // shared-memory address of the packet (0 when not staged)
     uint32_t qn_len;         // QNAME wire length incl. terminator
     uint32_t ttl, val;
@@ -91,17 +91,14 @@ __device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
     uint32_t qd = be16(p + 4), an = be16(p + 6), ns = be16(p + 8), ar = be16(p + 10);
     if (qd != 1 || an != 0 || ns != 0 || ar > 1) return false;
     uint32_t pos = 12;
-    uint64_t lm = 0;
     for (;;) {
         if (pos >= len) return false;
         uint32_t c = p[pos];
         if (c == 0) { ++pos; break; }
         if (c > 63 || pos + 1 + c > len) return false;
-        if (pos - 12 < 64) lm |= 1ull << (pos - 12);
         pos += 1 + c;
         if (pos - 12 + 1 > 255) return false;
     }
-    r.lenmask = lm;
     r.qn_len = pos - 12;
     if (pos + 4 > len) return false;
     r.qtype = (uint16_t)be16(p + pos);
@@ -119,18 +116,15 @@ __device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
 
 // ---- zkCache.lookup / reverseLookup ------------------------------------------------------
 // The key is produced twice (hash, then compare) by the same generator so that nothing is
-// materialised.  Forward keys: the domain part in dotted lower case.  Reverse keys: the
-// labels before "in-addr.arpa", reversed, joined by '.'.
+// materialised.  Forward keys (zone_image.h): the wire labels in front of the dnsDomain suffix,
+// lower-cased (length bytes are below 'A').  Reverse keys: the labels before "in-addr.arpa",
+// reversed, joined by '.'.
 struct FwdKey {
-    const uint8_t* nm; uint32_t d_off, d_end;
-    uint32_t pos, nlp;
-    __device__ uint32_t length() const { return d_end - d_off - 1; }
-    __device__ void start() { pos = d_off + 1; nlp = d_off + 1 + nm[d_off]; }
-    __device__ uint32_t next() {
-        uint32_t c;
-        if (pos == nlp) { c = '.'; nlp = pos + 1 + nm[pos]; } else c = lower8(nm[pos]);
-        ++pos; return c;
-    }
+    const uint8_t* nm; uint32_t k0, k1;      // wire range [k0, k1) of the QNAME
+    uint32_t pos;
+    __device__ uint32_t length() const { return k1 - k0; }
+    __device__ void start() { pos = k0; }
+    __device__ uint32_t next() { return lower8(nm[pos++]); }
 };
 struct RevKey {
     const uint8_t* nm; uint32_t nlab;       // labels before in-addr.arpa
@@ -161,22 +155,21 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
     const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, h2, P.mask) };
     for (int c = 0; c < 2; c++) {
         const Slot* s = P.table + cand[c];
-        uint4 hd = __ldg((const uint4*)s);                  // hash | klen,kind,ns,flags | ttl | val
-        uint32_t sk = (hd.y >> 8) & 0xFF;
+        uint4 hd = __ldg((const uint4*)s);                  // klen,kind,ns,flags | ttl | val | key[0..3]
+        uint32_t sk = (hd.x >> 8) & 0xFF;
         if (sk == K_EMPTY) continue;
-        if (hd.x == h && ((hd.y >> 16) & 1) == ns) {
-            uint32_t sl = hd.y & 0xFF;
-            const uint8_t* kb = nullptr;
-            if (sl == KLEN_OVERFLOW) {
-                uint32_t off = __ldg((const uint32_t*)s->key), l = __ldg((const uint32_t*)(s->key + 4));
-                if (l == klen) kb = P.arena + off;
-            } else if (sl == klen) kb = s->key;
-            if (kb) {
-                kg.start();
-                bool eq = true;
-                for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
-                if (eq) { kind = sk; ttl = hd.z; val = hd.w; return true; }
-            }
+        if (((hd.x >> 16) & 0xFF) != ns) continue;
+        uint32_t sl = hd.x & 0xFF;
+        const uint8_t* kb = nullptr;
+        if (sl == KLEN_OVERFLOW) {
+            uint32_t off = hd.w, l = __ldg((const uint32_t*)(s->key + 4)), sh = __ldg((const uint32_t*)(s->key + 8));
+            if (l == klen && sh == h) kb = P.arena + off;
+        } else if (sl == klen) kb = s->key;
+        if (kb) {
+            kg.start();
+            bool eq = true;
+            for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
+            if (eq) { kind = sk; ttl = hd.y; val = hd.z; return true; }
         }
     }
     return false;
@@ -205,16 +198,51 @@ __device__ __forceinline__ uint32_t perm_at(const Res& r, uint32_t t, uint64_t s
     return r.nk <= 16 ? (uint32_t)(r.perm >> (4 * t)) & 15 : perm_at_slow(t, r.nk, seed, qidx);
 }
 
+// A service record in the arena (zone_image.h): 32-byte header, nkids 16-byte child records, the children's RR bytes.
 struct SvcView {
-    const uint8_t* base; const uint8_t* arena; const uint32_t* kid_off;
+    const uint8_t* base; const uint8_t* arena;
+    uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports ; hflags,sp_len,dom_wl,sp[13]
     __device__ void open(const uint8_t* arena_, uint32_t off) {
         arena = arena_; base = arena_ + off;
-        const SvcHdr* h = (const SvcHdr*)base;
-        uint32_t sl = h->srvce_len == 0xFF ? 0 : h->srvce_len, pl = h->proto_len == 0xFF ? 0 : h->proto_len;
-        kid_off = (const uint32_t*)(base + ((sizeof(SvcHdr) + sl + pl + 3) & ~3u));
+        h0 = __ldg((const uint4*)base); h1 = __ldg((const uint4*)base + 1);
     }
-    __device__ const SvcHdr* hdr() const { return (const SvcHdr*)base; }
-    __device__ const KidRec* kid(uint32_t i) const { return (const KidRec*)(arena + kid_off[i]); }
+    __device__ uint32_t ttl() const { return h0.x; }
+    __device__ uint32_t nkids() const { return h0.y & 0xFFFF; }
+    __device__ uint32_t n_valid() const { return h0.y >> 16; }
+    __device__ uint32_t sum_ports() const { return h0.z & 0xFFFF; }
+    __device__ uint32_t sum_wl() const { return h0.z >> 16; }
+    __device__ uint32_t sum_wl_ports() const { return h0.w; }
+    __device__ uint32_t hflags() const { return h1.x & 0xFF; }
+    __device__ uint32_t sp_len() const { return (h1.x >> 8) & 0xFF; }
+    __device__ uint32_t dom_wl() const { return (h1.x >> 16) & 0xFF; }
+    // byte i of "_srvce._proto." as wire labels
+    __device__ uint32_t sp_byte(uint32_t i) const {
+        if (hflags() & SVC_SP_EXT) { const uint32_t off = (h1.x >> 24) | (h1.y << 8); return __ldg(arena + off + i); }
+        const uint32_t j = i + 3;                                   // sp starts at byte 3 of h1
+        const uint32_t w = j < 4 ? h1.x : j < 8 ? h1.y : j < 12 ? h1.z : h1.w;
+        return (w >> (8 * (j & 3))) & 0xFF;
+    }
+};
+// One child record (one 16-byte load) and where its ready RR bytes are.
+struct KidView {
+    uint4 a;                 // addr | rttl | flags,wire_len,nports,pad | rr_off
+    const uint8_t* rr;       // its RR bytes: [A answer 16][additional, pad 16][SRV answers]
+    uint32_t dwl;            // the service's dom_wl
+    __device__ void load(const SvcView& sv, uint32_t i) {
+        a = __ldg((const uint4*)(sv.base + sizeof(SvcHdr) + sizeof(KidRec) * (size_t)i));
+        rr = sv.base + a.w; dwl = sv.dom_wl();
+    }
+    __device__ uint32_t addr() const { return a.x; }
+    __device__ uint32_t rttl() const { return a.y; }
+    __device__ uint32_t flags() const { return a.z & 0xFF; }
+    __device__ uint32_t wire_len() const { return (a.z >> 8) & 0xFF; }
+    __device__ uint32_t nports() const { return (a.z >> 16) & 0xFF; }
+    __device__ const uint8_t* a_rr() const { return rr; }
+    __device__ const uint8_t* add_rr() const { return rr + 16; }                                   // starts with the child's labels
+    __device__ const uint8_t* srv_rr() const { return rr + 16 + ((kid_add_len(wire_len()) + 15) & ~15u); }
+    __device__ uint32_t srv_len() const { return kid_srv_len(wire_len(), dwl); }
+    __device__ uint32_t port(uint32_t c) const { const uint8_t* p = srv_rr() + c * srv_len() + 16; return (uint32_t)__ldg(p) << 8 | __ldg(p + 1); }
+    __device__ uint32_t name_byte(uint32_t i) const { return __ldg(add_rr() + i); }
 };
 
 // owner-name sizes for this query's domain part (DESIGN.md "Wire spec: compression")
@@ -223,58 +251,48 @@ __device__ __forceinline__ uint32_t dom_owner_len(const Res& r) {
 }
 __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_t)(r.d_end - r.d_off) + 1; }
 
-// Sizing pass over a service's children in shuffled order (lib/server.js:361-416).
-#ifndef BB_HOST_EMU
-__device__ __forceinline__ unsigned long long gtime_early() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
-#endif
-#define STAMP_SVC(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * 16 + (k)] = gtime_early(); } while (0)
-__device__ void size_service(const Params& P, Res& r, uint32_t qidx, bool srv, uint32_t fixed) {
-    STAMP_SVC(11);
-    SvcView sv; sv.open(P.arena, r.val);
-    {   // The record (header, child offsets, children) is contiguous: touch all of its cache lines now,
-        // with independent loads, so that the dependent walks below (and in the emit pass) hit in
-        // L1/L2 instead of paying a DRAM round trip per child.
-        const uint32_t rl = sv.hdr()->rec_len;
-        const uint8_t* b0 = (const uint8_t*)((uintptr_t)sv.base & ~(uintptr_t)127);
-        const uint8_t* e0 = sv.base + rl;
-#ifndef BB_HOST_EMU
-        for (const uint8_t* q = b0 + 128; q < e0; q += 128) asm volatile("prefetch.global.L1 [%0];" :: "l"(q));
-#endif
-    }
-    uint32_t nk = sv.hdr()->nkids;
+// Sizing of a service answer (lib/server.js:361-416).  When no child is malformed for this query type the
+// sums taken at build time size it from the header alone; the children are walked (in shuffled order) only to
+// find where a malformed child cuts the answer short, or which prefix of the RRs survives truncation.
+__device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_t qidx, bool srv, uint32_t fixed) {
+    const uint32_t nk = sv.nkids();
     r.nk = (uint16_t)nk;
-    STAMP_SVC(12);
     r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
-    STAMP_SVC(13);
     const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
     uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
     const uint8_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
-    for (uint32_t t = 0; t < nk; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        uint32_t fl = k->flags;
-        if (fl & badbit) { r.rcode = RC_SERVFAIL; n_walk = t; break; }       // :366-376
-        if (fl & KID_ADDR_NULL) continue;                                     // :378-381
+    if (!(sv.hflags() & (srv ? SVC_BAD_SRV : SVC_BAD_A))) {
         if (srv) {
-            ans_b += (uint32_t)k->nports * (18 + k->wire_len + dwl); n_ans += k->nports;
-            add_b += k->wire_len + dol + 14; n_add++;
-        } else { ans_b += dol + 14; n_ans++; }
+            n_ans = sv.sum_ports(); ans_b = n_ans * (18 + dwl) + sv.sum_wl_ports();
+            n_add = sv.n_valid(); add_b = sv.sum_wl() + n_add * (dol + 14);
+        } else { n_ans = sv.n_valid(); ans_b = n_ans * (dol + 14); }
+    } else {
+        for (uint32_t t = 0; t < nk; t++) {
+            KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+            const uint32_t fl = k.flags();
+            if (fl & badbit) { r.rcode = RC_SERVFAIL; n_walk = t; break; }      // :366-376
+            if (fl & KID_ADDR_NULL) continue;                                    // :378-381
+            if (srv) {
+                ans_b += k.nports() * (18 + k.wire_len() + dwl); n_ans += k.nports();
+                add_b += k.wire_len() + dol + 14; n_add++;
+            } else { ans_b += dol + 14; n_ans++; }
+        }
     }
     r.n_walk = (uint16_t)n_walk;
-    STAMP_SVC(14);
     if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = (uint16_t)n_ans; r.keep_add = (uint16_t)n_add; r.rlen = (uint16_t)(fixed + ans_b + add_b); return; }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits
     r.tc = 1;
     uint32_t total = fixed, ka = 0, kd = 0; bool full = false;
     for (uint32_t t = 0; t < n_walk && !full; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        if (k->flags & KID_ADDR_NULL) continue;
-        uint32_t each = srv ? 18 + k->wire_len + dwl : dol + 14, cnt = srv ? k->nports : 1;
+        KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+        if (k.flags() & KID_ADDR_NULL) continue;
+        uint32_t each = srv ? 18 + k.wire_len() + dwl : dol + 14, cnt = srv ? k.nports() : 1;
         for (uint32_t c = 0; c < cnt; c++) { if (total + each > r.maxsz) { full = true; break; } total += each; ++ka; }
     }
     if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {
-        const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-        if (k->flags & KID_ADDR_NULL) continue;
-        uint32_t each = k->wire_len + dol + 14;
+        KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+        if (k.flags() & KID_ADDR_NULL) continue;
+        uint32_t each = k.wire_len() + dol + 14;
         if (total + each > r.maxsz) break;
         total += each; ++kd;
     }
@@ -351,18 +369,16 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     if (kind == K_UNKNOWN) { r.rcode = RC_NOTIMP; return; }                   // :419-424 + :346-350
     // K_SERVICE (:313-417)
     SvcView sv; sv.open(P.arena, val);
-    const SvcHdr* h = sv.hdr();
-    r.ttl = h->ttl;
-    if (srv) {
-        const uint8_t* sb = sv.base + sizeof(SvcHdr);
-        bool match = h->srvce_len == l0 && h->proto_len == l1;
-        for (uint32_t i = 0; match && i < l0; i++) if (sb[i] != nm[1 + i]) match = false;
-        for (uint32_t i = 0; match && i < l1; i++) if (sb[l0 + i] != nm[2 + l0 + i]) match = false;
-        if (!match) { r.rcode = RC_NXDOMAIN; return; }                        // :334-345
+    r.ttl = sv.ttl();
+    if (srv) {                                                                // :334-345: service === s.srvce && protocol === s.proto
+        const uint32_t n = sv.sp_len();
+        bool match = !(sv.hflags() & SVC_SP_NEVER) && n == l0 + l1 + 2;      // the two length bytes are part of the comparison
+        for (uint32_t i = 0; match && i < n; i++) if (sv.sp_byte(i) != nm[i]) match = false;
+        if (!match) { r.rcode = RC_NXDOMAIN; return; }
     }
     r.rcode = RC_NOERROR;                                                     // :351
     r.rk = srv ? RK_SVC_SRV : RK_SVC_A;
-    size_service(P, r, qidx, srv, fixed);
+    size_service(P, r, sv, qidx, srv, fixed);
 }
 
 #ifndef BB_HOST_EMU
@@ -414,11 +430,10 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
     if (w2 != 0u && w2 != 0x01000000u) return false;                          // NSCOUNT=0, ARCOUNT<=1
     const uint32_t nm = sp + 12, lim = len - 12;                              // name bytes available
     // label hop: one dependent shared-memory byte per label; validity is accumulated, not branched on
-    uint32_t pos = 0, lo = 0, hi = 0, bad = 0, c = lds8(nm);
+    uint32_t pos = 0, bad = 0, c = lds8(nm);
 #pragma unroll 1
     while (c != 0) {
         bad |= c > 63;                                                        // pointers / extended label types
-        lo |= shl_clamp(1u, pos); hi |= shl_clamp(1u, pos - 32u);             // positions >= 64 fall off (shl.b32 clamps its count)
         pos += 1 + c;
         if (pos >= lim || pos > 254) { bad = 1; break; }
         c = lds8(nm + pos);
@@ -426,7 +441,6 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
     if (bad) return false;
     if (pos + 1 + 4 > lim) return false;
     r.qn_len = pos + 1;
-    r.lenmask = (uint64_t)lo | ((uint64_t)hi << 32);
     const uint32_t tc = ldsu32(nm + pos + 1);                                 // QTYPE, QCLASS (big-endian)
     r.qtype = (uint16_t)(((tc & 0xFF) << 8) | ((tc >> 8) & 0xFF));
     if ((tc >> 16) != 0x0100u) return false;                                  // class IN
@@ -453,47 +467,92 @@ __device__ __forceinline__ uint32_t bad_chars(uint32_t lo) {
     return ~ok & 0x80808080u;
 }
 
-#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
-// The same 32-byte half (32-byte aligned) of BOTH candidate slots through the read-only path, two 256-bit loads in
-// ONE asm statement: the compiler cannot make the second slot's load conditional on the first slot's compare
-// (it does that to separate statements, turning one memory round trip into two).
-__device__ __forceinline__ void ldg256_pair(const uint4* pa, const uint4* pb, uint4& a_lo, uint4& a_hi, uint4& b_lo, uint4& b_hi) {
-    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%16];\n\t"
-                 "ld.global.nc.v8.b32 {%8, %9, %10, %11, %12, %13, %14, %15}, [%17];"
-                 : "=r"(a_lo.x), "=r"(a_lo.y), "=r"(a_lo.z), "=r"(a_lo.w), "=r"(a_hi.x), "=r"(a_hi.y), "=r"(a_hi.z), "=r"(a_hi.w),
-                   "=r"(b_lo.x), "=r"(b_lo.y), "=r"(b_lo.z), "=r"(b_lo.w), "=r"(b_hi.x), "=r"(b_hi.y), "=r"(b_hi.z), "=r"(b_hi.w)
-                 : "l"(pa), "l"(pb));
+// Classification of a name the lean path could not settle with a clean hit, the way resolve() does before its
+// lookup: a character outside [a-z0-9_.-] after toLowerCase (lib/server.js:207-215) or a '.' inside a label
+// (DESIGN.md "in-label dots") -> bit 0; a line terminator in a label (the SRV regex's group 3 stops there, :141)
+// -> bit 1.  Walks the labels of QNAME wire range [k0, k1) (already validated).  Out of line: it runs for misses
+// and unusual keys only and must not cost the hit path registers.
+__device__ __noinline__ uint32_t classify_labels(uint32_t nm, uint32_t k0, uint32_t k1) {
+    uint32_t res = 0;
+    for (uint32_t pos = k0; pos < k1;) {
+        const uint32_t l = lds8(nm + pos); ++pos;
+        for (uint32_t i = 0; i < l && pos < k1; i++, pos++) {
+            const uint32_t c = lower8(lds8(nm + pos));
+            if (!((c - 'a' < 26u) || (c - '0' < 10u) || c == '_' || c == '-')) res |= 1u;
+            if (c == '\n' || c == '\r') res |= 2u;
+        }
+    }
+    return res;
 }
-#endif
+// Where the owner name's compression pointer may land when the domain carries upper-case letters: the first label
+// boundary after the last upper-case byte of [k0, k1) — k1 (the start of the dnsDomain suffix, all lower case) at the latest.
+__device__ __noinline__ uint32_t ptr_target_after_upper(uint32_t nm, uint32_t k0, uint32_t k1) {
+    uint32_t tgt = k0;
+    for (uint32_t pos = k0; pos < k1;) {
+        const uint32_t l = lds8(nm + pos);
+        bool up = false;
+        for (uint32_t i = 1; i <= l; i++) { const uint32_t c = lds8(nm + pos + i); up |= (c - 'A' < 26u); }
+        pos += 1 + l;
+        if (up) tgt = pos;
+    }
+    return tgt;
+}
 
-__device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t qidx, uint32_t fixed) {
-    const EngineConst* E = P.eng;
-    if (!P.ready && !P.route) return false;            // not-ready engines: exact ordering of refusals lives in the generic path
-    const uint32_t nm = r.sp + 12;
-    const bool srv = r.qtype == QT_SRV;
-    const uint32_t d_end = r.qn_len - 1;
+// ---- the lean front end of onQuery/resolve() -------------------------------------------------------------
+// The common shape, settled in one pass over the packet's words: a query staged in shared memory, QDCOUNT 1, no
+// trailing bytes (ARCOUNT 0, or one bare OPT), QNAME <= 64 wire bytes that ENDS with dnsDomain's wire labels.
+// Because the terminator's position follows from the packet length, the name is validated without hopping over
+// every label: the bytes in front of the terminator must equal dnsDomain's labels (a word compare, which is also
+// resolve()'s case-sensitive suffix gate, lib/server.js:157-166), and walking the labels in FRONT of them must
+// land exactly on their first length byte.  Walking from the start is what decode() does, so a name accepted
+// here is exactly the name decode() accepts (and its fields are the same); anything else returns 0 and takes the
+// complete decoder and the generic path.  The lookup key is those front labels, lower-cased (zone_image.h).
+// Returns 1 when r is complete (answer sized, or DROPPED), 0 when the caller must run the general path.
+__device__ int lean_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
+    const uint32_t sp = r.sp;
+    if (len < 12 + 2 + 5) return 0;
+    const uint32_t hb = sp & ~3u, hs = (sp & 3u) * 8;
+    const uint32_t t0w = lds32(hb), t1w = lds32(hb + 4), t2w = lds32(hb + 8), t3w = lds32(hb + 12);
+    const uint32_t w0 = __funnelshift_r(t0w, t1w, hs), w1 = __funnelshift_r(t1w, t2w, hs), w2 = __funnelshift_r(t2w, t3w, hs);
+    const uint32_t fl = (w0 >> 16) & 0xFF;                                    // byte 2: QR opcode AA TC RD
+    if ((fl & 0x80) || w1 != 0x00000100u || (w2 != 0u && w2 != 0x01000000u)) { r.status = ST_DROPPED; return 1; }   // as decode()
+    r.opcode = (fl >> 3) & 0xF; r.rd = fl & 1;
+    const uint32_t nm = sp + 12;
+    uint32_t tail = 5;                                                        // terminator + QTYPE + QCLASS
+    r.edns = 0; r.adv = 0;
+    if (w2) {                                                                 // one additional RR: a bare OPT at the very end?
+        if (len < 12 + 2 + 5 + 11) return 0;
+        const uint32_t q = sp + len - 11;
+        const uint32_t a = ldsu32(q), b = ldsu32(q + 4), c2 = ldsu32(q + 8);
+        if ((a & 0xFFFFFFu) != 0x290000u) return 0;                           // root owner, TYPE 41
+        if ((c2 >> 8) & 0xFFFFu) return 0;                                    // RDLEN != 0: options follow
+        r.adv = (uint16_t)(((a >> 24) << 8) | (b & 0xFF));
+        r.edns = 1; tail = 16;
+    }
+    const uint32_t d_end = len - 12 - tail;                                   // where the terminator must be
+    if (d_end > 63) return 0;
+    const uint32_t tq = ldsu32(nm + d_end);                                   // 00 | QTYPE | QCLASS hi
+    if ((tq & 0xFFu) != 0 || (tq >> 24) != 0 || lds8(nm + d_end + 4) != 1) return 0;
+    const uint32_t qtype = ((tq >> 8) & 0xFF) << 8 | ((tq >> 16) & 0xFF);
+    const bool srv = qtype == QT_SRV;
+    // SRV: /^(_[^_.]*)[.](_[^_.]*)[.](.*)/ (:141-154) — the first two labels
     uint32_t d_off = 0, l0 = 0, l1 = 0;
     bool refuse = false;
-    if (srv) {                                                                // :141-154
+    if (srv) {
         l0 = lds8(nm);
-        if (l0 == 0) { r.rcode = RC_REFUSED; return true; }
+        if (l0 == 0 || l0 > 63 || 1 + l0 >= d_end) return 0;
         const uint32_t p1 = 1 + l0; l1 = lds8(nm + p1);
-        if (l1 == 0) { r.rcode = RC_REFUSED; return true; }
+        if (l1 == 0 || l1 > 63 || p1 + 1 + l1 >= d_end) return 0;
         for (uint32_t i = 1; i <= l0; i++) { const uint32_t c = lds8(nm + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
         for (uint32_t i = 1; i <= l1; i++) { const uint32_t c = lds8(nm + p1 + i); refuse |= (i == 1) ? (c != '_') : (c == '_' || c == '.'); }
         d_off = p1 + 1 + l1;
-        if (lds8(nm + d_off) == 0) { r.rcode = RC_REFUSED; return true; }
     }
-    if (d_end <= d_off + 1) { r.rcode = RC_REFUSED; return true; }            // root name
-    const uint32_t dl = d_end - d_off - 1;
-    if (dl > KEY_INLINE_MAX) return false;
-    // suffix gate (:157-166), case-sensitive, on the raw wire bytes: the domain's last sl bytes must be
-    // dnsDomain's wire labels and start at a label boundary ('.' + dnsDomain in the dotted view)
+    // the name must end with dnsDomain's labels, with at least one label in front of them
     const uint32_t sl = P.suffix_len;
-    if (dl < sl) { r.rcode = RC_REFUSED; return true; }       // (a truncated SRV domain is shorter still)
+    if (d_end < d_off + sl + 2) return 0;
+    const uint32_t k1 = d_end - sl;                                           // the suffix's first length byte
     {
-        const uint32_t t0 = d_end - sl;                                       // where the suffix's first length byte must sit
-        uint32_t bad = ((r.lenmask >> t0) & 1ull) ? 0u : 1u;
+        uint32_t bad = 0;
         const uint32_t nw = (sl + 3) >> 2;
         for (uint32_t j = 0; j < nw; j++) {                                   // words right-aligned to the end of the name
             const uint32_t x = ldsu32(nm + d_end - 4 * (j + 1));
@@ -502,117 +561,118 @@ __device__ bool fast_forward(const Params& P, Res& r, uint32_t s_sfx, uint32_t q
             const uint32_t cm = rem >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - rem)));
             bad |= (x ^ e) & cm;
         }
-        if (bad) { if (srv) return false; r.rcode = RC_REFUSED; return true; }   // SRV: the regex group may stop at a line terminator (:141) -> generic path
+        if (bad) return 0;
     }
-    // normalise (dotted view, toLowerCase :207) + hash, four bytes per step
-    const uint64_t lm = r.lenmask >> (d_off + 1);
-    const uint32_t nwords = (dl + 3) >> 2;
-    const uint32_t tailm = (dl & 3) ? ((1u << (8 * (dl & 3))) - 1) : 0xFFFFFFFFu;
-    uint32_t kw[12];
-    uint32_t h = hash_init(NS_FORWARD), g = hash2_init(NS_FORWARD);
-    uint32_t upw = 0, upi = 0;
-    // consecutive unaligned words share their aligned halves: one LDS per word, not two
-    const uint32_t ka = nm + d_off + 1, kb = ka & ~3u, ksh = (ka & 3u) * 8;
+    {                                                                         // the labels in front: must land on k1
+        uint32_t pos = d_off;
+#pragma unroll 1
+        while (pos < k1) { const uint32_t c = lds8(nm + pos); if (c == 0 || c > 63) return 0; pos += 1 + c; }
+        if (pos != k1) return 0;
+    }
+    // ---- a valid query (what decode() returns for it) ----
+    r.qn_len = d_end + 1; r.qtype = (uint16_t)qtype;
+    r.maxsz = P.tcp ? (uint16_t)65535 : r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
+    const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
+    r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
+    if (r.opcode != 0 || !(qtype == QT_A || srv)) {
+        if (r.opcode == 0 && qtype == QT_PTR) return 0;                       // resolvePtr: general path
+        r.rcode = RC_NOTIMP; return 1;                                        // :500-505
+    }
+    if (!P.ready && !P.route) return 0;                // not-ready engines: exact ordering of refusals lives in the generic path
+    STAMP(3);
+    // lower-case + hash the key bytes [d_off, k1), four at a time (length bytes < 'A' pass through unchanged)
+    const uint32_t pl = k1 - d_off;
+    if (pl > 48) return 0;
+    const uint32_t nwords = (pl + 3) >> 2;
+    const uint32_t tailm = (pl & 3) ? ((1u << (8 * (pl & 3))) - 1) : 0xFFFFFFFFu;
+    const uint32_t ka = nm + d_off, kb = ka & ~3u, ksh = (ka & 3u) * 8;
+    uint32_t kw[5];
+    uint32_t h = hash_init(NS_FORWARD), g = hash2_init(NS_FORWARD), anyup = 0;
     uint32_t wprev = lds32(kb);
 #pragma unroll
-    for (int i = 0; i < 12; i++) {
+    for (int i = 0; i < 5; i++) {
         kw[i] = 0;
         if ((uint32_t)i < nwords) {
             const uint32_t wnext = lds32(kb + 4 * (i + 1));
-            const uint32_t x = __funnelshift_r(wprev, wnext, ksh);
+            uint32_t x = __funnelshift_r(wprev, wnext, ksh);
             wprev = wnext;
-            const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
-            const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;          // label-boundary positions
-            uint32_t xd = (x & ~m8) | (0x2E2E2E2Eu & m8);
-            if ((uint32_t)i == nwords - 1) xd &= tailm;
-            const uint32_t up = upper_bytes(xd);
-            if (up) { upw = up; upi = i; }
-            const uint32_t lo = xd | (up >> 2);
+            if ((uint32_t)i == nwords - 1) x &= tailm;
+            const uint32_t up = upper_bytes(x);
+            anyup |= up;
+            const uint32_t lo = x | (up >> 2);
             kw[i] = lo;
             h = hash_word(h, lo); g = hash2_word(g, lo);
         }
     }
-    h = hash_finish(h, dl);
-    const uint32_t h2 = hash2_finish(g, dl);
-    STAMP(4);
-    if (refuse) { r.rcode = RC_REFUSED; return true; }
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return true; }   // sharding: who would answer
-    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
-    if (!upw) r.ptr_tgt = (uint16_t)d_off;
-    else {
-        const uint32_t pu = d_off + 1 + 4 * upi + ((31 - __clz(upw)) >> 3);  // wire position of the last upper-case byte
-        const uint64_t m = pu + 1 < 64 ? (r.lenmask >> (pu + 1)) : 0ull;
-        r.ptr_tgt = m ? (uint16_t)(pu + 1 + (__ffsll((long long)m) - 1)) : (uint16_t)NONE16;
+#pragma unroll 1
+    for (uint32_t i = 5; i < nwords; i++) {                                   // keys over 20 bytes (they live in the arena)
+        const uint32_t wnext = lds32(kb + 4 * (i + 1));
+        uint32_t x = __funnelshift_r(wprev, wnext, ksh);
+        wprev = wnext;
+        if (i == nwords - 1) x &= tailm;
+        const uint32_t up = upper_bytes(x);
+        anyup |= up;
+        const uint32_t lo = x | (up >> 2);
+        h = hash_word(h, lo); g = hash2_word(g, lo);
     }
-    // zk.lookup(domain): one 64-byte slot per probe, compared as words.  The header compare also
-    // carries the key's dot count: a query with a '.' inside a label has fewer label boundaries than
-    // any key that spells the same, so it can never match here.
-    const uint32_t ndots = (uint32_t)__popcll(r.lenmask >> (d_off + 1));
-    const uint32_t want = dl | ((NS_FORWARD | (ndots << 1)) << 16);
+    h = hash_finish(h, pl);
+    const uint32_t h2 = hash2_finish(g, pl);
+    STAMP(4);
+    if (refuse) { r.rcode = RC_REFUSED; return 1; }
+    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return 1; }      // sharding: who would answer
+    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
+    r.ptr_tgt = anyup ? (uint16_t)ptr_target_after_upper(nm, d_off, k1) : (uint16_t)d_off;
+    // zk.lookup(domain): both cuckoo candidates — one 32-byte sector each — are fetched together: one DRAM round
+    // trip per lookup, hit or miss, for every lane of the warp
     uint32_t kind = 0, ttl = 0, val = 0;
     bool hit = false, clean = false;
     {
-        // 2-choice cuckoo: both candidate slots are fetched together — one DRAM round trip per lookup,
-        // hit or miss, for every lane of the warp
         const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
         const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
-#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
-        // Experiment for the next round (off by default, not yet measured): sm_100 has 256-bit global loads
-        // (LDG.E.256), so a 64-byte slot is two load instructions instead of four — half the passes through the
-        // load/store pipe for the same bytes and the same 32 registers.  Seen in the SASS so far: ptxas sinks the
-        // second slot's loads behind the first slot's compare (a lazy second probe: two round trips for keys in
-        // their second slot and for misses), even with both slots' loads in one asm statement; with the branch-free
-        // selection below it issues all four loads unconditionally but still waits for the first slot's data before
-        // the second slot's loads (8-register-aligned destinations under the 64-register cap).  Needs the key out of
-        // registers (shared memory) before it is worth a GPU run.
-        uint4 a0, a1, a2, a3, b0, b1, b2, b3;
-        ldg256_pair(sa, sb, a0, a1, b0, b1); ldg256_pair(sa + 2, sb + 2, a2, a3, b2, b3);
-#else
-        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1), a2 = __ldg(sa + 2), a3 = __ldg(sa + 3);
-        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1), b2 = __ldg(sb + 2), b3 = __ldg(sb + 3);
-#endif
-        const uint32_t da = (a0.x ^ h) | ((a0.y & 0x00FF00FFu) ^ want) |
-                            (kw[0] ^ a1.x) | (kw[1] ^ a1.y) | (kw[2] ^ a1.z) | (kw[3] ^ a1.w) |
-                            (kw[4] ^ a2.x) | (kw[5] ^ a2.y) | (kw[6] ^ a2.z) | (kw[7] ^ a2.w) |
-                            (kw[8] ^ a3.x) | (kw[9] ^ a3.y) | (kw[10] ^ a3.z) | (kw[11] ^ a3.w);
-        const uint32_t db = (b0.x ^ h) | ((b0.y & 0x00FF00FFu) ^ want) |
-                            (kw[0] ^ b1.x) | (kw[1] ^ b1.y) | (kw[2] ^ b1.z) | (kw[3] ^ b1.w) |
-                            (kw[4] ^ b2.x) | (kw[5] ^ b2.y) | (kw[6] ^ b2.z) | (kw[7] ^ b2.w) |
-                            (kw[8] ^ b3.x) | (kw[9] ^ b3.y) | (kw[10] ^ b3.z) | (kw[11] ^ b3.w);
-        // an empty slot has kind 0 and klen 0, so it can never equal `want` (dl >= 1)
-#if defined(BB_LDG256) && !defined(BB_HOST_EMU)
-        {   // branch-free selection: both compares feed the result, so neither slot's loads can be made conditional
-            const uint32_t ma = da == 0 ? 0xFFFFFFFFu : 0u, mb = (db == 0 ? 0xFFFFFFFFu : 0u) & ~ma;
-            const uint32_t hy = (a0.y & ma) | (b0.y & mb);
-            hit = (ma | mb) != 0; kind = (hy >> 8) & 0xFF; ttl = (a0.z & ma) | (b0.z & mb); val = (a0.w & ma) | (b0.w & mb);
-            clean = (hy >> 24) & SLOT_KEY_CLEAN;
+        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1);
+        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1);
+        uint32_t da, db;
+        if (pl <= KEY_INLINE_MAX) {
+            // header: klen | kind | ns | flags; an empty slot has klen 0 and cannot equal `want` (pl >= 2)
+            const uint32_t want = pl | (NS_FORWARD << 16);
+            da = ((a0.x & 0x00FF00FFu) ^ want) | (kw[0] ^ a0.w) | (kw[1] ^ a1.x) | (kw[2] ^ a1.y) | (kw[3] ^ a1.z) | (kw[4] ^ a1.w);
+            db = ((b0.x & 0x00FF00FFu) ^ want) | (kw[0] ^ b0.w) | (kw[1] ^ b1.x) | (kw[2] ^ b1.y) | (kw[3] ^ b1.z) | (kw[4] ^ b1.w);
+        } else {
+            // the slot names the key by arena offset, length and hash; the bytes are compared in the arena
+            const uint32_t want = KLEN_OVERFLOW | (NS_FORWARD << 16);
+            da = ((a0.x & 0x00FF00FFu) ^ want) | (a1.x ^ pl) | (a1.y ^ h);
+            db = ((b0.x & 0x00FF00FFu) ^ want) | (b1.x ^ pl) | (b1.y ^ h);
+            if (da == 0 || db == 0) {
+                const uint32_t* kp = (const uint32_t*)(P.arena + (da == 0 ? a0.w : b0.w));     // 4-byte aligned, zero padded
+                uint32_t diff = 0, wp2 = lds32(kb);
+#pragma unroll 1
+                for (uint32_t i = 0; i < nwords; i++) {
+                    const uint32_t wnext = lds32(kb + 4 * (i + 1));
+                    uint32_t x = __funnelshift_r(wp2, wnext, ksh);
+                    wp2 = wnext;
+                    if (i == nwords - 1) x &= tailm;
+                    x |= upper_bytes(x) >> 2;
+                    uint32_t kwd = __ldg(kp + i);
+                    if (i == nwords - 1) kwd &= tailm;
+                    diff |= x ^ kwd;
+                }
+                if (da == 0) da = diff; else db = diff;
+            }
         }
-#else
-        if (da == 0) { hit = true; kind = (a0.y >> 8) & 0xFF; ttl = a0.z; val = a0.w; clean = (a0.y >> 24) & SLOT_KEY_CLEAN; }
-        else if (db == 0) { hit = true; kind = (b0.y >> 8) & 0xFF; ttl = b0.z; val = b0.w; clean = (b0.y >> 24) & SLOT_KEY_CLEAN; }
-#endif
+        if (da == 0) { hit = true; kind = (a0.x >> 8) & 0xFF; ttl = a0.y; val = a0.z; clean = (a0.x >> 24) & SLOT_KEY_CLEAN; }
+        else if (db == 0) { hit = true; kind = (b0.x >> 8) & 0xFF; ttl = b0.y; val = b0.z; clean = (b0.x >> 24) & SLOT_KEY_CLEAN; }
     }
     STAMP(5);
     if (!(hit && clean)) {
-        // Not a clean hit: classify the name the way resolve() does before its lookup — a '.' inside a
-        // label, a character outside [a-z0-9_.-] (:208-215) -> REFUSED; an SRV name with a
-        // line terminator goes to the generic path (its regex group stops there, :141).
-        uint32_t bad = 0, nlc = 0;
-#pragma unroll
-        for (int i = 0; i < 12; i++) {
-            if ((uint32_t)i < nwords) {
-                const uint32_t bits = (uint32_t)(lm >> (4 * i)) & 0xFu;
-                const uint32_t m8 = ((bits * 0x00204081u) & 0x01010101u) * 0xFFu;
-                const uint32_t tm = ((uint32_t)i == nwords - 1) ? tailm : 0xFFFFFFFFu;
-                bad |= bad_chars(kw[i]) & ~m8 & tm;
-                nlc |= (zero_bytes(kw[i] ^ 0x0A0A0A0Au) | zero_bytes(kw[i] ^ 0x0D0D0D0Du)) & ~m8 & tm;
-            }
-        }
-        if (srv && nlc) return false;
-        if (bad) { r.rcode = RC_REFUSED; return true; }
+        // Not a clean hit: classify the name the way resolve() does before its lookup — a character outside
+        // [a-z0-9_.-], a '.' inside a label -> REFUSED (:208-215); an SRV name with a line terminator goes to
+        // the generic path (its regex group stops there, :141)
+        const uint32_t cls = classify_labels(nm, d_off, k1);
+        if (srv && (cls & 2u)) return 0;
+        if (cls & 1u) { r.rcode = RC_REFUSED; return 1; }
     }
     finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
-    return true;
+    return 1;
 }
 
 // ---- resolve (lib/server.js:136-429) -------------------------------------------------------
@@ -671,7 +731,8 @@ __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t
     r.ptr_tgt = (need_b || r.trunc) ? (uint16_t)NONE16 : (uint16_t)ptr_tgt;
     r.lastlen = (uint16_t)lastlen;
 
-    FwdKey kg; kg.nm = nm; kg.d_off = d_off; kg.d_end = d_end;
+    // the lookup key (zone_image.h): the labels in front of the suffix the gate has just matched
+    FwdKey kg; kg.nm = nm; kg.k0 = d_off; kg.k1 = d_end - sl;
     uint32_t kind = 0, ttl = 0, val = 0;
     const bool hit = probe(P, r, NS_FORWARD, kg, kind, ttl, val);
     finish_forward(P, r, qidx, fixed, srv, hit, kind, ttl, val, l0, l1);
@@ -704,17 +765,27 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 }
 
 // onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
-__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
+__device__ __forceinline__ void res_init(Res& r) {
     r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
     r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
+}
+#ifdef BB_HOST_EMU        /* the CPU emulation counts which front end settled each query (tests/test_host_emulation.py) */
+extern unsigned long long bb_emu_lean_count, bb_emu_general_count;
+#define BB_EMU_COUNT(x) (++(x))
+#else
+#define BB_EMU_COUNT(x) ((void)0)
+#endif
+__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
+    res_init(r);
+    if (r.sp && P.lean_ok && lean_query(P, r, len, qidx, s_sfx)) { BB_EMU_COUNT(bb_emu_lean_count); return; }
+    BB_EMU_COUNT(bb_emu_general_count);
+    res_init(r);
     if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
     r.maxsz = P.tcp ? (uint16_t)65535 : r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
     const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
     r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
     const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
     if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
-    STAMP(3);
-    if (r.sp && r.qtype != QT_PTR && r.qn_len <= 64 && fast_forward(P, r, s_sfx, qidx, fixed)) return;
     const uint8_t* nm = r.p + 12;
     for (uint32_t q = 0; nm[q];) {                                            // DESIGN.md "in-label dots"
         uint32_t l = nm[q];
@@ -784,31 +855,32 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
         SvcView sv; sv.open(P.arena, r.val);
         uint32_t left = r.keep_ans;
         for (uint32_t t = 0; t < r.n_walk && left; t++) {
-            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-            if (k->flags & KID_ADDR_NULL) continue;
+            KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+            if (k.flags() & KID_ADDR_NULL) continue;
             if (srv) {                                                        // :396-400
-                const uint8_t* ports = (const uint8_t*)(k + 1);
-                const uint8_t* kw = ports + 2 * k->nports;
-                for (uint32_t c = 0; c < k->nports && left; c++, left--) {
-                    w.u16(0xC00C); put_rr_head(w, QT_SRV, r.ttl, 6 + k->wire_len + dom_wire_len(r));
-                    w.u16(0); w.u16(10); w.u16(ld16a(ports + 2 * c));
-                    w.copy(kw, k->wire_len); put_dom_labels(w, r, r.d_end); w.u8(0);
+                const uint32_t np = k.nports(), wl = k.wire_len();
+                for (uint32_t c = 0; c < np && left; c++, left--) {
+                    w.u16(0xC00C); put_rr_head(w, QT_SRV, r.ttl, 6 + wl + dom_wire_len(r));
+                    w.u16(0); w.u16(10); w.u16(k.port(c));
+                    for (uint32_t i = 0; i < wl; i++) w.u8(k.name_byte(i));
+                    put_dom_labels(w, r, r.d_end); w.u8(0);
                 }
             } else {                                                          // :411-414
-                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                uint32_t rttl = (k.flags() & KID_HAS_RTTL) ? k.rttl() : r.ttl;
                 if (r.ttl < rttl) rttl = r.ttl;
-                put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
+                put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k.addr()); --left;
             }
         }
         if (srv) {
             if (!opt_done) { w.copy(opt, 11); opt_done = true; }
             left = r.keep_add;
             for (uint32_t t = 0; t < r.n_walk && left; t++) {                 // :401-402
-                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-                if (k->flags & KID_ADDR_NULL) continue;
-                const uint8_t* kw = (const uint8_t*)(k + 1) + 2 * k->nports;
-                uint32_t rttl = (k->flags & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                w.copy(kw, k->wire_len); put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k->addr); --left;
+                KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+                if (k.flags() & KID_ADDR_NULL) continue;
+                const uint32_t wl = k.wire_len();
+                uint32_t rttl = (k.flags() & KID_HAS_RTTL) ? k.rttl() : r.ttl;
+                for (uint32_t i = 0; i < wl; i++) w.u8(k.name_byte(i));
+                put_dom_owner(w, r); put_rr_head(w, QT_A, rttl, 4); w.u32(k.addr()); --left;
             }
         }
     }
@@ -915,6 +987,23 @@ __device__ __forceinline__ void put_global_bytes(W& w, const uint8_t* s, uint32_
     for (uint32_t i = 0; i < n; i++) w.put(__ldg(s + i), 1);
 }
 
+// n bytes from the arena (16-byte aligned source, readable up to the next multiple of 16) into the stream
+template <class W>
+__device__ __forceinline__ void copy_arena_w(W& w, const uint8_t* src, uint32_t n) {
+    const uint4* q = (const uint4*)src;
+    uint32_t i = 0;
+#pragma unroll 1
+    for (; i + 16 <= n; i += 16) { const uint4 x = __ldg(q++); w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); }
+    if (i < n) {
+        const uint4 x = __ldg(q);
+        const uint32_t rem = n - i;
+        if (rem >= 4) w.put4(x.x); else { w.put(x.x & ((1u << (8 * rem)) - 1), rem); return; }
+        if (rem >= 8) w.put4(x.y); else { if (rem > 4) w.put(x.y & ((1u << (8 * (rem - 4))) - 1), rem - 4); return; }
+        if (rem >= 12) w.put4(x.z); else { if (rem > 8) w.put(x.z & ((1u << (8 * (rem - 8))) - 1), rem - 8); return; }
+        if (rem > 12) w.put(x.w & ((1u << (8 * (rem - 12))) - 1), rem - 12);
+    }
+}
+
 template <class W>
 __device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
     const uint32_t p = r.sp;
@@ -952,44 +1041,47 @@ __device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
         put_global_bytes(w, E->soa, P.soa_len);
         w.put4(0); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(10)); w.put4(bswap32(r.ttl));
     } else if (r.rk == RK_SVC_A || r.rk == RK_SVC_SRV) {
+        // The children's RRs are ready wire bytes in the service record (zone_image.h): answering is copying them in
+        // shuffled child order.  SRV answers never depend on how the query is spelled; the A answers and the additional
+        // RRs carry an owner pointer that is this query's only when its domain part has no upper-case letter
+        // (`lower`) — otherwise they are written field by field.
         const bool srv = r.rk == RK_SVC_SRV;
+        const bool lower = r.ptr_tgt == r.d_off;
         SvcView sv; sv.open(P.arena, r.val);
-        const uint32_t dwl = dom_wire_len(r);
         uint32_t left = r.keep_ans;
         for (uint32_t t = 0; t < r.n_walk && left; t++) {
-            const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-            const uint32_t fl = k->flags;
+            KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+            const uint32_t fl = k.flags();
             if (fl & KID_ADDR_NULL) continue;
             if (srv) {                                                          // :396-400
-                const uint32_t np = k->nports, wl = k->wire_len;
-                const uint8_t* ports = (const uint8_t*)(k + 1);
-                const uint8_t* kwp = ports + 2 * np;
-                for (uint32_t c = 0; c < np && left; c++, left--) {
-                    w.put(0x0CC0u, 2); w.put4(0x01002100u); w.put4(bswap32(r.ttl)); w.put(bswap16(6 + wl + dwl), 2);
-                    w.put4(0x0A000000u);                                        // priority 0, weight 10
-                    w.put(bswap16(ld16a(ports + 2 * c)), 2);
-                    put_global_bytes(w, kwp, wl);
-                    put_dom_labels_w(w, r, r.d_end); w.put(0, 1);
-                }
-            } else {                                                            // :411-414
-                uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
+                const uint32_t n = min(k.nports(), left);
+                copy_arena_w(w, k.srv_rr(), n * k.srv_len());
+                left -= n;
+            } else if (lower) {                                                 // :411-414
+                const uint4 x = __ldg((const uint4*)k.a_rr());
+                w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); --left;
+            } else {
+                uint32_t rttl = (fl & KID_HAS_RTTL) ? k.rttl() : r.ttl;
                 if (r.ttl < rttl) rttl = r.ttl;
                 put_dom_owner_w(w, r);
-                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
+                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k.addr())); --left;
             }
         }
         if (srv) {
             if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); opt_done = true; }
             left = r.keep_add;
             for (uint32_t t = 0; t < r.n_walk && left; t++) {                   // :401-402
-                const KidRec* k = sv.kid(perm_at(r, t, P.seed, qidx));
-                const uint32_t fl = k->flags;
+                KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
+                const uint32_t fl = k.flags();
                 if (fl & KID_ADDR_NULL) continue;
-                const uint8_t* kwp = (const uint8_t*)(k + 1) + 2 * k->nports;
-                const uint32_t rttl = (fl & KID_HAS_RTTL) ? k->rttl : r.ttl;
-                put_global_bytes(w, kwp, k->wire_len);
-                put_dom_owner_w(w, r);
-                w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k->addr)); --left;
+                if (lower) copy_arena_w(w, k.add_rr(), kid_add_len(k.wire_len()));
+                else {
+                    const uint32_t rttl = (fl & KID_HAS_RTTL) ? k.rttl() : r.ttl;
+                    copy_arena_w(w, k.add_rr(), k.wire_len());
+                    put_dom_owner_w(w, r);
+                    w.put4(0x01000100u); w.put4(bswap32(rttl)); w.put(0x0400u, 2); w.put4(bswap32(k.addr()));
+                }
+                --left;
             }
         }
     }

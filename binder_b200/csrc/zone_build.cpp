@@ -419,86 +419,111 @@ struct TableBuilder {
     ZoneImage* z = nullptr;
     std::vector<uint8_t> arena;
     uint32_t mask = 0;
-    uint32_t arena_put(const void* p, size_t n) {
-        while (arena.size() & 3) arena.push_back(0);
+    std::string suffix;          // '.' + dnsDomain: what every reachable forward key ends with
+    uint32_t arena_put(const void* p, size_t n, size_t align = 4) {
+        while (arena.size() & (align - 1)) arena.push_back(0);
         uint32_t off = (uint32_t)arena.size();
         arena.insert(arena.end(), (const uint8_t*)p, (const uint8_t*)p + n);
         return off;
     }
-    bool key_eq(const Slot& s, uint32_t ns, const uint8_t* k, uint32_t len) const {
-        if ((uint32_t)(s.ns & 1) != ns) return false;
+    // A key as the callers spell it (forward: lower-cased dotted fqdn, reverse: address string) -> the form the
+    // table stores and the kernel derives from a query (zone_image.h): forward = wire labels of what precedes
+    // '.' + dnsDomain (the root domain itself = the empty key, which no query can spell).  false: a forward name no
+    // query can reach (empty or over-long label in front of the suffix) — it is not stored.
+    bool canon(uint32_t ns, const uint8_t* k, uint32_t len, std::string& out) const {
+        if (ns != NS_FORWARD) { out.assign((const char*)k, len); return true; }
+        out.clear();
+        if (len + 1 == suffix.size() && memcmp(k, suffix.data() + 1, len) == 0) return true;         // the root
+        if (len <= suffix.size() || memcmp(k + len - suffix.size(), suffix.data(), suffix.size())) return false;
+        return to_wire((const char*)k, len - suffix.size(), out);
+    }
+    bool key_eq(const Slot& s, uint32_t ns, uint32_t h, const uint8_t* k, uint32_t len) const {
+        if ((uint32_t)s.ns != ns) return false;
         if (len <= KEY_INLINE_MAX) return s.klen == len && memcmp(s.key, k, len) == 0;
         if (s.klen != KLEN_OVERFLOW) return false;
-        uint32_t off, l; memcpy(&off, s.key, 4); memcpy(&l, s.key + 4, 4);
-        return l == len && memcmp(arena.data() + off, k, len) == 0;
+        uint32_t off, l, sh; memcpy(&off, s.key, 4); memcpy(&l, s.key + 4, 4); memcpy(&sh, s.key + 8, 4);
+        return l == len && sh == h && memcmp(arena.data() + off, k, len) == 0;
     }
     uint32_t nranks = 1, rank = 0;
-    bool mine(uint32_t ns, const uint8_t* k, uint32_t len) const { return nranks == 1 || owner_of(hash_key(ns, k, len), nranks) == rank; }
+    bool mine(uint32_t ns, const uint8_t* dk, uint32_t dlen) const {
+        if (nranks == 1) return true;
+        std::string c;
+        if (!canon(ns, dk, dlen, c)) return false;
+        return owner_of(hash_key(ns, (const uint8_t*)c.data(), (uint32_t)c.size()), nranks) == rank;
+    }
     bool failed = false;         // a cuckoo insertion ran out of kicks: the caller rebuilds with a larger table
-    // host-side only, per slot: second hash of the resident key (evictions need it) and the node that wrote it
-    std::vector<uint32_t> h2s, own;
+    // host-side only, per slot: both hashes of the resident key (evictions need them) and the node that wrote it
+    std::vector<uint32_t> h1s, h2s, own;
     uint64_t count = 0;          // resident keys
     // slots changed since the device last saw the table (bb_zone_apply -> bb_engine_apply_update)
     bool track = false; std::vector<uint32_t> dirty; std::vector<uint8_t> dirty_mark;
     void touch(uint32_t pos) { if (track && !dirty_mark[pos]) { dirty_mark[pos] = 1; dirty.push_back(pos); } }
     void reset(ZoneImage* img, uint32_t nslots) {
         z = img; mask = nslots - 1; failed = false; count = 0;
-        h2s.assign(nslots, 0); own.assign(nslots, 0);
+        h1s.assign(nslots, 0); h2s.assign(nslots, 0); own.assign(nslots, 0);
         dirty.clear(); dirty_mark.assign(nslots, 0);
-        arena.assign(4, 0);                                   // offset 0 is never a valid record
+        arena.assign(32, 0);                                  // offset 0 is never a valid record
     }
     void fill(Slot& s, uint32_t h, uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val) {
         memset(&s, 0, sizeof s);
-        s.hash = h;
-        uint32_t dots = 0; bool clean = true;
-        for (uint32_t i = 0; i < len; i++) {
-            const uint8_t c = k[i];
-            dots += c == '.';
-            if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-' || c == '.')) clean = false;
+        bool clean = ns == NS_FORWARD;
+        for (uint32_t i = 0; clean && i < len;) {             // wire labels: length byte, then that many label bytes
+            const uint32_t l = k[i++];
+            for (uint32_t j = 0; j < l && i < len; j++, i++) {
+                const uint8_t c = k[i];
+                if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-')) clean = false;
+            }
         }
-        s.ns = (uint8_t)(ns | (ns == NS_FORWARD ? (dots & 127) << 1 : 0));
-        s.flags = (ns == NS_FORWARD && clean) ? SLOT_KEY_CLEAN : 0;
+        s.ns = (uint8_t)ns;
+        s.flags = clean ? SLOT_KEY_CLEAN : 0;
         if (len <= KEY_INLINE_MAX) { s.klen = (uint8_t)len; memcpy(s.key, k, len); }
-        else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); }
+        else { s.klen = KLEN_OVERFLOW; uint32_t off = arena_put(k, len); memcpy(s.key, &off, 4); memcpy(s.key + 4, &len, 4); memcpy(s.key + 8, &h, 4); }
         s.kind = kind; s.ttl = ttl; s.val = val;
     }
-    // slot holding the key, or -1
-    int64_t find(uint32_t ns, const uint8_t* k, uint32_t len) const {
+    int64_t find_canon(uint32_t ns, const uint8_t* k, uint32_t len) const {
         uint32_t h2;
         const uint32_t h = hash_key2(ns, k, len, &h2);
         for (uint32_t i : { slot1_of(h, mask), slot2_of(h, h2, mask) }) {
             const Slot& s = z->slots[i];
-            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) return i;
+            if (s.kind != K_EMPTY && key_eq(s, ns, h, k, len)) return i;
         }
         return -1;
     }
+    // slot holding the key (as the caller spells it), or -1
+    int64_t find(uint32_t ns, const uint8_t* dk, uint32_t dlen) const {
+        std::string c;
+        if (!canon(ns, dk, dlen, c)) return -1;
+        return find_canon(ns, (const uint8_t*)c.data(), (uint32_t)c.size());
+    }
     // a cuckoo table needs no tombstones: a lookup only ever reads the key's two slots
-    void erase(uint32_t pos) { memset(&z->slots[pos], 0, sizeof(Slot)); h2s[pos] = 0; own[pos] = 0; --count; touch(pos); }
+    void erase(uint32_t pos) { memset(&z->slots[pos], 0, sizeof(Slot)); h1s[pos] = 0; h2s[pos] = 0; own[pos] = 0; --count; touch(pos); }
     // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo.
     // Returns true when the key is new.
-    bool put(uint32_t ns, const uint8_t* k, uint32_t len, uint8_t kind, uint32_t ttl, uint32_t val, uint32_t owner) {
+    bool put(uint32_t ns, const uint8_t* dk, uint32_t dlen, uint8_t kind, uint32_t ttl, uint32_t val, uint32_t owner) {
+        std::string c;
+        if (!canon(ns, dk, dlen, c)) return false;
+        const uint8_t* k = (const uint8_t*)c.data(); const uint32_t len = (uint32_t)c.size();
         uint32_t h2;
         const uint32_t h = hash_key2(ns, k, len, &h2);
         const uint32_t i1 = slot1_of(h, mask), i2 = slot2_of(h, h2, mask);
         for (uint32_t i : { i1, i2 }) {
             Slot& s = z->slots[i];
-            if (s.kind != K_EMPTY && s.hash == h && key_eq(s, ns, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; own[i] = owner; touch(i); return false; }
+            if (s.kind != K_EMPTY && key_eq(s, ns, h, k, len)) { s.kind = kind; s.ttl = ttl; s.val = val; own[i] = owner; touch(i); return false; }
         }
         Slot cur; fill(cur, h, ns, k, len, kind, ttl, val);
-        uint32_t cur_h2 = h2, cur_own = owner;
+        uint32_t cur_h1 = h, cur_h2 = h2, cur_own = owner;
         uint32_t pos = z->slots[i1].kind == K_EMPTY ? i1 : (z->slots[i2].kind == K_EMPTY ? i2 : i1);
         ++count;
         for (int kick = 0; kick < 2000; kick++) {
             Slot& s = z->slots[pos];
             touch(pos);
-            if (s.kind == K_EMPTY) { s = cur; h2s[pos] = cur_h2; own[pos] = cur_own; return true; }
+            if (s.kind == K_EMPTY) { s = cur; h1s[pos] = cur_h1; h2s[pos] = cur_h2; own[pos] = cur_own; return true; }
             Slot ev = s; s = cur; cur = ev;                          // evict the resident, move it to its other slot
-            const uint32_t ev_h2 = h2s[pos]; h2s[pos] = cur_h2; cur_h2 = ev_h2;
-            const uint32_t ev_own = own[pos]; own[pos] = cur_own; cur_own = ev_own;
-            const uint32_t a = slot1_of(cur.hash, mask), b = slot2_of(cur.hash, cur_h2, mask);
+            std::swap(h1s[pos], cur_h1); std::swap(h2s[pos], cur_h2); std::swap(own[pos], cur_own);
+            const uint32_t a = slot1_of(cur_h1, mask), b = slot2_of(cur_h1, cur_h2, mask);
             pos = pos == a ? b : a;
         }
-        if (getenv("BB_DEBUG")) fprintf(stderr, "cuckoo fail: ns=%u len=%u key=%.*s h=%08x i1=%u i2=%u mask=%u\n", ns, len, (int)len, (const char*)k, h, i1, i2, mask);
+        if (getenv("BB_DEBUG")) fprintf(stderr, "cuckoo fail: ns=%u len=%u h=%08x i1=%u i2=%u mask=%u\n", ns, len, h, i1, i2, mask);
         failed = true;                                           // one key fell out: the caller lays the table out again
         return true;
     }
@@ -539,24 +564,29 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib)
             if ((B.nodes[k].flags & (NF_KIDTYPE | NF_DEAD)) == NF_KIDTYPE) kids.push_back(k);
         if (kids.size() > 65535) return false;
-        std::vector<uint8_t> rec;
-        SvcHdr h; h.ttl = si.ttl; h.nkids = (uint16_t)kids.size(); h.rec_len = 0;
-        bool s_ok = si.has_srvce && si.srvce.size() < 255, p_ok = si.has_proto && si.proto.size() < 255;
-        h.srvce_len = s_ok ? (uint8_t)si.srvce.size() : 0xFF;
-        h.proto_len = p_ok ? (uint8_t)si.proto.size() : 0xFF;
-        rec.insert(rec.end(), (uint8_t*)&h, (uint8_t*)&h + sizeof h);
-        if (s_ok) rec.insert(rec.end(), si.srvce.begin(), si.srvce.end());
-        if (p_ok) rec.insert(rec.end(), si.proto.begin(), si.proto.end());
-        while (rec.size() & 3) rec.push_back(0);
-        size_t tab = rec.size();
-        rec.resize(tab + 4 * kids.size());
-        while (T.arena.size() & 3) T.arena.push_back(0);
-        uint32_t base = (uint32_t)T.arena.size();
+        // header (32 bytes) + one 16-byte record per child + the children's RRs as ready wire bytes (zone_image.h),
+        // contiguous and 32-byte aligned
+        std::vector<uint8_t> rec(sizeof(SvcHdr) + sizeof(KidRec) * kids.size(), 0);
+        SvcHdr h; memset(&h, 0, sizeof h);
+        h.ttl = si.ttl; h.nkids = (uint16_t)kids.size();
+        h.dom_wl = (uint8_t)(dom_wire.size() + 1);
+        {
+            std::string sp;
+            const bool s_ok = si.has_srvce && si.srvce.size() >= 1 && si.srvce.size() <= 63;
+            const bool p_ok = si.has_proto && si.proto.size() >= 1 && si.proto.size() <= 63;
+            if (!s_ok || !p_ok) h.hflags |= SVC_SP_NEVER;
+            else {
+                sp.push_back((char)si.srvce.size()); sp += si.srvce; sp.push_back((char)si.proto.size()); sp += si.proto;
+                h.sp_len = (uint8_t)sp.size();
+                if (sp.size() <= sizeof h.sp) memcpy(h.sp, sp.data(), sp.size());
+                else { h.hflags |= SVC_SP_EXT; const uint32_t off = T.arena_put(sp.data(), sp.size()); memcpy(h.sp, &off, 4); }
+            }
+        }
+        auto be16 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
+        auto be32 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
+        uint64_t n_valid = 0, sum_ports = 0, sum_wl = 0, sum_wl_ports = 0;
         for (size_t ki = 0; ki < kids.size(); ki++) {
             const Node& kn = B.nodes[kids[ki]];
-            while (rec.size() & 3) rec.push_back(0);
-            uint32_t koff = base + (uint32_t)rec.size();
-            memcpy(rec.data() + tab + 4 * ki, &koff, 4);
             KidRec kr; memset(&kr, 0, sizeof kr);
             std::vector<uint16_t> pl;
             bool name_ok = to_wire(B.pool.data() + kn.name_off, kn.name_len, kw) && kw.size() + dom_wire.size() + 1 <= 255;
@@ -575,12 +605,31 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
             }
             if (!name_ok) kw.clear();
             kr.wire_len = (uint8_t)kw.size(); kr.nports = (uint8_t)pl.size();
-            rec.insert(rec.end(), (uint8_t*)&kr, (uint8_t*)&kr + sizeof kr);
-            rec.insert(rec.end(), (uint8_t*)pl.data(), (uint8_t*)pl.data() + 2 * pl.size());
+            if (kr.flags & KID_BAD_A) h.hflags |= SVC_BAD_A;
+            if (kr.flags & KID_BAD_SRV) h.hflags |= SVC_BAD_SRV;
+            if (!(kr.flags & KID_ADDR_NULL)) { ++n_valid; sum_ports += pl.size(); sum_wl += kw.size(); sum_wl_ports += pl.size() * kw.size(); }
+            // the child's RRs as wire bytes: A answer | additional | SRV answers, each part padded to 16
+            while (rec.size() & 15) rec.push_back(0);
+            kr.rr_off = (uint32_t)rec.size();
+            const uint32_t rttl = (kr.flags & KID_HAS_RTTL) ? kr.rttl : si.ttl;
+            be16(rec, 0xC00C); be16(rec, 1); be16(rec, 1); be32(rec, si.ttl < rttl ? si.ttl : rttl); be16(rec, 4); be32(rec, kr.addr);
             rec.insert(rec.end(), kw.begin(), kw.end());
+            be16(rec, 0xC000u | (12u + h.sp_len)); be16(rec, 1); be16(rec, 1); be32(rec, rttl); be16(rec, 4); be32(rec, kr.addr);
+            while (rec.size() & 15) rec.push_back(0);
+            for (uint16_t port : pl) {
+                be16(rec, 0xC00C); be16(rec, 33); be16(rec, 1); be32(rec, si.ttl); be16(rec, (uint32_t)(6 + kw.size() + dom_wire.size() + 1));
+                be16(rec, 0); be16(rec, 10); be16(rec, port);
+                rec.insert(rec.end(), kw.begin(), kw.end());
+                rec.insert(rec.end(), dom_wire.begin(), dom_wire.end()); rec.push_back(0);
+            }
+            memcpy(rec.data() + sizeof(SvcHdr) + sizeof(KidRec) * ki, &kr, sizeof kr);
         }
-        { uint32_t rl = (uint32_t)rec.size(); memcpy(rec.data() + offsetof(SvcHdr, rec_len), &rl, 4); }
-        val = T.arena_put(rec.data(), rec.size());
+        while (rec.size() & 15) rec.push_back(0);
+        // sums the kernel sizes an answer from without walking the children; a service too large for them is walked
+        if (n_valid > 0xFFFF || sum_ports > 0xFFFF || sum_wl > 0xFFFF) h.hflags |= SVC_BAD_A | SVC_BAD_SRV;
+        h.n_valid = (uint16_t)n_valid; h.sum_ports = (uint16_t)sum_ports; h.sum_wl = (uint16_t)sum_wl; h.sum_wl_ports = (uint32_t)sum_wl_ports;
+        memcpy(rec.data(), &h, sizeof h);
+        val = T.arena_put(rec.data(), rec.size(), 32);
     }
     uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;
     if (T.put(NS_FORWARD, (const uint8_t*)dom.data(), (uint32_t)dom.size(), nd.kind, ttl, val, id)) zn.img.n_fwd++;
@@ -648,7 +697,7 @@ int layout(bb_zone& zn) {
         if (!T.failed) break;
         if (grow > 3) return BB_ERR_NOMEM;
     }
-    while (T.arena.size() & 15) T.arena.push_back(0);
+    while (T.arena.size() & 31) T.arena.push_back(0);
     Z.arena = T.arena.data(); Z.arena_len = T.arena.size();
     Z.ready = 1;                                              // the root TreeNode exists (lib/zk.js:55-58)
     zn.relaid = true; zn.arena_synced = 0; zn.arena_base = Z.arena_len;
@@ -741,6 +790,7 @@ extern "C" bb_zone* bb_zone_build_shard(const char* buf, size_t len, const char*
     Builder& B = zone->B;
     auto bail = [&](int e) -> bb_zone* { bb_zone_free(zone); return fail(e); };
     B.dns_domain = dns_domain;
+    zone->T.suffix = std::string(".") + dns_domain;
     // ZKCache.isReady() compares with options.domain verbatim (lib/zk.js:55-58) while keys are
     // lower-cased (:84): an upper-case domain is never ready.  We require lower case instead.
     for (char c : B.dns_domain) if (c >= 'A' && c <= 'Z') return bail(BB_ERR_DOMAIN);
@@ -849,17 +899,17 @@ extern "C" int bb_zone_apply(bb_zone* zone, const char* buf, size_t len) {
         if ((created || v >= 0) && !refresh_parent(id)) return BB_ERR_SNAPSHOT;
         return BB_OK;
     });
-    if (rc != BB_OK) return rc;
-    // a cuckoo insertion that failed, a table filling past what two choices sustain, or an arena that is
-    // mostly superseded records (every re-derived service / PTR record is appended): lay it out again
-    if (T.failed || T.count * 100 > (uint64_t)zone->img.nslots * 47 || T.arena.size() > 2 * zone->arena_base + (16u << 20)) {
-        rc = layout(*zone);
-        if (rc != BB_OK) return rc;
-    }
-    while (T.arena.size() & 15) T.arena.push_back(0);
+    // Whatever happened to the lines — earlier lines of a delta stay applied when a later one is bad — the image must
+    // describe the builder's state again before anyone reads it: records appended above may have moved the arena.
+    // A cuckoo insertion that failed, a table filling past what two choices sustain, or an arena that is mostly
+    // superseded records (every re-derived service / PTR record is appended): lay it out again.
+    int rc2 = BB_OK;
+    if (T.failed || T.count * 100 > (uint64_t)zone->img.nslots * 47 || T.arena.size() > 2 * zone->arena_base + (16u << 20))
+        rc2 = layout(*zone);
+    while (T.arena.size() & 31) T.arena.push_back(0);
     zone->img.arena = T.arena.data(); zone->img.arena_len = T.arena.size();
     zone->img.n_nodes = B.nodes.size();
-    return BB_OK;
+    return rc != BB_OK ? rc : rc2;
 }
 
 // What the device has not seen yet (used by bb_engine_apply_update in engine.cu).
@@ -911,16 +961,15 @@ extern "C" int bb_zone_probe(const bb_zone* z, uint32_t ns, const uint8_t* key, 
     std::string out;
     const uint8_t* A = z->T.arena.data();
     if (s.kind == bb::K_SERVICE) {
-        const bb::SvcHdr* h = (const bb::SvcHdr*)(A + s.val);
-        out.append((const char*)&h->ttl, 4); out.append((const char*)&h->nkids, 2);
-        out.push_back((char)h->srvce_len); out.push_back((char)h->proto_len);
-        const uint32_t sl = h->srvce_len == 0xFF ? 0 : h->srvce_len, pl = h->proto_len == 0xFF ? 0 : h->proto_len;
-        const uint8_t* q = A + s.val + sizeof(bb::SvcHdr);
-        out.append((const char*)q, sl + pl);
-        const uint32_t* tab = (const uint32_t*)(A + s.val + ((sizeof(bb::SvcHdr) + sl + pl + 3) & ~3u));
-        for (uint32_t k = 0; k < h->nkids; k++) {
-            const bb::KidRec* kr = (const bb::KidRec*)(A + tab[k]);
-            out.append((const char*)kr, sizeof *kr + 2u * kr->nports + kr->wire_len);
+        bb::SvcHdr h; memcpy(&h, A + s.val, sizeof h);
+        std::string ext;
+        if (h.hflags & bb::SVC_SP_EXT) { uint32_t off; memcpy(&off, h.sp, 4); ext.assign((const char*)A + off, h.sp_len); memset(h.sp, 0, 4); }
+        out.append((const char*)&h, sizeof h); out += ext;
+        for (uint32_t k = 0; k < h.nkids; k++) {
+            bb::KidRec kr; memcpy(&kr, A + s.val + sizeof(bb::SvcHdr) + sizeof(bb::KidRec) * k, sizeof kr);
+            const uint32_t end = bb::kid_srv_off(kr.rr_off, kr.wire_len) + kr.nports * bb::kid_srv_len(kr.wire_len, h.dom_wl);
+            out.append((const char*)&kr, sizeof kr);              // offsets are relative to the record: position independent
+            out.append((const char*)(A + s.val + kr.rr_off), end - kr.rr_off);
         }
     } else if (s.kind == bb::K_PTR) {
         out.append((const char*)(A + s.val + 1), A[s.val]);

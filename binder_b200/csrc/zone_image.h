@@ -1,19 +1,26 @@
 // Zone image: the HBM-resident, flattened form of binder's ZKCache (lib/zk.js:20-119).
 //
-// One 2-choice cuckoo table (power-of-two, load factor < 0.46) of 64-byte slots holds BOTH of
-// ZKCache's maps (a key lives in slot hash & mask or slot hash2 & mask — two independent hashes of
-// the key — never anywhere else, so a lookup — hit or
-// miss — is two independent 64-byte reads issued together: one DRAM round trip per warp):
+// One 2-choice cuckoo table (power-of-two, load factor < 0.46) of 32-byte slots — ONE DRAM sector each —
+// holds BOTH of ZKCache's maps (a key lives in slot hash & mask or slot hash2 & mask — two independent
+// hashes of the key — never anywhere else, so a lookup — hit or miss — is two independent 32-byte reads
+// issued together: one DRAM round trip per warp, 64 bytes of traffic):
 //   forward  ca_treeNodes[lower-cased fqdn]  (lib/zk.js:62-64, keys written at :84,96)
 //   reverse  ca_revLookup[address string]    (lib/zk.js:65-67, keys written at :187-188)
-// distinguished by a namespace bit that also seeds the hash.  Everything lib/server.js
-// computes per query from the JSON record that does not depend on the query (record
-// validation :251-260, ttl selection :270-274, url.parse :297-298, the service child filter
-// :352-360 and per-child validation :366-393) is evaluated once at build time and stored as
-// a `kind` + payload, so the kernel never touches JSON.
+// distinguished by a namespace bit that also seeds the hash.
 //
-// A slot is one 64-byte, 64-byte-aligned unit = two 32-byte DRAM sectors: a host A record
-// (the common case) resolves with exactly one random 64-byte read.
+// Forward keys are stored in CANONICAL form: the lower-cased fqdn minus the '.' + dnsDomain every reachable
+// key ends with, as DNS wire labels (length byte + bytes per label).  resolve() only looks a name up after its
+// case-sensitive suffix gate (lib/server.js:157-166) has shown that the name ends with '.' + dnsDomain, so
+// string equality of the full names is equality of what precedes the suffix; and a query name without a '.'
+// inside a label equals a key string exactly when their label sequences are equal.  The kernel therefore
+// hashes and compares the query's own wire bytes (lower-cased; length bytes 1..63 are not letters) and never
+// builds the dotted string: "h0001234.g0012.dc1.example.com" is the 15-byte key \x08h0001234\x05g0012.
+// Reverse keys are the address strings themselves.
+//
+// Everything lib/server.js computes per query from the JSON record that does not depend on the query (record
+// validation :251-260, ttl selection :270-274, url.parse :297-298, the service child filter :352-360 and
+// per-child validation :366-393) is evaluated once at build time and stored as a `kind` + payload, so the
+// kernel never touches JSON.
 #ifndef BB_ZONE_IMAGE_H
 #define BB_ZONE_IMAGE_H
 
@@ -43,66 +50,88 @@ enum : uint8_t {
 
 constexpr uint32_t NS_FORWARD = 0;
 constexpr uint32_t NS_REVERSE = 1;
-constexpr uint32_t KEY_INLINE_MAX = 48;
+constexpr uint32_t KEY_INLINE_MAX = 20;
 constexpr uint8_t  KLEN_OVERFLOW = 0xFF;      // key bytes live in the arena
 constexpr uint8_t  SLOT_KEY_CLEAN = 1;
 
-struct alignas(64) Slot {
-    uint32_t hash;       // full 32-bit key hash (compared before the key bytes)
-    uint8_t  klen;       // key length 1..48, or KLEN_OVERFLOW
+struct alignas(32) Slot {
+    uint8_t  klen;       // key length 0..20 (0: the root domain's own key, which no query can spell), or KLEN_OVERFLOW
     uint8_t  kind;       // K_*
-    uint8_t  ns;         // bit 0: NS_*; bits 1..7: number of '.' in a forward key (a query whose label
-                         // count disagrees cannot be this key: it carries a '.' inside a label)
-    uint8_t  flags;      // SLOT_KEY_CLEAN: every key byte is in [a-z0-9_.-] (lib/server.js:208)
+    uint8_t  ns;         // NS_*
+    uint8_t  flags;      // SLOT_KEY_CLEAN: every label byte of a forward key is in [a-z0-9_-] (lib/server.js:208)
     uint32_t ttl;        // record ttl (lib/server.js:270-274)
     uint32_t val;        // IPv4 (network order bytes packed big-endian) or arena offset
-    uint8_t  key[48];    // inline key; overflow: key[0..3] = arena offset, key[4..7] = length
+    uint8_t  key[20];    // inline key, zero padded; overflow: key[0..3] = arena offset, [4..7] = length, [8..11] = hash
 };
-static_assert(sizeof(Slot) == 64, "slot must be one 64-byte unit");
+static_assert(sizeof(Slot) == 32, "slot must be one 32-byte sector");
 
-// ---- service record in the arena (4-byte aligned) --------------------------------------
-struct SvcHdr {
+// ---- service record in the arena (32-byte aligned): header, nkids child records, then the children's RRs ----
+// Sizing a service answer is one header read unless a child is malformed or the answer must be truncated:
+// the sums over the children that answer are taken at build time.  So are the resource records themselves:
+// everything in an answer RR except the bytes of the question is known when the zone is built (the SRV target is
+// the child's name + the service's own lower-cased fqdn — which the query's name equals, or it would not have hit —
+// the ttls, the ports, the owner pointers), so each child carries its RRs as ready wire bytes and answering is
+// copying them in shuffled child order (lib/server.js:361-416):
+//   [A answer, 16 B]            C00C | A IN | min(ttl, rttl) | 4 | addr                        (:411-414)
+//   [additional, pad to 16]     child labels | C0 ptr to the domain part of the QNAME | A IN | rttl | 4 | addr   (:401-402)
+//   [SRV answers, pad to 16]    per port: C00C | SRV IN | ttl | rdlen | 0 | 10 | port | child labels | fqdn | 0  (:396-400)
+// A query whose domain part carries upper-case letters (the owner pointers then land elsewhere), a truncated
+// answer or a malformed child take the field-by-field writer instead, which reads names and ports out of the same bytes.
+enum : uint8_t {
+    SVC_BAD_A = 1,       // some child is "bad zk info" for an A query (:366-376): the walk must find where
+    SVC_BAD_SRV = 2,     // same for SRV
+    SVC_SP_NEVER = 4,    // s.srvce / s.proto absent, not strings, or not spellable as labels: never equal (:334-335)
+    SVC_SP_EXT = 8,      // the two labels do not fit `sp`: sp[0..3] = arena offset of the bytes
+};
+struct alignas(32) SvcHdr {
     uint32_t ttl;            // after record.ttl / service.ttl / service.service.ttl (:270-274,331-332)
     uint16_t nkids;          // children that pass the type filter (:352-360), in child order
-    uint8_t  srvce_len;      // 0xFF: s.srvce absent or not a string -> never equal (:334-335)
-    uint8_t  proto_len;      // same for s.proto
-    uint32_t rec_len;        // bytes of the whole record (header .. last child): one prefetch burst covers it
-    // followed by: srvce bytes, proto bytes, pad to 4, uint32_t kid_off[nkids] (arena offsets)
+    uint16_t n_valid;        // of those, the ones with an address (not KID_ADDR_NULL): one A / one additional each
+    uint16_t sum_ports;      // sum of nports over them: SRV answers
+    uint16_t sum_wl;         // sum of wire_len over them
+    uint32_t sum_wl_ports;   // sum of nports * wire_len over them
+    uint8_t  hflags;         // SVC_*
+    uint8_t  sp_len;         // bytes of "_srvce._proto." on the wire = where the domain part of a matching SRV QNAME starts
+    uint8_t  dom_wl;         // the service's fqdn as wire labels + terminator (what every SRV target ends with)
+    uint8_t  sp[13];         // len, srvce bytes, len, proto bytes — as the query spells them
 };
+static_assert(sizeof(SvcHdr) == 32, "service header is one sector");
 enum : uint8_t {
     KID_BAD_A = 1,       // "bad zk info" when serving A        (:366-376 + contract)
     KID_BAD_SRV = 2,     // "bad zk info" when serving SRV
     KID_ADDR_NULL = 4,   // address === null -> skipped          (:378-381)
     KID_HAS_RTTL = 8,    // child carries its own ttl            (:389-393)
 };
-struct KidRec {
+struct alignas(16) KidRec {
     uint32_t addr;           // IPv4 packed big-endian
     uint32_t rttl;
     uint8_t  flags;          // KID_*
     uint8_t  wire_len;       // child name as wire labels, no terminator (knode.name, :396)
     uint8_t  nports;         // SRV ports: krec[type].ports or [s.port]  (:383-385)
     uint8_t  pad;
-    // followed by: uint16_t ports[nports], uint8_t wire[wire_len], pad to 4
+    uint32_t rr_off;         // this child's RR bytes, relative to the record's first byte (16-byte aligned)
 };
+static_assert(sizeof(KidRec) == 16, "child record is one 16-byte load");
+BB_HD uint32_t kid_add_len(uint32_t wire_len) { return wire_len + 16; }                            // additional RR
+BB_HD uint32_t kid_srv_len(uint32_t wire_len, uint32_t dom_wl) { return 18 + wire_len + dom_wl; }  // one SRV answer RR
+// the three parts are 16-byte aligned (rr_off is): they are streamed with 16-byte loads
+BB_HD uint32_t kid_add_off(uint32_t rr_off) { return rr_off + 16; }
+BB_HD uint32_t kid_srv_off(uint32_t rr_off, uint32_t wire_len) { return rr_off + 16 + ((kid_add_len(wire_len) + 15) & ~15u); }
 
-// ---- key hash (murmur3-32 over little-endian words, zero-padded tail) ------------------
-BB_HD uint32_t rotl32(uint32_t x, int r) { return (x << r) | (x >> (32 - r)); }
+// ---- key hash: two independent multiply-fold accumulators over little-endian words, zero-padded tail -----
+// (one IMAD.WIDE + one LOP3 per accumulator per word on the device)
 BB_HD uint32_t fmix32(uint32_t h) {
     h ^= h >> 16; h *= 0x85EBCA6Bu; h ^= h >> 13; h *= 0xC2B2AE35u; h ^= h >> 16; return h;
 }
+BB_HD uint32_t mulfold(uint32_t x, uint32_t k) { const uint64_t p = (uint64_t)x * k; return (uint32_t)p ^ (uint32_t)(p >> 32); }
 BB_HD uint32_t hash_init(uint32_t ns) { return ns ? 0x52455631u : 0x42494E44u; }
-BB_HD uint32_t hash_word(uint32_t h, uint32_t w) {
-    w *= 0xCC9E2D51u; w = rotl32(w, 15); w *= 0x1B873593u;
-    h ^= w; h = rotl32(h, 13); h = h * 5u + 0xE6546B64u;
-    return h;
-}
+BB_HD uint32_t hash_word(uint32_t h, uint32_t w) { return mulfold(h ^ w, 0x9E3779B1u); }
 BB_HD uint32_t hash_finish(uint32_t h, uint32_t len) { return fmix32(h ^ len); }
-
-// Second, independent hash over the same words (two ALU ops per word): it picks the key's second
-// cuckoo slot, so two keys whose 32-bit hashes collide do not also share both of their slots.
+// Second hash over the same words: it picks the key's second cuckoo slot, so two keys whose 32-bit
+// hashes collide do not also share both of their slots.
 BB_HD uint32_t hash2_init(uint32_t ns) { return ns ? 0x7F4A7C15u : 0x2545F491u; }
-BB_HD uint32_t hash2_word(uint32_t g, uint32_t w) { return (g ^ w) * 0x9E3779B1u; }
-BB_HD uint32_t hash2_finish(uint32_t g, uint32_t len) { return fmix32(g ^ (len * 0x85EBCA77u)); }
+BB_HD uint32_t hash2_word(uint32_t g, uint32_t w) { return mulfold(g ^ w, 0x85EBCA77u); }
+BB_HD uint32_t hash2_finish(uint32_t g, uint32_t len) { return fmix32(g + len * 0xC2B2AE3Du); }
 
 // -> primary hash; *h2 = second hash
 inline uint32_t hash_key2(uint32_t ns, const uint8_t* k, uint32_t len, uint32_t* h2) {
@@ -148,7 +177,7 @@ struct EngineConst {
     uint32_t suffix_len;         // strlen('.' + dnsDomain); 0 when dnsDomain === '' (:157)
     uint32_t soa_len;            // SOA rdata up to (not including) the trailing 5 x u32
     uint32_t recursion;          // options.recursion present (:110,222)
-    uint32_t pad;
+    uint32_t lean_ok;            // every dnsDomain byte is in [a-z0-9_.-]: the charset test of lib/server.js:208 can only fail in front of it
     uint8_t  suffix[256];        // '.' + dnsDomain, as query.name() would spell it
     uint8_t  soa[528];           // mname wire + rname wire of SOARecord(dnsDomain) (:286-287)
     uint8_t  wire_tail[256];     // dnsDomain as wire labels (no terminator), right-aligned: ends at wire_tail[256]
@@ -201,6 +230,8 @@ inline bool make_engine_const(const char* dns_domain, bool recursion, EngineCons
     C.soa_len = (uint32_t)(wl + 1 + hl + 1);
     for (size_t i = 0; i < wl; i++) C.wire_tail[256 - wl + i] = w[i];     // word-wise suffix gate compares the name's tail with this
     C.recursion = recursion ? 1 : 0;
+    C.lean_ok = 1;
+    for (size_t i = 0; i < n; i++) { const char c = dns_domain[i]; if (!((c >= 'a' && c <= 'z') || (c >= '0' && c <= '9') || c == '_' || c == '-' || c == '.')) C.lean_ok = 0; }
     return true;
 }
 // lib/recursion.js:329-344 pre-filter fields (see bb_engine_set_recursion_filter).  false: bad arguments.

@@ -22,8 +22,35 @@ def fmix32(h):
     return h
 
 
-def hash_keys(keys, ns=0):
-    """bb::hash_key (zone_image.h) for a list of equal-length byte keys, vectorised."""
+def canon_forward(key, dns_domain):
+    """The form the table stores a forward key in (TableBuilder::canon, zone_build.cpp): the lower-cased fqdn minus
+    '.' + dnsDomain, as DNS wire labels; b'' for the root domain itself; None for a name no query can spell."""
+    if isinstance(key, str):
+        key = key.encode('latin-1')
+    dom = dns_domain.encode('latin-1') if isinstance(dns_domain, str) else dns_domain
+    if key == dom:
+        return b''
+    if len(key) <= len(dom) + 1 or key[-len(dom) - 1:] != b'.' + dom:
+        return None
+    out = bytearray()
+    for lab in key[:-len(dom) - 1].split(b'.'):
+        if not 1 <= len(lab) <= 63:
+            return None
+        out.append(len(lab))
+        out += lab
+    return bytes(out)
+
+
+def _mulfold(x, k):
+    p = x * np.uint64(k)
+    return (p ^ (p >> np.uint64(32))) & np.uint64(0xFFFFFFFF)
+
+
+def hash_keys(keys, ns=0, dns_domain=None):
+    """bb::hash_key (zone_image.h) for a list of equal-length byte keys, vectorised.  Forward keys (ns 0) are given
+    as lower-cased fqdns together with dns_domain and hashed in their canonical form (all must be reachable)."""
+    if ns == 0 and dns_domain is not None:
+        keys = [canon_forward(k, dns_domain) for k in keys]
     arr = np.frombuffer(b''.join(keys), dtype=np.uint8).reshape(len(keys), -1)
     n, L = arr.shape
     pad = (-L) % 4
@@ -31,15 +58,9 @@ def hash_keys(keys, ns=0):
         arr = np.concatenate([arr, np.zeros((n, pad), np.uint8)], axis=1)
     words = arr.reshape(n, -1, 4).astype(np.uint64)
     w = words[:, :, 0] | words[:, :, 1] << np.uint64(8) | words[:, :, 2] << np.uint64(16) | words[:, :, 3] << np.uint64(24)
-    M = np.uint64(0xFFFFFFFF)
     h = np.full(n, 0x52455631 if ns else 0x42494E44, dtype=np.uint64)
     for i in range(w.shape[1]):
-        x = (w[:, i] * np.uint64(0xCC9E2D51)) & M
-        x = ((x << np.uint64(15)) | (x >> np.uint64(17))) & M
-        x = (x * np.uint64(0x1B873593)) & M
-        h ^= x
-        h = ((h << np.uint64(13)) | (h >> np.uint64(19))) & M
-        h = (h * np.uint64(5) + np.uint64(0xE6546B64)) & M
+        h = _mulfold(h ^ w[:, i], 0x9E3779B1)
     return fmix32(h ^ np.uint64(L))
 
 

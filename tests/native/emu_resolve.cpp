@@ -7,6 +7,7 @@
 #include "cuda_shim.h"
 #include "../../binder_b200/csrc/zone_image.h"
 #include "../../include/binder_b200.h"
+namespace bbk { unsigned long long bb_emu_lean_count = 0, bb_emu_general_count = 0; }
 #include "../../binder_b200/csrc/resolve_device.cuh"
 
 #include <vector>
@@ -16,11 +17,11 @@ extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
 
 namespace {
 using namespace bbk;
-constexpr size_t OFF_IN = 0;                               // s_in  [S_IN + 32]
+constexpr size_t OFF_IN = 16;                              // s_in  [S_IN + 32]; never 0: Res::sp == 0 means "not staged"
 constexpr size_t OFF_OUT = 9216;                           // s_out [S_OUT], 1024-aligned like the kernel's
 constexpr size_t OFF_SFX = OFF_OUT + ((S_OUT + 1023) / 1024) * 1024;
 constexpr size_t SMEM_BYTES = OFF_SFX + 256 + 64;
-static_assert(OFF_OUT >= S_IN + 32 && OFF_OUT % 1024 == 0, "layout");
+static_assert(OFF_OUT >= OFF_IN + S_IN + 32 && OFF_OUT % 1024 == 0, "layout");
 }
 
 extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain, int recursion,
@@ -38,7 +39,7 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
     P.pkts = pkts; P.pkt_off = pkt_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = out; P.out_cap = out_cap; P.out_off = out_off; P.out_len = out_len; P.status = status; P.miss_idx = miss_idx;
     P.table = img ? img->slots : nullptr; P.mask = img ? img->nslots - 1 : 0; P.arena = img ? img->arena : nullptr;
-    P.ready = img && img->ready; P.eng = &C; P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion;
+    P.ready = img && img->ready; P.eng = &C; P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion; P.lean_ok = C.lean_ok;
     P.nranks = 1; P.tcp = tcp ? 1u : 0u;
     (void)ordered;                                          // one tile at a time: arrival order IS query order here
     uint8_t* s_in = bb_emu_smem + OFF_IN; uint8_t* s_out = bb_emu_smem + OFF_OUT; uint8_t* s_sfx = bb_emu_smem + OFF_SFX;
@@ -97,6 +98,12 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
     return BB_OK;
 }
 
+// which front end settled the queries so far: [0] lean_query, [1] complete decoder + generic path
+extern "C" void bb_emu_path_counts(unsigned long long* out, int reset) {
+    out[0] = bbk::bb_emu_lean_count; out[1] = bbk::bb_emu_general_count;
+    if (reset) bbk::bb_emu_lean_count = bbk::bb_emu_general_count = 0;
+}
+
 // Route mode (the ingress half of the sharded path, route_push_kernel's per-query step): which rank owns each
 // query's lookup key; queries that need no lookup stay on `rank`.
 extern "C" int bb_emu_route_batch(const char* dns_domain, int recursion, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n,
@@ -107,7 +114,7 @@ extern "C" int bb_emu_route_batch(const char* dns_domain, int recursion, const u
     if (!bb::make_engine_const(dns_domain, recursion != 0, C)) return BB_ERR_DOMAIN;
     Params P; memset(&P, 0, sizeof P);
     P.pkts = pkts; P.pkt_off = pkt_off; P.n = n; P.eng = &C; P.ready = 1;
-    P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion;
+    P.suffix_len = C.suffix_len; P.soa_len = C.soa_len; P.recursion = C.recursion; P.lean_ok = C.lean_ok;
     P.route = 1; P.nranks = nranks; P.rank = rank;
     uint8_t* s_in = bb_emu_smem + OFF_IN;
     memcpy(bb_emu_smem + OFF_SFX, C.wire_tail, 256);

@@ -170,3 +170,49 @@ def test_emulated_sharded_pipeline(L, seed, world):
         assert sorted(int(idx[m]) for m in miss) == [int(i) for i in o_miss if owner[i] == r]
         seen += idx.size
     assert seen == n
+
+
+def _path_counts(L, reset=True):
+    c = (ctypes.c_ulonglong * 2)()
+    L.bb_emu_path_counts(c, int(reset))
+    return int(c[0]), int(c[1])
+
+
+@pytest.mark.parametrize('workload', ['config2', 'config3', 'config4', 'config5'])
+def test_workloads_take_the_lean_front_end(L, workload):
+    """Every query shape of the BASELINE.json configs is settled by lean_query (the word-wise front end): the general
+    path (complete decoder + byte-serial resolve) is for unusual packets only.  Also bit-exact against the oracle,
+    hits, misses, services, NOTIMP and EDNS included."""
+    desc, service_frac, mix, miss_frac, recursion = synth.WORKLOADS[workload]
+    z = synth.gen_zone(30000, service_frac=service_frac)
+    emu = EmuEngine(L, z.dns_domain, z.jsonl, recursion)
+    orc = H.make_impl('oracle', z.dns_domain, z.jsonl, recursion=recursion)
+    data, off, meta = synth.gen_batch(z, 6000, 5, mix, miss_frac)
+    _path_counts(L)
+    assert_same(emu, orc, data, off, seed=11)
+    lean, general = _path_counts(L)
+    assert general == 0 and lean == 6000, (lean, general)
+    # the same names with an OPT, upper-case letters, RD=0: still the lean path
+    pk = []
+    for i in range(0, 6000, 7):
+        k, ix = int(meta['kind'][i]), int(meta['idx'][i])
+        name = synth.host_name(ix) if k <= synth.K_HOST_AAAA else synth.svc_name(ix)
+        cut = len(name) - len(z.dns_domain)                 # the suffix gate is case-sensitive: only what precedes dnsDomain varies
+        name = (name[:cut].upper() if i % 3 == 0 else name[:3].upper() + name[3:cut]) + name[cut:]
+        if k == synth.K_SVC_SRV:
+            name = '_http._tcp.' + name
+        pk.append(synth.make_query(name, {0: 1, 1: 28, 2: 1, 3: 33}[k], i & 0xFFFF, rd=bool(i & 1), edns=(4096 if i % 2 else 600)))
+    d2, o2 = synth.pack_batch(pk)
+    assert_same(emu, orc, d2, o2, seed=12)
+    lean, general = _path_counts(L)
+    assert general == 0, (lean, general)
+
+
+def test_fuzz_queries_mostly_lean(L):
+    snap, info = fuzzgen.gen_zone(5, n_top=40)
+    emu = EmuEngine(L, info['dns_domain'], snap, True)
+    data, off = synth.pack_batch(fuzzgen.gen_queries(5, info, n=3000))
+    _path_counts(L)
+    emu.resolve_batch(data, off, seed=1)
+    lean, general = _path_counts(L)
+    assert lean > general, (lean, general)

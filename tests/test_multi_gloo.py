@@ -20,7 +20,7 @@ def _worker(rank, world, port, q):
     st = Zone(z.jsonl, z.dns_domain, world, rank).stat()
     # the host-side owner function on the same keys
     names = [synth.host_name(i).encode() for i in range(z.n_hosts)]
-    own = owner_of(hash_keys(names, 0), world)
+    own = owner_of(hash_keys(names, 0, z.dns_domain), world)
     addrs = [synth.host_addr(i).encode() for i in range(z.n_hosts)]
     by_len = {}
     for a in addrs:
