@@ -89,7 +89,8 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const uint32_t nq = min((uint32_t)T, n - q0);
 
     // ---- stage this tile's packets ---------------------------------------------------------
-    for (int i = tid; i <= (int)nq; i += T) s_off[i] = r_pkt_off[q0 + i];
+    if (tid < (int)nq) s_off[tid] = r_pkt_off[q0 + tid];
+    if (tid == 0) s_off[nq] = r_pkt_off[q0 + nq];
     __syncthreads();
     STAMP(1);
     const uint32_t b0 = s_off[0], b1 = s_off[nq];
@@ -570,6 +571,11 @@ bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
     if (o->device < 0 || o->device >= ndev) return fail(BB_ERR_ARG);
     bb_engine* e = new bb_engine();
     if (!bb::make_engine_const(o->dns_domain, o->recursion != 0, e->hconst)) { delete e; return fail(BB_ERR_DOMAIN); }
+    // A probe wants ONE 32-byte sector of a table far larger than L2; by default an L2 miss fetches 128 bytes from
+    // DRAM around it (measured: tools/micro/probe_gran.cu, 4 sectors of dram__bytes_read per sector asked for).
+    // Sector-granular fetches cut the probe's DRAM traffic 4x; streaming reads ask for whole lines anyway.
+    if (cudaSetDevice(o->device) == cudaSuccess) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    cudaGetLastError();
     e->device = o->device; e->ordered = o->ordered_output ? 1 : 0;
     e->max_batch = o->max_batch ? o->max_batch : (1u << 20);
     if (e->max_batch > (1u << 22)) { delete e; return fail(BB_ERR_ARG); }

@@ -53,13 +53,14 @@ struct Res {
     uint32_t qn_len;         // QNAME wire length incl. terminator
     uint32_t ttl, val;
     uint64_t perm;           // shuffled child order, 4 bits each (nk <= 16)
-    uint16_t rlen, maxsz, qtype, adv;
-    uint16_t d_off, d_end;   // domain part [d_off, d_end) in QNAME wire coordinates
-    uint16_t ptr_tgt;        // label boundary the owner's compression pointer targets, or NONE16
-    uint16_t lastlen;        // position of the domain's last length byte
-    uint16_t keep_ans, keep_add, n_walk, nk;
-    uint8_t status, rk, rcode, tc, opcode, rd, edns, trunc;
-    uint8_t owner;           // route mode: rank that owns this query's lookup key
+    // one 32-bit register each: narrower fields cost a mask or a byte-permute at every write
+    uint32_t rlen, maxsz, qtype, adv;
+    uint32_t d_off, d_end;   // domain part [d_off, d_end) in QNAME wire coordinates
+    uint32_t ptr_tgt;        // label boundary the owner's compression pointer targets, or NONE16
+    uint32_t lastlen;        // position of the domain's last length byte
+    uint32_t keep_ans, keep_add, n_walk, nk;
+    uint32_t status, rk, rcode, tc, opcode, rd, edns, trunc;
+    uint32_t owner;          // route mode: rank that owns this query's lookup key
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -101,13 +102,13 @@ __device__ bool decode(const uint8_t* p, uint32_t len, Res& r) {
     }
     r.qn_len = pos - 12;
     if (pos + 4 > len) return false;
-    r.qtype = (uint16_t)be16(p + pos);
+    r.qtype = be16(p + pos);
     if (be16(p + pos + 2) != 1) return false;
     pos += 4;
     r.edns = 0; r.adv = 0;
     if (ar == 1) {
         if (pos + 11 > len || p[pos] != 0 || be16(p + pos + 1) != QT_OPT) return false;
-        r.adv = (uint16_t)be16(p + pos + 3);
+        r.adv = be16(p + pos + 3);
         if (pos + 11 + be16(p + pos + 9) > len) return false;
         r.edns = 1;
     }
@@ -150,27 +151,30 @@ __device__ bool probe(const Params& P, Res& r, uint32_t ns, KG& kg, uint32_t& ki
     for (uint32_t i = 0; i < klen; i++) kh.feed(kg.next());
     uint32_t h2;
     uint32_t h = kh.finish(h2);
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return false; }   // sharding: who would answer
-    // 2-choice cuckoo: the key is in slot1_of(h) or slot2_of(h) or nowhere
+    if (P.route) { r.owner = owner_of(h, P.nranks); return false; }   // sharding: who would answer
+    // 2-choice cuckoo: the key is in slot1_of(h), or — only when that position says some key was displaced — in
+    // slot2_of(h), or nowhere
     const uint32_t cand[2] = { slot1_of(h, P.mask), slot2_of(h, h2, P.mask) };
     for (int c = 0; c < 2; c++) {
         const Slot* s = P.table + cand[c];
         uint4 hd = __ldg((const uint4*)s);                  // klen,kind,ns,flags | ttl | val | key[0..3]
+        const bool more = c == 0 && ((hd.x >> 24) & SLOT_DISPLACED);
         uint32_t sk = (hd.x >> 8) & 0xFF;
-        if (sk == K_EMPTY) continue;
-        if (((hd.x >> 16) & 0xFF) != ns) continue;
-        uint32_t sl = hd.x & 0xFF;
-        const uint8_t* kb = nullptr;
-        if (sl == KLEN_OVERFLOW) {
-            uint32_t off = hd.w, l = __ldg((const uint32_t*)(s->key + 4)), sh = __ldg((const uint32_t*)(s->key + 8));
-            if (l == klen && sh == h) kb = P.arena + off;
-        } else if (sl == klen) kb = s->key;
-        if (kb) {
-            kg.start();
-            bool eq = true;
-            for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
-            if (eq) { kind = sk; ttl = hd.y; val = hd.z; return true; }
+        if (sk != K_EMPTY && ((hd.x >> 16) & 0xFF) == ns) {
+            uint32_t sl = hd.x & 0xFF;
+            const uint8_t* kb = nullptr;
+            if (sl == KLEN_OVERFLOW) {
+                uint32_t off = hd.w, l = __ldg((const uint32_t*)(s->key + 4)), sh = __ldg((const uint32_t*)(s->key + 8));
+                if (l == klen && sh == h) kb = P.arena + off;
+            } else if (sl == klen) kb = s->key;
+            if (kb) {
+                kg.start();
+                bool eq = true;
+                for (uint32_t j = 0; j < klen; j++) if (__ldg(kb + j) != kg.next()) { eq = false; break; }
+                if (eq) { kind = sk; ttl = hd.y; val = hd.z; return true; }
+            }
         }
+        if (!more) break;
     }
     return false;
 }
@@ -256,7 +260,7 @@ __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_
 // find where a malformed child cuts the answer short, or which prefix of the RRs survives truncation.
 __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_t qidx, bool srv, uint32_t fixed) {
     const uint32_t nk = sv.nkids();
-    r.nk = (uint16_t)nk;
+    r.nk = nk;
     r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
     const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
     uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
@@ -278,8 +282,8 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
             } else { ans_b += dol + 14; n_ans++; }
         }
     }
-    r.n_walk = (uint16_t)n_walk;
-    if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = (uint16_t)n_ans; r.keep_add = (uint16_t)n_add; r.rlen = (uint16_t)(fixed + ans_b + add_b); return; }
+    r.n_walk = n_walk;
+    if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = n_ans; r.keep_add = n_add; r.rlen = (fixed + ans_b + add_b); return; }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits
     r.tc = 1;
     uint32_t total = fixed, ka = 0, kd = 0; bool full = false;
@@ -296,13 +300,13 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
         if (total + each > r.maxsz) break;
         total += each; ++kd;
     }
-    r.keep_ans = (uint16_t)ka; r.keep_add = (uint16_t)kd; r.rlen = (uint16_t)total;
+    r.keep_ans = ka; r.keep_add = kd; r.rlen = total;
 }
 
 // one RR that either fits or is dropped (TC)
 __device__ __forceinline__ void size_single(Res& r, uint32_t fixed, uint32_t rr) {
-    if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
-    else { r.rlen = (uint16_t)fixed; r.keep_ans = 0; r.tc = 1; }
+    if (fixed + rr <= r.maxsz) { r.rlen = (fixed + rr); r.keep_ans = 1; }
+    else { r.rlen = fixed; r.keep_ans = 0; r.tc = 1; }
 }
 
 // Recursion.resolve()'s quick rejects (lib/recursion.js:329-344), for a miss that would otherwise be handed
@@ -360,7 +364,7 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     if (srv && kind != K_SERVICE) {                                           // :276-292 NODATA + SOA
         r.rcode = RC_NOERROR; r.rk = RK_SOA;
         uint32_t rr = dom_owner_len(r) + 10 + E->soa_len + 20;
-        if (fixed + rr <= r.maxsz) { r.rlen = (uint16_t)(fixed + rr); r.keep_ans = 1; }
+        if (fixed + rr <= r.maxsz) { r.rlen = (fixed + rr); r.keep_ans = 1; }
         else { r.keep_ans = 0; r.tc = 1; }
         return;
     }
@@ -386,7 +390,13 @@ __device__ __forceinline__ unsigned long long gtime() { unsigned long long t; as
 #endif
 // per-stage stamps of one tile, the batched analogue of query._stamp() (lib/server.js:479-483)
 constexpr int NSTAGE = 16;
+// Compiled in only with -DBB_STAGE_LOG (tools/stage_times.py builds such a library): eleven tests of a kernel parameter
+// per query are ~5 % of the hot path's instructions.
+#ifdef BB_STAGE_LOG
 #define STAMP(k) do { if (P.stage_log && threadIdx.x == 0) P.stage_log[(size_t)blockIdx.x * NSTAGE + (k)] = gtime(); } while (0)
+#else
+#define STAMP(k) ((void)0)
+#endif
 
 // ---- word-wise front end of resolve() -----------------------------------------------------
 // Same decisions as resolve_forward() below, four name bytes per step, for the common case:
@@ -442,7 +452,7 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
     if (pos + 1 + 4 > lim) return false;
     r.qn_len = pos + 1;
     const uint32_t tc = ldsu32(nm + pos + 1);                                 // QTYPE, QCLASS (big-endian)
-    r.qtype = (uint16_t)(((tc & 0xFF) << 8) | ((tc >> 8) & 0xFF));
+    r.qtype = (((tc & 0xFF) << 8) | ((tc >> 8) & 0xFF));
     if ((tc >> 16) != 0x0100u) return false;                                  // class IN
     r.edns = 0; r.adv = 0;
     if (w2) {
@@ -450,7 +460,7 @@ __device__ bool decode_staged(uint32_t sp, uint32_t len, Res& r) {
         if (pos + 5 + 11 > lim) return false;
         const uint32_t a = ldsu32(q), b = ldsu32(q + 4), c2 = ldsu32(q + 8);
         if ((a & 0xFFFFFF) != 0x290000u) return false;                        // root owner, TYPE 41
-        r.adv = (uint16_t)(((a >> 24) << 8) | (b & 0xFF));
+        r.adv = (((a >> 24) << 8) | (b & 0xFF));
         const uint32_t rdlen = (((c2 >> 8) & 0xFF) << 8) | ((c2 >> 16) & 0xFF);
         if (pos + 5 + 11 + rdlen > lim) return false;
         r.edns = 1;
@@ -526,7 +536,7 @@ __device__ int lean_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, 
         const uint32_t a = ldsu32(q), b = ldsu32(q + 4), c2 = ldsu32(q + 8);
         if ((a & 0xFFFFFFu) != 0x290000u) return 0;                           // root owner, TYPE 41
         if ((c2 >> 8) & 0xFFFFu) return 0;                                    // RDLEN != 0: options follow
-        r.adv = (uint16_t)(((a >> 24) << 8) | (b & 0xFF));
+        r.adv = (((a >> 24) << 8) | (b & 0xFF));
         r.edns = 1; tail = 16;
     }
     const uint32_t d_end = len - 12 - tail;                                   // where the terminator must be
@@ -554,8 +564,14 @@ __device__ int lean_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, 
     {
         uint32_t bad = 0;
         const uint32_t nw = (sl + 3) >> 2;
-        for (uint32_t j = 0; j < nw; j++) {                                   // words right-aligned to the end of the name
-            const uint32_t x = ldsu32(nm + d_end - 4 * (j + 1));
+        // words right-aligned to the end of the name, from the end backwards; consecutive unaligned words share
+        // their aligned halves (one LDS per word)
+        const uint32_t ea = nm + d_end, eb = ea & ~3u, esh = (ea & 3u) * 8;
+        uint32_t hi = lds32(eb);
+        for (uint32_t j = 0; j < nw; j++) {
+            const uint32_t lo = lds32(eb - 4 * (j + 1));
+            const uint32_t x = __funnelshift_r(lo, hi, esh);                  // bytes [ea - 4(j+1), ea - 4j)
+            hi = lo;
             const uint32_t e = lds32(s_sfx + 256 - 4 * (j + 1));
             const uint32_t rem = sl - 4 * j;                                  // bytes of this word that belong to the suffix
             const uint32_t cm = rem >= 4 ? 0xFFFFFFFFu : (0xFFFFFFFFu << (8 * (4 - rem)));
@@ -570,10 +586,10 @@ __device__ int lean_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, 
         if (pos != k1) return 0;
     }
     // ---- a valid query (what decode() returns for it) ----
-    r.qn_len = d_end + 1; r.qtype = (uint16_t)qtype;
-    r.maxsz = P.tcp ? (uint16_t)65535 : r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
+    r.qn_len = d_end + 1; r.qtype = qtype;
+    r.maxsz = P.tcp ? 65535 : r.edns ? min(max((uint32_t)r.adv, 512u), 1200u) : 512;
     const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
-    r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
+    r.rk = RK_HEADER; r.rlen = fixed;
     if (r.opcode != 0 || !(qtype == QT_A || srv)) {
         if (r.opcode == 0 && qtype == QT_PTR) return 0;                       // resolvePtr: general path
         r.rcode = RC_NOTIMP; return 1;                                        // :500-505
@@ -619,48 +635,48 @@ __device__ int lean_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, 
     const uint32_t h2 = hash2_finish(g, pl);
     STAMP(4);
     if (refuse) { r.rcode = RC_REFUSED; return 1; }
-    if (P.route) { r.owner = (uint8_t)owner_of(h, P.nranks); return 1; }      // sharding: who would answer
-    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end; r.trunc = 0; r.lastlen = (uint16_t)d_off;
-    r.ptr_tgt = anyup ? (uint16_t)ptr_target_after_upper(nm, d_off, k1) : (uint16_t)d_off;
-    // zk.lookup(domain): both cuckoo candidates — one 32-byte sector each — are fetched together: one DRAM round
-    // trip per lookup, hit or miss, for every lane of the warp
+    if (P.route) { r.owner = owner_of(h, P.nranks); return 1; }      // sharding: who would answer
+    r.d_off = d_off; r.d_end = d_end; r.trunc = 0; r.lastlen = d_off;
+    r.ptr_tgt = anyup ? ptr_target_after_upper(nm, d_off, k1) : d_off;
+    // zk.lookup(domain): the key's first slot — one 32-byte sector, one random DRAM access — and its second slot only
+    // when the first position is flagged (some key was displaced from it): ~1.1 accesses per lookup, hit or miss
     uint32_t kind = 0, ttl = 0, val = 0;
     bool hit = false, clean = false;
     {
         const uint4* sa = (const uint4*)(P.table + slot1_of(h, P.mask));
-        const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
-        const uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1);
-        const uint4 b0 = __ldg(sb), b1 = __ldg(sb + 1);
-        uint32_t da, db;
-        if (pl <= KEY_INLINE_MAX) {
-            // header: klen | kind | ns | flags; an empty slot has klen 0 and cannot equal `want` (pl >= 2)
-            const uint32_t want = pl | (NS_FORWARD << 16);
-            da = ((a0.x & 0x00FF00FFu) ^ want) | (kw[0] ^ a0.w) | (kw[1] ^ a1.x) | (kw[2] ^ a1.y) | (kw[3] ^ a1.z) | (kw[4] ^ a1.w);
-            db = ((b0.x & 0x00FF00FFu) ^ want) | (kw[0] ^ b0.w) | (kw[1] ^ b1.x) | (kw[2] ^ b1.y) | (kw[3] ^ b1.z) | (kw[4] ^ b1.w);
-        } else {
-            // the slot names the key by arena offset, length and hash; the bytes are compared in the arena
-            const uint32_t want = KLEN_OVERFLOW | (NS_FORWARD << 16);
-            da = ((a0.x & 0x00FF00FFu) ^ want) | (a1.x ^ pl) | (a1.y ^ h);
-            db = ((b0.x & 0x00FF00FFu) ^ want) | (b1.x ^ pl) | (b1.y ^ h);
-            if (da == 0 || db == 0) {
-                const uint32_t* kp = (const uint32_t*)(P.arena + (da == 0 ? a0.w : b0.w));     // 4-byte aligned, zero padded
-                uint32_t diff = 0, wp2 = lds32(kb);
+        uint4 a0 = __ldg(sa), a1 = __ldg(sa + 1);
 #pragma unroll 1
-                for (uint32_t i = 0; i < nwords; i++) {
-                    const uint32_t wnext = lds32(kb + 4 * (i + 1));
-                    uint32_t x = __funnelshift_r(wp2, wnext, ksh);
-                    wp2 = wnext;
-                    if (i == nwords - 1) x &= tailm;
-                    x |= upper_bytes(x) >> 2;
-                    uint32_t kwd = __ldg(kp + i);
-                    if (i == nwords - 1) kwd &= tailm;
-                    diff |= x ^ kwd;
+        for (int c = 0; c < 2; c++) {
+            uint32_t da;
+            if (pl <= KEY_INLINE_MAX) {
+                // header: klen | kind | ns | flags; an empty slot has klen 0 and cannot equal `want` (pl >= 2)
+                const uint32_t want = pl | (NS_FORWARD << 16);
+                da = ((a0.x & 0x00FF00FFu) ^ want) | (kw[0] ^ a0.w) | (kw[1] ^ a1.x) | (kw[2] ^ a1.y) | (kw[3] ^ a1.z) | (kw[4] ^ a1.w);
+            } else {
+                // the slot names the key by arena offset, length and hash; the bytes are compared in the arena
+                const uint32_t want = KLEN_OVERFLOW | (NS_FORWARD << 16);
+                da = ((a0.x & 0x00FF00FFu) ^ want) | (a1.x ^ pl) | (a1.y ^ h);
+                if (da == 0) {
+                    const uint32_t* kp = (const uint32_t*)(P.arena + a0.w);                  // 4-byte aligned, zero padded
+                    uint32_t wp2 = lds32(kb);
+#pragma unroll 1
+                    for (uint32_t i = 0; i < nwords; i++) {
+                        const uint32_t wnext = lds32(kb + 4 * (i + 1));
+                        uint32_t x = __funnelshift_r(wp2, wnext, ksh);
+                        wp2 = wnext;
+                        if (i == nwords - 1) x &= tailm;
+                        x |= upper_bytes(x) >> 2;
+                        uint32_t kwd = __ldg(kp + i);
+                        if (i == nwords - 1) kwd &= tailm;
+                        da |= x ^ kwd;
+                    }
                 }
-                if (da == 0) da = diff; else db = diff;
             }
+            if (da == 0) { hit = true; kind = (a0.x >> 8) & 0xFF; ttl = a0.y; val = a0.z; clean = (a0.x >> 24) & SLOT_KEY_CLEAN; break; }
+            if (c || !((a0.x >> 24) & SLOT_DISPLACED)) break;
+            const uint4* sb = (const uint4*)(P.table + slot2_of(h, h2, P.mask));
+            a0 = __ldg(sb); a1 = __ldg(sb + 1);
         }
-        if (da == 0) { hit = true; kind = (a0.x >> 8) & 0xFF; ttl = a0.y; val = a0.z; clean = (a0.x >> 24) & SLOT_KEY_CLEAN; }
-        else if (db == 0) { hit = true; kind = (b0.x >> 8) & 0xFF; ttl = b0.y; val = b0.z; clean = (b0.x >> 24) & SLOT_KEY_CLEAN; }
     }
     STAMP(5);
     if (!(hit && clean)) {
@@ -701,7 +717,7 @@ __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t
         }
         if (d_end - d_off - 1 < 1 || d_end <= d_off + 1) { r.rcode = RC_REFUSED; return; }   // :144
     }
-    r.d_off = (uint16_t)d_off; r.d_end = (uint16_t)d_end;
+    r.d_off = d_off; r.d_end = d_end;
     if (d_end <= d_off + 1 && !srv) {                                         // root name: ''
         // isSuffix('.dom', '') is false -> refused; with no dnsDomain: length < 1 -> refused (:198)
         r.rcode = P.ready || E->suffix_len ? RC_REFUSED : RC_SERVFAIL; return;
@@ -728,8 +744,8 @@ __device__ void resolve_forward(const Params& P, Res& r, uint32_t qidx, uint32_t
     if (!suffix_ok) { r.rcode = RC_REFUSED; return; }
     if (!P.ready && !P.route) { r.rcode = RC_SERVFAIL; return; }             // :186-192
     if (!charset_ok) { r.rcode = RC_REFUSED; return; }
-    r.ptr_tgt = (need_b || r.trunc) ? (uint16_t)NONE16 : (uint16_t)ptr_tgt;
-    r.lastlen = (uint16_t)lastlen;
+    r.ptr_tgt = (need_b || r.trunc) ? NONE16 : ptr_tgt;
+    r.lastlen = lastlen;
 
     // the lookup key (zone_image.h): the labels in front of the suffix the gate has just matched
     FwdKey kg; kg.nm = nm; kg.k0 = d_off; kg.k1 = d_end - sl;
@@ -767,7 +783,7 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 // onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
 __device__ __forceinline__ void res_init(Res& r) {
     r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
-    r.ptr_tgt = (uint16_t)NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
+    r.ptr_tgt = NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
 }
 #ifdef BB_HOST_EMU        /* the CPU emulation counts which front end settled each query (tests/test_host_emulation.py) */
 extern unsigned long long bb_emu_lean_count, bb_emu_general_count;
@@ -781,9 +797,9 @@ __device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qi
     BB_EMU_COUNT(bb_emu_general_count);
     res_init(r);
     if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
-    r.maxsz = P.tcp ? (uint16_t)65535 : r.edns ? (uint16_t)min(max((uint32_t)r.adv, 512u), 1200u) : (uint16_t)512;
+    r.maxsz = P.tcp ? 65535 : r.edns ? min(max((uint32_t)r.adv, 512u), 1200u) : 512;
     const uint32_t fixed = 12 + r.qn_len + 4 + (r.edns ? 11 : 0);
-    r.rk = RK_HEADER; r.rlen = (uint16_t)fixed;
+    r.rk = RK_HEADER; r.rlen = fixed;
     const bool handled = r.opcode == 0 && (r.qtype == QT_A || r.qtype == QT_SRV || r.qtype == QT_PTR);
     if (!handled) { r.rcode = RC_NOTIMP; return; }                            // :500-505
     const uint8_t* nm = r.p + 12;
@@ -948,6 +964,12 @@ struct WrT {
     // n bytes from shared memory (consecutive unaligned words share their aligned halves)
     __device__ void copy(uint32_t src, uint32_t n) {
         const uint32_t b = src & ~3u, sh = (src & 3u) * 8;
+        if ((sh | fill) == 0 && !(HEADCHK && head)) {     // word-aligned on both sides: no shifting, no carry
+            uint32_t i = 0;
+            for (; i + 4 <= n; i += 4) { st32(wp, lds32(b + i)); wp += 4; }
+            if (i < n) { acc = lds32(b + i) & ((1u << (8 * (n - i))) - 1); fill = n - i; }
+            return;
+        }
         uint32_t prev = lds32(b), i = 0, k = 1;
         for (; i + 4 <= n; i += 4, k++) { const uint32_t nx = lds32(b + 4 * k); put4(__funnelshift_r(prev, nx, sh)); prev = nx; }
         if (i < n) { const uint32_t nx = lds32(b + 4 * k); put(__funnelshift_r(prev, nx, sh) & ((1u << (8 * (n - i))) - 1), n - i); }

@@ -460,7 +460,7 @@ struct TableBuilder {
     void touch(uint32_t pos) { if (track && !dirty_mark[pos]) { dirty_mark[pos] = 1; dirty.push_back(pos); } }
     void reset(ZoneImage* img, uint32_t nslots) {
         z = img; mask = nslots - 1; failed = false; count = 0;
-        h1s.assign(nslots, 0); h2s.assign(nslots, 0); own.assign(nslots, 0);
+        h1s.assign(nslots, 0); h2s.assign(nslots, 0); own.assign(nslots, 0); disp.assign(nslots, 0);
         dirty.clear(); dirty_mark.assign(nslots, 0);
         arena.assign(32, 0);                                  // offset 0 is never a valid record
     }
@@ -495,9 +495,34 @@ struct TableBuilder {
         if (!canon(ns, dk, dlen, c)) return -1;
         return find_canon(ns, (const uint8_t*)c.data(), (uint32_t)c.size());
     }
+    // ---- residents and the SLOT_DISPLACED flag of their first slots -------------------------------------------
+    // disp[p] = keys whose first slot is p but which live in their second slot; the flag at p mirrors disp[p] > 0.
+    std::vector<uint32_t> disp;
+    void set_resident(uint32_t pos, const Slot& c, uint32_t h1, uint32_t h2, uint32_t owner) {
+        Slot& s = z->slots[pos];
+        const uint8_t posflag = s.flags & SLOT_DISPLACED;
+        s = c; s.flags = (uint8_t)((c.flags & ~SLOT_DISPLACED) | posflag);
+        h1s[pos] = h1; h2s[pos] = h2; own[pos] = owner;
+        touch(pos);
+        const uint32_t first = slot1_of(h1, mask);
+        if (first != pos && disp[first]++ == 0) { z->slots[first].flags |= SLOT_DISPLACED; touch(first); }
+    }
+    // the resident of pos leaves it (erased, or evicted by a kick); returns what it was
+    Slot take_resident(uint32_t pos) {
+        Slot& s = z->slots[pos];
+        Slot was = s;
+        const uint8_t posflag = s.flags & SLOT_DISPLACED;
+        const uint32_t first = slot1_of(h1s[pos], mask);
+        if (first != pos && --disp[first] == 0) { z->slots[first].flags &= (uint8_t)~SLOT_DISPLACED; touch(first); }
+        memset(&s, 0, sizeof s); s.flags = posflag;
+        h1s[pos] = 0; h2s[pos] = 0; own[pos] = 0;
+        touch(pos);
+        was.flags &= (uint8_t)~SLOT_DISPLACED;
+        return was;
+    }
     // a cuckoo table needs no tombstones: a lookup only ever reads the key's two slots
-    void erase(uint32_t pos) { memset(&z->slots[pos], 0, sizeof(Slot)); h1s[pos] = 0; h2s[pos] = 0; own[pos] = 0; --count; touch(pos); }
-    // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo.
+    void erase(uint32_t pos) { take_resident(pos); --count; }
+    // insert or overwrite ("last writer wins", like assigning into a JS object); 2-choice cuckoo, first slot preferred.
     // Returns true when the key is new.
     bool put(uint32_t ns, const uint8_t* dk, uint32_t dlen, uint8_t kind, uint32_t ttl, uint32_t val, uint32_t owner) {
         std::string c;
@@ -515,11 +540,12 @@ struct TableBuilder {
         uint32_t pos = z->slots[i1].kind == K_EMPTY ? i1 : (z->slots[i2].kind == K_EMPTY ? i2 : i1);
         ++count;
         for (int kick = 0; kick < 2000; kick++) {
-            Slot& s = z->slots[pos];
-            touch(pos);
-            if (s.kind == K_EMPTY) { s = cur; h1s[pos] = cur_h1; h2s[pos] = cur_h2; own[pos] = cur_own; return true; }
-            Slot ev = s; s = cur; cur = ev;                          // evict the resident, move it to its other slot
-            std::swap(h1s[pos], cur_h1); std::swap(h2s[pos], cur_h2); std::swap(own[pos], cur_own);
+            if (z->slots[pos].kind == K_EMPTY) { set_resident(pos, cur, cur_h1, cur_h2, cur_own); return true; }
+            // evict the resident, move it to its other slot
+            const uint32_t ev_h1 = h1s[pos], ev_h2 = h2s[pos], ev_own = own[pos];
+            const Slot ev = take_resident(pos);
+            set_resident(pos, cur, cur_h1, cur_h2, cur_own);
+            cur = ev; cur_h1 = ev_h1; cur_h2 = ev_h2; cur_own = ev_own;
             const uint32_t a = slot1_of(cur_h1, mask), b = slot2_of(cur_h1, cur_h2, mask);
             pos = pos == a ? b : a;
         }
@@ -942,6 +968,7 @@ extern "C" uint64_t bb_zone_stat(const bb_zone* z, int what) {
     case 5: return z->img.arena_len;
     case 6: return z->T.dirty.size();                          // slots changed since the device last saw the table
     case 7: return z->relaid ? 1 : 0;
+    case 8: { uint64_t d = 0; for (uint32_t v : z->T.disp) d += v; return d; }      // keys living in their second slot
     }
     return 0;
 }

@@ -1,9 +1,12 @@
 // Zone image: the HBM-resident, flattened form of binder's ZKCache (lib/zk.js:20-119).
 //
 // One 2-choice cuckoo table (power-of-two, load factor < 0.46) of 32-byte slots — ONE DRAM sector each —
-// holds BOTH of ZKCache's maps (a key lives in slot hash & mask or slot hash2 & mask — two independent
-// hashes of the key — never anywhere else, so a lookup — hit or miss — is two independent 32-byte reads
-// issued together: one DRAM round trip per warp, 64 bytes of traffic):
+// holds BOTH of ZKCache's maps.  A key lives in slot hash & mask (its first slot, where the builder puts it
+// whenever it can: ~87 % of the keys at these load factors) or in slot hash2 & mask — two independent hashes of
+// the key — never anywhere else; the first slot's position carries a flag when some key had to go to its second
+// slot.  A lookup — hit or miss — therefore reads ONE random sector, and a second one only behind that flag:
+// random DRAM accesses (row activations: ~44 G/s on a B200, measured with tools/micro/probe_gran.cu), not bytes,
+// are what bounds a hash probe in HBM:
 //   forward  ca_treeNodes[lower-cased fqdn]  (lib/zk.js:62-64, keys written at :84,96)
 //   reverse  ca_revLookup[address string]    (lib/zk.js:65-67, keys written at :187-188)
 // distinguished by a namespace bit that also seeds the hash.
@@ -53,6 +56,8 @@ constexpr uint32_t NS_REVERSE = 1;
 constexpr uint32_t KEY_INLINE_MAX = 20;
 constexpr uint8_t  KLEN_OVERFLOW = 0xFF;      // key bytes live in the arena
 constexpr uint8_t  SLOT_KEY_CLEAN = 1;
+constexpr uint8_t  SLOT_DISPLACED = 2;        // a property of the POSITION, not of the resident: some key whose first slot is this
+                                              // one lives in its second slot — only then does a lookup read a second slot
 
 struct alignas(32) Slot {
     uint8_t  klen;       // key length 0..20 (0: the root domain's own key, which no query can spell), or KLEN_OVERFLOW

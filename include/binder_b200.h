@@ -67,7 +67,8 @@ bb_zone* bb_zone_build_shard(const char* snapshot_jsonl, size_t len, const char*
 void     bb_zone_free(bb_zone* z);
 /* introspection: znodes mirrored (root included), forward keys, reverse keys, table bytes */
 uint64_t bb_zone_stat(const bb_zone* z, int what);   /* what: 0 nodes 1 fwd 2 rev 3 slots 4 image bytes 5 arena bytes
-                                                         6 slots changed since the device last saw the table 7 table laid out again */
+                                                         6 slots changed since the device last saw the table 7 table laid out again
+                                                         8 keys living in their second cuckoo slot (a lookup reads a second sector for these) */
 /*
  * Watch events on a built zone (lib/zk.js:120-208), batched as JSON lines:
  *   {"path": P, "data": D} | {"path": P, "raw": "<znode bytes>"}   the znode now holds this content (dataChanged,
@@ -214,7 +215,8 @@ uint64_t bb_engine_launch_count(const bb_engine* e);
 /* Epoch (launch number, low 32 bits) of the most recent resolve call on this engine. */
 uint32_t bb_engine_launch_epoch(const bb_engine* e);
 /*
- * Stage timers, the batched analogue of query._stamp() (lib/server.js:479-483): when d_log is
+ * Stage timers, the batched analogue of query._stamp() (lib/server.js:479-483); compiled in only when the library is
+ * built with -DBB_STAGE_LOG (tools/stage_times.py does that; the default build has no stamps): when d_log is
  * a device buffer of ceil(n/128) x 16 uint64, every 128-query tile of later launches stores
  * %globaltimer (ns) at: 0 start, 1 offsets in, 2 packets staged, 3 decoded, 4 normalised+hashed,
  * 5 probed, 6 sized, 7 tile scan, 8 placed (claim / look-back), 9 responses assembled,

@@ -6,7 +6,11 @@ from binder_b200 import synth, build
 from binder_b200.engine import Engine
 from binder_b200._lib import lib
 
-build.build()
+# the stamps are compiled in only with -DBB_STAGE_LOG: build such a library for this run, restore the default afterwards
+import atexit
+os.environ['BB_NVCC_DEFINES'] = (os.environ.get('BB_NVCC_DEFINES', '') + ' -DBB_STAGE_LOG').strip()
+build.build(force=True)
+atexit.register(lambda: (os.environ.pop('BB_NVCC_DEFINES', None), build.build(force=True)))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 WL = os.environ.get('BB_WL', 'config2')
 zone = synth.gen_zone(1000000, service_frac=0.15 if WL == 'config3' else 0.0)
