@@ -56,6 +56,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
+    __shared__ uint32_t s_rstart[NROUNDS + 1];                // multi-round emit: tile offset of each round's first response
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -193,19 +194,22 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
     // ---- emit ---------------------------------------------------------------------------------------
-    // A tile whose responses fit the staging window is assembled in (swizzled) shared memory and
-    // flushed with aligned 16-byte stores.  A larger tile (service answers are ~250 B each), or one
-    // with a query on the generic byte path, writes straight to global memory instead: every thread's
-    // response is one long contiguous run, and L2 merges its 4-byte stores.
-    const bool generic_emit = my_len && !(r.sp && !r.trunc);
-    const bool direct = __syncthreads_or(generic_emit) || tile_bytes > (uint32_t)CAPW;
+    // Responses are assembled in (swizzled) shared memory and flushed with aligned 16-byte stores, one WINDOW of the
+    // tile's output at a time: round k takes the responses that START in bytes [k*WIN, (k+1)*WIN) of the tile (whole
+    // warps, since offsets grow with the thread index; a response may run up to MAXRESP past the window's end, which
+    // the buffer allows for), then all threads flush that range.  A 64-byte-answer tile is one round; a tile of
+    // ~300-byte service answers three or four.  (Writing such tiles straight to global memory, four bytes per lane
+    // and 32 scattered lines per store instruction, kept the store path busier than everything else together.)
+    // Only a tile with a query on the generic byte path, or with a response over MAXRESP (TCP), writes directly.
+    const bool odd_emit = my_len && (!(r.sp && !r.trunc) || my_len > (uint32_t)MAXRESP);
+    const bool direct = __syncthreads_or(odd_emit);
     if (!overflow && direct) {
         // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
         // coalesced 16-byte stores (the bytes are still in L2)
         uint8_t* const dst = r_bounce ? r_bounce : r_out;
         if (my_len) {
-            if (generic_emit) emit_response(P, r, dst + gbase + my_o, qidx);
+            if (!(r.sp && !r.trunc)) emit_response(P, r, dst + gbase + my_o, qidx);
             else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
         }
         STAMP(9);
@@ -222,21 +226,37 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
         }
     } else if (!overflow && tile_bytes) {
-        const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
-        if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
-        __syncthreads();
+        const uint32_t nr = (tile_bytes + WIN - 1) / WIN;                     // <= NROUNDS
+        const uint32_t kr = my_o / WIN;
+        if (nr > 1) {                                                         // where each round's first response starts
+            if (tid <= (int)NROUNDS) s_rstart[tid] = 0xFFFFFFFFu;
+            __syncthreads();
+            if (my_len) atomicMin(&s_rstart[kr], my_o);
+            __syncthreads();
+        }
+        for (uint32_t k = 0; k < nr; k++) {
+            uint32_t x0 = 0, x1 = tile_bytes;                                 // this round's byte range of the tile
+            if (nr > 1) {
+                x0 = s_rstart[k];
+                if (x0 == 0xFFFFFFFFu) continue;                              // no response starts in this window (uniform)
+                for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; break; }
+            }
+            const uint32_t wbase = k * WIN;                                   // tile offset the buffer's byte `shift` stands for
+            const uint32_t shift = (uint32_t)((gbase + wbase) & 15);          // same 16-byte phase in shared and global memory
+            if (my_len && kr == k) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o - wbase); emit_fast(P, r, w, qidx); }
+            __syncthreads();
+            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[swz(shift + x - wbase)]
+            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);      // up to 16-byte alignment of the global address
+            if (head > x1 - x0) head = x1 - x0;
+            if (tid < (int)head) g[x0 + tid] = s_out[swz(shift + x0 + tid - wbase)];
+            x0 += head;
+            const uint32_t nv = (x1 - x0) >> 4;
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i - wbase));
+            x0 += nv << 4;
+            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid - wbase)];
+            if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
+        }
         STAMP(9);
-        uint8_t* g = r_out + gbase;                                           // g[x] <-> s_out[swz(shift + x)]
-        uint32_t x0 = 0;
-        const uint32_t x1 = tile_bytes;
-        uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);                 // up to 16-byte alignment of the global address
-        if (head > x1) head = x1;
-        if (tid < (int)head) g[tid] = s_out[swz(shift + tid)];
-        x0 = head;
-        const uint32_t nv = (x1 - x0) >> 4;
-        for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i));
-        x0 += nv << 4;
-        if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid)];
     }
 
     STAMP(10);

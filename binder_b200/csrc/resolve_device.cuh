@@ -12,6 +12,9 @@ constexpr int S_IN = 8192;                // staged input bytes per tile
 constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
+constexpr int WIN = CAPW - MAXRESP;       // output window of one emit round: a response starting in it ends inside the buffer
+constexpr int NROUNDS = (T * MAXRESP + WIN - 1) / WIN;        // rounds a tile of maximal responses needs
+static_assert(WIN % 16 == 0 && WIN > 0, "windows keep the 16-byte phase");
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -202,13 +205,26 @@ __device__ __forceinline__ uint32_t perm_at(const Res& r, uint32_t t, uint64_t s
     return r.nk <= 16 ? (uint32_t)(r.perm >> (4 * t)) & 15 : perm_at_slow(t, r.nk, seed, qidx);
 }
 
+// 16 bytes of a record that is read front to back (a service's header, child records and ready RRs): ask L2 to bring the
+// surrounding 256 bytes in from DRAM.  The engine runs with sector-granular L2 fetches (bb_engine_create: a probe wants
+// one 32-byte slot of a table far larger than L2), which would otherwise turn such a walk into one DRAM round trip per sector.
+#ifdef BB_HOST_EMU
+static inline uint4 ldg_stream(const uint4* p) { return *p; }
+#else
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L2::256B.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+#endif
+
 // A service record in the arena (zone_image.h): 32-byte header, nkids 16-byte child records, the children's RR bytes.
 struct SvcView {
     const uint8_t* base; const uint8_t* arena;
     uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports ; hflags,sp_len,dom_wl,sp[13]
     __device__ void open(const uint8_t* arena_, uint32_t off) {
         arena = arena_; base = arena_ + off;
-        h0 = __ldg((const uint4*)base); h1 = __ldg((const uint4*)base + 1);
+        h0 = ldg_stream((const uint4*)base); h1 = ldg_stream((const uint4*)base + 1);
     }
     __device__ uint32_t ttl() const { return h0.x; }
     __device__ uint32_t nkids() const { return h0.y & 0xFFFF; }
@@ -233,7 +249,7 @@ struct KidView {
     const uint8_t* rr;       // its RR bytes: [A answer 16][additional, pad 16][SRV answers]
     uint32_t dwl;            // the service's dom_wl
     __device__ void load(const SvcView& sv, uint32_t i) {
-        a = __ldg((const uint4*)(sv.base + sizeof(SvcHdr) + sizeof(KidRec) * (size_t)i));
+        a = ldg_stream((const uint4*)(sv.base + sizeof(SvcHdr) + sizeof(KidRec) * (size_t)i));
         rr = sv.base + a.w; dwl = sv.dom_wl();
     }
     __device__ uint32_t addr() const { return a.x; }
@@ -1015,9 +1031,9 @@ __device__ __forceinline__ void copy_arena_w(W& w, const uint8_t* src, uint32_t 
     const uint4* q = (const uint4*)src;
     uint32_t i = 0;
 #pragma unroll 1
-    for (; i + 16 <= n; i += 16) { const uint4 x = __ldg(q++); w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); }
+    for (; i + 16 <= n; i += 16) { const uint4 x = ldg_stream(q++); w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); }
     if (i < n) {
-        const uint4 x = __ldg(q);
+        const uint4 x = ldg_stream(q);
         const uint32_t rem = n - i;
         if (rem >= 4) w.put4(x.x); else { w.put(x.x & ((1u << (8 * rem)) - 1), rem); return; }
         if (rem >= 8) w.put4(x.y); else { if (rem > 4) w.put(x.y & ((1u << (8 * (rem - 4))) - 1), rem - 4); return; }
@@ -1080,7 +1096,7 @@ __device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
                 copy_arena_w(w, k.srv_rr(), n * k.srv_len());
                 left -= n;
             } else if (lower) {                                                 // :411-414
-                const uint4 x = __ldg((const uint4*)k.a_rr());
+                const uint4 x = ldg_stream((const uint4*)k.a_rr());
                 w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); --left;
             } else {
                 uint32_t rttl = (fl & KID_HAS_RTTL) ? k.rttl() : r.ttl;

@@ -68,14 +68,13 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             tile_bytes += r[t].rlen; tile_miss += r[t].status == ST_MISS;
         }
         if (gbase + tile_bytes > out_cap) return BB_ERR_CAPACITY;
-        bool any_generic = false;
+        bool odd = false;
         for (uint32_t t = 0; t < nq; t++) {
             out_off[q0 + t] = (uint32_t)(gbase + my_o[t]); out_len[q0 + t] = r[t].rlen; status[q0 + t] = r[t].status;
             if (r[t].status == ST_MISS) miss_idx[mbase + my_m[t]] = q0 + t;
-            any_generic |= r[t].rlen && !(r[t].sp && !r[t].trunc);
+            odd |= r[t].rlen && (!(r[t].sp && !r[t].trunc) || r[t].rlen > (uint32_t)MAXRESP);
         }
-        const bool direct = any_generic || tile_bytes > (uint32_t)CAPW;
-        if (direct) {
+        if (odd) {
             for (uint32_t t = 0; t < nq; t++) {
                 if (!r[t].rlen) continue;
                 threadIdx.x = t;
@@ -83,13 +82,24 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                 else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
             }
         } else if (tile_bytes) {
-            const uint32_t shift = (uint32_t)(gbase & 15);
-            for (uint32_t t = 0; t < nq; t++) {
-                if (!r[t].rlen) continue;
-                threadIdx.x = t;
-                WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t]); emit_fast(P, r[t], w, qidx[t]);
+            // the kernel's emit rounds: round k = the responses that start in window k of the tile, flushed together
+            const uint32_t nr = (tile_bytes + WIN - 1) / WIN;
+            for (uint32_t k = 0; k < nr; k++) {
+                const uint32_t wbase = k * WIN, shift = (uint32_t)((gbase + wbase) & 15);
+                uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes;
+                for (uint32_t t = 0; t < nq; t++) {
+                    if (!r[t].rlen) continue;
+                    const uint32_t kr = my_o[t] / WIN;
+                    if (kr == k) {
+                        x0 = std::min(x0, my_o[t]);
+                        threadIdx.x = t;
+                        WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t] - wbase); emit_fast(P, r[t], w, qidx[t]);
+                    } else if (kr > k) x1 = std::min(x1, my_o[t]);
+                }
+                if (x0 == 0xFFFFFFFFu) continue;
+                if (shift + x1 - wbase > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                       // cannot happen: WIN + MAXRESP <= CAPW
+                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(shift + x - wbase)];     // the flush
             }
-            for (uint32_t x = 0; x < tile_bytes; x++) out[gbase + x] = s_out[swz(shift + x)];     // the flush: g[x] <-> s_out[swz(shift + x)]
         }
         gbase += tile_bytes; mbase += tile_miss;
     }
