@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 }
 
 #ifndef BB_MIN_BLOCKS
-#define BB_MIN_BLOCKS 8      /* 64 registers, no spills: 8 tiles (1024 threads) resident per SM */
+#define BB_MIN_BLOCKS 7      /* 72 registers; 30.9 KB of shared memory per tile allows 7 tiles (896 threads) per SM anyway */
 #endif
 // ORDERED: responses packed in query order (tile bases from a decoupled look-back; a tile waits
 // for its predecessors' sizes).  !ORDERED ("arrival" packing): a tile claims its output range
@@ -56,7 +56,9 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_rstart[NROUNDS + 1];                // multi-round emit: tile offset of each round's first response
+    __shared__ uint32_t s_rstart[NROUNDS + 1], s_tstart[NROUNDS + 1];   // emit rounds: tile offset of each round's first piece, index of its first job
+    __shared__ Task s_task[TASKCAP];                           // copy jobs of the tile's task-mode service answers
+    __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -108,7 +110,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     STAMP(2);
     // ---- parse + lookup + size ----------------------------------------------------------------
     Res r;
-    r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE;
+    r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE; r.ntask = 0;
     const uint32_t qidx = (r_qidx_map && tid < (int)nq) ? r_qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
     if (tid < (int)nq) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
@@ -195,14 +197,21 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
 
     // ---- emit ---------------------------------------------------------------------------------------
     // Responses are assembled in (swizzled) shared memory and flushed with aligned 16-byte stores, one WINDOW of the
-    // tile's output at a time: round k takes the responses that START in bytes [k*WIN, (k+1)*WIN) of the tile (whole
-    // warps, since offsets grow with the thread index; a response may run up to MAXRESP past the window's end, which
-    // the buffer allows for), then all threads flush that range.  A 64-byte-answer tile is one round; a tile of
-    // ~300-byte service answers three or four.  (Writing such tiles straight to global memory, four bytes per lane
-    // and 32 scattered lines per store instruction, kept the store path busier than everything else together.)
-    // Only a tile with a query on the generic byte path, or with a response over MAXRESP (TCP), writes directly.
+    // tile's output at a time.  The work is a set of PIECES, each a run of bytes with a known place in the tile:
+    //   * a response's own part — header + question, or the whole response — written by the thread that resolved it;
+    //   * the copy jobs of task-mode service answers (plan_service): a child's ready RRs, run by ANY thread, so that a
+    //     tile of ~300-byte service answers keeps all 128 threads busy with independent loads instead of each thread
+    //     walking its own service record one dependent load after another.
+    // Round k runs the pieces that START in bytes [k*WIN, (k+1)*WIN) of the tile (a piece is at most MAXRESP bytes, which
+    // the buffer allows for past the window) and flushes from its first piece to the first piece of the next round.
+    // A 64-byte-answer tile is one round with no jobs.  Only a tile with a query on the generic byte path, or with a
+    // response over MAXRESP (TCP), writes straight to global memory.
     const bool odd_emit = my_len && (!(r.sp && !r.trunc) || my_len > (uint32_t)MAXRESP);
+#ifdef BB_DIRECT_BIG      /* experiment switch: tiles over one window write straight to global memory (the round-1 behaviour) */
+    const bool direct = __syncthreads_or(odd_emit) || tile_bytes > (uint32_t)WIN;
+#else
     const bool direct = __syncthreads_or(odd_emit);
+#endif
     if (!overflow && direct) {
         // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
@@ -226,34 +235,66 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
         }
     } else if (!overflow && tile_bytes) {
+        const uint32_t s_out_a = (uint32_t)__cvta_generic_to_shared(s_out);
         const uint32_t nr = (tile_bytes + WIN - 1) / WIN;                     // <= NROUNDS
-        const uint32_t kr = my_o / WIN;
-        if (nr > 1) {                                                         // where each round's first response starts
-            if (tid <= (int)NROUNDS) s_rstart[tid] = 0xFFFFFFFFu;
+        // copy jobs of the tile: exclusive scan of the per-response job counts
+        uint32_t my_nt = my_len ? r.ntask : 0u, tbase = 0, ntasks = 0;
+        const bool any_task = __syncthreads_or(my_nt != 0);
+        if (any_task) {
+            uint32_t inc2 = my_nt;
+            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t; }
+            if (lane == 31) s_wsum[warp] = inc2;
             __syncthreads();
-            if (my_len) atomicMin(&s_rstart[kr], my_o);
+            for (int w = 0; w < T / 32; w++) { const uint32_t x = s_wsum[w]; if (w < warp) tbase += x; ntasks += x; }
+            tbase += inc2 - my_nt;
+            if (tbase + my_nt > (uint32_t)TASKCAP) { my_nt = 0; r.ntask = 0; }   // the list is full: this response is written whole by its thread
+            if (ntasks > (uint32_t)TASKCAP) ntasks = TASKCAP;                 // (a thread past the cap never writes a job: indices stay dense)
+        }
+        if (nr > 1 || any_task) {                                             // where each round's first piece / first job is
+            if (tid <= (int)NROUNDS) { s_rstart[tid] = 0xFFFFFFFFu; s_tstart[tid] = 0xFFFFFFFFu; }
+            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+            __syncthreads();
+            if (my_len) atomicMin(&s_rstart[my_o / WIN], my_o);
+            if (my_nt) {
+                struct Sink {
+                    Task* tasks; uint32_t* rstart; uint32_t* tstart; uint32_t idx;
+                    __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
+                        tasks[idx].src = src; tasks[idx].w = dst | (len << 18) | (sm << 31);
+                        atomicMin(&rstart[dst / WIN], dst); atomicMin(&tstart[dst / WIN], idx);
+                        ++idx;
+                    }
+                } sink = { s_task, s_rstart, s_tstart, tbase };
+                plan_service(P, r, qidx, my_o, (uint32_t)__cvta_generic_to_shared(s_opt), sink);
+            }
             __syncthreads();
         }
         for (uint32_t k = 0; k < nr; k++) {
-            uint32_t x0 = 0, x1 = tile_bytes;                                 // this round's byte range of the tile
-            if (nr > 1) {
+            uint32_t x0 = 0, x1 = tile_bytes, t0 = 0, t1 = 0;                 // this round's byte range and job range
+            if (nr > 1 || any_task) {
                 x0 = s_rstart[k];
-                if (x0 == 0xFFFFFFFFu) continue;                              // no response starts in this window (uniform)
+                if (x0 == 0xFFFFFFFFu) continue;                              // no piece starts in this window (uniform)
                 for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; break; }
+                t0 = s_tstart[k]; t1 = ntasks;
+                if (t0 == 0xFFFFFFFFu) t0 = t1 = 0;
+                else for (uint32_t j = k + 1; j < nr; j++) if (s_tstart[j] != 0xFFFFFFFFu) { t1 = s_tstart[j]; break; }
             }
-            const uint32_t wbase = k * WIN;                                   // tile offset the buffer's byte `shift` stands for
-            const uint32_t shift = (uint32_t)((gbase + wbase) & 15);          // same 16-byte phase in shared and global memory
-            if (my_len && kr == k) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o - wbase); emit_fast(P, r, w, qidx); }
+            const uint32_t shift = (uint32_t)((gbase + x0) & 15);             // same 16-byte phase in shared and global memory
+            const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[swz(delta + x)]
+            if (my_len && my_o / WIN == k) {
+                WrT<1> w; w.begin(s_out_a, delta + my_o);
+                if (my_nt) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
+            }
+            for (uint32_t ti = t0 + tid; ti < t1; ti += T) run_task(P, s_task[ti], s_out_a, delta);
             __syncthreads();
-            uint8_t* g = r_out + gbase;                                       // g[x] <-> s_out[swz(shift + x - wbase)]
+            uint8_t* g = r_out + gbase;
             uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);      // up to 16-byte alignment of the global address
             if (head > x1 - x0) head = x1 - x0;
-            if (tid < (int)head) g[x0 + tid] = s_out[swz(shift + x0 + tid - wbase)];
+            if (tid < (int)head) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
             x0 += head;
             const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i - wbase));
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(delta + x0 + 16 * i));
             x0 += nv << 4;
-            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid - wbase)];
+            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
             if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
         }
         STAMP(9);

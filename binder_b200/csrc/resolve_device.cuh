@@ -15,6 +15,7 @@ constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte r
 constexpr int WIN = CAPW - MAXRESP;       // output window of one emit round: a response starting in it ends inside the buffer
 constexpr int NROUNDS = (T * MAXRESP + WIN - 1) / WIN;        // rounds a tile of maximal responses needs
 static_assert(WIN % 16 == 0 && WIN > 0, "windows keep the 16-byte phase");
+constexpr int TASKCAP = 1024;             // copy jobs per tile (8 KB of shared memory); responses beyond it are written whole by their threads
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -64,6 +65,7 @@ struct Res {
     uint32_t keep_ans, keep_add, n_walk, nk;
     uint32_t status, rk, rcode, tc, opcode, rd, edns, trunc;
     uint32_t owner;          // route mode: rank that owns this query's lookup key
+    uint32_t ntask;          // > 0: a service answer assembled from copy jobs (plan_service): header + question by this thread, the RRs by anyone
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -208,8 +210,10 @@ __device__ __forceinline__ uint32_t perm_at(const Res& r, uint32_t t, uint64_t s
 // 16 bytes of a record that is read front to back (a service's header, child records and ready RRs): ask L2 to bring the
 // surrounding 256 bytes in from DRAM.  The engine runs with sector-granular L2 fetches (bb_engine_create: a probe wants
 // one 32-byte slot of a table far larger than L2), which would otherwise turn such a walk into one DRAM round trip per sector.
-#ifdef BB_HOST_EMU
+#if defined(BB_HOST_EMU)
 static inline uint4 ldg_stream(const uint4* p) { return *p; }
+#elif defined(BB_NO_STREAM_HINT)    /* experiment switch */
+__device__ __forceinline__ uint4 ldg_stream(const uint4* p) { return __ldg(p); }
 #else
 __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
     uint4 v;
@@ -218,10 +222,10 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 }
 #endif
 
-// A service record in the arena (zone_image.h): 32-byte header, nkids 16-byte child records, the children's RR bytes.
+// A service record in the arena (zone_image.h): 32-byte header, kid_info, fixed-stride child blocks.
 struct SvcView {
     const uint8_t* base; const uint8_t* arena;
-    uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports ; hflags,sp_len,dom_wl,sp[13]
+    uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports ; hflags,sp_len,dom_wl,sp[11],stride16
     __device__ void open(const uint8_t* arena_, uint32_t off) {
         arena = arena_; base = arena_ + off;
         h0 = ldg_stream((const uint4*)base); h1 = ldg_stream((const uint4*)base + 1);
@@ -235,6 +239,10 @@ struct SvcView {
     __device__ uint32_t hflags() const { return h1.x & 0xFF; }
     __device__ uint32_t sp_len() const { return (h1.x >> 8) & 0xFF; }
     __device__ uint32_t dom_wl() const { return (h1.x >> 16) & 0xFF; }
+    __device__ uint32_t stride() const { return (h1.w >> 16) << 4; }
+    __device__ uint32_t blocks_off() const { return svc_blocks_off(nkids()); }
+    // flags | wire_len << 8 | nports << 16 of child i
+    __device__ uint32_t info(uint32_t i) const { return __ldg((const uint32_t*)(base + sizeof(SvcHdr)) + i); }
     // byte i of "_srvce._proto." as wire labels
     __device__ uint32_t sp_byte(uint32_t i) const {
         if (hflags() & SVC_SP_EXT) { const uint32_t off = (h1.x >> 24) | (h1.y << 8); return __ldg(arena + off + i); }
@@ -243,23 +251,24 @@ struct SvcView {
         return (w >> (8 * (j & 3))) & 0xFF;
     }
 };
-// One child record (one 16-byte load) and where its ready RR bytes are.
+// One child's block: KidRec | A answer | additional | SRV answers (the field-by-field paths read it through this).
 struct KidView {
-    uint4 a;                 // addr | rttl | flags,wire_len,nports,pad | rr_off
-    const uint8_t* rr;       // its RR bytes: [A answer 16][additional, pad 16][SRV answers]
+    uint4 a;                 // addr | rttl | flags,wire_len,nports,pad | -
+    const uint8_t* blk;
     uint32_t dwl;            // the service's dom_wl
     __device__ void load(const SvcView& sv, uint32_t i) {
-        a = ldg_stream((const uint4*)(sv.base + sizeof(SvcHdr) + sizeof(KidRec) * (size_t)i));
-        rr = sv.base + a.w; dwl = sv.dom_wl();
+        blk = sv.base + sv.blocks_off() + (size_t)sv.stride() * i;
+        a = ldg_stream((const uint4*)blk);
+        dwl = sv.dom_wl();
     }
     __device__ uint32_t addr() const { return a.x; }
     __device__ uint32_t rttl() const { return a.y; }
     __device__ uint32_t flags() const { return a.z & 0xFF; }
     __device__ uint32_t wire_len() const { return (a.z >> 8) & 0xFF; }
     __device__ uint32_t nports() const { return (a.z >> 16) & 0xFF; }
-    __device__ const uint8_t* a_rr() const { return rr; }
-    __device__ const uint8_t* add_rr() const { return rr + 16; }                                   // starts with the child's labels
-    __device__ const uint8_t* srv_rr() const { return rr + 16 + ((kid_add_len(wire_len()) + 15) & ~15u); }
+    __device__ const uint8_t* a_rr() const { return blk + KID_A_OFF; }
+    __device__ const uint8_t* add_rr() const { return blk + KID_ADD_OFF; }                         // starts with the child's labels
+    __device__ const uint8_t* srv_rr() const { return blk + kid_srv_off(wire_len()); }
     __device__ uint32_t srv_len() const { return kid_srv_len(wire_len(), dwl); }
     __device__ uint32_t port(uint32_t c) const { const uint8_t* p = srv_rr() + c * srv_len() + 16; return (uint32_t)__ldg(p) << 8 | __ldg(p + 1); }
     __device__ uint32_t name_byte(uint32_t i) const { return __ldg(add_rr() + i); }
@@ -276,43 +285,48 @@ __device__ __forceinline__ uint32_t dom_wire_len(const Res& r) { return (uint32_
 // find where a malformed child cuts the answer short, or which prefix of the RRs survives truncation.
 __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_t qidx, bool srv, uint32_t fixed) {
     const uint32_t nk = sv.nkids();
-    r.nk = nk;
+    r.nk = nk; r.ntask = 0;
     r.perm = nk <= 16 ? make_perm(nk, P.seed, qidx) : 0;
     const uint32_t dol = dom_owner_len(r), dwl = dom_wire_len(r);
     uint32_t ans_b = 0, add_b = 0, n_ans = 0, n_add = 0, n_walk = nk;
-    const uint8_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
-    if (!(sv.hflags() & (srv ? SVC_BAD_SRV : SVC_BAD_A))) {
+    const uint32_t badbit = srv ? KID_BAD_SRV : KID_BAD_A;
+    const bool sums = !(sv.hflags() & (srv ? SVC_BAD_SRV : SVC_BAD_A));
+    if (sums) {
         if (srv) {
             n_ans = sv.sum_ports(); ans_b = n_ans * (18 + dwl) + sv.sum_wl_ports();
             n_add = sv.n_valid(); add_b = sv.sum_wl() + n_add * (dol + 14);
         } else { n_ans = sv.n_valid(); ans_b = n_ans * (dol + 14); }
     } else {
         for (uint32_t t = 0; t < nk; t++) {
-            KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
-            const uint32_t fl = k.flags();
+            const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), fl = inf & 0xFF, wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
             if (fl & badbit) { r.rcode = RC_SERVFAIL; n_walk = t; break; }      // :366-376
             if (fl & KID_ADDR_NULL) continue;                                    // :378-381
-            if (srv) {
-                ans_b += k.nports() * (18 + k.wire_len() + dwl); n_ans += k.nports();
-                add_b += k.wire_len() + dol + 14; n_add++;
-            } else { ans_b += dol + 14; n_ans++; }
+            if (srv) { ans_b += np * (18 + wl + dwl); n_ans += np; add_b += wl + dol + 14; n_add++; }
+            else { ans_b += dol + 14; n_ans++; }
         }
     }
     r.n_walk = n_walk;
-    if (fixed + ans_b + add_b <= r.maxsz) { r.keep_ans = n_ans; r.keep_add = n_add; r.rlen = (fixed + ans_b + add_b); return; }
+    if (fixed + ans_b + add_b <= r.maxsz) {
+        r.keep_ans = n_ans; r.keep_add = n_add; r.rlen = fixed + ans_b + add_b;
+        // The whole answer is the header, the question and the children's ready RRs: it can be assembled as independent
+        // copy jobs (engine.cu) when the prebuilt owner pointers are this query's (no upper-case letter in its domain part).
+        if (sums && nk <= 16 && r.ptr_tgt == r.d_off && r.rlen <= (uint32_t)MAXRESP && sv.n_valid())
+            r.ntask = (srv ? 2 * sv.n_valid() : sv.n_valid()) + (r.edns ? 1u : 0u);
+        return;
+    }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits
     r.tc = 1;
     uint32_t total = fixed, ka = 0, kd = 0; bool full = false;
     for (uint32_t t = 0; t < n_walk && !full; t++) {
-        KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
-        if (k.flags() & KID_ADDR_NULL) continue;
-        uint32_t each = srv ? 18 + k.wire_len() + dwl : dol + 14, cnt = srv ? k.nports() : 1;
+        const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
+        if (inf & KID_ADDR_NULL) continue;
+        uint32_t each = srv ? 18 + wl + dwl : dol + 14, cnt = srv ? np : 1;
         for (uint32_t c = 0; c < cnt; c++) { if (total + each > r.maxsz) { full = true; break; } total += each; ++ka; }
     }
     if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {
-        KidView k; k.load(sv, perm_at(r, t, P.seed, qidx));
-        if (k.flags() & KID_ADDR_NULL) continue;
-        uint32_t each = k.wire_len() + dol + 14;
+        const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), wl = (inf >> 8) & 0xFF;
+        if (inf & KID_ADDR_NULL) continue;
+        uint32_t each = wl + dol + 14;
         if (total + each > r.maxsz) break;
         total += each; ++kd;
     }
@@ -798,7 +812,7 @@ __device__ void resolve_ptr(const Params& P, Res& r, uint32_t fixed) {
 
 // onQuery (lib/server.js:471-507) + sizing.  Leaves r ready for emit_response().
 __device__ __forceinline__ void res_init(Res& r) {
-    r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0;
+    r.status = ST_ANSWERED; r.rk = RK_NONE; r.rlen = 0; r.tc = 0; r.keep_ans = r.keep_add = 0; r.nk = 0; r.n_walk = 0; r.ntask = 0;
     r.ptr_tgt = NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
 }
 #ifdef BB_HOST_EMU        /* the CPU emulation counts which front end settled each query (tests/test_host_emulation.py) */
@@ -1025,25 +1039,82 @@ __device__ __forceinline__ void put_global_bytes(W& w, const uint8_t* s, uint32_
     for (uint32_t i = 0; i < n; i++) w.put(__ldg(s + i), 1);
 }
 
-// n bytes from the arena (16-byte aligned source, readable up to the next multiple of 16) into the stream
+// up to 16 bytes held in registers into the stream
+template <class W>
+__device__ __forceinline__ void put_chunk_w(W& w, const uint4 x, uint32_t rem) {
+    if (rem >= 16) { w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); return; }
+    if (rem >= 4) w.put4(x.x); else { w.put(x.x & ((1u << (8 * rem)) - 1), rem); return; }
+    if (rem >= 8) w.put4(x.y); else { if (rem > 4) w.put(x.y & ((1u << (8 * (rem - 4))) - 1), rem - 4); return; }
+    if (rem >= 12) w.put4(x.z); else { if (rem > 8) w.put(x.z & ((1u << (8 * (rem - 8))) - 1), rem - 8); return; }
+    if (rem > 12) w.put(x.w & ((1u << (8 * (rem - 12))) - 1), rem - 12);
+}
+// n bytes from the arena (16-byte aligned source, readable up to the next multiple of 16) into the stream; up to four
+// 16-byte loads are in flight before the first byte is written (one memory round trip per 64 bytes, not per 16)
 template <class W>
 __device__ __forceinline__ void copy_arena_w(W& w, const uint8_t* src, uint32_t n) {
     const uint4* q = (const uint4*)src;
-    uint32_t i = 0;
 #pragma unroll 1
-    for (; i + 16 <= n; i += 16) { const uint4 x = ldg_stream(q++); w.put4(x.x); w.put4(x.y); w.put4(x.z); w.put4(x.w); }
-    if (i < n) {
-        const uint4 x = ldg_stream(q);
-        const uint32_t rem = n - i;
-        if (rem >= 4) w.put4(x.x); else { w.put(x.x & ((1u << (8 * rem)) - 1), rem); return; }
-        if (rem >= 8) w.put4(x.y); else { if (rem > 4) w.put(x.y & ((1u << (8 * (rem - 4))) - 1), rem - 4); return; }
-        if (rem >= 12) w.put4(x.z); else { if (rem > 8) w.put(x.z & ((1u << (8 * (rem - 8))) - 1), rem - 8); return; }
-        if (rem > 12) w.put(x.w & ((1u << (8 * (rem - 12))) - 1), rem - 12);
+    while (n) {
+        const uint32_t m = n < 64 ? n : 64;
+        const uint4 z = make_uint4(0, 0, 0, 0);
+        const uint4 x0 = ldg_stream(q);
+        const uint4 x1 = m > 16 ? ldg_stream(q + 1) : z;
+        const uint4 x2 = m > 32 ? ldg_stream(q + 2) : z;
+        const uint4 x3 = m > 48 ? ldg_stream(q + 3) : z;
+        put_chunk_w(w, x0, m);
+        if (m > 16) put_chunk_w(w, x1, m - 16);
+        if (m > 32) put_chunk_w(w, x2, m - 32);
+        if (m > 48) put_chunk_w(w, x3, m - 48);
+        q += 4; n -= m;
     }
 }
 
+// ---- copy jobs: a service answer as independent pieces (engine.cu runs them, any thread any job) ---------------
+// word 1: tile offset of the first byte (18 bits) | length (13 bits) << 18 | source is a shared address << 31
+struct Task { uint32_t src, w; };
+constexpr uint32_t TASK_LEN_MAX = 8191;
+__device__ __forceinline__ uint32_t task_dst(const Task& t) { return t.w & 0x3FFFFu; }
+__device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 18) & 0x1FFFu; }
+__device__ __forceinline__ bool task_smem(const Task& t) { return (t.w >> 31) != 0; }
+
+// The jobs of one task-mode response (Res::ntask of them, in ascending destination order), given where the response
+// starts in its tile: the children's ready RRs in shuffled child order (lib/server.js:361-416) and, for EDNS, the OPT
+// (from `opt_sp`, a shared address holding its 11 bytes).  The header and the question are the owning thread's.
+template <class Sink>
+__device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint32_t my_o, uint32_t opt_sp, Sink& sink) {
+    const bool srv = r.rk == RK_SVC_SRV;
+    SvcView sv; sv.open(P.arena, r.val);
+    const uint32_t blocks = r.val + sv.blocks_off(), stride = sv.stride(), dwl = sv.dom_wl();
+    uint32_t dst = my_o + 12 + r.qn_len + 4;
+    for (uint32_t t = 0; t < r.nk; t++) {
+        const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
+        if (inf & KID_ADDR_NULL) continue;
+        const uint32_t wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
+        if (srv) { const uint32_t len = np * kid_srv_len(wl, dwl); if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0); else sink.put(0, dst, 0, 0); dst += len; }
+        else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0); dst += 16; }
+    }
+    if (srv) {
+        if (r.edns) { sink.put(opt_sp, dst, 11, 1); dst += 11; }
+        for (uint32_t t = 0; t < r.nk; t++) {
+            const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
+            if (inf & KID_ADDR_NULL) continue;
+            const uint32_t wl = (inf >> 8) & 0xFF;
+            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0); dst += kid_add_len(wl);
+        }
+    } else if (r.edns) sink.put(opt_sp, dst, 11, 1);                          // the OPT is the only additional RR of an A answer
+}
+// run one job into the (swizzled) staging buffer: tile byte x lives at shared offset buf + delta + x
+__device__ __forceinline__ void run_task(const Params& P, const Task t, uint32_t buf, uint32_t delta) {
+    const uint32_t len = task_len(t);
+    if (!len) return;
+    WrT<1, true> w; w.begin(buf, delta + task_dst(t));
+    if (task_smem(t)) w.copy(t.src, len); else copy_arena_w(w, P.arena + t.src, len);
+    w.end();
+}
+
+// header + question (verbatim) of a response; the stream stays open
 template <class W>
-__device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
+__device__ __forceinline__ void emit_head_w(const Res& r, W& w) {
     const uint32_t p = r.sp;
     uint32_t an = 0, ns = 0, ar = r.edns ? 1 : 0;
     switch (r.rk) {
@@ -1056,6 +1127,11 @@ __device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
     w.put4(0x00000100u | (bswap16(an) << 16));                                  // QDCOUNT=1, ANCOUNT
     w.put4(bswap16(ns) | (bswap16(ar) << 16));                                  // NSCOUNT, ARCOUNT
     w.copy(p + 12, r.qn_len + 4);                                               // question, verbatim
+}
+
+template <class W>
+__device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
+    emit_head_w(r, w);
     bool opt_done = !r.edns;
     if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310
         const uint32_t bt = bswap32(r.ttl);

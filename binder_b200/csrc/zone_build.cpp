@@ -590,9 +590,7 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib)
             if ((B.nodes[k].flags & (NF_KIDTYPE | NF_DEAD)) == NF_KIDTYPE) kids.push_back(k);
         if (kids.size() > 65535) return false;
-        // header (32 bytes) + one 16-byte record per child + the children's RRs as ready wire bytes (zone_image.h),
-        // contiguous and 32-byte aligned
-        std::vector<uint8_t> rec(sizeof(SvcHdr) + sizeof(KidRec) * kids.size(), 0);
+        // header | kid_info | one fixed-stride block per child with its RRs as ready wire bytes (zone_image.h)
         SvcHdr h; memset(&h, 0, sizeof h);
         h.ttl = si.ttl; h.nkids = (uint16_t)kids.size();
         h.dom_wl = (uint8_t)(dom_wire.size() + 1);
@@ -611,6 +609,9 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         auto be16 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
         auto be32 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
         uint64_t n_valid = 0, sum_ports = 0, sum_wl = 0, sum_wl_ports = 0;
+        std::vector<std::vector<uint8_t>> blocks(kids.size());
+        std::vector<uint32_t> info(kids.size(), 0);
+        size_t stride = 16;
         for (size_t ki = 0; ki < kids.size(); ki++) {
             const Node& kn = B.nodes[kids[ki]];
             KidRec kr; memset(&kr, 0, sizeof kr);
@@ -634,27 +635,33 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
             if (kr.flags & KID_BAD_A) h.hflags |= SVC_BAD_A;
             if (kr.flags & KID_BAD_SRV) h.hflags |= SVC_BAD_SRV;
             if (!(kr.flags & KID_ADDR_NULL)) { ++n_valid; sum_ports += pl.size(); sum_wl += kw.size(); sum_wl_ports += pl.size() * kw.size(); }
-            // the child's RRs as wire bytes: A answer | additional | SRV answers, each part padded to 16
-            while (rec.size() & 15) rec.push_back(0);
-            kr.rr_off = (uint32_t)rec.size();
+            info[ki] = (uint32_t)kr.flags | (uint32_t)kr.wire_len << 8 | (uint32_t)kr.nports << 16;
+            // the block: KidRec | A answer | additional (pad 16) | SRV answers (pad 16)
+            std::vector<uint8_t>& blk = blocks[ki];
+            blk.insert(blk.end(), (uint8_t*)&kr, (uint8_t*)&kr + sizeof kr);
             const uint32_t rttl = (kr.flags & KID_HAS_RTTL) ? kr.rttl : si.ttl;
-            be16(rec, 0xC00C); be16(rec, 1); be16(rec, 1); be32(rec, si.ttl < rttl ? si.ttl : rttl); be16(rec, 4); be32(rec, kr.addr);
-            rec.insert(rec.end(), kw.begin(), kw.end());
-            be16(rec, 0xC000u | (12u + h.sp_len)); be16(rec, 1); be16(rec, 1); be32(rec, rttl); be16(rec, 4); be32(rec, kr.addr);
-            while (rec.size() & 15) rec.push_back(0);
+            be16(blk, 0xC00C); be16(blk, 1); be16(blk, 1); be32(blk, si.ttl < rttl ? si.ttl : rttl); be16(blk, 4); be32(blk, kr.addr);
+            blk.insert(blk.end(), kw.begin(), kw.end());
+            be16(blk, 0xC000u | (12u + h.sp_len)); be16(blk, 1); be16(blk, 1); be32(blk, rttl); be16(blk, 4); be32(blk, kr.addr);
+            while (blk.size() & 15) blk.push_back(0);
             for (uint16_t port : pl) {
-                be16(rec, 0xC00C); be16(rec, 33); be16(rec, 1); be32(rec, si.ttl); be16(rec, (uint32_t)(6 + kw.size() + dom_wire.size() + 1));
-                be16(rec, 0); be16(rec, 10); be16(rec, port);
-                rec.insert(rec.end(), kw.begin(), kw.end());
-                rec.insert(rec.end(), dom_wire.begin(), dom_wire.end()); rec.push_back(0);
+                be16(blk, 0xC00C); be16(blk, 33); be16(blk, 1); be32(blk, si.ttl); be16(blk, (uint32_t)(6 + kw.size() + dom_wire.size() + 1));
+                be16(blk, 0); be16(blk, 10); be16(blk, port);
+                blk.insert(blk.end(), kw.begin(), kw.end());
+                blk.insert(blk.end(), dom_wire.begin(), dom_wire.end()); blk.push_back(0);
             }
-            memcpy(rec.data() + sizeof(SvcHdr) + sizeof(KidRec) * ki, &kr, sizeof kr);
+            while (blk.size() & 15) blk.push_back(0);
+            if (blk.size() > stride) stride = blk.size();
         }
-        while (rec.size() & 15) rec.push_back(0);
+        if (stride / 16 > 0xFFFF) return false;
+        h.stride16 = (uint16_t)(stride / 16);
         // sums the kernel sizes an answer from without walking the children; a service too large for them is walked
         if (n_valid > 0xFFFF || sum_ports > 0xFFFF || sum_wl > 0xFFFF) h.hflags |= SVC_BAD_A | SVC_BAD_SRV;
         h.n_valid = (uint16_t)n_valid; h.sum_ports = (uint16_t)sum_ports; h.sum_wl = (uint16_t)sum_wl; h.sum_wl_ports = (uint32_t)sum_wl_ports;
+        std::vector<uint8_t> rec(svc_blocks_off((uint32_t)kids.size()) + stride * kids.size(), 0);
         memcpy(rec.data(), &h, sizeof h);
+        if (!info.empty()) memcpy(rec.data() + sizeof h, info.data(), 4 * info.size());
+        for (size_t ki = 0; ki < kids.size(); ki++) memcpy(rec.data() + svc_blocks_off((uint32_t)kids.size()) + stride * ki, blocks[ki].data(), blocks[ki].size());
         val = T.arena_put(rec.data(), rec.size(), 32);
     }
     uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;
@@ -991,13 +998,9 @@ extern "C" int bb_zone_probe(const bb_zone* z, uint32_t ns, const uint8_t* key, 
         bb::SvcHdr h; memcpy(&h, A + s.val, sizeof h);
         std::string ext;
         if (h.hflags & bb::SVC_SP_EXT) { uint32_t off; memcpy(&off, h.sp, 4); ext.assign((const char*)A + off, h.sp_len); memset(h.sp, 0, 4); }
-        out.append((const char*)&h, sizeof h); out += ext;
-        for (uint32_t k = 0; k < h.nkids; k++) {
-            bb::KidRec kr; memcpy(&kr, A + s.val + sizeof(bb::SvcHdr) + sizeof(bb::KidRec) * k, sizeof kr);
-            const uint32_t end = bb::kid_srv_off(kr.rr_off, kr.wire_len) + kr.nports * bb::kid_srv_len(kr.wire_len, h.dom_wl);
-            out.append((const char*)&kr, sizeof kr);              // offsets are relative to the record: position independent
-            out.append((const char*)(A + s.val + kr.rr_off), end - kr.rr_off);
-        }
+        out.append((const char*)&h, sizeof h); out += ext;                 // offsets are relative to the record: position independent
+        const size_t body = bb::svc_blocks_off(h.nkids) + (size_t)h.stride16 * 16 * h.nkids - sizeof h;
+        out.append((const char*)(A + s.val + sizeof h), body);
     } else if (s.kind == bb::K_PTR) {
         out.append((const char*)(A + s.val + 1), A[s.val]);
     }

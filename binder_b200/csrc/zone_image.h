@@ -70,16 +70,21 @@ struct alignas(32) Slot {
 };
 static_assert(sizeof(Slot) == 32, "slot must be one 32-byte sector");
 
-// ---- service record in the arena (32-byte aligned): header, nkids child records, then the children's RRs ----
+// ---- service record in the arena (32-byte aligned) ---------------------------------------------------------
+//   SvcHdr (32 B) | kid_info[nkids] (4 B each, padded to 16) | nkids blocks of `stride` bytes, child order:
+//   block = KidRec (16 B) | A answer (16 B) | additional RR (wire_len + 16, padded to 16) | SRV answers (padded to 16)
 // Sizing a service answer is one header read unless a child is malformed or the answer must be truncated:
 // the sums over the children that answer are taken at build time.  So are the resource records themselves:
 // everything in an answer RR except the bytes of the question is known when the zone is built (the SRV target is
 // the child's name + the service's own lower-cased fqdn — which the query's name equals, or it would not have hit —
 // the ttls, the ports, the owner pointers), so each child carries its RRs as ready wire bytes and answering is
 // copying them in shuffled child order (lib/server.js:361-416):
-//   [A answer, 16 B]            C00C | A IN | min(ttl, rttl) | 4 | addr                        (:411-414)
-//   [additional, pad to 16]     child labels | C0 ptr to the domain part of the QNAME | A IN | rttl | 4 | addr   (:401-402)
-//   [SRV answers, pad to 16]    per port: C00C | SRV IN | ttl | rdlen | 0 | 10 | port | child labels | fqdn | 0  (:396-400)
+//   A answer       C00C | A IN | min(ttl, rttl) | 4 | addr                                             (:411-414)
+//   additional     child labels | C0 ptr to the domain part of the QNAME | A IN | rttl | 4 | addr      (:401-402)
+//   SRV answers    per port: C00C | SRV IN | ttl | rdlen | 0 | 10 | port | child labels | fqdn | 0     (:396-400)
+// kid_info (flags | wire_len << 8 | nports << 16 per child) sits next to the header so that one memory round trip
+// tells where every child's bytes are and how long they are: the blocks have one stride, and the kernel turns an
+// answer into a list of independent copy jobs (engine.cu) instead of walking the children one load after another.
 // A query whose domain part carries upper-case letters (the owner pointers then land elsewhere), a truncated
 // answer or a malformed child take the field-by-field writer instead, which reads names and ports out of the same bytes.
 enum : uint8_t {
@@ -98,7 +103,8 @@ struct alignas(32) SvcHdr {
     uint8_t  hflags;         // SVC_*
     uint8_t  sp_len;         // bytes of "_srvce._proto." on the wire = where the domain part of a matching SRV QNAME starts
     uint8_t  dom_wl;         // the service's fqdn as wire labels + terminator (what every SRV target ends with)
-    uint8_t  sp[13];         // len, srvce bytes, len, proto bytes — as the query spells them
+    uint8_t  sp[11];         // len, srvce bytes, len, proto bytes — as the query spells them
+    uint16_t stride16;       // bytes per child block / 16
 };
 static_assert(sizeof(SvcHdr) == 32, "service header is one sector");
 enum : uint8_t {
@@ -114,14 +120,16 @@ struct alignas(16) KidRec {
     uint8_t  wire_len;       // child name as wire labels, no terminator (knode.name, :396)
     uint8_t  nports;         // SRV ports: krec[type].ports or [s.port]  (:383-385)
     uint8_t  pad;
-    uint32_t rr_off;         // this child's RR bytes, relative to the record's first byte (16-byte aligned)
+    uint32_t pad2;
 };
 static_assert(sizeof(KidRec) == 16, "child record is one 16-byte load");
 BB_HD uint32_t kid_add_len(uint32_t wire_len) { return wire_len + 16; }                            // additional RR
 BB_HD uint32_t kid_srv_len(uint32_t wire_len, uint32_t dom_wl) { return 18 + wire_len + dom_wl; }  // one SRV answer RR
-// the three parts are 16-byte aligned (rr_off is): they are streamed with 16-byte loads
-BB_HD uint32_t kid_add_off(uint32_t rr_off) { return rr_off + 16; }
-BB_HD uint32_t kid_srv_off(uint32_t rr_off, uint32_t wire_len) { return rr_off + 16 + ((kid_add_len(wire_len) + 15) & ~15u); }
+// offsets inside a record / a block (every part 16-byte aligned: they are streamed with 16-byte loads)
+BB_HD uint32_t svc_blocks_off(uint32_t nkids) { return 32 + ((4 * nkids + 15) & ~15u); }
+constexpr uint32_t KID_A_OFF = 16, KID_ADD_OFF = 32;
+BB_HD uint32_t kid_srv_off(uint32_t wire_len) { return KID_ADD_OFF + ((kid_add_len(wire_len) + 15) & ~15u); }
+BB_HD uint32_t kid_block_len(uint32_t wire_len, uint32_t nports, uint32_t dom_wl) { return kid_srv_off(wire_len) + ((nports * kid_srv_len(wire_len, dom_wl) + 15) & ~15u); }
 
 // ---- key hash: two independent multiply-fold accumulators over little-endian words, zero-padded tail -----
 // (one IMAD.WIDE + one LOP3 per accumulator per word on the device)

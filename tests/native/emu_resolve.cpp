@@ -20,7 +20,8 @@ using namespace bbk;
 constexpr size_t OFF_IN = 16;                              // s_in  [S_IN + 32]; never 0: Res::sp == 0 means "not staged"
 constexpr size_t OFF_OUT = 9216;                           // s_out [S_OUT], 1024-aligned like the kernel's
 constexpr size_t OFF_SFX = OFF_OUT + ((S_OUT + 1023) / 1024) * 1024;
-constexpr size_t SMEM_BYTES = OFF_SFX + 256 + 64;
+constexpr size_t OFF_OPT = OFF_SFX + 256 + 64;              // the OPT RR's bytes (a copy-job source)
+constexpr size_t SMEM_BYTES = OFF_OPT + 16 + 64;
 static_assert(OFF_OUT >= OFF_IN + S_IN + 32 && OFF_OUT % 1024 == 0, "layout");
 }
 
@@ -56,7 +57,7 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
         uint32_t tile_bytes = 0, tile_miss = 0, my_o[T], my_m[T];
         for (uint32_t t = 0; t < nq; t++) {
             threadIdx.x = t;
-            r[t].status = ST_DROPPED; r[t].rlen = 0; r[t].rk = RK_NONE; r[t].trunc = 0; r[t].sp = 0;
+            r[t].status = ST_DROPPED; r[t].rlen = 0; r[t].rk = RK_NONE; r[t].trunc = 0; r[t].sp = 0; r[t].ntask = 0;
             qidx[t] = qidx_map ? qidx_map[q0 + t] : qidx_base + q0 + t;     // routed batches carry their ingress index
             const uint32_t o0 = s_off[t], o1 = s_off[t + 1];
             if (o1 >= o0 && o1 - o0 <= 65535u) {
@@ -82,23 +83,38 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                 else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
             }
         } else if (tile_bytes) {
-            // the kernel's emit rounds: round k = the responses that start in window k of the tile, flushed together
+            // the kernel's emit rounds over PIECES: a response's own part (header + question, or all of it) and the copy
+            // jobs of task-mode service answers; round k = the pieces that start in window k of the tile, flushed together
+            struct Sink { std::vector<Task>* v; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { v->push_back(Task{ src, dst | (len << 18) | (sm << 31) }); } };
+            std::vector<Task> tasks;
+            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
+            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
+            for (uint32_t t = 0; t < nq; t++) {
+                if (!r[t].rlen || !r[t].ntask) continue;
+                if (tasks.size() + r[t].ntask > (size_t)TASKCAP) { r[t].ntask = 0; continue; }
+                const size_t before = tasks.size();
+                Sink sink{ &tasks };
+                threadIdx.x = t;
+                plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, sink);
+                if (tasks.size() - before != r[t].ntask) return BB_ERR_ARG;                              // the plan must match the count it was sized with
+            }
+            for (size_t i = 1; i < tasks.size(); i++) if (task_dst(tasks[i]) < task_dst(tasks[i - 1])) return BB_ERR_ARG;   // the kernel relies on ascending destinations
             const uint32_t nr = (tile_bytes + WIN - 1) / WIN;
             for (uint32_t k = 0; k < nr; k++) {
-                const uint32_t wbase = k * WIN, shift = (uint32_t)((gbase + wbase) & 15);
                 uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes;
-                for (uint32_t t = 0; t < nq; t++) {
-                    if (!r[t].rlen) continue;
-                    const uint32_t kr = my_o[t] / WIN;
-                    if (kr == k) {
-                        x0 = std::min(x0, my_o[t]);
-                        threadIdx.x = t;
-                        WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t] - wbase); emit_fast(P, r[t], w, qidx[t]);
-                    } else if (kr > k) x1 = std::min(x1, my_o[t]);
-                }
+                for (uint32_t t = 0; t < nq; t++) if (r[t].rlen) { const uint32_t kr = my_o[t] / WIN; if (kr == k) x0 = std::min(x0, my_o[t]); else if (kr > k) x1 = std::min(x1, my_o[t]); }
+                for (const Task& tk : tasks) { const uint32_t kr = task_dst(tk) / WIN; if (kr == k) x0 = std::min(x0, task_dst(tk)); else if (kr > k) x1 = std::min(x1, task_dst(tk)); }
                 if (x0 == 0xFFFFFFFFu) continue;
-                if (shift + x1 - wbase > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                       // cannot happen: WIN + MAXRESP <= CAPW
-                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(shift + x - wbase)];     // the flush
+                const uint32_t shift = (uint32_t)((gbase + x0) & 15), delta = shift - x0;
+                if (shift + (x1 - x0) > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                        // cannot happen: WIN + MAXRESP <= CAPW
+                for (uint32_t t = 0; t < nq; t++) {
+                    if (!r[t].rlen || my_o[t] / WIN != k) continue;
+                    threadIdx.x = t;
+                    WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]);
+                    if (r[t].ntask) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
+                }
+                for (const Task& tk : tasks) if (task_dst(tk) / WIN == k) run_task(P, tk, (uint32_t)OFF_OUT, delta);
+                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];              // the flush
             }
         }
         gbase += tile_bytes; mbase += tile_miss;

@@ -13,15 +13,15 @@ build.build(force=True)
 atexit.register(lambda: (os.environ.pop('BB_NVCC_DEFINES', None), build.build(force=True)))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 65536
 WL = os.environ.get('BB_WL', 'config2')
-zone = synth.gen_zone(1000000, service_frac=0.15 if WL == 'config3' else 0.0)
+zone = synth.gen_zone(int(os.environ.get('BB_ZONE', '1000000')), service_frac=synth.WORKLOADS[WL][1])
 ORDERED = os.environ.get('BB_ORDERED', '0') == '1'
 eng = Engine(zone.dns_domain, zone.datacenter, device=0, max_batch=B, max_batch_bytes=B * 64, snapshot=zone.jsonl, ordered=ORDERED)
 dev = torch.device('cuda:0')
 bufs = []
 for r in range(8):
-    data, off = synth.batch_host_a_fast(zone, B, seed=r) if WL != 'config3' else synth.pack_batch(synth.batch_service(zone, B, seed=r))
+    data, off = synth.gen_batch(zone, B, r, synth.WORKLOADS[WL][2], synth.WORKLOADS[WL][3])[:2]
     bufs.append((torch.from_numpy(data).to(dev), torch.from_numpy(off.view(np.int32)).to(dev)))
-out = torch.empty(B * 400, dtype=torch.uint8, device=dev); oo = torch.empty(B + 1, dtype=torch.int32, device=dev)
+out = torch.empty(B * 512, dtype=torch.uint8, device=dev); oo = torch.empty(B + 1, dtype=torch.int32, device=dev)
 st = torch.empty(B, dtype=torch.uint8, device=dev); ms = torch.empty(B, dtype=torch.int32, device=dev)
 tot = torch.zeros(4, dtype=torch.int32, device=dev); ol = torch.empty(B, dtype=torch.int16, device=dev)
 nt = (B + 127) // 128
@@ -48,7 +48,3 @@ for a in acc[-3:]:
     print('  stage durations us (mean / max over tiles): ' + ', '.join('%s %.2f/%.2f' % (names[i + 1], d[:, i].mean(), d[:, i].max()) for i in range(10)))
     print('  completion time of each stage, max over tiles: ' + ', '.join('%s %.2f' % (names[i], rel[:, i].max()) for i in range(11)))
 
-if WL == 'config3':
-    ok = (svc > 0).all(axis=1)
-    d = np.diff(svc[ok], axis=1) / 1000.0
-    print('  service sizing (thread 0 of tiles whose first query is a service): record opened %.2f us, permutation %.2f us, child walk %.2f us' % tuple(d.mean(axis=0)))
