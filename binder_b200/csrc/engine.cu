@@ -41,7 +41,7 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 }
 
 #ifndef BB_MIN_BLOCKS
-#define BB_MIN_BLOCKS 7      /* 72 registers; 30.9 KB of shared memory per tile allows 7 tiles (896 threads) per SM anyway */
+#define BB_MIN_BLOCKS 8      /* 64 registers: 8 tiles (1024 threads) resident per SM */
 #endif
 // ORDERED: responses packed in query order (tile bases from a decoupled look-back; a tile waits
 // for its predecessors' sizes).  !ORDERED ("arrival" packing): a tile claims its output range
@@ -56,8 +56,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_rstart[NROUNDS + 1], s_tstart[NROUNDS + 1];   // emit rounds: tile offset of each round's first piece, index of its first job
-    __shared__ Task s_task[TASKCAP];                           // copy jobs of the tile's task-mode service answers
+    __shared__ uint32_t s_cnt[4];                              // big tiles: jobs in each of the four lists
     __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
@@ -196,30 +195,68 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
     // ---- emit ---------------------------------------------------------------------------------------
-    // Responses are assembled in (swizzled) shared memory and flushed with aligned 16-byte stores, one WINDOW of the
-    // tile's output at a time.  The work is a set of PIECES, each a run of bytes with a known place in the tile:
-    //   * a response's own part — header + question, or the whole response — written by the thread that resolved it;
-    //   * the copy jobs of task-mode service answers (plan_service): a child's ready RRs, run by ANY thread, so that a
-    //     tile of ~300-byte service answers keeps all 128 threads busy with independent loads instead of each thread
-    //     walking its own service record one dependent load after another.
-    // Round k runs the pieces that START in bytes [k*WIN, (k+1)*WIN) of the tile (a piece is at most MAXRESP bytes, which
-    // the buffer allows for past the window) and flushes from its first piece to the first piece of the next round.
-    // A 64-byte-answer tile is one round with no jobs.  Only a tile with a query on the generic byte path, or with a
-    // response over MAXRESP (TCP), writes straight to global memory.
+    // A tile whose responses fit one staging window (128 x 64-byte answers do) is assembled in (swizzled) shared memory and
+    // flushed with aligned 16-byte stores.  A BIG tile — ~300-byte service answers — writes straight to global memory,
+    // and splits the work so that all 128 threads stay busy with independent loads: each thread writes the header and the
+    // question of its own response, and turns the rest of a service answer — the children's ready RRs — into copy jobs
+    // (plan_service), sorted into four lists by length class, that ANY thread runs (a thread walking its own service
+    // record child by child is one dependent DRAM round trip after another, and warps of mixed answer sizes idle most lanes).
+    // A tile with a query on the generic byte path or with a response over MAXRESP (TCP) also writes directly, without jobs.
     const bool odd_emit = my_len && (!(r.sp && !r.trunc) || my_len > (uint32_t)MAXRESP);
-#ifdef BB_DIRECT_BIG      /* experiment switch: tiles over one window write straight to global memory (the round-1 behaviour) */
-    const bool direct = __syncthreads_or(odd_emit) || tile_bytes > (uint32_t)WIN;
-#else
     const bool direct = __syncthreads_or(odd_emit);
-#endif
-    if (!overflow && direct) {
+    const bool big = !direct && tile_bytes > (uint32_t)WIN;
+    if (!overflow && (direct || big)) {
         // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
         // coalesced 16-byte stores (the bytes are still in L2)
         uint8_t* const dst = r_bounce ? r_bounce : r_out;
+        Task* const tl = (Task*)s_out;                                        // the job lists alias the (unused) staging buffer
+        constexpr uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
+        constexpr uint32_t lbase[4] = { 0, TASK_CAP0, TASK_CAP0 + TASK_CAP1, TASK_CAP0 + TASK_CAP1 + TASK_CAP2 };
+        bool jobs = big && my_len && r.ntask;
+        if (big) {
+            if (tid < 4) s_cnt[tid] = 0;
+            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+            __syncthreads();
+            if (jobs) {                                                       // count, reserve a run of each list, fill
+                const uint32_t opt_sp = (uint32_t)__cvta_generic_to_shared(s_opt);
+                TaskCount tc = { 0, 0, 0, 0 };
+                plan_service(P, r, qidx, my_o, opt_sp, tc);
+                const uint32_t a0 = tc.n0 ? atomicAdd(&s_cnt[0], tc.n0) : 0u, a1 = tc.n1 ? atomicAdd(&s_cnt[1], tc.n1) : 0u;
+                const uint32_t a2 = tc.n2 ? atomicAdd(&s_cnt[2], tc.n2) : 0u, a3 = tc.n3 ? atomicAdd(&s_cnt[3], tc.n3) : 0u;
+                if (a0 + tc.n0 <= cap[0] && a1 + tc.n1 <= cap[1] && a2 + tc.n2 <= cap[2] && a3 + tc.n3 <= cap[3]) {
+                    struct Fill {
+                        Task* tl; uint32_t i0, i1, i2, i3;
+                        __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
+                            uint32_t i;
+                            if (len <= 16) i = i0++; else if (len <= 32) i = i1++; else if (len <= 64) i = i2++; else i = i3++;
+                            tl[i].src = src; tl[i].w = dst | (len << 18) | (sm << 31);
+                        }
+                    } fill = { tl, lbase[0] + a0, lbase[1] + a1, lbase[2] + a2, lbase[3] + a3 };
+                    plan_service(P, r, qidx, my_o, opt_sp, fill);
+                } else {                                                      // a list is full: empty jobs in what was reserved, and this thread writes it all
+                    jobs = false;
+                    for (uint32_t i = a0; i < a0 + tc.n0 && i < cap[0]; i++) { tl[lbase[0] + i].src = 0; tl[lbase[0] + i].w = 0; }
+                    for (uint32_t i = a1; i < a1 + tc.n1 && i < cap[1]; i++) { tl[lbase[1] + i].src = 0; tl[lbase[1] + i].w = 0; }
+                    for (uint32_t i = a2; i < a2 + tc.n2 && i < cap[2]; i++) { tl[lbase[2] + i].src = 0; tl[lbase[2] + i].w = 0; }
+                    for (uint32_t i = a3; i < a3 + tc.n3 && i < cap[3]; i++) { tl[lbase[3] + i].src = 0; tl[lbase[3] + i].w = 0; }
+                }
+            }
+        }
         if (my_len) {
             if (!(r.sp && !r.trunc)) emit_response(P, r, dst + gbase + my_o, qidx);
-            else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
+            else {
+                WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o));
+                if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
+            }
+        }
+        if (big) {
+            __syncthreads();
+            const uint32_t goff = (uint32_t)gbase;
+            for (uint32_t ti = tid, n = min(s_cnt[0], cap[0]); ti < n; ti += T) run_task_g<0>(P, tl[lbase[0] + ti], dst, goff);
+            for (uint32_t ti = tid, n = min(s_cnt[1], cap[1]); ti < n; ti += T) run_task_g<1>(P, tl[lbase[1] + ti], dst, goff);
+            for (uint32_t ti = tid, n = min(s_cnt[2], cap[2]); ti < n; ti += T) run_task_g<2>(P, tl[lbase[2] + ti], dst, goff);
+            for (uint32_t ti = tid, n = min(s_cnt[3], cap[3]); ti < n; ti += T) run_task_g<3>(P, tl[lbase[3] + ti], dst, goff);
         }
         STAMP(9);
         if (r_bounce && tile_bytes) {
@@ -235,69 +272,21 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
         }
     } else if (!overflow && tile_bytes) {
-        const uint32_t s_out_a = (uint32_t)__cvta_generic_to_shared(s_out);
-        const uint32_t nr = (tile_bytes + WIN - 1) / WIN;                     // <= NROUNDS
-        // copy jobs of the tile: exclusive scan of the per-response job counts
-        uint32_t my_nt = my_len ? r.ntask : 0u, tbase = 0, ntasks = 0;
-        const bool any_task = __syncthreads_or(my_nt != 0);
-        if (any_task) {
-            uint32_t inc2 = my_nt;
-            for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t; }
-            if (lane == 31) s_wsum[warp] = inc2;
-            __syncthreads();
-            for (int w = 0; w < T / 32; w++) { const uint32_t x = s_wsum[w]; if (w < warp) tbase += x; ntasks += x; }
-            tbase += inc2 - my_nt;
-            if (tbase + my_nt > (uint32_t)TASKCAP) { my_nt = 0; r.ntask = 0; }   // the list is full: this response is written whole by its thread
-            if (ntasks > (uint32_t)TASKCAP) ntasks = TASKCAP;                 // (a thread past the cap never writes a job: indices stay dense)
-        }
-        if (nr > 1 || any_task) {                                             // where each round's first piece / first job is
-            if (tid <= (int)NROUNDS) { s_rstart[tid] = 0xFFFFFFFFu; s_tstart[tid] = 0xFFFFFFFFu; }
-            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-            __syncthreads();
-            if (my_len) atomicMin(&s_rstart[my_o / WIN], my_o);
-            if (my_nt) {
-                struct Sink {
-                    Task* tasks; uint32_t* rstart; uint32_t* tstart; uint32_t idx;
-                    __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
-                        tasks[idx].src = src; tasks[idx].w = dst | (len << 18) | (sm << 31);
-                        atomicMin(&rstart[dst / WIN], dst); atomicMin(&tstart[dst / WIN], idx);
-                        ++idx;
-                    }
-                } sink = { s_task, s_rstart, s_tstart, tbase };
-                plan_service(P, r, qidx, my_o, (uint32_t)__cvta_generic_to_shared(s_opt), sink);
-            }
-            __syncthreads();
-        }
-        for (uint32_t k = 0; k < nr; k++) {
-            uint32_t x0 = 0, x1 = tile_bytes, t0 = 0, t1 = 0;                 // this round's byte range and job range
-            if (nr > 1 || any_task) {
-                x0 = s_rstart[k];
-                if (x0 == 0xFFFFFFFFu) continue;                              // no piece starts in this window (uniform)
-                for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; break; }
-                t0 = s_tstart[k]; t1 = ntasks;
-                if (t0 == 0xFFFFFFFFu) t0 = t1 = 0;
-                else for (uint32_t j = k + 1; j < nr; j++) if (s_tstart[j] != 0xFFFFFFFFu) { t1 = s_tstart[j]; break; }
-            }
-            const uint32_t shift = (uint32_t)((gbase + x0) & 15);             // same 16-byte phase in shared and global memory
-            const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[swz(delta + x)]
-            if (my_len && my_o / WIN == k) {
-                WrT<1> w; w.begin(s_out_a, delta + my_o);
-                if (my_nt) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
-            }
-            for (uint32_t ti = t0 + tid; ti < t1; ti += T) run_task(P, s_task[ti], s_out_a, delta);
-            __syncthreads();
-            uint8_t* g = r_out + gbase;
-            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);      // up to 16-byte alignment of the global address
-            if (head > x1 - x0) head = x1 - x0;
-            if (tid < (int)head) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
-            x0 += head;
-            const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(delta + x0 + 16 * i));
-            x0 += nv << 4;
-            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
-            if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
-        }
+        const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
+        if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
+        __syncthreads();
         STAMP(9);
+        uint8_t* g = r_out + gbase;                                           // g[x] <-> s_out[swz(shift + x)]
+        uint32_t x0 = 0;
+        const uint32_t x1 = tile_bytes;
+        uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);                 // up to 16-byte alignment of the global address
+        if (head > x1) head = x1;
+        if (tid < (int)head) g[tid] = s_out[swz(shift + tid)];
+        x0 = head;
+        const uint32_t nv = (x1 - x0) >> 4;
+        for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i));
+        x0 += nv << 4;
+        if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid)];
     }
 
     STAMP(10);

@@ -12,10 +12,11 @@ constexpr int S_IN = 8192;                // staged input bytes per tile
 constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
-constexpr int WIN = CAPW - MAXRESP;       // output window of one emit round: a response starting in it ends inside the buffer
-constexpr int NROUNDS = (T * MAXRESP + WIN - 1) / WIN;        // rounds a tile of maximal responses needs
-static_assert(WIN % 16 == 0 && WIN > 0, "windows keep the 16-byte phase");
-constexpr int TASKCAP = 1024;             // copy jobs per tile (8 KB of shared memory); responses beyond it are written whole by their threads
+constexpr int WIN = CAPW;                  // a tile whose responses total at most this is staged in shared memory
+// copy jobs of a big tile, in four lists by length class (<= 16, <= 32, <= 64, longer): the lists live in the staging
+// buffer, which a big tile does not use; a response whose jobs do not fit is written whole by its thread
+constexpr int TASK_CAP0 = 640, TASK_CAP1 = 400, TASK_CAP2 = 400, TASK_CAP3 = 128;
+static_assert((TASK_CAP0 + TASK_CAP1 + TASK_CAP2 + TASK_CAP3) * 8 <= S_OUT, "the job lists alias the staging buffer");
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -65,7 +66,7 @@ struct Res {
     uint32_t keep_ans, keep_add, n_walk, nk;
     uint32_t status, rk, rcode, tc, opcode, rd, edns, trunc;
     uint32_t owner;          // route mode: rank that owns this query's lookup key
-    uint32_t ntask;          // > 0: a service answer assembled from copy jobs (plan_service): header + question by this thread, the RRs by anyone
+    uint32_t ntask;          // 1: a service answer that can be assembled from copy jobs (plan_service): header + question by this thread, the RRs by anyone
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -306,12 +307,13 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
         }
     }
     r.n_walk = n_walk;
+    // The answer is the header, the question and (a prefix of) the children's ready RRs: it can be assembled as
+    // independent copy jobs (engine.cu) when the prebuilt owner pointers are this query's — no upper-case letter in its
+    // domain part — whether or not it is truncated or cut short by a malformed child.
+    const bool jobs_ok = nk <= 16 && r.ptr_tgt == r.d_off;
     if (fixed + ans_b + add_b <= r.maxsz) {
         r.keep_ans = n_ans; r.keep_add = n_add; r.rlen = fixed + ans_b + add_b;
-        // The whole answer is the header, the question and the children's ready RRs: it can be assembled as independent
-        // copy jobs (engine.cu) when the prebuilt owner pointers are this query's (no upper-case letter in its domain part).
-        if (sums && nk <= 16 && r.ptr_tgt == r.d_off && r.rlen <= (uint32_t)MAXRESP && sv.n_valid())
-            r.ntask = (srv ? 2 * sv.n_valid() : sv.n_valid()) + (r.edns ? 1u : 0u);
+        r.ntask = jobs_ok && (n_ans + n_add) && r.rlen <= (uint32_t)MAXRESP;
         return;
     }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits
@@ -331,6 +333,7 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
         total += each; ++kd;
     }
     r.keep_ans = ka; r.keep_add = kd; r.rlen = total;
+    r.ntask = jobs_ok && (ka + kd) && total <= (uint32_t)MAXRESP;
 }
 
 // one RR that either fits or is dropped (TC)
@@ -1077,38 +1080,57 @@ __device__ __forceinline__ uint32_t task_dst(const Task& t) { return t.w & 0x3FF
 __device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 18) & 0x1FFFu; }
 __device__ __forceinline__ bool task_smem(const Task& t) { return (t.w >> 31) != 0; }
 
-// The jobs of one task-mode response (Res::ntask of them, in ascending destination order), given where the response
-// starts in its tile: the children's ready RRs in shuffled child order (lib/server.js:361-416) and, for EDNS, the OPT
-// (from `opt_sp`, a shared address holding its 11 bytes).  The header and the question are the owning thread's.
+__device__ __forceinline__ uint32_t task_class(uint32_t len) { return len <= 16 ? 0u : len <= 32 ? 1u : len <= 64 ? 2u : 3u; }
+// The jobs of one job-mode response, given where the response starts in its tile: (a prefix of) the children's ready RRs
+// in shuffled child order (lib/server.js:361-416) — the same walk as emit_fast's, counters included — and, for EDNS, the
+// OPT (from `opt_sp`, a shared address holding its 11 bytes).  The header and the question are the owning thread's.
 template <class Sink>
 __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint32_t my_o, uint32_t opt_sp, Sink& sink) {
     const bool srv = r.rk == RK_SVC_SRV;
     SvcView sv; sv.open(P.arena, r.val);
     const uint32_t blocks = r.val + sv.blocks_off(), stride = sv.stride(), dwl = sv.dom_wl();
     uint32_t dst = my_o + 12 + r.qn_len + 4;
-    for (uint32_t t = 0; t < r.nk; t++) {
+    uint32_t left = r.keep_ans;
+    for (uint32_t t = 0; t < r.n_walk && left; t++) {
         const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
         if (inf & KID_ADDR_NULL) continue;
         const uint32_t wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
-        if (srv) { const uint32_t len = np * kid_srv_len(wl, dwl); if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0); else sink.put(0, dst, 0, 0); dst += len; }
-        else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0); dst += 16; }
+        if (srv) {
+            const uint32_t n = min(np, left), len = n * kid_srv_len(wl, dwl);
+            if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0);
+            dst += len; left -= n;
+        } else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0); dst += 16; --left; }
     }
+    if (r.edns) { sink.put(opt_sp, dst, 11, 1); dst += 11; }                  // the OPT leads the additional section
     if (srv) {
-        if (r.edns) { sink.put(opt_sp, dst, 11, 1); dst += 11; }
-        for (uint32_t t = 0; t < r.nk; t++) {
+        left = r.keep_add;
+        for (uint32_t t = 0; t < r.n_walk && left; t++) {
             const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
             if (inf & KID_ADDR_NULL) continue;
             const uint32_t wl = (inf >> 8) & 0xFF;
-            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0); dst += kid_add_len(wl);
+            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0); dst += kid_add_len(wl); --left;
         }
-    } else if (r.edns) sink.put(opt_sp, dst, 11, 1);                          // the OPT is the only additional RR of an A answer
+    }
 }
-// run one job into the (swizzled) staging buffer: tile byte x lives at shared offset buf + delta + x
-__device__ __forceinline__ void run_task(const Params& P, const Task t, uint32_t buf, uint32_t delta) {
+// counts the jobs per length class (the sizing pass of plan_service)
+struct TaskCount {           // (scalars: an array indexed by the class would live in local memory)
+    uint32_t n0, n1, n2, n3;
+    __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; }
+};
+// run one job of length class C straight into global memory: tile byte x lives at g[x]; every load of the job is issued
+// before its first byte is written
+template <int C>
+__device__ __forceinline__ void run_task_g(const Params& P, const Task t, uint8_t* g, uint32_t goff) {
     const uint32_t len = task_len(t);
     if (!len) return;
-    WrT<1, true> w; w.begin(buf, delta + task_dst(t));
-    if (task_smem(t)) w.copy(t.src, len); else copy_arena_w(w, P.arena + t.src, len);
+    WrT<2, true> w; w.begin_global(g, goff + task_dst(t));
+    if (task_smem(t)) w.copy(t.src, len);
+    else {
+        const uint4* q = (const uint4*)(P.arena + t.src);
+        if (C == 0) put_chunk_w(w, ldg_stream(q), len);
+        else if (C == 1) { const uint4 x0 = ldg_stream(q), x1 = ldg_stream(q + 1); put_chunk_w(w, x0, len); put_chunk_w(w, x1, len - 16); }
+        else copy_arena_w(w, P.arena + t.src, len);
+    }
     w.end();
 }
 

@@ -75,47 +75,44 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             if (r[t].status == ST_MISS) miss_idx[mbase + my_m[t]] = q0 + t;
             odd |= r[t].rlen && (!(r[t].sp && !r[t].trunc) || r[t].rlen > (uint32_t)MAXRESP);
         }
-        if (odd) {
+        const bool big = !odd && tile_bytes > (uint32_t)WIN;
+        if (odd || big) {
+            // straight to the output; in a big tile the job-mode service answers become copy jobs in four lists by length
+            // class (the kernel's reservation with atomics, here in thread order), run after every thread wrote its own part
+            const uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
+            std::vector<Task> lists[4];
+            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
+            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
+            struct Fill { std::vector<Task>* l; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { l[task_class(len)].push_back(Task{ src, dst | (len << 18) | (sm << 31) }); } };
             for (uint32_t t = 0; t < nq; t++) {
                 if (!r[t].rlen) continue;
                 threadIdx.x = t;
-                if (!(r[t].sp && !r[t].trunc)) emit_response(P, r[t], out + gbase + my_o[t], qidx[t]);
-                else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
-            }
-        } else if (tile_bytes) {
-            // the kernel's emit rounds over PIECES: a response's own part (header + question, or all of it) and the copy
-            // jobs of task-mode service answers; round k = the pieces that start in window k of the tile, flushed together
-            struct Sink { std::vector<Task>* v; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { v->push_back(Task{ src, dst | (len << 18) | (sm << 31) }); } };
-            std::vector<Task> tasks;
-            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
-            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
-            for (uint32_t t = 0; t < nq; t++) {
-                if (!r[t].rlen || !r[t].ntask) continue;
-                if (tasks.size() + r[t].ntask > (size_t)TASKCAP) { r[t].ntask = 0; continue; }
-                const size_t before = tasks.size();
-                Sink sink{ &tasks };
-                threadIdx.x = t;
-                plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, sink);
-                if (tasks.size() - before != r[t].ntask) return BB_ERR_ARG;                              // the plan must match the count it was sized with
-            }
-            for (size_t i = 1; i < tasks.size(); i++) if (task_dst(tasks[i]) < task_dst(tasks[i - 1])) return BB_ERR_ARG;   // the kernel relies on ascending destinations
-            const uint32_t nr = (tile_bytes + WIN - 1) / WIN;
-            for (uint32_t k = 0; k < nr; k++) {
-                uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes;
-                for (uint32_t t = 0; t < nq; t++) if (r[t].rlen) { const uint32_t kr = my_o[t] / WIN; if (kr == k) x0 = std::min(x0, my_o[t]); else if (kr > k) x1 = std::min(x1, my_o[t]); }
-                for (const Task& tk : tasks) { const uint32_t kr = task_dst(tk) / WIN; if (kr == k) x0 = std::min(x0, task_dst(tk)); else if (kr > k) x1 = std::min(x1, task_dst(tk)); }
-                if (x0 == 0xFFFFFFFFu) continue;
-                const uint32_t shift = (uint32_t)((gbase + x0) & 15), delta = shift - x0;
-                if (shift + (x1 - x0) > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                        // cannot happen: WIN + MAXRESP <= CAPW
-                for (uint32_t t = 0; t < nq; t++) {
-                    if (!r[t].rlen || my_o[t] / WIN != k) continue;
-                    threadIdx.x = t;
-                    WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]);
-                    if (r[t].ntask) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
+                bool jobs = big && r[t].ntask;
+                if (jobs) {
+                    TaskCount tc = { 0, 0, 0, 0 };
+                    plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, tc);
+                    const uint32_t n[4] = { tc.n0, tc.n1, tc.n2, tc.n3 };
+                    for (int c = 0; c < 4; c++) if (lists[c].size() + n[c] > cap[c]) jobs = false;
+                    if (jobs) { Fill f{ lists }; plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, f); }
                 }
-                for (const Task& tk : tasks) if (task_dst(tk) / WIN == k) run_task(P, tk, (uint32_t)OFF_OUT, delta);
-                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];              // the flush
+                if (!(r[t].sp && !r[t].trunc)) emit_response(P, r[t], out + gbase + my_o[t], qidx[t]);
+                else {
+                    WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t]));
+                    if (jobs) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
+                }
             }
+            for (const Task& tk : lists[0]) run_task_g<0>(P, tk, out, (uint32_t)gbase);
+            for (const Task& tk : lists[1]) run_task_g<1>(P, tk, out, (uint32_t)gbase);
+            for (const Task& tk : lists[2]) run_task_g<2>(P, tk, out, (uint32_t)gbase);
+            for (const Task& tk : lists[3]) run_task_g<3>(P, tk, out, (uint32_t)gbase);
+        } else if (tile_bytes) {
+            const uint32_t shift = (uint32_t)(gbase & 15);
+            for (uint32_t t = 0; t < nq; t++) {
+                if (!r[t].rlen) continue;
+                threadIdx.x = t;
+                WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t]); emit_fast(P, r[t], w, qidx[t]);
+            }
+            for (uint32_t x = 0; x < tile_bytes; x++) out[gbase + x] = s_out[swz(shift + x)];     // the flush: g[x] <-> s_out[swz(shift + x)]
         }
         gbase += tile_bytes; mbase += tile_miss;
     }
