@@ -118,6 +118,13 @@ static napi_value ResolveBatch(napi_env env, napi_callback_info info) {
     napi_typedarray_type tt; size_t offn; void* offp; napi_value ab; size_t bo;
     NAPI_OK(napi_get_typedarray_info(env, argv[2], &tt, &offn, &offp, &ab, &bo));
     uint64_t seed = 0; bool lossless; napi_get_value_bigint_uint64(env, argv[3], &seed, &lossless);
+    // pktOff: at least one entry, ascending, ending inside the pkts Buffer (the engine trusts only what it can check cheaply)
+    if (tt != napi_uint32_array || offn < 1 || offn > (1u << 22) + 1) return Throw(env, BB_ERR_ARG);
+    {
+        const uint32_t* po = (const uint32_t*)offp;
+        for (size_t i = 1; i < offn; i++) if (po[i] < po[i - 1]) return Throw(env, BB_ERR_ARG);
+        if (po[offn - 1] > pklen) return Throw(env, BB_ERR_ARG);
+    }
     const uint32_t n = (uint32_t)offn - 1;
     const uint32_t cap = n * (tcp ? 16384u : 1232u);
     void *out, *oo, *ol, *st, *ms; napi_value o_out, a_oo, a_ol, a_st, a_ms, t_oo, t_ol, t_st, t_ms;

@@ -29,6 +29,8 @@ SYMBOLS = {
                                     _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                     _c.c_void_p]),
     'bb_engine_slots': (_c.c_int, [_c.c_void_p]),
+    'bb_engine_max_batch': (_c.c_uint32, [_c.c_void_p]),
+    'bb_engine_max_batch_bytes': (_c.c_uint32, [_c.c_void_p]),
     'bb_resolve_submit': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,
                                      _c.c_uint32, _c.c_void_p, _c.c_uint32, _c.c_void_p, _c.c_void_p, _c.c_void_p,
                                      _c.c_void_p, _c.c_void_p]),

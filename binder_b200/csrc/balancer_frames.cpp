@@ -84,7 +84,8 @@ struct bb_backend {
     uint8_t* status = nullptr; uint32_t* miss = nullptr;
     std::vector<uint8_t> out;                          // frames to write back
     std::vector<uint8_t> m_pkts; std::vector<uint32_t> m_off, m_ip, m_port;    // handed-off misses of the last feed
-    uint64_t n_udp = 0, n_answered = 0, n_missed = 0, n_dropped = 0;
+    uint64_t n_udp = 0, n_answered = 0, n_missed = 0, n_dropped = 0, n_failed = 0;
+    uint32_t qidx_next = 0;                             // query index of the next batch's first query (keys the shuffle)
 };
 
 extern "C" {
@@ -92,8 +93,11 @@ extern "C" {
 bb_backend* bb_backend_create(bb_engine* e, uint32_t max_batch, int* err) {
     if (err) *err = BB_OK;
     if (!e || max_batch == 0) { if (err) *err = BB_ERR_ARG; return nullptr; }
+    // never parse a batch the engine would refuse: its own limits bound the session's
+    if (max_batch > bb_engine_max_batch(e)) max_batch = bb_engine_max_batch(e);
     bb_backend* b = new bb_backend();
     b->e = e; b->max_batch = max_batch; b->max_bytes = max_batch * 64u > (1u << 16) ? max_batch * 64u : (1u << 16);
+    if (b->max_bytes > bb_engine_max_batch_bytes(e)) b->max_bytes = bb_engine_max_batch_bytes(e);
     b->resp_cap = max_batch * 512u > (1u << 20) ? max_batch * 512u : (1u << 20);
     b->pkts = (uint8_t*)bb_host_alloc(b->max_bytes + 64); b->pkt_off = (uint32_t*)bb_host_alloc(((size_t)max_batch + 1) * 4);
     b->ip = (uint32_t*)bb_host_alloc((size_t)max_batch * 4); b->port = (uint32_t*)bb_host_alloc((size_t)max_batch * 4);
@@ -128,9 +132,21 @@ int bb_backend_feed(bb_backend* b, const uint8_t* in, size_t in_len, uint64_t sh
         if (n == 0 && nc == 0) break;
         uint32_t n_miss = 0;
         if (n) {
-            int r2 = bb_resolve_batch(b->e, b->pkts, b->pkt_off, n, shuffle_seed, 0, b->resp, b->resp_cap, b->resp_off, b->resp_len,
+            // qidx_base advances per batch: the service shuffle (keyed on seed and query index) does not repeat across the
+            // batches of one feed
+            int r2 = bb_resolve_batch(b->e, b->pkts, b->pkt_off, n, shuffle_seed, b->qidx_next, b->resp, b->resp_cap, b->resp_off, b->resp_len,
                                       b->status, b->miss, &n_miss);
-            if (r2 != BB_OK) { rc = r2; break; }
+            b->qidx_next += n;
+            if (r2 != BB_OK) {
+                // the batch's queries are lost (counted), the control frames parsed with it are still answered
+                rc = r2; b->n_failed += n;
+                size_t need = 0;
+                bb_frames_build(b->resp, b->resp_off, b->resp_len, b->status, b->ip, b->port, 0, control, nc, nullptr, 0, &need);
+                const size_t at = b->out.size();
+                b->out.resize(at + need);
+                if (need) bb_frames_build(b->resp, b->resp_off, b->resp_len, b->status, b->ip, b->port, 0, control, nc, b->out.data() + at, need, &need);
+                break;
+            }
             b->n_udp += n; b->n_missed += n_miss;
             for (uint32_t i = 0; i < n; i++) { b->n_answered += b->status[i] == BB_ANSWERED; b->n_dropped += b->status[i] == BB_DROPPED; }
             for (uint32_t k = 0; k < n_miss; k++) {                     // lib/server.js:110-113,222-225: these go to recursion
@@ -157,7 +173,7 @@ int bb_backend_feed(bb_backend* b, const uint8_t* in, size_t in_len, uint64_t sh
 
 uint64_t bb_backend_stat(const bb_backend* b, int what) {
     if (!b) return 0;
-    switch (what) { case 0: return b->n_udp; case 1: return b->n_answered; case 2: return b->n_missed; case 3: return b->n_dropped; case 4: return b->pending.size(); }
+    switch (what) { case 0: return b->n_udp; case 1: return b->n_answered; case 2: return b->n_missed; case 3: return b->n_dropped; case 4: return b->pending.size(); case 5: return b->n_failed; }
     return 0;
 }
 

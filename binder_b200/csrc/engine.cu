@@ -113,7 +113,9 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const uint32_t qidx = (r_qidx_map && tid < (int)nq) ? r_qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
     if (tid < (int)nq) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
-        if (o1 >= o0 && o1 - o0 <= 65535u) {
+        // a packet must lie inside its tile's byte range [b0, b1] (the host checked the tile boundaries against the
+        // batch's size): offsets that run backwards or jump out are dropped, never dereferenced
+        if (o0 >= b0 && o1 >= o0 && o1 <= b1 && o1 - o0 <= 65535u) {
             r.p = staged ? s_in + (o0 - a0) : r_pkts + o0;
             r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
             resolve_query(P, r, o1 - o0, qidx, (uint32_t)__cvta_generic_to_shared(s_sfx));
@@ -390,7 +392,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
     const bool have = tid < (int)nq;
     if (have) {
         const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
-        if (o1 >= o0 && o1 - o0 <= 65535u) {
+        if (o0 >= b0 && o1 >= o0 && o1 <= b1 && o1 - o0 <= 65535u) {
             len = o1 - o0;
             r.p = staged ? s_in + (o0 - a0) : P.pkts + o0;
             r.sp = staged ? (uint32_t)__cvta_generic_to_shared(s_in) + (o0 - a0) : 0u;
@@ -722,6 +724,8 @@ int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, cons
 }
 int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }
 int bb_engine_slots(const bb_engine*) { return NSLOTS; }
+uint32_t bb_engine_max_batch(const bb_engine* e) { return e ? e->max_batch : 0; }
+uint32_t bb_engine_max_batch_bytes(const bb_engine* e) { return e ? e->max_bytes : 0; }
 uint64_t bb_engine_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
 uint32_t bb_engine_launch_epoch(const bb_engine* e) { return e ? (uint32_t)e->epoch : 0; }
 void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log) { if (e) e->stage_log = d_log; }
@@ -774,6 +778,13 @@ int bb_resolve_submit_ex(bb_engine* e, int slot, const uint8_t* pkts, const uint
     if (s.busy || n > e->max_batch) return BB_ERR_ARG;
     const uint32_t total_in = pkt_off[n];
     if (total_in > e->max_bytes) return BB_ERR_ARG;
+    // every tile's byte range must be inside the batch and the ranges in order (the kernel holds each packet to its
+    // tile's range): a bad offset array is an argument error, not an illegal address on the device
+    for (uint32_t q = 0, prev = 0; q <= n; q += (q + bbk::T <= n || q == n) ? bbk::T : n - q) {
+        if (pkt_off[q] < prev || pkt_off[q] > total_in) return BB_ERR_ARG;
+        prev = pkt_off[q];
+        if (q == n) break;
+    }
     CK(cudaSetDevice(e->device));
     if (total_in) CK(cudaMemcpyAsync(s.d_pkts, pkts, total_in, cudaMemcpyHostToDevice, s.stream));
     CK(cudaMemcpyAsync(s.d_off, pkt_off, ((size_t)n + 1) * 4, cudaMemcpyHostToDevice, s.stream));
@@ -1062,7 +1073,7 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
     const uint32_t n = hdr[0];
     *n_out = n; *n_miss = n ? tot[1] : 0; *total_out = n ? tot[0] : 0;
     if (!n) return BB_OK;
-    if (tot[0] > out_cap) return BB_ERR_CAPACITY;
+    if (tot[2] == s->resolve_epoch || tot[0] > s->out_cap || tot[0] > out_cap) return BB_ERR_CAPACITY;   // the region's responses overflowed the shard's buffer / the caller's
     CK(cudaMemcpy(out, s->d_out + src * s->out_stride, tot[0], cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out_off, s->d_out_off + src * s->off_stride, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(out_len, s->d_out_len + src * s->len_stride, (size_t)n * 2, cudaMemcpyDeviceToHost));

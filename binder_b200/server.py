@@ -16,6 +16,7 @@ The resolver is injected, so the CPU-only plumbing test (BASELINE config 1) driv
 with the CPU oracle, while production passes an Engine.
 """
 import select
+import selectors
 import socket
 import struct
 import threading
@@ -62,6 +63,14 @@ def pack_packets(pkts):
     return np.frombuffer(blob + b'\0' * ((-len(blob)) % 16 + 16), dtype=np.uint8), off
 
 
+class TcpConn(object):
+    """One TCP connection: reassembly state, bytes still to send, queries it is owed answers for."""
+    __slots__ = ('framer', 'outq', 'waiting', 'eof', 'last')
+
+    def __init__(self, now):
+        self.framer, self.outq, self.waiting, self.eof, self.last = TcpFramer(), bytearray(), 0, False, now
+
+
 class Server(object):
     def __init__(self, options):
         for k in ('dnsDomain', 'resolver'):
@@ -75,7 +84,8 @@ class Server(object):
         self.max_batch = options.get('max_batch', 4096)
         self.recursion = options.get('recursion')
         self.counters = {'queries': 0, 'answered': 0, 'missed': 0, 'dropped': 0, 'batches': 0,
-                         'tcp_queries': 0, 'tcp_batches': 0, 'tcp_connections': 0}
+                         'tcp_queries': 0, 'tcp_batches': 0, 'tcp_connections': 0, 'tcp_refused': 0, 'failed_batches': 0}
+        self._lock = threading.Lock()                # one engine, two listener threads
         self.tcp = options.get('tcp', True)
         self._sock = None
         self._tsock = None
@@ -137,88 +147,155 @@ class Server(object):
             self._sock.settimeout(0.05)
             self._resolve_and_send(batch)
 
+    def _resolve(self, data, off, tcp=False):
+        """One batch through the resolver.  The UDP and the TCP listener share ONE engine (bb_resolve_batch uses the
+        engine's slot 0): calls are serialised here, and a failed batch is dropped and counted, not allowed to kill the
+        listener thread.  -> (out, out_off, out_len, status, miss) or None."""
+        with self._lock:
+            self._seed += 1
+            try:
+                if tcp:
+                    return self.resolver.resolve_batch(data, off, seed=self._seed, qidx_base=0, tcp=True)
+                return self.resolver.resolve_batch(data, off, seed=self._seed, qidx_base=0)
+            except Exception:                        # BinderError (capacity, CUDA), or a resolver bug: this batch gets no answers
+                self.counters['failed_batches'] += 1
+                return None
+
     # ---- TCP: accept, reassemble, aggregate, answer ------------------------------------------------
+    # One selector (epoll) for the listening socket and every connection; writes never block: each connection has an
+    # output queue drained when the socket is writable.  Connections are capped (max_tcp_conns) and closed when idle.
     def _tcp_loop(self):
-        conns = {}                                   # socket -> TcpFramer
+        sel = selectors.DefaultSelector()
+        sel.register(self._tsock, selectors.EVENT_READ)
+        conns = {}                                   # socket -> TcpConn
         pending = []                                 # (message, socket) completed in the current window
         deadline = None
+        max_conns = self.options.get('max_tcp_conns', 1024)
+        idle_s = self.options.get('tcp_idle_s', 30.0)
+
+        def close(s):
+            c = conns.pop(s, None)
+            if c is not None:
+                try:
+                    sel.unregister(s)
+                except (KeyError, ValueError):
+                    pass
+                s.close()
+
+        def want(s):                                 # (re)register for the events this connection needs
+            c = conns[s]
+            ev = (0 if c.eof else selectors.EVENT_READ) | (selectors.EVENT_WRITE if c.outq else 0)
+            if ev:
+                sel.modify(s, ev)
+            elif not c.waiting:                      # peer closed its side, nothing owed, nothing left to send
+                close(s)
+
+        last_sweep = time.perf_counter()
         while not self._stop.is_set():
             timeout = 0.05 if deadline is None else max(deadline - time.perf_counter(), 0.0)
             try:
-                ready, _, _ = select.select([self._tsock] + list(conns), [], [], timeout)
-            except (OSError, ValueError):
+                events = sel.select(timeout)
+            except OSError:
                 break
-            for s in ready:
+            now = time.perf_counter()
+            for key, ev in events:
+                s = key.fileobj
                 if s is self._tsock:
                     try:
                         c, _ = self._tsock.accept()
                     except OSError:
                         continue
+                    if len(conns) >= max_conns:
+                        c.close()
+                        self.counters['tcp_refused'] += 1
+                        continue
                     c.setblocking(False)
-                    conns[c] = TcpFramer()
+                    conns[c] = TcpConn(now)
+                    sel.register(c, selectors.EVENT_READ)
                     self.counters['tcp_connections'] += 1
                     continue
-                try:
-                    chunk = s.recv(65536)
-                except (BlockingIOError, InterruptedError):
+                c = conns.get(s)
+                if c is None:
                     continue
-                except OSError:
-                    chunk = b''
-                fr = conns[s]
-                msgs = fr.feed(chunk) if chunk else []
-                for m in msgs:
-                    pending.append((m, s))
-                if msgs and deadline is None:
-                    deadline = time.perf_counter() + self.window_s
-                if not chunk or fr.bad:              # peer closed (its complete messages are still answered) / bad frame
-                    del conns[s]
-                    if not any(ps is s for _, ps in pending):
-                        s.close()
+                if ev & selectors.EVENT_WRITE and c.outq:
+                    try:
+                        n = s.send(c.outq)
+                        del c.outq[:n]
+                        c.last = now
+                    except (BlockingIOError, InterruptedError):
+                        pass
+                    except OSError:
+                        close(s)
+                        continue
+                if ev & selectors.EVENT_READ and not c.eof:
+                    try:
+                        chunk = s.recv(65536)
+                    except (BlockingIOError, InterruptedError):
+                        chunk = None
+                    except OSError:
+                        chunk = b''
+                    if chunk:
+                        c.last = now
+                        msgs = c.framer.feed(chunk)
+                        for m in msgs:
+                            pending.append((m, s))
+                        c.waiting += len(msgs)
+                        if msgs and deadline is None:
+                            deadline = now + self.window_s
+                    if chunk == b'' or c.framer.bad:  # peer closed (its complete messages are still answered) / bad frame
+                        c.eof = True
+                if s in conns:
+                    want(s)
             if pending and (len(pending) >= self.max_batch or time.perf_counter() >= deadline):
                 self._resolve_and_send_tcp(pending, conns)
+                for s in set(ps for _, ps in pending):
+                    if s in conns:
+                        want(s)
                 pending, deadline = [], None
-        for s in conns:
-            s.close()
+            if now - last_sweep > 1.0:                # idle connections
+                last_sweep = now
+                for s in [s for s, c in conns.items() if now - c.last > idle_s and not c.waiting and not c.outq]:
+                    close(s)
+        for s in list(conns):
+            close(s)
+        sel.close()
 
     def _resolve_and_send_tcp(self, pending, conns):
         pkts = [m for m, _ in pending]
         data, off = pack_packets(pkts)
-        self._seed += 1
-        out, out_off, out_len, status, miss = self.resolver.resolve_batch(data, off, seed=self._seed, qidx_base=0, tcp=True)
+        res = self._resolve(data, off, tcp=True)
         c = self.counters
         c['tcp_batches'] += 1
         c['tcp_queries'] += len(pkts)
-        replies = {}                                 # per connection, in arrival order
-        for i, (_, s) in enumerate(pending):
+        for _, s in pending:
+            if s in conns:
+                conns[s].waiting -= 1
+        if res is None:
+            return
+        out, out_off, out_len, status, miss = res
+        for i, (_, s) in enumerate(pending):         # per connection, in arrival order
             if status[i] == 0:
-                replies.setdefault(s, []).append(TcpFramer.frame(out[out_off[i]:out_off[i] + out_len[i]].tobytes()))
+                if s in conns:
+                    conns[s].outq += TcpFramer.frame(out[out_off[i]:out_off[i] + out_len[i]].tobytes())
                 c['answered'] += 1
             elif status[i] == 2:
                 c['dropped'] += 1
-        for s, parts in replies.items():
-            try:
-                s.setblocking(True)
-                s.sendall(b''.join(parts))
-                s.setblocking(False)
-            except OSError:
-                pass
         for i in miss:
             c['missed'] += 1
             if self.recursion is not None:
                 self.recursion.resolve(pkts[int(i)], None, pending[int(i)][1])
-        for s in set(ps for _, ps in pending):
-            if s not in conns:                       # the peer had already closed its side
-                s.close()
 
     def _resolve_and_send(self, batch):
         pkts = [p for p, _ in batch if len(p) <= MAX_UDP]
         addrs = [a for p, a in batch if len(p) <= MAX_UDP]
         data, off = pack_packets(pkts)
-        self._seed += 1
-        out, out_off, out_len, status, miss = self.resolver.resolve_batch(data, off, seed=self._seed, qidx_base=0)
+        res = self._resolve(data, off)
         c = self.counters
         c['batches'] += 1
         c['queries'] += len(pkts)
+        if res is None:
+            return
+        out, out_off, out_len, status, miss = res
         for i, a in enumerate(addrs):
             if status[i] == 0:
                 self._sock.sendto(out[out_off[i]:out_off[i] + out_len[i]].tobytes(), a)

@@ -143,6 +143,8 @@ int bb_engine_apply_update(bb_engine* e, bb_zone* z);
 int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, const char* const* dc_names,
                                    uint32_t n_dc, int ptr_forwardable);
 int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/zk.js:55-58 */
+uint32_t bb_engine_max_batch(const bb_engine* e);        /* the limits the engine was created with */
+uint32_t bb_engine_max_batch_bytes(const bb_engine* e);
 
 /*
  * Resolve one batch of raw DNS query packets held in HOST memory: the batched form of
@@ -312,7 +314,7 @@ bb_backend* bb_backend_create(bb_engine* e, uint32_t max_batch, int* err);
 void        bb_backend_destroy(bb_backend* b);
 int         bb_backend_feed(bb_backend* b, const uint8_t* in, size_t in_len, uint64_t shuffle_seed,
                             const uint8_t** out, size_t* out_len, bb_backend_misses* misses);
-uint64_t    bb_backend_stat(const bb_backend* b, int what);   /* 0 udp frames 1 answered 2 missed 3 dropped 4 pending bytes */
+uint64_t    bb_backend_stat(const bb_backend* b, int what);   /* 0 udp frames 1 answered 2 missed 3 dropped 4 pending bytes 5 queries of failed batches */
 
 /* pinned host memory for the batch containers */
 void* bb_host_alloc(size_t bytes);

@@ -61,3 +61,17 @@ def test_zone_build_survives_hash_collisions():
     z = synth.gen_zone(1500000, service_frac=0.15)
     st = Zone(z.jsonl, z.dns_domain).stat()
     assert st['slots'] == 8388608 and st['forward_keys'] == st['nodes']
+
+
+def test_napi_addon_compiles_against_the_header():
+    """Node.js is absent here, so the N-API shim (addon/binder_b200_napi.cc) is compiled against a mock <node_api.h>
+    carrying the documented N-API signatures: every bb_* call in it must match include/binder_b200.h."""
+    import shutil
+    import subprocess
+    cxx = shutil.which('g++')
+    if not cxx:
+        pytest.skip('no g++')
+    p = subprocess.run([cxx, '-std=c++17', '-fsyntax-only', '-Wall', '-Wno-comment', '-Werror',
+                        '-I', os.path.join(ROOT, 'tests', 'native', 'mock_node'), '-I', os.path.join(ROOT, 'include'),
+                        os.path.join(ROOT, 'addon', 'binder_b200_napi.cc')], capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr[-3000:]

@@ -199,3 +199,22 @@ def test_sharded_zones_take_the_same_delta(seed):
     assert n_present > 20
     assert sum(z.stat()['forward_keys'] for z in shards) == whole.stat()['forward_keys']
     assert sum(z.stat()['reverse_keys'] for z in shards) == whole.stat()['reverse_keys']
+
+
+def test_failed_delta_leaves_a_usable_image():
+    """A delta whose LAST line is junk returns BB_ERR_SNAPSHOT with the earlier lines applied (include/binder_b200.h).
+    Those lines grew the arena (a service record per new child): the image must point at the builder's current arena,
+    not at the freed one — probing the zone and building fresh from the same events must agree."""
+    from binder_b200.engine import Zone
+    from binder_b200._lib import BinderError
+    z = Zone(H.snapshot(ZONE0), 'foo.com')
+    kids = [('/com/foo/svc/extra%04d' % i, {'type': 'load_balancer', 'load_balancer': {'address': '10.7.%d.%d' % (i >> 8, i & 255)}}) for i in range(2000)]
+    delta = H.snapshot(kids) + b'this is not json\n'
+    with pytest.raises(BinderError):
+        z.apply(delta)
+    fresh = Zone(H.snapshot(ZONE0 + kids), 'foo.com')
+    assert z.probe('svc.foo.com') == fresh.probe('svc.foo.com')
+    assert z.probe('extra1999.svc.foo.com') == fresh.probe('extra1999.svc.foo.com')
+    assert z.stat()['arena_bytes'] >= fresh.stat()['arena_bytes']
+    z.apply(H.snapshot([('/com/foo/svc/extra0000', {'type': 'load_balancer', 'load_balancer': {'address': '10.9.9.9'}})]))   # and it keeps working
+    assert z.probe('10.9.9.9', reverse=True) is not None
