@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_cnt[4];                              // big tiles: jobs in each of the four lists
+    __shared__ uint8_t s_perm[T];                              // which query of the tile each thread takes (grouped by question type)
     __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
@@ -108,11 +109,36 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
 
     STAMP(2);
     // ---- parse + lookup + size ----------------------------------------------------------------
+    // Which query this thread takes.  With arrival packing the order inside a tile is free, so the tile is partitioned by
+    // question type: SRV queries (long, child-by-child answers) share warps with SRV queries and the rest with the
+    // rest, instead of half of every warp idling through the other half's loops.  (Query-order packing keeps tid.)
+    uint32_t qi = (uint32_t)tid;
+    if (!ORDERED && staged) {
+        bool srvq = false;
+        if (tid < (int)nq) {
+            const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
+            if (o0 >= b0 && o1 >= o0 + 17 && o1 <= b1) {                      // QTYPE sits 4 bytes (15 with a bare OPT) before the end
+                const uint8_t* pk = s_in + (o0 - a0);
+                const uint32_t back = pk[11] ? 15u : 4u, len = o1 - o0;
+                srvq = len >= 12 + back && pk[len - back] == 0 && pk[len - back + 1] == QT_SRV;
+            }
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, srvq), before = __popc(bal & ((1u << lane) - 1));
+        if (lane == 0) s_wsum[warp] = __popc(bal);
+        __syncthreads();
+        uint32_t srv_before = before, srv_total = 0;
+        for (int w = 0; w < T / 32; w++) { const uint32_t x = s_wsum[w]; if (w < warp) srv_before += x; srv_total += x; }
+        // the others first (in order), then the SRV queries (in order)
+        const uint32_t pos = srvq ? (uint32_t)T - srv_total + srv_before : (uint32_t)tid - srv_before;
+        s_perm[pos] = (uint8_t)tid;
+        __syncthreads();
+        qi = s_perm[tid];
+    }
     Res r;
     r.status = ST_DROPPED; r.rlen = 0; r.rk = RK_NONE; r.ntask = 0;
-    const uint32_t qidx = (r_qidx_map && tid < (int)nq) ? r_qidx_map[q0 + tid] : P.qidx_base + q0 + tid;
-    if (tid < (int)nq) {
-        const uint32_t o0 = s_off[tid], o1 = s_off[tid + 1];
+    const uint32_t qidx = (r_qidx_map && qi < nq) ? r_qidx_map[q0 + qi] : P.qidx_base + q0 + qi;
+    if (qi < nq) {
+        const uint32_t o0 = s_off[qi], o1 = s_off[qi + 1];
         // a packet must lie inside its tile's byte range [b0, b1] (the host checked the tile boundaries against the
         // batch's size): offsets that run backwards or jump out are dropped, never dereferenced
         if (o0 >= b0 && o1 >= o0 && o1 <= b1 && o1 - o0 <= 65535u) {
@@ -122,7 +148,7 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         }
     }
     const uint32_t my_len = r.rlen;
-    const uint32_t my_miss = (tid < (int)nq && r.status == ST_MISS) ? 1u : 0u;
+    const uint32_t my_miss = (qi < nq && r.status == ST_MISS) ? 1u : 0u;
 
     STAMP(6);
     // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
@@ -187,12 +213,12 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     const bool overflow = gbase + tile_bytes > (uint64_t)P.out_cap;
 
     // ---- per-query outputs ---------------------------------------------------------------------
-    if (tid < (int)nq) {
-        r_out_off[q0 + tid] = (uint32_t)(gbase + my_o);
-        r_out_len[q0 + tid] = (uint16_t)my_len;
-        r_status[q0 + tid] = r.status;
-        if (my_miss) r_miss_idx[mbase + my_mrank] = q0 + tid;
-        if (MULTI && r_qidx_out) r_qidx_out[q0 + tid] = qidx;
+    if (qi < nq) {
+        r_out_off[q0 + qi] = (uint32_t)(gbase + my_o);
+        r_out_len[q0 + qi] = (uint16_t)my_len;
+        r_status[q0 + qi] = r.status;
+        if (my_miss) r_miss_idx[mbase + my_mrank] = q0 + qi;
+        if (MULTI && r_qidx_out) r_qidx_out[q0 + qi] = qidx;
     }
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
@@ -884,6 +910,10 @@ struct bb_shard {
     uint8_t* h_out = nullptr; uint8_t* h_out_off = nullptr; uint8_t* h_out_len = nullptr; uint8_t* h_status = nullptr;
     uint8_t* h_miss = nullptr; uint8_t* h_totals = nullptr; uint8_t* h_qidx = nullptr;
     bool host = false; uint32_t resolve_epoch = 0;
+    // collective exchange (bb_shard_use_exchange_buffers): route+push fills LOCAL send regions (one per destination), the
+    // caller moves them with its collective into the receive regions below, resolve reads those
+    uint8_t* x_send = nullptr; uint8_t* x_recv = nullptr;
+    uint8_t* recv_base() const { return x_recv ? x_recv : recv; }
 };
 
 extern "C" {
@@ -957,10 +987,32 @@ int bb_shard_open_peers(bb_shard* s, const void* handles) {
     return BB_OK;
 }
 
+// Collective exchange instead of peer stores (the NCCL all-to-all baseline of SURVEY.md section 8e): with two caller-owned
+// device buffers of bb_shard_exchange_bytes() each, bb_shard_route_push fills LOCAL send regions — region d of the current
+// set = what this rank routes to rank d, laid out exactly like a receive region — and bb_shard_resolve (wait_for_peers = 0)
+// reads the receive buffer, into which the caller's collective has moved every rank's region for this rank.  The set in use
+// alternates per step: set = step parity (bb_shard_exchange_set).  NULL, NULL returns to peer stores.
+int bb_shard_use_exchange_buffers(bb_shard* s, void* d_send, void* d_recv) {
+    if (!s || (!d_send) != (!d_recv) || ((uintptr_t)d_send & 255) || ((uintptr_t)d_recv & 255)) return BB_ERR_ARG;
+    CK(cudaSetDevice(s->e->device));
+    CK(cudaDeviceSynchronize());
+    s->x_send = (uint8_t*)d_send; s->x_recv = (uint8_t*)d_recv;
+    return BB_OK;
+}
+size_t bb_shard_exchange_bytes(const bb_shard* s) { return s ? s->reg_size * s->nranks * 2 : 0; }
+uint32_t bb_shard_exchange_set(const bb_shard* s) { return s ? (s->epoch & 1) : 0; }
+// geometry of one region: [0] bytes per region, [1] capacity in queries, [2] byte offset of the u32 offset array (cap + 1
+// entries), [3] of the u32 ingress-index array (cap entries), [4] of the packed packet bytes; the first 16 bytes are the
+// header {count, packet bytes, epoch, sender overflow flag}
+void bb_shard_region_layout(const bb_shard* s, uint64_t out[5]) {
+    if (!s || !out) return;
+    out[0] = s->reg_size; out[1] = s->cap_q; out[2] = bbk::region_off_array(s->cap_q); out[3] = bbk::region_qidx_array(s->cap_q); out[4] = bbk::region_bytes(s->cap_q);
+}
+
 // Ingress: route every query of a device-resident batch to its owner and push it there.
 int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pkt_off, uint32_t n, uint32_t qidx_base, void* stream) {
     if (!s || n > s->max_batch || ((uintptr_t)d_pkts & 15)) return BB_ERR_ARG;
-    for (uint32_t r = 0; r < s->nranks; r++) if (!s->peer_recv[r]) return BB_ERR_ARG;
+    for (uint32_t r = 0; r < s->nranks; r++) if (!s->x_send && !s->peer_recv[r]) return BB_ERR_ARG;
     bb_engine* e = s->e;
     bbk::PushParams A; memset(&A, 0, sizeof A);
     A.P.pkts = d_pkts; A.P.pkt_off = d_pkt_off; A.P.n = n; A.P.eng = e->d_const; A.P.ready = 1;
@@ -968,7 +1020,9 @@ int bb_shard_route_push(bb_shard* s, const uint8_t* d_pkts, const uint32_t* d_pk
     A.P.route = 1; A.P.nranks = s->nranks; A.P.rank = s->rank; A.P.table = e->d_table; A.P.mask = e->mask; A.P.arena = e->d_arena;
     A.epoch = ++s->epoch;
     const size_t set = (size_t)(s->epoch & 1) * s->nranks;
-    for (uint32_t r = 0; r < s->nranks; r++) A.region[r] = s->peer_recv[r] + (set + s->rank) * s->reg_size;
+    for (uint32_t r = 0; r < s->nranks; r++)
+        A.region[r] = s->x_send ? s->x_send + (set + r) * s->reg_size                 // local send region for destination r
+                                : s->peer_recv[r] + (set + s->rank) * s->reg_size;    // region (this rank -> r) in r's HBM
     A.cap_q = s->cap_q; A.cap_b = s->cap_b; A.cursor = s->cursor; A.done = s->done; A.err = s->err;
     A.qidx_base = qidx_base; A.P.stage_log = e->stage_log;
     // n == 0 still publishes empty region headers (one block, no queries)
@@ -986,11 +1040,11 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     bb_engine* e = s->e;
     cudaStream_t main = (cudaStream_t)stream;
     if (wait_for_peers) {
-        bbk::wait_regions_kernel<<<1, 32, 0, main>>>(s->recv + (size_t)(s->epoch & 1) * s->nranks * s->reg_size, s->reg_size, s->nranks,
+        bbk::wait_regions_kernel<<<1, 32, 0, main>>>(s->recv_base() + (size_t)(s->epoch & 1) * s->nranks * s->reg_size, s->reg_size, s->nranks,
                                                       s->epoch, s->err);
         CK(cudaGetLastError());
     }
-    uint8_t* reg = s->recv + (size_t)(s->epoch & 1) * s->nranks * s->reg_size;          // region 0 of the set just pushed
+    uint8_t* reg = s->recv_base() + (size_t)(s->epoch & 1) * s->nranks * s->reg_size;   // region 0 of the set just pushed
     bbk::Params P; memset(&P, 0, sizeof P);
     P.pkts = reg + bbk::region_bytes(s->cap_q); P.pkt_off = (const uint32_t*)(reg + bbk::region_off_array(s->cap_q));
     P.n = 0; P.n_dev = (const uint32_t*)reg; P.qidx_map = (const uint32_t*)(reg + bbk::region_qidx_array(s->cap_q));
@@ -1064,7 +1118,7 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
                    uint8_t* status, uint32_t* qidx, uint32_t* miss_idx, uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out) {
     if (!s || src >= s->nranks || s->host) return BB_ERR_ARG;       // host mirrors on: use bb_shard_results
     CK(cudaSetDevice(s->e->device));
-    uint8_t* reg = s->recv + ((size_t)(s->epoch & 1) * s->nranks + src) * s->reg_size;
+    uint8_t* reg = s->recv_base() + ((size_t)(s->epoch & 1) * s->nranks + src) * s->reg_size;
     uint32_t hdr[4], tot[4];
     CK(cudaMemcpy(hdr, reg, 16, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(tot, s->d_totals + src * s->totals_stride, 16, cudaMemcpyDeviceToHost));

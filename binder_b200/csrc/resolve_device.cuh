@@ -73,6 +73,12 @@ __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) 
 __device__ __forceinline__ uint32_t be16(const uint8_t* p) { return (uint32_t)p[0] << 8 | p[1]; }
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) { return *(const uint32_t*)p; }    // 4-byte aligned
 __device__ __forceinline__ uint32_t ld16a(const uint8_t* p) { return *(const uint16_t*)p; }   // 2-byte aligned
+#ifndef BB_HOST_EMU        /* the host emulation (tests/native/cuda_shim.h) supplies these over an emulated shared memory */
+__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
+__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+#endif
 
 // byte-fed murmur (same result as bb::hash_key over the materialised key)
 struct KeyHash {
@@ -322,8 +328,10 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
     for (uint32_t t = 0; t < n_walk && !full; t++) {
         const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
         if (inf & KID_ADDR_NULL) continue;
-        uint32_t each = srv ? 18 + wl + dwl : dol + 14, cnt = srv ? np : 1;
-        for (uint32_t c = 0; c < cnt; c++) { if (total + each > r.maxsz) { full = true; break; } total += each; ++ka; }
+        const uint32_t each = srv ? 18 + wl + dwl : dol + 14, cnt = srv ? np : 1;
+        const uint32_t fit = (r.maxsz - total) / each, take = min(cnt, fit);      // total <= maxsz throughout
+        total += take * each; ka += take;
+        if (take < cnt) full = true;
     }
     if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {
         const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), wl = (inf >> 8) & 0xFF;
@@ -410,7 +418,18 @@ __device__ void finish_forward(const Params& P, Res& r, uint32_t qidx, uint32_t 
     if (srv) {                                                                // :334-345: service === s.srvce && protocol === s.proto
         const uint32_t n = sv.sp_len();
         bool match = !(sv.hflags() & SVC_SP_NEVER) && n == l0 + l1 + 2;      // the two length bytes are part of the comparison
-        for (uint32_t i = 0; match && i < n; i++) if (sv.sp_byte(i) != nm[i]) match = false;
+        if (match && r.sp && !(sv.hflags() & SVC_SP_EXT)) {
+            // the 11 bytes of sp sit in the header's registers (bytes 3..13 of h1): three word compares against the QNAME's
+            // first bytes, the last one masked to n
+            const uint32_t a = r.sp + 12, b = a & ~3u, sh = (a & 3u) * 8;
+            const uint32_t t0 = lds32(b), t1 = lds32(b + 4), t2 = lds32(b + 8), t3 = lds32(b + 12);
+            const uint32_t q0 = __funnelshift_r(t0, t1, sh), q1 = __funnelshift_r(t1, t2, sh), q2 = __funnelshift_r(t2, t3, sh);
+            const uint32_t s0 = __funnelshift_r(sv.h1.x, sv.h1.y, 24), s1 = __funnelshift_r(sv.h1.y, sv.h1.z, 24), s2 = __funnelshift_r(sv.h1.z, sv.h1.w, 24);
+            const uint32_t m0 = n >= 4 ? 0xFFFFFFFFu : (1u << (8 * n)) - 1, m1 = n >= 8 ? 0xFFFFFFFFu : n > 4 ? (1u << (8 * (n - 4))) - 1 : 0u;
+            const uint32_t m2 = n >= 12 ? 0xFFFFFFFFu : n > 8 ? (1u << (8 * (n - 8))) - 1 : 0u;
+            match = (((q0 ^ s0) & m0) | ((q1 ^ s1) & m1) | ((q2 ^ s2) & m2)) == 0;
+        } else
+            for (uint32_t i = 0; match && i < n; i++) if (sv.sp_byte(i) != nm[i]) match = false;
         if (!match) { r.rcode = RC_NXDOMAIN; return; }
     }
     r.rcode = RC_NOERROR;                                                     // :351
@@ -435,12 +454,6 @@ constexpr int NSTAGE = 16;
 // Same decisions as resolve_forward() below, four name bytes per step, for the common case:
 // packet staged in shared memory, QNAME <= 64 wire bytes, lookup key <= 48 bytes (inline slot
 // keys).  Anything else returns false and takes the generic path.
-#ifndef BB_HOST_EMU        /* the host emulation (tests/native/cuda_shim.h) supplies these over an emulated shared memory */
-__device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
-__device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-__device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
-#endif
 // unaligned 32-bit load from shared memory (the staging buffers carry read slack)
 __device__ __forceinline__ uint32_t ldsu32(uint32_t a) {
     const uint32_t b = a & ~3u;
@@ -1091,8 +1104,9 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
     const uint32_t blocks = r.val + sv.blocks_off(), stride = sv.stride(), dwl = sv.dom_wl();
     uint32_t dst = my_o + 12 + r.qn_len + 4;
     uint32_t left = r.keep_ans;
-    for (uint32_t t = 0; t < r.n_walk && left; t++) {
-        const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
+    uint64_t pm = r.perm;                                                     // job mode implies nk <= 16: four bits per position
+    for (uint32_t t = 0; t < r.n_walk && left; t++, pm >>= 4) {
+        const uint32_t k = (uint32_t)pm & 15u, inf = sv.info(k);
         if (inf & KID_ADDR_NULL) continue;
         const uint32_t wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
         if (srv) {
@@ -1103,9 +1117,9 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
     }
     if (r.edns) { sink.put(opt_sp, dst, 11, 1); dst += 11; }                  // the OPT leads the additional section
     if (srv) {
-        left = r.keep_add;
-        for (uint32_t t = 0; t < r.n_walk && left; t++) {
-            const uint32_t k = perm_at(r, t, P.seed, qidx), inf = sv.info(k);
+        left = r.keep_add; pm = r.perm;
+        for (uint32_t t = 0; t < r.n_walk && left; t++, pm >>= 4) {
+            const uint32_t k = (uint32_t)pm & 15u, inf = sv.info(k);
             if (inf & KID_ADDR_NULL) continue;
             const uint32_t wl = (inf >> 8) & 0xFF;
             sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0); dst += kid_add_len(wl); --left;

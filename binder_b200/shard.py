@@ -94,7 +94,21 @@ class ShardedEngine(object):
                 check(lib().bb_shard_host_results(h, 1))
         self._h = self._lanes[0]
         self.cap_q = lib().bb_shard_region_capacity(self._h)
-        if world > 1:
+        self._xch = []
+        if sync == 'nccl_a2a':
+            # the collective baseline: per lane a local send buffer and a receive buffer (torch tensors), exchanged with
+            # grouped ncclSend/ncclRecv (torch.distributed.batch_isend_irecv) instead of peer stores
+            import torch
+            lay = (ctypes.c_uint64 * 5)()
+            lib().bb_shard_region_layout(self._h, lay)
+            self._lay = [int(x) for x in lay]
+            nb = int(lib().bb_shard_exchange_bytes(self._h))
+            for h in self._lanes:
+                snd = torch.zeros(nb, dtype=torch.uint8, device='cuda')
+                rcv = torch.zeros(nb, dtype=torch.uint8, device='cuda')
+                check(lib().bb_shard_use_exchange_buffers(h, snd.data_ptr(), rcv.data_ptr()))
+                self._xch.append((snd, rcv, torch.empty((world, 4), dtype=torch.int32).pin_memory(), torch.empty((world, 4), dtype=torch.int32).pin_memory()))
+        if world > 1 and sync != 'nccl_a2a':
             hs = lib().bb_shard_ipc_handle_size()
             for h in self._lanes:
                 mine = (ctypes.c_uint8 * hs)()
@@ -126,10 +140,52 @@ class ShardedEngine(object):
         wait = 1 if (self.sync == 'flags' and self.world > 1) else 0
         check(lib().bb_shard_resolve(self._lanes[lane], seed, wait, stream))
 
+    def exchange(self, lane=0):
+        """sync='nccl_a2a': move every send region to its destination's receive region with ONE grouped exchange of
+        ncclSend/ncclRecv (headers first — their counts size the rest, which costs a host round trip per step: that is
+        what a collective on data-dependent sizes needs).  Runs on the current torch stream."""
+        import torch
+        dist = self.dist
+        W, R = self.world, self.rank
+        snd, rcv, h_s, h_r = self._xch[lane]
+        reg, cap, o_off, o_qi, o_by = self._lay
+        st = int(lib().bb_shard_exchange_set(self._lanes[lane]))
+        sreg = lambda d: snd[(st * W + d) * reg:(st * W + d + 1) * reg]
+        rreg = lambda s_: rcv[(st * W + s_) * reg:(st * W + s_ + 1) * reg]
+        hs = torch.stack([sreg(d)[:16].view(torch.int32) for d in range(W)])         # what this rank sends to each rank
+        hr = torch.empty_like(hs)
+        if W > 1:
+            dist.all_to_all_single(hr, hs)
+        else:
+            hr.copy_(hs)
+        h_s.copy_(hs, non_blocking=True); h_r.copy_(hr, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        ops = []
+        for p in range(W):
+            cs, bs = int(h_s[p, 0]), int(h_s[p, 1])
+            cr, br = int(h_r[p, 0]), int(h_r[p, 1])
+            rreg(p)[:16].view(torch.int32).copy_(hr[p])
+            if p == R:                               # own region: device copies
+                for o, n in ((o_off, 4 * (cs + 1)), (o_qi, 4 * cs), (o_by, (bs + 15) // 16 * 16)):
+                    if n:
+                        rreg(p)[o:o + n].copy_(sreg(p)[o:o + n])
+                continue
+            for o, n in ((o_off, 4 * (cs + 1)), (o_qi, 4 * cs), (o_by, (bs + 15) // 16 * 16)):
+                if n:
+                    ops.append(dist.P2POp(dist.isend, sreg(p)[o:o + n], p))
+            for o, n in ((o_off, 4 * (cr + 1)), (o_qi, 4 * cr), (o_by, (br + 15) // 16 * 16)):
+                if n:
+                    ops.append(dist.P2POp(dist.irecv, rreg(p)[o:o + n], p))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
     def step(self, d_pkts, d_off, n, qidx_base, seed, stream, lane=0):
         self.route_push(d_pkts, d_off, n, qidx_base, stream, lane)
         if self.sync == 'nccl':
             self.barrier()
+        elif self.sync == 'nccl_a2a':
+            self.exchange(lane)
         self.resolve(seed, stream, lane)
 
     def _bufs(self, lane, src):

@@ -275,6 +275,20 @@ int bb_shard_fetch(bb_shard* s, uint32_t src, uint8_t* out, uint32_t out_cap, ui
                    uint16_t* out_len, uint8_t* status, uint32_t* qidx, uint32_t* miss_idx,
                    uint32_t* n_out, uint32_t* n_miss, uint32_t* total_out);
 
+/* The collective baseline ("one all-to-all of routed records"): with caller-owned exchange buffers
+ * route_push fills LOCAL send regions (region d of the current set = the records for rank d, in the receive-region layout)
+ * and bb_shard_resolve(wait_for_peers = 0) reads the receive buffer the caller's collective filled — ncclSend/ncclRecv of
+ * the header, offset, ingress-index and packet arrays of every region (binder_b200/shard.py, sync='nccl_a2a').
+ *   bb_shard_exchange_bytes   size of each buffer (2 sets x nranks regions)
+ *   bb_shard_exchange_set     set (0/1) the last route_push wrote = the one the next resolve reads
+ *   bb_shard_region_layout    out[5] = {bytes per region, capacity in queries, offset of the u32 offsets array (cap+1), of the
+ *                             u32 ingress-index array (cap), of the packet bytes}; a region starts with the 16-byte header
+ *                             {count, packet bytes, epoch, sender overflow flag} */
+int      bb_shard_use_exchange_buffers(bb_shard* s, void* d_send, void* d_recv);
+size_t   bb_shard_exchange_bytes(const bb_shard* s);
+uint32_t bb_shard_exchange_set(const bb_shard* s);
+void     bb_shard_region_layout(const bb_shard* s, uint64_t out[5]);
+
 int bb_shard_host_results(bb_shard* s, int enable);
 int bb_shard_results(bb_shard* s, uint32_t src, const uint8_t** out, const uint32_t** out_off,
                      const uint16_t** out_len, const uint8_t** status, const uint32_t** qidx,
