@@ -85,7 +85,7 @@ struct bb_backend {
     std::vector<uint8_t> out;                          // frames to write back
     std::vector<uint8_t> m_pkts; std::vector<uint32_t> m_off, m_ip, m_port;    // handed-off misses of the last feed
     uint64_t n_udp = 0, n_answered = 0, n_missed = 0, n_dropped = 0, n_failed = 0;
-    uint32_t qidx_next = 0;                             // query index of the next batch's first query (keys the shuffle)
+    uint32_t qidx_next = 0;                             // query index of the next batch's first query within the current feed (keys the shuffle)
 };
 
 extern "C" {
@@ -124,6 +124,7 @@ int bb_backend_feed(bb_backend* b, const uint8_t* in, size_t in_len, uint64_t sh
     b->pending.insert(b->pending.end(), in, in + in_len);
     b->out.clear(); b->m_pkts.clear(); b->m_off.assign(1, 0); b->m_ip.clear(); b->m_port.clear();
     size_t pos = 0; int rc = BB_OK;
+    b->qidx_next = 0;                                   // (seed, index) keys the shuffle: indices run over the queries of this feed
     for (;;) {
         uint32_t n = 0, nc = 0, control[64]; size_t used = 0;
         rc = bb_frames_parse(b->pending.data() + pos, b->pending.size() - pos, b->pkts, b->max_bytes, b->pkt_off, b->ip, b->port,

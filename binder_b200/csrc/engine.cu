@@ -281,10 +281,10 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
         if (big) {
             __syncthreads();
             const uint32_t goff = (uint32_t)gbase;
-            for (uint32_t ti = tid, n = min(s_cnt[0], cap[0]); ti < n; ti += T) run_task_g<0>(P, tl[lbase[0] + ti], dst, goff);
-            for (uint32_t ti = tid, n = min(s_cnt[1], cap[1]); ti < n; ti += T) run_task_g<1>(P, tl[lbase[1] + ti], dst, goff);
-            for (uint32_t ti = tid, n = min(s_cnt[2], cap[2]); ti < n; ti += T) run_task_g<2>(P, tl[lbase[2] + ti], dst, goff);
-            for (uint32_t ti = tid, n = min(s_cnt[3], cap[3]); ti < n; ti += T) run_task_g<3>(P, tl[lbase[3] + ti], dst, goff);
+            run_jobs<0>(P, tl + lbase[0], min(s_cnt[0], cap[0]), (uint32_t)tid, dst, goff);
+            run_jobs<1>(P, tl + lbase[1], min(s_cnt[1], cap[1]), (uint32_t)tid, dst, goff);
+            run_jobs<2>(P, tl + lbase[2], min(s_cnt[2], cap[2]), (uint32_t)tid, dst, goff);
+            run_jobs<3>(P, tl + lbase[3], min(s_cnt[3], cap[3]), (uint32_t)tid, dst, goff);
         }
         STAMP(9);
         if (r_bounce && tile_bytes) {

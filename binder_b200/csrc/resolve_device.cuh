@@ -1131,21 +1131,59 @@ struct TaskCount {           // (scalars: an array indexed by the class would li
     uint32_t n0, n1, n2, n3;
     __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; }
 };
-// run one job of length class C straight into global memory: tile byte x lives at g[x]; every load of the job is issued
-// before its first byte is written
-template <int C>
-__device__ __forceinline__ void run_task_g(const Params& P, const Task t, uint8_t* g, uint32_t goff) {
+// Run the jobs of one length class straight into global memory (tile byte x lives at g[goff + x]).  A thread takes several
+// jobs per pass and issues ALL their loads before it writes the first byte: the jobs are independent, and what bounds this
+// phase is how many DRAM round trips a thread makes one after another, not how many bytes it moves.
+__device__ __forceinline__ void job_write(const Params& P, const Task t, uint8_t* g, uint32_t goff, const uint4 x0, const uint4 x1, const uint4 x2, const uint4 x3) {
     const uint32_t len = task_len(t);
     if (!len) return;
     WrT<2, true> w; w.begin_global(g, goff + task_dst(t));
     if (task_smem(t)) w.copy(t.src, len);
     else {
-        const uint4* q = (const uint4*)(P.arena + t.src);
-        if (C == 0) put_chunk_w(w, ldg_stream(q), len);
-        else if (C == 1) { const uint4 x0 = ldg_stream(q), x1 = ldg_stream(q + 1); put_chunk_w(w, x0, len); put_chunk_w(w, x1, len - 16); }
-        else copy_arena_w(w, P.arena + t.src, len);
+        put_chunk_w(w, x0, len);
+        if (len > 16) put_chunk_w(w, x1, len - 16);
+        if (len > 32) put_chunk_w(w, x2, len - 32);
+        if (len > 48) put_chunk_w(w, x3, len - 48);
     }
     w.end();
+}
+__device__ __forceinline__ uint4 job_load(const Params& P, const Task t, uint32_t chunk) {
+    return (!task_smem(t) && task_len(t) > 16 * chunk) ? ldg_stream((const uint4*)(P.arena + t.src) + chunk) : make_uint4(0, 0, 0, 0);
+}
+template <int C>
+__device__ void run_jobs(const Params& P, const Task* tl, uint32_t n, uint32_t tid, uint8_t* g, uint32_t goff) {
+    const Task none = { 0, 0 };
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    if (C == 0) {                                      // <= 16 bytes: four jobs, four loads in flight
+        for (uint32_t ti = tid; ti < n; ti += 4 * T) {
+            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none, c = ti + 2 * T < n ? tl[ti + 2 * T] : none, d = ti + 3 * T < n ? tl[ti + 3 * T] : none;
+            const uint4 xa = job_load(P, a, 0), xb = job_load(P, b, 0), xc = job_load(P, c, 0), xd = job_load(P, d, 0);
+            job_write(P, a, g, goff, xa, z, z, z); job_write(P, b, g, goff, xb, z, z, z);
+            job_write(P, c, g, goff, xc, z, z, z); job_write(P, d, g, goff, xd, z, z, z);
+        }
+    } else if (C == 1) {                               // <= 32 bytes: two jobs, four loads
+        for (uint32_t ti = tid; ti < n; ti += 2 * T) {
+            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none;
+            const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), b0 = job_load(P, b, 0), b1 = job_load(P, b, 1);
+            job_write(P, a, g, goff, a0, a1, z, z); job_write(P, b, g, goff, b0, b1, z, z);
+        }
+    } else if (C == 2) {                               // <= 64 bytes: two jobs, up to eight loads
+        for (uint32_t ti = tid; ti < n; ti += 2 * T) {
+            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none;
+            const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), a2 = job_load(P, a, 2), a3 = job_load(P, a, 3);
+            const uint4 b0 = job_load(P, b, 0), b1 = job_load(P, b, 1), b2 = job_load(P, b, 2), b3 = job_load(P, b, 3);
+            job_write(P, a, g, goff, a0, a1, a2, a3); job_write(P, b, g, goff, b0, b1, b2, b3);
+        }
+    } else {                                           // longer: 64 bytes per round trip
+        for (uint32_t ti = tid; ti < n; ti += T) {
+            const Task t = tl[ti];
+            const uint32_t len = task_len(t);
+            if (!len) continue;
+            WrT<2, true> w; w.begin_global(g, goff + task_dst(t));
+            if (task_smem(t)) w.copy(t.src, len); else copy_arena_w(w, P.arena + t.src, len);
+            w.end();
+        }
+    }
 }
 
 // header + question (verbatim) of a response; the stream stays open

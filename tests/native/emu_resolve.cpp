@@ -101,10 +101,13 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                     if (jobs) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
                 }
             }
-            for (const Task& tk : lists[0]) run_task_g<0>(P, tk, out, (uint32_t)gbase);
-            for (const Task& tk : lists[1]) run_task_g<1>(P, tk, out, (uint32_t)gbase);
-            for (const Task& tk : lists[2]) run_task_g<2>(P, tk, out, (uint32_t)gbase);
-            for (const Task& tk : lists[3]) run_task_g<3>(P, tk, out, (uint32_t)gbase);
+            // the kernel's job passes, thread by thread (a thread takes jobs tid, tid + T, ... of each list)
+            for (uint32_t t = 0; t < (uint32_t)T; t++) {
+                run_jobs<0>(P, lists[0].data(), (uint32_t)lists[0].size(), t, out, (uint32_t)gbase);
+                run_jobs<1>(P, lists[1].data(), (uint32_t)lists[1].size(), t, out, (uint32_t)gbase);
+                run_jobs<2>(P, lists[2].data(), (uint32_t)lists[2].size(), t, out, (uint32_t)gbase);
+                run_jobs<3>(P, lists[3].data(), (uint32_t)lists[3].size(), t, out, (uint32_t)gbase);
+            }
         } else if (tile_bytes) {
             const uint32_t shift = (uint32_t)(gbase & 15);
             for (uint32_t t = 0; t < nq; t++) {

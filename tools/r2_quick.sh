@@ -1,7 +1,7 @@
 # quick A/B on one GPU: parity subset + kernel-path numbers of config3(+config4) and config2 (no oracle, no e2e)
 mkdir -p gpurun_out
 TAG=${1:-q}
-timeout 900 python -m pytest tests -x -q -m gpu 2>&1 | tail -2
+timeout 900 python -m pytest tests -x -q -m gpu > gpurun_out/${TAG}_pytest.log 2>&1; tail -3 gpurun_out/${TAG}_pytest.log
 timeout 600 python bench.py --no-cpu --no-e2e > gpurun_out/${TAG}_config3.json 2> gpurun_out/${TAG}_config3.err || tail -5 gpurun_out/${TAG}_config3.err
 timeout 300 python bench.py --workload config2 --no-cpu --no-e2e > gpurun_out/${TAG}_config2.json 2> gpurun_out/${TAG}_config2.err || tail -5 gpurun_out/${TAG}_config2.err
 python - <<PY
