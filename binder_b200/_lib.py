@@ -33,6 +33,7 @@ SYMBOLS = {
     'bb_shard_exchange_bytes': (_c.c_size_t, [_c.c_void_p]),
     'bb_shard_exchange_set': (_c.c_uint32, [_c.c_void_p]),
     'bb_shard_region_layout': (None, [_c.c_void_p, _c.c_void_p]),
+    'bb_engine_set_kernel_profile': (_c.c_int, [_c.c_void_p, _c.c_int]),
     'bb_engine_max_batch': (_c.c_uint32, [_c.c_void_p]),
     'bb_engine_max_batch_bytes': (_c.c_uint32, [_c.c_void_p]),
     'bb_resolve_submit': (_c.c_int, [_c.c_void_p, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_uint32, _c.c_uint64,

@@ -48,8 +48,11 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
 // with one atomicAdd and never waits; response i is still out[out_off[i] .. +out_len[i]).
 // MULTI: one launch over several receive regions (routed batches, grid.y = source rank): every
 // per-batch pointer advances by its stride per region, sizes and shuffle indices come from device memory.
-template <bool ORDERED, bool MULTI>
-__global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params P) {
+// SVC: the variant for batches of long (service) answers — copy-job lists in shared memory and emit rounds; it fits 7 tiles per
+// SM instead of 8, which batches of 64-byte answers would feel, so the host picks per batch (engine: the previous batch's
+// mean response size).  Both variants answer every batch correctly.
+template <bool ORDERED, bool MULTI, bool SVC>
+__global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) resolve_kernel(const Params P) {
     // the packets start 16 bytes in: a staged packet's shared address is never 0 (Res::sp == 0 means "not staged")
     __shared__ __align__(16) uint8_t s_inbuf[16 + S_IN + 32];
     uint8_t* const s_in = s_inbuf + 16;
@@ -57,6 +60,8 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
     __shared__ uint32_t s_cnt[4];                              // big tiles: jobs in each of the four lists
+    __shared__ uint32_t s_rstart[NROUNDS + 1];                 // big tiles: tile offset of each emit round's first response
+    __shared__ Task s_task[SVC ? TASKCAP : 1];                 // big tiles: the copy jobs
     __shared__ uint8_t s_perm[T];                              // which query of the tile each thread takes (grouped by question type)
     __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
@@ -223,68 +228,28 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
     if (overflow && tid == 0) r_totals[2] = P.epoch;
 
     // ---- emit ---------------------------------------------------------------------------------------
-    // A tile whose responses fit one staging window (128 x 64-byte answers do) is assembled in (swizzled) shared memory and
-    // flushed with aligned 16-byte stores.  A BIG tile — ~300-byte service answers — writes straight to global memory,
-    // and splits the work so that all 128 threads stay busy with independent loads: each thread writes the header and the
-    // question of its own response, and turns the rest of a service answer — the children's ready RRs — into copy jobs
-    // (plan_service), sorted into four lists by length class, that ANY thread runs (a thread walking its own service
-    // record child by child is one dependent DRAM round trip after another, and warps of mixed answer sizes idle most lanes).
-    // A tile with a query on the generic byte path or with a response over MAXRESP (TCP) also writes directly, without jobs.
+    // Responses are assembled in (swizzled) shared memory and flushed with aligned 16-byte stores: scattered 4-byte stores
+    // straight to global memory cost one L1->L2 request per lane, and that request path — not DRAM, not the ALUs — is what
+    // a tile of ~300-byte service answers saturates.  A tile whose responses fit one staging window (128 x 64-byte answers
+    // do) is one round: every thread writes its response, all flush.
+    // A BIG tile in the service variant of the kernel (SVC) goes through the window in ROUNDS and splits the work so that all
+    // 128 threads stay busy with independent loads.  Round k = the responses that START in bytes [k*WIN, (k+1)*WIN) of the
+    // tile (each at most MAXRESP long, which the buffer allows for past the window).  Their threads write the header and the
+    // question; the rest of a service answer — the children's ready RRs — became copy jobs (plan_service) in four lists
+    // by length class, tagged with the round, that ANY thread runs.  (A thread walking its own service record child by
+    // child is one dependent DRAM round trip after another, and warps of mixed answer sizes idle most lanes.)
+    // Without SVC a big tile writes straight to global memory, thread per response; so does, in either variant, a tile with a
+    // query on the generic byte path or a response over MAXRESP (TCP).
     const bool odd_emit = my_len && (!(r.sp && !r.trunc) || my_len > (uint32_t)MAXRESP);
-    const bool direct = __syncthreads_or(odd_emit);
-    const bool big = !direct && tile_bytes > (uint32_t)WIN;
-    if (!overflow && (direct || big)) {
+    const bool direct = __syncthreads_or(odd_emit) || (!SVC && tile_bytes > (uint32_t)WIN);
+    if (!overflow && direct) {
         // `out` may be pinned host memory (zero-copy results): 4-byte stores over PCIe would be ruinous,
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
         // coalesced 16-byte stores (the bytes are still in L2)
         uint8_t* const dst = r_bounce ? r_bounce : r_out;
-        Task* const tl = (Task*)s_out;                                        // the job lists alias the (unused) staging buffer
-        constexpr uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
-        constexpr uint32_t lbase[4] = { 0, TASK_CAP0, TASK_CAP0 + TASK_CAP1, TASK_CAP0 + TASK_CAP1 + TASK_CAP2 };
-        bool jobs = big && my_len && r.ntask;
-        if (big) {
-            if (tid < 4) s_cnt[tid] = 0;
-            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-            __syncthreads();
-            if (jobs) {                                                       // count, reserve a run of each list, fill
-                const uint32_t opt_sp = (uint32_t)__cvta_generic_to_shared(s_opt);
-                TaskCount tc = { 0, 0, 0, 0 };
-                plan_service(P, r, qidx, my_o, opt_sp, tc);
-                const uint32_t a0 = tc.n0 ? atomicAdd(&s_cnt[0], tc.n0) : 0u, a1 = tc.n1 ? atomicAdd(&s_cnt[1], tc.n1) : 0u;
-                const uint32_t a2 = tc.n2 ? atomicAdd(&s_cnt[2], tc.n2) : 0u, a3 = tc.n3 ? atomicAdd(&s_cnt[3], tc.n3) : 0u;
-                if (a0 + tc.n0 <= cap[0] && a1 + tc.n1 <= cap[1] && a2 + tc.n2 <= cap[2] && a3 + tc.n3 <= cap[3]) {
-                    struct Fill {
-                        Task* tl; uint32_t i0, i1, i2, i3;
-                        __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
-                            uint32_t i;
-                            if (len <= 16) i = i0++; else if (len <= 32) i = i1++; else if (len <= 64) i = i2++; else i = i3++;
-                            tl[i].src = src; tl[i].w = dst | (len << 18) | (sm << 31);
-                        }
-                    } fill = { tl, lbase[0] + a0, lbase[1] + a1, lbase[2] + a2, lbase[3] + a3 };
-                    plan_service(P, r, qidx, my_o, opt_sp, fill);
-                } else {                                                      // a list is full: empty jobs in what was reserved, and this thread writes it all
-                    jobs = false;
-                    for (uint32_t i = a0; i < a0 + tc.n0 && i < cap[0]; i++) { tl[lbase[0] + i].src = 0; tl[lbase[0] + i].w = 0; }
-                    for (uint32_t i = a1; i < a1 + tc.n1 && i < cap[1]; i++) { tl[lbase[1] + i].src = 0; tl[lbase[1] + i].w = 0; }
-                    for (uint32_t i = a2; i < a2 + tc.n2 && i < cap[2]; i++) { tl[lbase[2] + i].src = 0; tl[lbase[2] + i].w = 0; }
-                    for (uint32_t i = a3; i < a3 + tc.n3 && i < cap[3]; i++) { tl[lbase[3] + i].src = 0; tl[lbase[3] + i].w = 0; }
-                }
-            }
-        }
         if (my_len) {
             if (!(r.sp && !r.trunc)) emit_response(P, r, dst + gbase + my_o, qidx);
-            else {
-                WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o));
-                if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
-            }
-        }
-        if (big) {
-            __syncthreads();
-            const uint32_t goff = (uint32_t)gbase;
-            run_jobs<0>(P, tl + lbase[0], min(s_cnt[0], cap[0]), (uint32_t)tid, dst, goff);
-            run_jobs<1>(P, tl + lbase[1], min(s_cnt[1], cap[1]), (uint32_t)tid, dst, goff);
-            run_jobs<2>(P, tl + lbase[2], min(s_cnt[2], cap[2]), (uint32_t)tid, dst, goff);
-            run_jobs<3>(P, tl + lbase[3], min(s_cnt[3], cap[3]), (uint32_t)tid, dst, goff);
+            else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
         }
         STAMP(9);
         if (r_bounce && tile_bytes) {
@@ -300,21 +265,79 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) resolve_kernel(const Params 
             if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
         }
     } else if (!overflow && tile_bytes) {
-        const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
-        if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
-        __syncthreads();
+        const uint32_t s_out_a = (uint32_t)__cvta_generic_to_shared(s_out);
+        const bool big = SVC && tile_bytes > (uint32_t)WIN;
+        const uint32_t nr = big ? (tile_bytes + WIN - 1) / WIN : 1u;          // <= NROUNDS
+        const uint32_t kr = big ? my_o / WIN : 0u;
+        bool jobs = false;
+        constexpr uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
+        constexpr uint32_t lbase[4] = { 0, TASK_CAP0, TASK_CAP0 + TASK_CAP1, TASK_CAP0 + TASK_CAP1 + TASK_CAP2 };
+        if (big) {
+            if (tid < 4) s_cnt[tid] = 0;
+            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
+            if (tid <= NROUNDS) s_rstart[tid] = 0xFFFFFFFFu;
+            __syncthreads();
+            if (my_len) atomicMin(&s_rstart[kr], my_o);                       // where each round's first response starts
+            if (my_len && r.ntask) {                                          // count, reserve a run of each list, fill
+                const uint32_t opt_sp = (uint32_t)__cvta_generic_to_shared(s_opt);
+                TaskCount tc = { 0, 0, 0, 0, 0 };
+                plan_service(P, r, qidx, my_o, opt_sp, tc);
+                if (!tc.toolong) {
+                    const uint32_t a0 = tc.n0 ? atomicAdd(&s_cnt[0], tc.n0) : 0u, a1 = tc.n1 ? atomicAdd(&s_cnt[1], tc.n1) : 0u;
+                    const uint32_t a2 = tc.n2 ? atomicAdd(&s_cnt[2], tc.n2) : 0u, a3 = tc.n3 ? atomicAdd(&s_cnt[3], tc.n3) : 0u;
+                    if (a0 + tc.n0 <= cap[0] && a1 + tc.n1 <= cap[1] && a2 + tc.n2 <= cap[2] && a3 + tc.n3 <= cap[3]) {
+                        struct Fill {
+                            Task* tl; uint32_t i0, i1, i2, i3, round;
+                            __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
+                                uint32_t i;
+                                if (len <= 16) i = i0++; else if (len <= 32) i = i1++; else if (len <= 64) i = i2++; else i = i3++;
+                                tl[i].src = src; tl[i].w = task_word(dst, round, len, sm);
+                            }
+                        } fill = { s_task, lbase[0] + a0, lbase[1] + a1, lbase[2] + a2, lbase[3] + a3, kr };
+                        plan_service(P, r, qidx, my_o, opt_sp, fill);
+                        jobs = true;
+                    } else {                                                  // a list is full: empty jobs in what was reserved, and this thread writes it all
+                        for (uint32_t i = a0; i < a0 + tc.n0 && i < cap[0]; i++) { s_task[lbase[0] + i].src = 0; s_task[lbase[0] + i].w = 0; }
+                        for (uint32_t i = a1; i < a1 + tc.n1 && i < cap[1]; i++) { s_task[lbase[1] + i].src = 0; s_task[lbase[1] + i].w = 0; }
+                        for (uint32_t i = a2; i < a2 + tc.n2 && i < cap[2]; i++) { s_task[lbase[2] + i].src = 0; s_task[lbase[2] + i].w = 0; }
+                        for (uint32_t i = a3; i < a3 + tc.n3 && i < cap[3]; i++) { s_task[lbase[3] + i].src = 0; s_task[lbase[3] + i].w = 0; }
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t k = 0; k < nr; k++) {
+            uint32_t x0 = 0, x1 = tile_bytes;                                 // this round's byte range of the tile
+            if (big) {
+                x0 = s_rstart[k];
+                if (x0 == 0xFFFFFFFFu) continue;                              // no response starts in this window (uniform)
+                for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; break; }
+            }
+            const uint32_t shift = (uint32_t)((gbase + x0) & 15);             // same 16-byte phase in shared and global memory
+            const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[swz(delta + x)]
+            if (my_len && kr == k) {
+                WrT<1> w; w.begin(s_out_a, delta + my_o);
+                if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
+            }
+            if (big) {
+                run_jobs<0>(P, s_task + lbase[0], min(s_cnt[0], cap[0]), k, (uint32_t)tid, s_out_a, delta);
+                run_jobs<1>(P, s_task + lbase[1], min(s_cnt[1], cap[1]), k, (uint32_t)tid, s_out_a, delta);
+                run_jobs<2>(P, s_task + lbase[2], min(s_cnt[2], cap[2]), k, (uint32_t)tid, s_out_a, delta);
+                run_jobs<3>(P, s_task + lbase[3], min(s_cnt[3], cap[3]), k, (uint32_t)tid, s_out_a, delta);
+            }
+            __syncthreads();
+            uint8_t* g = r_out + gbase;
+            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);      // up to 16-byte alignment of the global address
+            if (head > x1 - x0) head = x1 - x0;
+            if (tid < (int)head) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
+            x0 += head;
+            const uint32_t nv = (x1 - x0) >> 4;
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(delta + x0 + 16 * i));
+            x0 += nv << 4;
+            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
+            if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
+        }
         STAMP(9);
-        uint8_t* g = r_out + gbase;                                           // g[x] <-> s_out[swz(shift + x)]
-        uint32_t x0 = 0;
-        const uint32_t x1 = tile_bytes;
-        uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);                 // up to 16-byte alignment of the global address
-        if (head > x1) head = x1;
-        if (tid < (int)head) g[tid] = s_out[swz(shift + tid)];
-        x0 = head;
-        const uint32_t nv = (x1 - x0) >> 4;
-        for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i));
-        x0 += nv << 4;
-        if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid)];
     }
 
     STAMP(10);
@@ -586,6 +609,10 @@ struct bb_engine {
     void* dev_stream[MAX_DEV_STREAMS] = {}; unsigned long long* dev_desc[MAX_DEV_STREAMS] = {}; int n_dev_streams = 0;
     uint64_t launches = 0, epoch = 0;
     unsigned long long* stage_log = nullptr;
+    // kernel variant per batch (bb_engine_set_kernel_profile): 0 = by the mean response size of the latest finished batch
+    int profile = 0; uint32_t mean_resp = 0;
+    static constexpr int FB = 64;                                // device-path feedback: totals of recent launches, copied back asynchronously
+    uint32_t* h_fb = nullptr; uint32_t fb_epoch[FB] = {}; uint32_t fb_n[FB] = {};
     // the zone this engine last synchronised with (incremental updates only continue from that state)
     const bb_zone* zone = nullptr; uint64_t zone_gen = 0; uint64_t arena_cap = 0;
 };
@@ -617,6 +644,9 @@ static int engine_alloc(bb_engine* e) {
     CK(cudaMalloc(&e->d_const, sizeof(bb::EngineConst)));
     CK(cudaMemcpy(e->d_const, &e->hconst, sizeof(bb::EngineConst), cudaMemcpyHostToDevice));
     e->max_tiles = (e->max_batch + bbk::T - 1) / bbk::T;
+    CK(cudaMallocHost(&e->h_fb, bb_engine::FB * 16));
+    memset(e->h_fb, 0, bb_engine::FB * 16);
+    if (const char* pf = getenv("BB_PROFILE")) e->profile = !strcmp(pf, "small") ? 1 : !strcmp(pf, "service") ? 2 : 0;
     uint64_t cap = (uint64_t)e->max_batch * 512;                 // device-side response buffer per slot
     if (cap < (1u << 20)) cap = 1u << 20;
     if (cap > 0xFFFFFF00ull) cap = 0xFFFFFF00ull;
@@ -674,6 +704,7 @@ void bb_engine_destroy(bb_engine* e) {
     }
     for (int i = 0; i < e->n_dev_streams; i++) cudaFree(e->dev_desc[i]);
     cudaFree(e->d_const); cudaFree(e->d_table); cudaFree(e->d_arena);
+    if (e->h_fb) cudaFreeHost(e->h_fb);
     delete e;
 }
 
@@ -750,6 +781,7 @@ int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, cons
 }
 int bb_engine_is_ready(const bb_engine* e) { return e && e->ready; }
 int bb_engine_slots(const bb_engine*) { return NSLOTS; }
+int bb_engine_set_kernel_profile(bb_engine* e, int profile) { if (!e || profile < 0 || profile > 2) return BB_ERR_ARG; e->profile = profile; return BB_OK; }
 uint32_t bb_engine_max_batch(const bb_engine* e) { return e ? e->max_batch : 0; }
 uint32_t bb_engine_max_batch_bytes(const bb_engine* e) { return e ? e->max_bytes : 0; }
 uint64_t bb_engine_launch_count(const bb_engine* e) { return e ? e->launches : 0; }
@@ -758,7 +790,8 @@ void bb_engine_set_stage_log(bb_engine* e, unsigned long long* d_log) { if (e) e
 
 static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts, const uint32_t* d_off, uint32_t n,
                   uint64_t seed, uint32_t qidx_base, uint8_t* d_out, uint32_t out_cap, uint32_t* d_out_off, uint16_t* d_out_len,
-                  uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st, uint8_t* bounce = nullptr, uint32_t flags = 0) {
+                  uint8_t* d_status, uint32_t* d_miss, uint32_t* d_totals, cudaStream_t st, uint8_t* bounce = nullptr, uint32_t flags = 0,
+                  bool feedback = false) {
     bbk::Params P;
     P.pkts = d_pkts; P.pkt_off = d_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = d_out; P.out_cap = out_cap; P.out_off = d_out_off; P.out_len = d_out_len; P.status = d_status; P.miss_idx = d_miss; P.totals = d_totals;
@@ -770,11 +803,29 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     P.stage_log = e->stage_log;
     P.n_dev = nullptr; P.qidx_map = nullptr; P.route = 0; P.nranks = 1; P.rank = 0; P.regions = 0; P.bounce = bounce; P.qidx_out = nullptr; P.err_in = nullptr; P.tcp = (flags & BB_BATCH_TCP) ? 1u : 0u;
     if (n == 0) { CK(cudaMemsetAsync(d_out_off, 0, 4, st)); CK(cudaMemsetAsync(d_totals, 0, 16, st)); return BB_OK; }
+    // Which variant: the service variant (copy jobs + emit rounds, 7 tiles per SM) pays off when answers are long.  Decided
+    // from the latest batch whose totals are known: the host path learns them in bb_resolve_wait, the device path from a
+    // 16-byte copy of d_totals that follows every launch (looked at only once its epoch has landed: no synchronisation).
+    for (int i = 0; i < bb_engine::FB; i++) {
+        const volatile uint32_t* f = e->h_fb + 4 * i;
+        if (e->fb_n[i] && f[3] == e->fb_epoch[i]) { e->mean_resp = f[0] / e->fb_n[i]; e->fb_n[i] = 0; }
+    }
+    const bool svc = e->profile == 2 || (e->profile == 0 && e->mean_resp > 96);
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
-    if (e->ordered) bbk::resolve_kernel<true, false><<<P.ntiles, bbk::T, 0, st>>>(P);
-    else bbk::resolve_kernel<false, false><<<P.ntiles, bbk::T, 0, st>>>(P);
+    if (svc) {
+        if (e->ordered) bbk::resolve_kernel<true, false, true><<<P.ntiles, bbk::T, 0, st>>>(P);
+        else bbk::resolve_kernel<false, false, true><<<P.ntiles, bbk::T, 0, st>>>(P);
+    } else {
+        if (e->ordered) bbk::resolve_kernel<true, false, false><<<P.ntiles, bbk::T, 0, st>>>(P);
+        else bbk::resolve_kernel<false, false, false><<<P.ntiles, bbk::T, 0, st>>>(P);
+    }
     CK(cudaGetLastError());
     e->launches++;
+    if (feedback) {
+        const int slot = (int)(P.epoch % bb_engine::FB);
+        if (cudaMemcpyAsync(e->h_fb + 4 * slot, d_totals, 16, cudaMemcpyDeviceToHost, st) == cudaSuccess) { e->fb_epoch[slot] = P.epoch; e->fb_n[slot] = n; }
+        else cudaGetLastError();
+    }
     return BB_OK;
 }
 
@@ -793,7 +844,7 @@ int bb_resolve_batch_device(bb_engine* e, const uint8_t* d_pkts, const uint32_t*
         si = e->n_dev_streams++; e->dev_stream[si] = stream; e->dev_desc[si] = dsc;
     }
     return launch(e, e->dev_desc[si], d_pkts, d_pkt_off, n, seed, qidx_base, d_out, out_cap, d_out_off, d_out_len, d_status, d_miss_idx,
-                  d_totals, (cudaStream_t)stream);
+                  d_totals, (cudaStream_t)stream, nullptr, 0, true);
 }
 
 int bb_resolve_submit_ex(bb_engine* e, int slot, const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed,
@@ -862,6 +913,7 @@ int bb_resolve_wait(bb_engine* e, int slot) {
     CK(cudaSetDevice(e->device));
     CK(cudaEventSynchronize(s.ev));
     const uint32_t total = s.n ? s.h_totals[0] : 0, nmiss = s.n ? s.h_totals[1] : 0;
+    if (s.n) e->mean_resp = total / s.n;
     const bool ovf = s.n && s.h_totals[2] == s.epoch;
     if (ovf || total > s.out_cap) { cudaStreamSynchronize(s.stream); return BB_ERR_CAPACITY; }
     if (s.zero_copy) { *s.n_miss = nmiss; return BB_OK; }        // everything is already in the caller's buffers
@@ -1065,8 +1117,8 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     P.regions = 1; P.in_stride = s->reg_size; P.out_stride = s->out_stride; P.off_stride = s->off_stride; P.len_stride = s->len_stride;
     P.status_stride = s->status_stride; P.miss_stride = s->miss_stride; P.totals_stride = s->totals_stride; P.desc_stride = s->desc_stride;
     const dim3 grid(P.ntiles, s->nranks);
-    if (e->ordered) bbk::resolve_kernel<true, true><<<grid, bbk::T, 0, main>>>(P);
-    else bbk::resolve_kernel<false, true><<<grid, bbk::T, 0, main>>>(P);
+    if (e->ordered) bbk::resolve_kernel<true, true, true><<<grid, bbk::T, 0, main>>>(P);
+    else bbk::resolve_kernel<false, true, true><<<grid, bbk::T, 0, main>>>(P);
     CK(cudaGetLastError());
     s->resolve_epoch = P.epoch;
     e->launches++;

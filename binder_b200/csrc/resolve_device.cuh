@@ -12,11 +12,13 @@ constexpr int S_IN = 8192;                // staged input bytes per tile
 constexpr int CAPW = 12288;               // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
-constexpr int WIN = CAPW;                  // a tile whose responses total at most this is staged in shared memory
-// copy jobs of a big tile, in four lists by length class (<= 16, <= 32, <= 64, longer): the lists live in the staging
-// buffer, which a big tile does not use; a response whose jobs do not fit is written whole by its thread
-constexpr int TASK_CAP0 = 640, TASK_CAP1 = 400, TASK_CAP2 = 400, TASK_CAP3 = 128;
-static_assert((TASK_CAP0 + TASK_CAP1 + TASK_CAP2 + TASK_CAP3) * 8 <= S_OUT, "the job lists alias the staging buffer");
+constexpr int WIN = CAPW - MAXRESP;        // output window of one emit round: a response STARTING in it ends inside the buffer
+// copy jobs of a big tile (the service variant of the kernel), in four lists by length class (<= 16, <= 32, <= 64, longer);
+// a response whose jobs do not fit is written whole by its thread
+constexpr int TASK_CAP0 = 448, TASK_CAP1 = 256, TASK_CAP2 = 256, TASK_CAP3 = 64;
+constexpr int TASKCAP = TASK_CAP0 + TASK_CAP1 + TASK_CAP2 + TASK_CAP3;       // 1024 jobs = 8 KB of shared memory
+constexpr int NROUNDS = 16;               // emit rounds of a big tile (4 bits in a job)
+static_assert(T * MAXRESP <= NROUNDS * (CAPW - MAXRESP), "a tile of maximal responses fits the rounds");
 constexpr uint32_t NONE16 = 0xFFFF;
 
 constexpr uint64_t D_FLAG_A = 1ull << 62, D_FLAG_P = 2ull << 62, D_VAL = (1ull << 62) - 1;
@@ -1086,13 +1088,15 @@ __device__ __forceinline__ void copy_arena_w(W& w, const uint8_t* src, uint32_t 
 }
 
 // ---- copy jobs: a service answer as independent pieces (engine.cu runs them, any thread any job) ---------------
-// word 1: tile offset of the first byte (18 bits) | length (13 bits) << 18 | source is a shared address << 31
+// word 1: tile offset of the first byte (18 bits) | emit round of its response (4 bits) << 18 | length (9 bits) << 22 |
+// source is a shared address << 31
 struct Task { uint32_t src, w; };
-constexpr uint32_t TASK_LEN_MAX = 8191;
+constexpr uint32_t TASK_LEN_MAX = 511;
+__device__ __forceinline__ uint32_t task_word(uint32_t dst, uint32_t round, uint32_t len, uint32_t sm) { return dst | (round << 18) | (len << 22) | (sm << 31); }
 __device__ __forceinline__ uint32_t task_dst(const Task& t) { return t.w & 0x3FFFFu; }
-__device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 18) & 0x1FFFu; }
+__device__ __forceinline__ uint32_t task_round(const Task& t) { return (t.w >> 18) & 15u; }
+__device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 22) & 0x1FFu; }
 __device__ __forceinline__ bool task_smem(const Task& t) { return (t.w >> 31) != 0; }
-
 __device__ __forceinline__ uint32_t task_class(uint32_t len) { return len <= 16 ? 0u : len <= 32 ? 1u : len <= 64 ? 2u : 3u; }
 // The jobs of one job-mode response, given where the response starts in its tile: (a prefix of) the children's ready RRs
 // in shuffled child order (lib/server.js:361-416) — the same walk as emit_fast's, counters included — and, for EDNS, the
@@ -1128,16 +1132,17 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
 }
 // counts the jobs per length class (the sizing pass of plan_service)
 struct TaskCount {           // (scalars: an array indexed by the class would live in local memory)
-    uint32_t n0, n1, n2, n3;
-    __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; }
+    uint32_t n0, n1, n2, n3, toolong;
+    __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; toolong |= len > TASK_LEN_MAX; }
 };
-// Run the jobs of one length class straight into global memory (tile byte x lives at g[goff + x]).  A thread takes several
-// jobs per pass and issues ALL their loads before it writes the first byte: the jobs are independent, and what bounds this
-// phase is how many DRAM round trips a thread makes one after another, not how many bytes it moves.
-__device__ __forceinline__ void job_write(const Params& P, const Task t, uint8_t* g, uint32_t goff, const uint4 x0, const uint4 x1, const uint4 x2, const uint4 x3) {
+// Run the jobs of one length class and one emit round into the (swizzled) staging buffer: tile byte x lives at shared
+// offset buf + delta + x.  A thread takes several jobs per pass and issues ALL their loads before it writes the first
+// byte: the jobs are independent, and what bounds this phase is how many DRAM round trips a thread makes one after
+// another, not how many bytes it moves.
+__device__ __forceinline__ void job_write(const Task t, uint32_t buf, uint32_t delta, const uint4 x0, const uint4 x1, const uint4 x2, const uint4 x3) {
     const uint32_t len = task_len(t);
     if (!len) return;
-    WrT<2, true> w; w.begin_global(g, goff + task_dst(t));
+    WrT<1, true> w; w.begin(buf, delta + task_dst(t));
     if (task_smem(t)) w.copy(t.src, len);
     else {
         put_chunk_w(w, x0, len);
@@ -1150,36 +1155,41 @@ __device__ __forceinline__ void job_write(const Params& P, const Task t, uint8_t
 __device__ __forceinline__ uint4 job_load(const Params& P, const Task t, uint32_t chunk) {
     return (!task_smem(t) && task_len(t) > 16 * chunk) ? ldg_stream((const uint4*)(P.arena + t.src) + chunk) : make_uint4(0, 0, 0, 0);
 }
+// job i of the list if it belongs to round k, else an empty job
+__device__ __forceinline__ Task job_take(const Task* tl, uint32_t i, uint32_t n, uint32_t k) {
+    Task t = { 0, 0 };
+    if (i < n) { t = tl[i]; if (task_round(t) != k) t.w = 0; }
+    return t;
+}
 template <int C>
-__device__ void run_jobs(const Params& P, const Task* tl, uint32_t n, uint32_t tid, uint8_t* g, uint32_t goff) {
-    const Task none = { 0, 0 };
+__device__ void run_jobs(const Params& P, const Task* tl, uint32_t n, uint32_t k, uint32_t tid, uint32_t buf, uint32_t delta) {
     const uint4 z = make_uint4(0, 0, 0, 0);
     if (C == 0) {                                      // <= 16 bytes: four jobs, four loads in flight
         for (uint32_t ti = tid; ti < n; ti += 4 * T) {
-            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none, c = ti + 2 * T < n ? tl[ti + 2 * T] : none, d = ti + 3 * T < n ? tl[ti + 3 * T] : none;
+            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k), c = job_take(tl, ti + 2 * T, n, k), d = job_take(tl, ti + 3 * T, n, k);
             const uint4 xa = job_load(P, a, 0), xb = job_load(P, b, 0), xc = job_load(P, c, 0), xd = job_load(P, d, 0);
-            job_write(P, a, g, goff, xa, z, z, z); job_write(P, b, g, goff, xb, z, z, z);
-            job_write(P, c, g, goff, xc, z, z, z); job_write(P, d, g, goff, xd, z, z, z);
+            job_write(a, buf, delta, xa, z, z, z); job_write(b, buf, delta, xb, z, z, z);
+            job_write(c, buf, delta, xc, z, z, z); job_write(d, buf, delta, xd, z, z, z);
         }
     } else if (C == 1) {                               // <= 32 bytes: two jobs, four loads
         for (uint32_t ti = tid; ti < n; ti += 2 * T) {
-            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none;
+            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k);
             const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), b0 = job_load(P, b, 0), b1 = job_load(P, b, 1);
-            job_write(P, a, g, goff, a0, a1, z, z); job_write(P, b, g, goff, b0, b1, z, z);
+            job_write(a, buf, delta, a0, a1, z, z); job_write(b, buf, delta, b0, b1, z, z);
         }
     } else if (C == 2) {                               // <= 64 bytes: two jobs, up to eight loads
         for (uint32_t ti = tid; ti < n; ti += 2 * T) {
-            const Task a = tl[ti], b = ti + T < n ? tl[ti + T] : none;
+            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k);
             const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), a2 = job_load(P, a, 2), a3 = job_load(P, a, 3);
             const uint4 b0 = job_load(P, b, 0), b1 = job_load(P, b, 1), b2 = job_load(P, b, 2), b3 = job_load(P, b, 3);
-            job_write(P, a, g, goff, a0, a1, a2, a3); job_write(P, b, g, goff, b0, b1, b2, b3);
+            job_write(a, buf, delta, a0, a1, a2, a3); job_write(b, buf, delta, b0, b1, b2, b3);
         }
     } else {                                           // longer: 64 bytes per round trip
         for (uint32_t ti = tid; ti < n; ti += T) {
-            const Task t = tl[ti];
+            const Task t = job_take(tl, ti, n, k);
             const uint32_t len = task_len(t);
             if (!len) continue;
-            WrT<2, true> w; w.begin_global(g, goff + task_dst(t));
+            WrT<1, true> w; w.begin(buf, delta + task_dst(t));
             if (task_smem(t)) w.copy(t.src, len); else copy_arena_w(w, P.arena + t.src, len);
             w.end();
         }

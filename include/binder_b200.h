@@ -143,6 +143,10 @@ int bb_engine_apply_update(bb_engine* e, bb_zone* z);
 int bb_engine_set_recursion_filter(bb_engine* e, const char* region_domain, const char* const* dc_names,
                                    uint32_t n_dc, int ptr_forwardable);
 int bb_engine_is_ready(const bb_engine* e);          /* zkCache.isReady(), lib/zk.js:55-58 */
+/* Two variants of the resolve kernel answer every batch identically: one sized for short answers (8 tiles of 128 queries
+ * per SM) and one for long service answers (copy jobs and emit rounds in shared memory, 7 tiles per SM).  0 (default): chosen
+ * per batch from the mean response size of the latest batch whose totals are known; 1: always the first; 2: always the second. */
+int bb_engine_set_kernel_profile(bb_engine* e, int profile);
 uint32_t bb_engine_max_batch(const bb_engine* e);        /* the limits the engine was created with */
 uint32_t bb_engine_max_batch_bytes(const bb_engine* e);
 

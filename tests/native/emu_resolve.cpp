@@ -75,47 +75,55 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             if (r[t].status == ST_MISS) miss_idx[mbase + my_m[t]] = q0 + t;
             odd |= r[t].rlen && (!(r[t].sp && !r[t].trunc) || r[t].rlen > (uint32_t)MAXRESP);
         }
-        const bool big = !odd && tile_bytes > (uint32_t)WIN;
-        if (odd || big) {
-            // straight to the output; in a big tile the job-mode service answers become copy jobs in four lists by length
-            // class (the kernel's reservation with atomics, here in thread order), run after every thread wrote its own part
-            const uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
-            std::vector<Task> lists[4];
-            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
-            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
-            struct Fill { std::vector<Task>* l; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { l[task_class(len)].push_back(Task{ src, dst | (len << 18) | (sm << 31) }); } };
+        if (odd) {
             for (uint32_t t = 0; t < nq; t++) {
                 if (!r[t].rlen) continue;
                 threadIdx.x = t;
-                bool jobs = big && r[t].ntask;
-                if (jobs) {
-                    TaskCount tc = { 0, 0, 0, 0 };
-                    plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, tc);
-                    const uint32_t n[4] = { tc.n0, tc.n1, tc.n2, tc.n3 };
-                    for (int c = 0; c < 4; c++) if (lists[c].size() + n[c] > cap[c]) jobs = false;
-                    if (jobs) { Fill f{ lists }; plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, f); }
-                }
                 if (!(r[t].sp && !r[t].trunc)) emit_response(P, r[t], out + gbase + my_o[t], qidx[t]);
-                else {
-                    WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t]));
-                    if (jobs) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
-                }
-            }
-            // the kernel's job passes, thread by thread (a thread takes jobs tid, tid + T, ... of each list)
-            for (uint32_t t = 0; t < (uint32_t)T; t++) {
-                run_jobs<0>(P, lists[0].data(), (uint32_t)lists[0].size(), t, out, (uint32_t)gbase);
-                run_jobs<1>(P, lists[1].data(), (uint32_t)lists[1].size(), t, out, (uint32_t)gbase);
-                run_jobs<2>(P, lists[2].data(), (uint32_t)lists[2].size(), t, out, (uint32_t)gbase);
-                run_jobs<3>(P, lists[3].data(), (uint32_t)lists[3].size(), t, out, (uint32_t)gbase);
+                else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
             }
         } else if (tile_bytes) {
-            const uint32_t shift = (uint32_t)(gbase & 15);
-            for (uint32_t t = 0; t < nq; t++) {
-                if (!r[t].rlen) continue;
+            // the service variant's emit: one round when the tile fits the window; else rounds over the responses that START in
+            // each window, the job-mode service answers as copy jobs in four lists by length class (the kernel reserves list
+            // space with atomics, here in thread order) run by every "thread" in every round
+            const bool big = tile_bytes > (uint32_t)WIN;
+            const uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
+            std::vector<Task> lists[4];
+            std::vector<uint8_t> jobs(nq, 0);
+            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
+            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
+            struct Fill { std::vector<Task>* l; uint32_t round; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { l[task_class(len)].push_back(Task{ src, task_word(dst, round, len, sm) }); } };
+            if (big) for (uint32_t t = 0; t < nq; t++) {
+                if (!r[t].rlen || !r[t].ntask) continue;
                 threadIdx.x = t;
-                WrT<1> w; w.begin((uint32_t)OFF_OUT, shift + my_o[t]); emit_fast(P, r[t], w, qidx[t]);
+                TaskCount tc = { 0, 0, 0, 0, 0 };
+                plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, tc);
+                const uint32_t n[4] = { tc.n0, tc.n1, tc.n2, tc.n3 };
+                bool ok = !tc.toolong;
+                for (int c = 0; c < 4; c++) if (lists[c].size() + n[c] > cap[c]) ok = false;
+                if (ok) { Fill f{ lists, my_o[t] / WIN }; plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, f); jobs[t] = 1; }
             }
-            for (uint32_t x = 0; x < tile_bytes; x++) out[gbase + x] = s_out[swz(shift + x)];     // the flush: g[x] <-> s_out[swz(shift + x)]
+            const uint32_t nr = big ? (tile_bytes + WIN - 1) / WIN : 1u;
+            for (uint32_t k = 0; k < nr; k++) {
+                uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes;
+                for (uint32_t t = 0; t < nq; t++) if (r[t].rlen) { const uint32_t kr = big ? my_o[t] / WIN : 0u; if (kr == k) x0 = std::min(x0, my_o[t]); else if (kr > k) x1 = std::min(x1, my_o[t]); }
+                if (x0 == 0xFFFFFFFFu) continue;
+                const uint32_t shift = (uint32_t)((gbase + x0) & 15), delta = shift - x0;
+                if (shift + (x1 - x0) > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                        // cannot happen: WIN + MAXRESP <= CAPW
+                for (uint32_t t = 0; t < nq; t++) {
+                    if (!r[t].rlen || (big ? my_o[t] / WIN : 0u) != k) continue;
+                    threadIdx.x = t;
+                    WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]);
+                    if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
+                }
+                if (big) for (uint32_t t = 0; t < (uint32_t)T; t++) {
+                    run_jobs<0>(P, lists[0].data(), (uint32_t)lists[0].size(), k, t, (uint32_t)OFF_OUT, delta);
+                    run_jobs<1>(P, lists[1].data(), (uint32_t)lists[1].size(), k, t, (uint32_t)OFF_OUT, delta);
+                    run_jobs<2>(P, lists[2].data(), (uint32_t)lists[2].size(), k, t, (uint32_t)OFF_OUT, delta);
+                    run_jobs<3>(P, lists[3].data(), (uint32_t)lists[3].size(), k, t, (uint32_t)OFF_OUT, delta);
+                }
+                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];              // the flush
+            }
         }
         gbase += tile_bytes; mbase += tile_miss;
     }
