@@ -320,10 +320,10 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
                 if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
             }
             if (big) {
-                run_jobs<0>(P, s_task + lbase[0], min(s_cnt[0], cap[0]), k, (uint32_t)tid, s_out_a, delta);
-                run_jobs<1>(P, s_task + lbase[1], min(s_cnt[1], cap[1]), k, (uint32_t)tid, s_out_a, delta);
-                run_jobs<2>(P, s_task + lbase[2], min(s_cnt[2], cap[2]), k, (uint32_t)tid, s_out_a, delta);
-                run_jobs<3>(P, s_task + lbase[3], min(s_cnt[3], cap[3]), k, (uint32_t)tid, s_out_a, delta);
+                run_chunks<0>(P, s_task + lbase[0], min(s_cnt[0], cap[0]), k, (uint32_t)tid, s_out_a + delta);
+                run_chunks<1>(P, s_task + lbase[1], min(s_cnt[1], cap[1]), k, (uint32_t)tid, s_out_a + delta);
+                run_chunks<2>(P, s_task + lbase[2], min(s_cnt[2], cap[2]), k, (uint32_t)tid, s_out_a + delta);
+                run_chunks<5>(P, s_task + lbase[3], min(s_cnt[3], cap[3]), k, (uint32_t)tid, s_out_a + delta);
             }
             __syncthreads();
             uint8_t* g = r_out + gbase;
@@ -360,6 +360,7 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
             if (lane == 0) {
                 const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
                 r_out_off[n] = tb; r_totals[0] = tb; r_totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); r_totals[3] = P.epoch;
+                if (!MULTI && P.fb) { P.fb[0] = tb; P.fb[1] = n; __threadfence_system(); P.fb[3] = P.epoch; }
                 if (MULTI) {                   // what a host reading only the totals needs to know about the region
                     r_totals[4] = n; r_totals[5] = r_n_dev ? r_n_dev[3] : 0u; r_totals[6] = P.err_in ? *(volatile const uint32_t*)P.err_in : 0u;
                 }
@@ -611,8 +612,8 @@ struct bb_engine {
     unsigned long long* stage_log = nullptr;
     // kernel variant per batch (bb_engine_set_kernel_profile): 0 = by the mean response size of the latest finished batch
     int profile = 0; uint32_t mean_resp = 0;
-    static constexpr int FB = 64;                                // device-path feedback: totals of recent launches, copied back asynchronously
-    uint32_t* h_fb = nullptr; uint32_t fb_epoch[FB] = {}; uint32_t fb_n[FB] = {};
+    static constexpr int FB = 64;                                // feedback ring (pinned): {response bytes, queries, -, epoch} written by a launch's last block
+    uint32_t* h_fb = nullptr;
     // the zone this engine last synchronised with (incremental updates only continue from that state)
     const bb_zone* zone = nullptr; uint64_t zone_gen = 0; uint64_t arena_cap = 0;
 };
@@ -806,11 +807,16 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     // Which variant: the service variant (copy jobs + emit rounds, 7 tiles per SM) pays off when answers are long.  Decided
     // from the latest batch whose totals are known: the host path learns them in bb_resolve_wait, the device path from a
     // 16-byte copy of d_totals that follows every launch (looked at only once its epoch has landed: no synchronisation).
-    for (int i = 0; i < bb_engine::FB; i++) {
-        const volatile uint32_t* f = e->h_fb + 4 * i;
-        if (e->fb_n[i] && f[3] == e->fb_epoch[i]) { e->mean_resp = f[0] / e->fb_n[i]; e->fb_n[i] = 0; }
+    {
+        uint32_t best = 0;                                       // the newest launch whose last block has reported
+        for (int i = 0; i < bb_engine::FB; i++) {
+            const volatile uint32_t* f = e->h_fb + 4 * i;
+            const uint32_t ep = f[3];
+            if (ep && f[1] && (best == 0 || (int32_t)(ep - best) > 0)) { best = ep; e->mean_resp = f[0] / f[1]; }
+        }
     }
     const bool svc = e->profile == 2 || (e->profile == 0 && e->mean_resp > 96);
+    P.fb = feedback ? e->h_fb + 4 * (P.epoch % bb_engine::FB) : nullptr;
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (svc) {
         if (e->ordered) bbk::resolve_kernel<true, false, true><<<P.ntiles, bbk::T, 0, st>>>(P);
@@ -821,11 +827,6 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     }
     CK(cudaGetLastError());
     e->launches++;
-    if (feedback) {
-        const int slot = (int)(P.epoch % bb_engine::FB);
-        if (cudaMemcpyAsync(e->h_fb + 4 * slot, d_totals, 16, cudaMemcpyDeviceToHost, st) == cudaSuccess) { e->fb_epoch[slot] = P.epoch; e->fb_n[slot] = n; }
-        else cudaGetLastError();
-    }
     return BB_OK;
 }
 

@@ -44,6 +44,8 @@ struct Params {
     uint32_t suffix_len, soa_len, recursion;   // copies of EngineConst scalars (constant bank instead of a global load)
     uint32_t lean_ok;        // dnsDomain is made of [a-z0-9_.-] only: a clean key hit proves the whole name passes lib/server.js:208
     uint32_t tcp;            // the batch arrived over TCP: no 512-byte / EDNS size limit (RFC 1035 4.2.2)
+    uint32_t* fb;            // when set (pinned host memory): the last block also leaves {response bytes, queries, -, epoch} here — what the
+                             // host picks the next batch's kernel variant from, without a copy or a synchronisation
     uint32_t* qidx_out;      // multi-region: each result's ingress index is also written here (host result mirrors)
     const uint32_t* err_in;  // multi-region: the shard's wait-timeout word, copied into totals[6]
     uint8_t* bounce;         // zero-copy results: device buffer (same offsets as `out`) that direct-emit tiles write to
@@ -1135,64 +1137,48 @@ struct TaskCount {           // (scalars: an array indexed by the class would li
     uint32_t n0, n1, n2, n3, toolong;
     __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; toolong |= len > TASK_LEN_MAX; }
 };
-// Run the jobs of one length class and one emit round into the (swizzled) staging buffer: tile byte x lives at shared
-// offset buf + delta + x.  A thread takes several jobs per pass and issues ALL their loads before it writes the first
-// byte: the jobs are independent, and what bounds this phase is how many DRAM round trips a thread makes one after
-// another, not how many bytes it moves.
-__device__ __forceinline__ void job_write(const Task t, uint32_t buf, uint32_t delta, const uint4 x0, const uint4 x1, const uint4 x2, const uint4 x3) {
-    const uint32_t len = task_len(t);
-    if (!len) return;
-    WrT<1, true> w; w.begin(buf, delta + task_dst(t));
-    if (task_smem(t)) w.copy(t.src, len);
-    else {
-        put_chunk_w(w, x0, len);
-        if (len > 16) put_chunk_w(w, x1, len - 16);
-        if (len > 32) put_chunk_w(w, x2, len - 32);
-        if (len > 48) put_chunk_w(w, x3, len - 48);
+// nb (1..16) bytes held in x to byte position pos of the (swizzled) staging buffer: whole words as words, the bytes a word
+// shares with a neighbouring piece — some other thread's — one by one
+__device__ __forceinline__ void put16_swz(uint32_t pos, const uint4 x, uint32_t nb) {
+    const uint32_t h = pos & 3u, s8 = 8 * h, base = pos - h, e = h + nb;      // the piece is stream bytes [h, e) counted from `base`
+    uint32_t w[5];
+    w[0] = x.x << s8; w[1] = __funnelshift_l(x.x, x.y, s8); w[2] = __funnelshift_l(x.y, x.z, s8);
+    w[3] = __funnelshift_l(x.z, x.w, s8); w[4] = __funnelshift_l(x.w, 0u, s8);
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+        const uint32_t lo = max(4u * j, h), hi = min(4u * j + 4u, e);
+        if (hi <= lo) continue;
+        const uint32_t a = base + 4 * j, sa = a ^ ((a >> 3) & 0x70u);
+        if (hi - lo == 4) sts32(sa, w[j]);
+        else for (uint32_t b = lo; b < hi; b++) sts8(sa + (b & 3u), (w[j] >> (8 * (b & 3u))) & 0xFF);
     }
-    w.end();
 }
-__device__ __forceinline__ uint4 job_load(const Params& P, const Task t, uint32_t chunk) {
-    return (!task_smem(t) && task_len(t) > 16 * chunk) ? ldg_stream((const uint4*)(P.arena + t.src) + chunk) : make_uint4(0, 0, 0, 0);
-}
-// job i of the list if it belongs to round k, else an empty job
-__device__ __forceinline__ Task job_take(const Task* tl, uint32_t i, uint32_t n, uint32_t k) {
-    Task t = { 0, 0 };
-    if (i < n) { t = tl[i]; if (task_round(t) != k) t.w = 0; }
-    return t;
-}
-template <int C>
-__device__ void run_jobs(const Params& P, const Task* tl, uint32_t n, uint32_t k, uint32_t tid, uint32_t buf, uint32_t delta) {
-    const uint4 z = make_uint4(0, 0, 0, 0);
-    if (C == 0) {                                      // <= 16 bytes: four jobs, four loads in flight
-        for (uint32_t ti = tid; ti < n; ti += 4 * T) {
-            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k), c = job_take(tl, ti + 2 * T, n, k), d = job_take(tl, ti + 3 * T, n, k);
-            const uint4 xa = job_load(P, a, 0), xb = job_load(P, b, 0), xc = job_load(P, c, 0), xd = job_load(P, d, 0);
-            job_write(a, buf, delta, xa, z, z, z); job_write(b, buf, delta, xb, z, z, z);
-            job_write(c, buf, delta, xc, z, z, z); job_write(d, buf, delta, xd, z, z, z);
+// Run the copy jobs of one list and one emit round into the staging buffer, a thread per 16-BYTE CHUNK of a job (a list holds
+// jobs of at most 16 << NCL bytes, so chunk v of the list is chunk v % (1 << NCL) of job v >> NCL): every thread does the same
+// small thing — one 16-byte load, one realigned write — four chunks per pass with all four loads issued first.  Tile byte
+// x lives at shared address delta + x (delta includes the buffer's address; the buffer is 1024-byte aligned).
+template <int NCL>
+__device__ void run_chunks(const Params& P, const Task* tl, uint32_t n, uint32_t k, uint32_t tid, uint32_t delta) {
+    const uint32_t nv = n << NCL;
+#pragma unroll 1
+    for (uint32_t v0 = tid; v0 < nv; v0 += 4 * T) {
+        uint4 x[4]; uint32_t pos[4], nb[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const uint32_t v = v0 + u * T;
+            nb[u] = 0; pos[u] = 0; x[u] = make_uint4(0, 0, 0, 0);
+            if (v < nv) {
+                const Task t = tl[v >> NCL];
+                const uint32_t off = 16u * (v & ((1u << NCL) - 1)), len = task_len(t);
+                if (task_round(t) == k && off < len) {
+                    nb[u] = min(16u, len - off); pos[u] = delta + task_dst(t) + off;
+                    if (task_smem(t)) { x[u].x = lds32(t.src + off); x[u].y = lds32(t.src + off + 4); x[u].z = lds32(t.src + off + 8); x[u].w = lds32(t.src + off + 12); }
+                    else x[u] = ldg_stream((const uint4*)(P.arena + t.src + off));
+                }
+            }
         }
-    } else if (C == 1) {                               // <= 32 bytes: two jobs, four loads
-        for (uint32_t ti = tid; ti < n; ti += 2 * T) {
-            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k);
-            const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), b0 = job_load(P, b, 0), b1 = job_load(P, b, 1);
-            job_write(a, buf, delta, a0, a1, z, z); job_write(b, buf, delta, b0, b1, z, z);
-        }
-    } else if (C == 2) {                               // <= 64 bytes: two jobs, up to eight loads
-        for (uint32_t ti = tid; ti < n; ti += 2 * T) {
-            const Task a = job_take(tl, ti, n, k), b = job_take(tl, ti + T, n, k);
-            const uint4 a0 = job_load(P, a, 0), a1 = job_load(P, a, 1), a2 = job_load(P, a, 2), a3 = job_load(P, a, 3);
-            const uint4 b0 = job_load(P, b, 0), b1 = job_load(P, b, 1), b2 = job_load(P, b, 2), b3 = job_load(P, b, 3);
-            job_write(a, buf, delta, a0, a1, a2, a3); job_write(b, buf, delta, b0, b1, b2, b3);
-        }
-    } else {                                           // longer: 64 bytes per round trip
-        for (uint32_t ti = tid; ti < n; ti += T) {
-            const Task t = job_take(tl, ti, n, k);
-            const uint32_t len = task_len(t);
-            if (!len) continue;
-            WrT<1, true> w; w.begin(buf, delta + task_dst(t));
-            if (task_smem(t)) w.copy(t.src, len); else copy_arena_w(w, P.arena + t.src, len);
-            w.end();
-        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) if (nb[u]) put16_swz(pos[u], x[u], nb[u]);
     }
 }
 

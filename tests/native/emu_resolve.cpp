@@ -117,10 +117,10 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                     if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
                 }
                 if (big) for (uint32_t t = 0; t < (uint32_t)T; t++) {
-                    run_jobs<0>(P, lists[0].data(), (uint32_t)lists[0].size(), k, t, (uint32_t)OFF_OUT, delta);
-                    run_jobs<1>(P, lists[1].data(), (uint32_t)lists[1].size(), k, t, (uint32_t)OFF_OUT, delta);
-                    run_jobs<2>(P, lists[2].data(), (uint32_t)lists[2].size(), k, t, (uint32_t)OFF_OUT, delta);
-                    run_jobs<3>(P, lists[3].data(), (uint32_t)lists[3].size(), k, t, (uint32_t)OFF_OUT, delta);
+                    run_chunks<0>(P, lists[0].data(), (uint32_t)lists[0].size(), k, t, (uint32_t)OFF_OUT + delta);
+                    run_chunks<1>(P, lists[1].data(), (uint32_t)lists[1].size(), k, t, (uint32_t)OFF_OUT + delta);
+                    run_chunks<2>(P, lists[2].data(), (uint32_t)lists[2].size(), k, t, (uint32_t)OFF_OUT + delta);
+                    run_chunks<5>(P, lists[3].data(), (uint32_t)lists[3].size(), k, t, (uint32_t)OFF_OUT + delta);
                 }
                 for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];              // the flush
             }
