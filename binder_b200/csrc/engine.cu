@@ -315,10 +315,14 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
             }
             const uint32_t shift = (uint32_t)((gbase + x0) & 15);             // same 16-byte phase in shared and global memory
             const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[swz(delta + x)]
-            if (my_len && kr == k) {
-                WrT<1> w; w.begin(s_out_a, delta + my_o);
-                if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
-            }
+            if (big) {                                                        // pieces are OR-ed into a zeroed buffer
+                for (uint32_t i = tid; i < (uint32_t)S_OUT / 16; i += T) ((uint4*)s_out)[i] = make_uint4(0, 0, 0, 0);
+                __syncthreads();
+                if (my_len && kr == k) {
+                    WrT<3> w; w.begin(s_out_a, delta + my_o);
+                    if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
+                }
+            } else if (my_len) { WrT<1> w; w.begin(s_out_a, delta + my_o); emit_fast(P, r, w, qidx); }
             if (big) {
                 run_chunks<0>(P, s_task + lbase[0], min(s_cnt[0], cap[0]), k, (uint32_t)tid, s_out_a + delta);
                 run_chunks<1>(P, s_task + lbase[1], min(s_cnt[1], cap[1]), k, (uint32_t)tid, s_out_a + delta);

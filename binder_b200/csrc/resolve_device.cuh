@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t lds32(uint32_t a) { uint32_t v; asm volatile
 __device__ __forceinline__ uint32_t lds8(uint32_t a) { uint32_t v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a)); return v; }
 __device__ __forceinline__ void sts32(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 __device__ __forceinline__ void sts8(uint32_t a, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
+__device__ __forceinline__ void sts_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" :: "r"(a), "r"(v) : "memory"); }
 #endif
 
 // byte-fed murmur (same result as bb::hash_key over the materialised key)
@@ -958,7 +959,8 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
 // only the bytes shared with the neighbouring responses (first / last partial word) go out as
 // single bytes, so two threads never write the same word.
 // MODE 0: plain shared buffer, 1: XOR-swizzled shared staging (buffer 1024-byte aligned, so the
-// swizzle applies to the address itself), 2: global memory (gbase + offset).
+// swizzle applies to the address itself), 2: global memory (gbase + offset), 3: like 1 for a ZEROED buffer that
+// copy jobs also fill (put16_or): single bytes — the words shared with a neighbouring piece — are OR-ed in.
 // HEADCHK: any put may be the one that completes the first word.  Without it the stream must open
 // with put4_first(), and every later store is a plain aligned word.
 template <int MODE, bool HEADCHK = false>
@@ -970,17 +972,18 @@ struct WrT {
     uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
     __device__ void begin(uint32_t buf, uint32_t off) {
         gbase = nullptr; head = off & 3u; acc = 0; fill = head;
-        if (MODE == 1) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
+        if (MODE == 1 || MODE == 3) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
     }
     // global: `g` must be 4-byte aligned (the output buffer is 16-byte aligned), off = byte offset in it
     __device__ void begin_global(uint8_t* g, uint32_t off) { base = 0; gbase = g; head = off & 3u; wp = off - head; acc = 0; fill = head; }
     __device__ __forceinline__ void st32(uint32_t pos, uint32_t v) {
         if (MODE == 2) *(uint32_t*)(gbase + pos) = v;
-        else if (MODE == 1) sts32(pos ^ ((pos >> 3) & 0x70u), v);
+        else if (MODE == 1 || MODE == 3) sts32(pos ^ ((pos >> 3) & 0x70u), v);
         else sts32(base + pos, v);
     }
     __device__ __forceinline__ void st8(uint32_t pos, uint32_t v) {
         if (MODE == 2) gbase[pos] = (uint8_t)v;
+        else if (MODE == 3) { const uint32_t a = pos & ~3u; sts_or(a ^ ((a >> 3) & 0x70u), (v & 0xFFu) << (8 * (pos & 3u))); }   // a word shared with a piece that is OR-ed in
         else if (MODE == 1) sts8(pos ^ ((pos >> 3) & 0x70u), v & 0xFF);
         else sts8(base + pos, v & 0xFF);
     }
@@ -1137,21 +1140,25 @@ struct TaskCount {           // (scalars: an array indexed by the class would li
     uint32_t n0, n1, n2, n3, toolong;
     __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; toolong |= len > TASK_LEN_MAX; }
 };
-// nb (1..16) bytes held in x to byte position pos of the (swizzled) staging buffer: whole words as words, the bytes a word
-// shares with a neighbouring piece — some other thread's — one by one
-__device__ __forceinline__ void put16_swz(uint32_t pos, const uint4 x, uint32_t nb) {
-    const uint32_t h = pos & 3u, s8 = 8 * h, base = pos - h, e = h + nb;      // the piece is stream bytes [h, e) counted from `base`
-    uint32_t w[5];
-    w[0] = x.x << s8; w[1] = __funnelshift_l(x.x, x.y, s8); w[2] = __funnelshift_l(x.y, x.z, s8);
-    w[3] = __funnelshift_l(x.z, x.w, s8); w[4] = __funnelshift_l(x.w, 0u, s8);
-#pragma unroll
-    for (int j = 0; j < 5; j++) {
-        const uint32_t lo = max(4u * j, h), hi = min(4u * j + 4u, e);
-        if (hi <= lo) continue;
-        const uint32_t a = base + 4 * j, sa = a ^ ((a >> 3) & 0x70u);
-        if (hi - lo == 4) sts32(sa, w[j]);
-        else for (uint32_t b = lo; b < hi; b++) sts8(sa + (b & 3u), (w[j] >> (8 * (b & 3u))) & 0xFF);
-    }
+// nb (1..16) bytes held in x to byte position pos of the (swizzled, zeroed) staging buffer, branch-free: the bytes are
+// shifted into place over five words and OR-ed in, so a word shared with the neighbouring piece — some other thread's —
+// needs no byte stores and no branches (short divergent branches are what this phase cannot afford: every taken branch is
+// an instruction-fetch bubble)
+__device__ __forceinline__ void put16_or(uint32_t pos, uint4 x, uint32_t nb) {
+    const uint32_t h = pos & 3u, s8 = 8 * h, base = pos - h;
+    // zero what lies beyond nb
+    x.x &= nb >= 4 ? 0xFFFFFFFFu : (1u << (8 * nb)) - 1;
+    x.y &= nb >= 8 ? 0xFFFFFFFFu : nb > 4 ? (1u << (8 * (nb - 4))) - 1 : 0u;
+    x.z &= nb >= 12 ? 0xFFFFFFFFu : nb > 8 ? (1u << (8 * (nb - 8))) - 1 : 0u;
+    x.w &= nb >= 16 ? 0xFFFFFFFFu : nb > 12 ? (1u << (8 * (nb - 12))) - 1 : 0u;
+    const uint32_t w0 = x.x << s8, w1 = __funnelshift_l(x.x, x.y, s8), w2 = __funnelshift_l(x.y, x.z, s8);
+    const uint32_t w3 = __funnelshift_l(x.z, x.w, s8), w4 = __funnelshift_l(x.w, 0u, s8);
+    const uint32_t a0 = base, a1 = base + 4, a2 = base + 8, a3 = base + 12, a4 = base + 16;
+    if (w0) sts_or(a0 ^ ((a0 >> 3) & 0x70u), w0);
+    if (w1) sts_or(a1 ^ ((a1 >> 3) & 0x70u), w1);
+    if (w2) sts_or(a2 ^ ((a2 >> 3) & 0x70u), w2);
+    if (w3) sts_or(a3 ^ ((a3 >> 3) & 0x70u), w3);
+    if (w4) sts_or(a4 ^ ((a4 >> 3) & 0x70u), w4);
 }
 // Run the copy jobs of one list and one emit round into the staging buffer, a thread per 16-BYTE CHUNK of a job (a list holds
 // jobs of at most 16 << NCL bytes, so chunk v of the list is chunk v % (1 << NCL) of job v >> NCL): every thread does the same
@@ -1178,7 +1185,7 @@ __device__ void run_chunks(const Params& P, const Task* tl, uint32_t n, uint32_t
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; u++) if (nb[u]) put16_swz(pos[u], x[u], nb[u]);
+        for (int u = 0; u < 4; u++) put16_or(pos[u], x[u], nb[u]);     // nb = 0: nothing but zeros to OR
     }
 }
 

@@ -45,6 +45,7 @@ static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, bb_emu_smem + 
 static inline uint32_t lds8(uint32_t a) { return bb_emu_smem[a]; }
 static inline void sts32(uint32_t a, uint32_t v) { memcpy(bb_emu_smem + a, &v, 4); }
 static inline void sts8(uint32_t a, uint32_t v) { bb_emu_smem[a] = (uint8_t)v; }
+static inline void sts_or(uint32_t a, uint32_t v) { uint32_t o; memcpy(&o, bb_emu_smem + a, 4); o |= v; memcpy(bb_emu_smem + a, &o, 4); }
 static inline uint32_t shl_clamp(uint32_t v, uint32_t n) { return n > 31 ? 0u : v << n; }     // shl.b32 clamps its count
 static inline unsigned long long gtime() { return 0; }
 static inline unsigned long long gtime_early() { return 0; }

@@ -110,11 +110,12 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
                 if (x0 == 0xFFFFFFFFu) continue;
                 const uint32_t shift = (uint32_t)((gbase + x0) & 15), delta = shift - x0;
                 if (shift + (x1 - x0) > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                        // cannot happen: WIN + MAXRESP <= CAPW
+                if (big) memset(s_out, 0, S_OUT);                                                         // pieces are OR-ed into a zeroed buffer
                 for (uint32_t t = 0; t < nq; t++) {
                     if (!r[t].rlen || (big ? my_o[t] / WIN : 0u) != k) continue;
                     threadIdx.x = t;
-                    WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]);
-                    if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]);
+                    if (big) { WrT<3> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]); if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]); }
+                    else { WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]); emit_fast(P, r[t], w, qidx[t]); }
                 }
                 if (big) for (uint32_t t = 0; t < (uint32_t)T; t++) {
                     run_chunks<0>(P, lists[0].data(), (uint32_t)lists[0].size(), k, t, (uint32_t)OFF_OUT + delta);
