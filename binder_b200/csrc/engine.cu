@@ -687,7 +687,10 @@ bb_engine* bb_engine_create(const bb_engine_opts* o, int* err) {
     // A probe wants ONE 32-byte sector of a table far larger than L2; by default an L2 miss fetches 128 bytes from
     // DRAM around it (measured: tools/micro/probe_gran.cu, 4 sectors of dram__bytes_read per sector asked for).
     // Sector-granular fetches cut the probe's DRAM traffic 4x; streaming reads ask for whole lines anyway.
-    if (cudaSetDevice(o->device) == cudaSuccess) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
+    if (cudaSetDevice(o->device) == cudaSuccess) {
+        const char* gr = getenv("BB_L2_GRAN");                     // experiments: 32 (default), 64, 128
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, gr ? (size_t)atoi(gr) : 32);
+    }
     cudaGetLastError();
     e->device = o->device; e->ordered = o->ordered_output ? 1 : 0;
     e->max_batch = o->max_batch ? o->max_batch : (1u << 20);
@@ -819,7 +822,9 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
             if (ep && f[1] && (best == 0 || (int32_t)(ep - best) > 0)) { best = ep; e->mean_resp = f[0] / f[1]; }
         }
     }
-    const bool svc = e->profile == 2 || (e->profile == 0 && e->mean_resp > 96);
+    // (the service variant measured slower than thread-per-response direct emit on every workload so far — DESIGN.md §5 —
+    // so it runs only when asked for: bb_engine_set_kernel_profile(e, 2) / BB_PROFILE=service)
+    const bool svc = e->profile == 2;
     P.fb = feedback ? e->h_fb + 4 * (P.epoch % bb_engine::FB) : nullptr;
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (svc) {
@@ -1122,8 +1127,8 @@ int bb_shard_resolve(bb_shard* s, uint64_t seed, int wait_for_peers, void* strea
     P.regions = 1; P.in_stride = s->reg_size; P.out_stride = s->out_stride; P.off_stride = s->off_stride; P.len_stride = s->len_stride;
     P.status_stride = s->status_stride; P.miss_stride = s->miss_stride; P.totals_stride = s->totals_stride; P.desc_stride = s->desc_stride;
     const dim3 grid(P.ntiles, s->nranks);
-    if (e->ordered) bbk::resolve_kernel<true, true, true><<<grid, bbk::T, 0, main>>>(P);
-    else bbk::resolve_kernel<false, true, true><<<grid, bbk::T, 0, main>>>(P);
+    if (e->ordered) bbk::resolve_kernel<true, true, false><<<grid, bbk::T, 0, main>>>(P);
+    else bbk::resolve_kernel<false, true, false><<<grid, bbk::T, 0, main>>>(P);
     CK(cudaGetLastError());
     s->resolve_epoch = P.epoch;
     e->launches++;
