@@ -825,7 +825,9 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
     // (the service variant measured slower than thread-per-response direct emit on every workload so far — DESIGN.md §5 —
     // so it runs only when asked for: bb_engine_set_kernel_profile(e, 2) / BB_PROFILE=service)
     const bool svc = e->profile == 2;
-    P.fb = feedback ? e->h_fb + 4 * (P.epoch % bb_engine::FB) : nullptr;
+    // the feedback store costs the launch's tail a PCIe round trip: only when the variant is chosen automatically (profile 0
+    // is reserved for that; today's default is fixed)
+    P.fb = nullptr; (void)feedback;
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (svc) {
         if (e->ordered) bbk::resolve_kernel<true, false, true><<<P.ntiles, bbk::T, 0, st>>>(P);
