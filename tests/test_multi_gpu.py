@@ -36,3 +36,18 @@ def test_sharded_single_rank(host_results):
                         '--master-addr', '127.0.0.1', '--master-port', '29534', os.path.join(ROOT, 'tools', 'multi_check.py')],
                        env=env, capture_output=True, text=True, timeout=600)
     assert 'MULTI_CHECK_OK world=1' in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('world', [2, 8])
+def test_sharded_ranks_collective_exchange(world):
+    """The same parity check with the routed records exchanged by ONE grouped ncclSend/ncclRecv all-to-all
+    (bb_shard_use_exchange_buffers, sync='nccl_a2a') instead of peer stores."""
+    import torch
+    if torch.cuda.device_count() < world:
+        pytest.skip('needs %d GPUs' % world)
+    env = dict(os.environ, BB_ORDERED='0', BB_HOST_RESULTS='0', BB_BATCH='20000', BB_ZONE='100000', BB_SYNC='nccl_a2a')
+    p = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
+                        '--master-addr', '127.0.0.1', '--master-port', str(29553 + world), os.path.join(ROOT, 'tools', 'multi_check.py')],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert 'MULTI_CHECK_OK world=%d' % world in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -15,7 +15,7 @@ from oracle_lib import Oracle
 def main():
     rank = int(os.environ['RANK']); world = int(os.environ['WORLD_SIZE']); lr = int(os.environ.get('LOCAL_RANK', rank))
     torch.cuda.set_device(lr)
-    dist.init_process_group('nccl')
+    dist.init_process_group('nccl', device_id=torch.device('cuda', lr))
     if rank == 0:
         build.build()
     dist.barrier()
