@@ -219,7 +219,7 @@ def main(args, rank, world, local_rank):
     if not args.no_e2e:
         ksteps = (max(8, min(K, 200)) + LANES - 1) // LANES * LANES
         h_ring = [(torch.from_numpy(x).pin_memory(), torch.from_numpy(o.view(np.int32)).pin_memory()) for x, o, _ in ring[:2]]
-        in_bytes = int(ring[0][1][B]) + (B + 1) * 4
+        in_bytes = int(np.mean([int(o[B]) for _, o, _ in ring[:2]])) + (B + 1) * 4
         if mode == 'replicas':
             import ctypes
             from binder_b200._lib import lib, check
@@ -249,14 +249,15 @@ def main(args, rank, world, local_rank):
             api = 'bb_resolve_submit/bb_resolve_wait per rank, pinned host buffers'
         else:
             se.set_host_results(True)
-            d_in = [(torch.empty_like(d[0][0]), torch.empty_like(d[0][1])) for _ in range(LANES)]
+            max_bytes = max(int(hp.numel()) for hp, _ in h_ring)              # the slices differ in size (mixed question types)
+            d_in = [(torch.empty(max_bytes, dtype=torch.uint8, device=dev), torch.empty_like(d[0][1])) for _ in range(LANES)]
             evs = [torch.cuda.Event() for _ in range(LANES)]
 
             def e2e_issue(k):
                 lane = k % LANES
                 hp, ho = h_ring[k % len(h_ring)]
                 with torch.cuda.stream(lane_streams[lane]):
-                    d_in[lane][0].copy_(hp, non_blocking=True); d_in[lane][1].copy_(ho, non_blocking=True)
+                    d_in[lane][0][:hp.numel()].copy_(hp, non_blocking=True); d_in[lane][1].copy_(ho, non_blocking=True)
                     se.step(d_in[lane][0].data_ptr(), d_in[lane][1].data_ptr(), B, rank * B, B1.SEED, lane_handles[lane], lane)
                     evs[lane].record(lane_streams[lane])
 
