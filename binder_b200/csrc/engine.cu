@@ -59,9 +59,10 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     __shared__ __align__(1024) uint8_t s_out[S_OUT];         // XOR-swizzled (swz()); 1024-aligned: WrT<1> swizzles addresses
     __shared__ uint32_t s_off[T + 1];
     __shared__ uint32_t s_wsum[8];
-    __shared__ uint32_t s_cnt[4];                              // big tiles: jobs in each of the four lists
     __shared__ uint32_t s_rstart[NROUNDS + 1];                 // big tiles: tile offset of each emit round's first response
-    __shared__ Task s_task[SVC ? TASKCAP : 1];                 // big tiles: the copy jobs
+    __shared__ uint32_t s_tstart[NROUNDS + 2];                 // big tiles: each emit round's first copy job; [NROUNDS + 1] = jobs that fit the list
+    __shared__ uint32_t s_wsum2[T / 32];                       // service variant: the warps' job counts (second scan)
+    __shared__ Task s_task[SVC ? TASKCAP : 1];                 // big tiles: the copy jobs, in tile-offset order
     __shared__ uint8_t s_perm[T];                              // which query of the tile each thread takes (grouped by question type)
     __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
@@ -154,16 +155,23 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     }
     const uint32_t my_len = r.rlen;
     const uint32_t my_miss = (qi < nq && r.status == ST_MISS) ? 1u : 0u;
+    // service variant: how many copy jobs this response becomes (its jobs go to the exclusive prefix of these counts)
+    uint32_t my_cnt = 0;
+    if (SVC && my_len && r.ntask) { TaskCount tc = { 0 }; plan_service(P, r, qidx, 0, 0, tc); my_cnt = tc.n; }
 
     STAMP(6);
     // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
     uint32_t v = my_len | (my_miss << 24);     // 128 x 1232 < 2^24
-    uint32_t inc = v;
-    for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_wsum[warp] = inc;
+    uint32_t inc = v, inc2 = my_cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t;
+        if (SVC) { uint32_t t2 = __shfl_up_sync(0xffffffffu, inc2, o); if (lane >= o) inc2 += t2; }
+    }
+    if (lane == 31) { s_wsum[warp] = inc; if (SVC) s_wsum2[warp] = inc2; }
     __syncthreads();
-    uint32_t wbase = 0, tot = 0;
+    uint32_t wbase = 0, tot = 0, tbase = inc2 - my_cnt, ttot = 0;
     for (int w = 0; w < T / 32; w++) { uint32_t x = s_wsum[w]; if (w < warp) wbase += x; tot += x; }
+    if (SVC) for (int w = 0; w < T / 32; w++) { uint32_t x = s_wsum2[w]; if (w < warp) tbase += x; ttot += x; }
     const uint32_t excl = wbase + inc - v;
     const uint32_t my_o = excl & 0xFFFFFF, my_mrank = excl >> 24;
     const uint32_t tile_bytes = tot & 0xFFFFFF, tile_miss = tot >> 24;
@@ -235,9 +243,11 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     // A BIG tile in the service variant of the kernel (SVC) goes through the window in ROUNDS and splits the work so that all
     // 128 threads stay busy with independent loads.  Round k = the responses that START in bytes [k*WIN, (k+1)*WIN) of the
     // tile (each at most MAXRESP long, which the buffer allows for past the window).  Their threads write the header and the
-    // question; the rest of a service answer — the children's ready RRs — became copy jobs (plan_service) in four lists
-    // by length class, tagged with the round, that ANY thread runs.  (A thread walking its own service record child by
-    // child is one dependent DRAM round trip after another, and warps of mixed answer sizes idle most lanes.)
+    // question; the rest of a service answer — the children's ready RRs — became copy jobs of at most 64 bytes
+    // (plan_service) that ANY thread runs, a thread per job: a thread walking its own service record child by child is one
+    // dependent DRAM round trip after another, and warps of mixed answer sizes idle most lanes.  The jobs of thread t sit
+    // at the exclusive prefix of the job counts (the second field of the CTA scan), so the list is sorted by tile offset and
+    // a round's jobs are one contiguous run of it — a round touches only its own jobs.
     // Without SVC a big tile writes straight to global memory, thread per response; so does, in either variant, a tile with a
     // query on the generic byte path or a response over MAXRESP (TCP).
     const bool odd_emit = my_len && (!(r.sp && !r.trunc) || my_len > (uint32_t)MAXRESP);
@@ -264,84 +274,72 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
             const uint32_t x0 = head + (nv << 4);
             if (x0 + tid < tile_bytes) g[x0 + tid] = src[x0 + tid];
         }
-    } else if (!overflow && tile_bytes) {
+    } else if (!overflow && SVC && tile_bytes > (uint32_t)WIN) {
         const uint32_t s_out_a = (uint32_t)__cvta_generic_to_shared(s_out);
-        const bool big = SVC && tile_bytes > (uint32_t)WIN;
-        const uint32_t nr = big ? (tile_bytes + WIN - 1) / WIN : 1u;          // <= NROUNDS
-        const uint32_t kr = big ? my_o / WIN : 0u;
+        const uint32_t nr = (tile_bytes + WIN - 1) / WIN;                     // <= NROUNDS
+        const uint32_t kr = my_o / WIN;
         bool jobs = false;
-        constexpr uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
-        constexpr uint32_t lbase[4] = { 0, TASK_CAP0, TASK_CAP0 + TASK_CAP1, TASK_CAP0 + TASK_CAP1 + TASK_CAP2 };
-        if (big) {
-            if (tid < 4) s_cnt[tid] = 0;
-            if (tid < 3) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;      // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-            if (tid <= NROUNDS) s_rstart[tid] = 0xFFFFFFFFu;
-            __syncthreads();
-            if (my_len) atomicMin(&s_rstart[kr], my_o);                       // where each round's first response starts
-            if (my_len && r.ntask) {                                          // count, reserve a run of each list, fill
-                const uint32_t opt_sp = (uint32_t)__cvta_generic_to_shared(s_opt);
-                TaskCount tc = { 0, 0, 0, 0, 0 };
-                plan_service(P, r, qidx, my_o, opt_sp, tc);
-                if (!tc.toolong) {
-                    const uint32_t a0 = tc.n0 ? atomicAdd(&s_cnt[0], tc.n0) : 0u, a1 = tc.n1 ? atomicAdd(&s_cnt[1], tc.n1) : 0u;
-                    const uint32_t a2 = tc.n2 ? atomicAdd(&s_cnt[2], tc.n2) : 0u, a3 = tc.n3 ? atomicAdd(&s_cnt[3], tc.n3) : 0u;
-                    if (a0 + tc.n0 <= cap[0] && a1 + tc.n1 <= cap[1] && a2 + tc.n2 <= cap[2] && a3 + tc.n3 <= cap[3]) {
-                        struct Fill {
-                            Task* tl; uint32_t i0, i1, i2, i3, round;
-                            __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) {
-                                uint32_t i;
-                                if (len <= 16) i = i0++; else if (len <= 32) i = i1++; else if (len <= 64) i = i2++; else i = i3++;
-                                tl[i].src = src; tl[i].w = task_word(dst, round, len, sm);
-                            }
-                        } fill = { s_task, lbase[0] + a0, lbase[1] + a1, lbase[2] + a2, lbase[3] + a3, kr };
-                        plan_service(P, r, qidx, my_o, opt_sp, fill);
-                        jobs = true;
-                    } else {                                                  // a list is full: empty jobs in what was reserved, and this thread writes it all
-                        for (uint32_t i = a0; i < a0 + tc.n0 && i < cap[0]; i++) { s_task[lbase[0] + i].src = 0; s_task[lbase[0] + i].w = 0; }
-                        for (uint32_t i = a1; i < a1 + tc.n1 && i < cap[1]; i++) { s_task[lbase[1] + i].src = 0; s_task[lbase[1] + i].w = 0; }
-                        for (uint32_t i = a2; i < a2 + tc.n2 && i < cap[2]; i++) { s_task[lbase[2] + i].src = 0; s_task[lbase[2] + i].w = 0; }
-                        for (uint32_t i = a3; i < a3 + tc.n3 && i < cap[3]; i++) { s_task[lbase[3] + i].src = 0; s_task[lbase[3] + i].w = 0; }
-                    }
-                }
-            }
-            __syncthreads();
+        if (tid < 4) s_opt[tid] = tid == 0 ? 0x04290000u : tid == 1 ? 0x000000B0u : 0u;          // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0, zero padded
+        if (tid <= NROUNDS) { s_rstart[tid] = 0xFFFFFFFFu; s_tstart[tid] = 0xFFFFFFFFu; }
+        if (tid == 0) s_tstart[NROUNDS + 1] = min(ttot, (uint32_t)TASKCAP);
+        __syncthreads();
+        if (my_len) { atomicMin(&s_rstart[kr], my_o); atomicMin(&s_tstart[kr], tbase); }         // where each round's responses and jobs start
+        if (my_cnt) {
+            // the list holds the jobs of the threads in front of the first one whose jobs do not fit; that thread and
+            // the ones behind it (their prefixes are larger still) write their responses themselves
+            if (tbase + my_cnt <= (uint32_t)TASKCAP) {
+                TaskFill fill = { s_task + tbase };
+                plan_service(P, r, qidx, my_o, (uint32_t)__cvta_generic_to_shared(s_opt), fill);
+                jobs = true;
+            } else atomicMin(&s_tstart[NROUNDS + 1], tbase);
         }
+        __syncthreads();
+        const uint32_t tv = s_tstart[NROUNDS + 1];
+        uint8_t* const g = r_out + gbase;
+#pragma unroll 1
         for (uint32_t k = 0; k < nr; k++) {
-            uint32_t x0 = 0, x1 = tile_bytes;                                 // this round's byte range of the tile
-            if (big) {
-                x0 = s_rstart[k];
-                if (x0 == 0xFFFFFFFFu) continue;                              // no response starts in this window (uniform)
-                for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; break; }
-            }
+            uint32_t x0 = s_rstart[k], x1 = tile_bytes;                       // this round's byte range of the tile
+            if (x0 == 0xFFFFFFFFu) continue;                                  // no response starts in this window (uniform)
+            uint32_t t0 = min(s_tstart[k], tv), t1 = tv;                      // and its run of the job list
+            for (uint32_t j = k + 1; j < nr; j++) if (s_rstart[j] != 0xFFFFFFFFu) { x1 = s_rstart[j]; t1 = min(s_tstart[j], tv); break; }
             const uint32_t shift = (uint32_t)((gbase + x0) & 15);             // same 16-byte phase in shared and global memory
-            const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[swz(delta + x)]
-            if (big) {                                                        // pieces are OR-ed into a zeroed buffer
-                for (uint32_t i = tid; i < (uint32_t)S_OUT / 16; i += T) ((uint4*)s_out)[i] = make_uint4(0, 0, 0, 0);
-                __syncthreads();
-                if (my_len && kr == k) {
-                    WrT<3> w; w.begin(s_out_a, delta + my_o);
-                    if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
-                }
-            } else if (my_len) { WrT<1> w; w.begin(s_out_a, delta + my_o); emit_fast(P, r, w, qidx); }
-            if (big) {
-                run_chunks<0>(P, s_task + lbase[0], min(s_cnt[0], cap[0]), k, (uint32_t)tid, s_out_a + delta);
-                run_chunks<1>(P, s_task + lbase[1], min(s_cnt[1], cap[1]), k, (uint32_t)tid, s_out_a + delta);
-                run_chunks<2>(P, s_task + lbase[2], min(s_cnt[2], cap[2]), k, (uint32_t)tid, s_out_a + delta);
-                run_chunks<5>(P, s_task + lbase[3], min(s_cnt[3], cap[3]), k, (uint32_t)tid, s_out_a + delta);
-            }
-            __syncthreads();
-            uint8_t* g = r_out + gbase;
-            uint32_t head = (uint32_t)((16 - ((gbase + x0) & 15)) & 15);      // up to 16-byte alignment of the global address
+            const uint32_t delta = shift - x0;                                // tile byte x <-> s_out[delta + x]: a linear buffer
+            uint32_t head = (16u - shift) & 15u;                              // up to 16-byte alignment of the global address
             if (head > x1 - x0) head = x1 - x0;
-            if (tid < (int)head) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
+            const uint32_t nz = (shift + (x1 - x0) + 15) >> 4;                // pieces are OR-ed into a zeroed buffer
+            for (uint32_t i = tid; i < nz; i += T) ((uint4*)s_out)[i] = make_uint4(0, 0, 0, 0);
+            __syncthreads();
+            if (my_len && kr == k) {
+                WrT<4> w; w.begin(s_out_a, delta + my_o);
+                if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
+            }
+            run_tasks(P, s_task, t0, t1, (uint32_t)tid, s_out_a + delta);
+            __syncthreads();
+            if (tid < (int)head) g[x0 + tid] = s_out[delta + x0 + tid];
             x0 += head;
             const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(delta + x0 + 16 * i));
+            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + delta + x0 + 16 * i);
             x0 += nv << 4;
-            if (x0 + tid < x1) g[x0 + tid] = s_out[swz(delta + x0 + tid)];
+            if (x0 + tid < x1) g[x0 + tid] = s_out[delta + x0 + tid];
             if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
         }
         STAMP(9);
+    } else if (!overflow && tile_bytes) {
+        const uint32_t shift = (uint32_t)(gbase & 15);                       // same 16-byte phase in shared and global memory
+        if (my_len) { WrT<1> w; w.begin((uint32_t)__cvta_generic_to_shared(s_out), shift + my_o); emit_fast(P, r, w, qidx); }
+        __syncthreads();
+        STAMP(9);
+        uint8_t* g = r_out + gbase;                                           // g[x] <-> s_out[swz(shift + x)]
+        uint32_t x0 = 0;
+        const uint32_t x1 = tile_bytes;
+        uint32_t head = (uint32_t)((16 - (gbase & 15)) & 15);                 // up to 16-byte alignment of the global address
+        if (head > x1) head = x1;
+        if (tid < (int)head) g[tid] = s_out[swz(shift + tid)];
+        x0 = head;
+        const uint32_t nv = (x1 - x0) >> 4;
+        for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + swz(shift + x0 + 16 * i));
+        x0 += nv << 4;
+        if (x0 + tid < x1) g[x0 + tid] = s_out[swz(shift + x0 + tid)];
     }
 
     STAMP(10);

@@ -13,11 +13,12 @@ constexpr int CAPW = 12288;               // output staging window per flush rou
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
 constexpr int WIN = CAPW - MAXRESP;        // output window of one emit round: a response STARTING in it ends inside the buffer
-// copy jobs of a big tile (the service variant of the kernel), in four lists by length class (<= 16, <= 32, <= 64, longer);
-// a response whose jobs do not fit is written whole by its thread
-constexpr int TASK_CAP0 = 448, TASK_CAP1 = 256, TASK_CAP2 = 256, TASK_CAP3 = 64;
-constexpr int TASKCAP = TASK_CAP0 + TASK_CAP1 + TASK_CAP2 + TASK_CAP3;       // 1024 jobs = 8 KB of shared memory
-constexpr int NROUNDS = 16;               // emit rounds of a big tile (4 bits in a job)
+// copy jobs of a big tile (the service variant of the kernel): ONE list in tile-offset order (a thread's jobs sit at the
+// exclusive prefix of the job counts, so the list is sorted by destination and every emit round owns a contiguous run
+// of it); a response whose jobs do not fit is written whole by its thread
+constexpr int TASKCAP = 1024;             // jobs = 8 KB of shared memory
+constexpr int TASK_BYTES = 64;            // a job copies at most this much: four 16-byte chunks, all loaded before the first is written
+constexpr int NROUNDS = 16;               // emit rounds of a big tile
 static_assert(T * MAXRESP <= NROUNDS * (CAPW - MAXRESP), "a tile of maximal responses fits the rounds");
 constexpr uint32_t NONE16 = 0xFFFF;
 
@@ -960,7 +961,8 @@ __device__ void emit_response(const Params& P, const Res& r, uint8_t* dst, uint3
 // single bytes, so two threads never write the same word.
 // MODE 0: plain shared buffer, 1: XOR-swizzled shared staging (buffer 1024-byte aligned, so the
 // swizzle applies to the address itself), 2: global memory (gbase + offset), 3: like 1 for a ZEROED buffer that
-// copy jobs also fill (put16_or): single bytes — the words shared with a neighbouring piece — are OR-ed in.
+// copy jobs also fill (put16_or): single bytes — the words shared with a neighbouring piece — are OR-ed in; 4: like 3
+// without the swizzle (the service variant's big tiles: lanes write pieces ~50 bytes apart, which spread over the banks by themselves).
 // HEADCHK: any put may be the one that completes the first word.  Without it the stream must open
 // with put4_first(), and every later store is a plain aligned word.
 template <int MODE, bool HEADCHK = false>
@@ -972,18 +974,20 @@ struct WrT {
     uint32_t head;       // bytes of the FIRST word that belong to the previous response (0..3)
     __device__ void begin(uint32_t buf, uint32_t off) {
         gbase = nullptr; head = off & 3u; acc = 0; fill = head;
-        if (MODE == 1 || MODE == 3) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
+        if (MODE == 1 || MODE == 3 || MODE == 4) { base = 0; wp = buf + off - head; } else { base = buf; wp = off - head; }
     }
     // global: `g` must be 4-byte aligned (the output buffer is 16-byte aligned), off = byte offset in it
     __device__ void begin_global(uint8_t* g, uint32_t off) { base = 0; gbase = g; head = off & 3u; wp = off - head; acc = 0; fill = head; }
     __device__ __forceinline__ void st32(uint32_t pos, uint32_t v) {
         if (MODE == 2) *(uint32_t*)(gbase + pos) = v;
         else if (MODE == 1 || MODE == 3) sts32(pos ^ ((pos >> 3) & 0x70u), v);
+        else if (MODE == 4) sts32(pos, v);
         else sts32(base + pos, v);
     }
     __device__ __forceinline__ void st8(uint32_t pos, uint32_t v) {
         if (MODE == 2) gbase[pos] = (uint8_t)v;
         else if (MODE == 3) { const uint32_t a = pos & ~3u; sts_or(a ^ ((a >> 3) & 0x70u), (v & 0xFFu) << (8 * (pos & 3u))); }   // a word shared with a piece that is OR-ed in
+        else if (MODE == 4) sts_or(pos & ~3u, (v & 0xFFu) << (8 * (pos & 3u)));
         else if (MODE == 1) sts8(pos ^ ((pos >> 3) & 0x70u), v & 0xFF);
         else sts8(base + pos, v & 0xFF);
     }
@@ -1093,19 +1097,19 @@ __device__ __forceinline__ void copy_arena_w(W& w, const uint8_t* src, uint32_t 
 }
 
 // ---- copy jobs: a service answer as independent pieces (engine.cu runs them, any thread any job) ---------------
-// word 1: tile offset of the first byte (18 bits) | emit round of its response (4 bits) << 18 | length (9 bits) << 22 |
-// source is a shared address << 31
+// word 1: tile offset of the first byte (18 bits) | length 1..TASK_BYTES (7 bits) << 18 | source is a shared address << 25 |
+// the source does not end in zero padding << 26 (a run of SRV answers cut short by truncation: its tail is masked)
 struct Task { uint32_t src, w; };
-constexpr uint32_t TASK_LEN_MAX = 511;
-__device__ __forceinline__ uint32_t task_word(uint32_t dst, uint32_t round, uint32_t len, uint32_t sm) { return dst | (round << 18) | (len << 22) | (sm << 31); }
+__device__ __forceinline__ uint32_t task_word(uint32_t dst, uint32_t len, uint32_t sm, uint32_t exact) { return dst | (len << 18) | (sm << 25) | (exact << 26); }
 __device__ __forceinline__ uint32_t task_dst(const Task& t) { return t.w & 0x3FFFFu; }
-__device__ __forceinline__ uint32_t task_round(const Task& t) { return (t.w >> 18) & 15u; }
-__device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 22) & 0x1FFu; }
-__device__ __forceinline__ bool task_smem(const Task& t) { return (t.w >> 31) != 0; }
-__device__ __forceinline__ uint32_t task_class(uint32_t len) { return len <= 16 ? 0u : len <= 32 ? 1u : len <= 64 ? 2u : 3u; }
-// The jobs of one job-mode response, given where the response starts in its tile: (a prefix of) the children's ready RRs
+__device__ __forceinline__ uint32_t task_len(const Task& t) { return (t.w >> 18) & 0x7Fu; }
+__device__ __forceinline__ bool task_smem(const Task& t) { return (t.w >> 25) & 1u; }
+__device__ __forceinline__ bool task_exact(const Task& t) { return (t.w >> 26) & 1u; }
+// The pieces of one job-mode response, given where the response starts in its tile: (a prefix of) the children's ready RRs
 // in shuffled child order (lib/server.js:361-416) — the same walk as emit_fast's, counters included — and, for EDNS, the
-// OPT (from `opt_sp`, a shared address holding its 11 bytes).  The header and the question are the owning thread's.
+// OPT (from `opt_sp`, a shared address holding its 11 bytes, zero padded to 16).  The header and the question are the
+// owning thread's.  Every arena piece ends in zero padding up to the next multiple of 16 (zone_build.cpp pads each part
+// of a child's block with zeros) unless it is a run of SRV answers cut short (`exact`).
 template <class Sink>
 __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint32_t my_o, uint32_t opt_sp, Sink& sink) {
     const bool srv = r.rk == RK_SVC_SRV;
@@ -1120,72 +1124,88 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
         const uint32_t wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
         if (srv) {
             const uint32_t n = min(np, left), len = n * kid_srv_len(wl, dwl);
-            if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0);
+            if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0, n < np);
             dst += len; left -= n;
-        } else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0); dst += 16; --left; }
+        } else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0, 0); dst += 16; --left; }
     }
-    if (r.edns) { sink.put(opt_sp, dst, 11, 1); dst += 11; }                  // the OPT leads the additional section
+    if (r.edns) { sink.put(opt_sp, dst, 11, 1, 0); dst += 11; }               // the OPT leads the additional section
     if (srv) {
         left = r.keep_add; pm = r.perm;
         for (uint32_t t = 0; t < r.n_walk && left; t++, pm >>= 4) {
             const uint32_t k = (uint32_t)pm & 15u, inf = sv.info(k);
             if (inf & KID_ADDR_NULL) continue;
             const uint32_t wl = (inf >> 8) & 0xFF;
-            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0); dst += kid_add_len(wl); --left;
+            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0, 0); dst += kid_add_len(wl); --left;
         }
     }
 }
-// counts the jobs per length class (the sizing pass of plan_service)
-struct TaskCount {           // (scalars: an array indexed by the class would live in local memory)
-    uint32_t n0, n1, n2, n3, toolong;
-    __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t) { n0 += len <= 16; n1 += len > 16 && len <= 32; n2 += len > 32 && len <= 64; n3 += len > 64; toolong |= len > TASK_LEN_MAX; }
+// a piece becomes ceil(len / TASK_BYTES) jobs
+struct TaskCount {
+    uint32_t n;
+    __device__ void put(uint32_t, uint32_t, uint32_t len, uint32_t, uint32_t) { n += (len + TASK_BYTES - 1) / TASK_BYTES; }
 };
-// nb (1..16) bytes held in x to byte position pos of the (swizzled, zeroed) staging buffer, branch-free: the bytes are
-// shifted into place over five words and OR-ed in, so a word shared with the neighbouring piece — some other thread's —
-// needs no byte stores and no branches (short divergent branches are what this phase cannot afford: every taken branch is
-// an instruction-fetch bubble)
-__device__ __forceinline__ void put16_or(uint32_t pos, uint4 x, uint32_t nb) {
+struct TaskFill {
+    Task* tl;
+    __device__ void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm, uint32_t exact) {
+        for (uint32_t off = 0; off < len; off += TASK_BYTES, tl++) {
+            const uint32_t l = min((uint32_t)TASK_BYTES, len - off);
+            tl->src = src + off; tl->w = task_word(dst + off, l, sm, exact && off + TASK_BYTES >= len);
+        }
+    }
+};
+// 16 bytes held in x to byte position pos of the (linear, zeroed) staging buffer: shifted into place over five words and
+// OR-ed in, so a word shared with the neighbouring piece — some other thread's — needs no byte stores and no branches.
+// Bytes of x beyond the piece must be zero (zero padding in the arena, or masked by the caller).
+#ifndef BB_HOST_EMU
+__device__ __forceinline__ void sts_or5(uint32_t base, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+    asm volatile("{\n\t.reg .pred p0, p1, p2, p3, p4;\n\t"
+                 "setp.ne.u32 p0, %1, 0;\n\tsetp.ne.u32 p1, %2, 0;\n\tsetp.ne.u32 p2, %3, 0;\n\tsetp.ne.u32 p3, %4, 0;\n\tsetp.ne.u32 p4, %5, 0;\n\t"
+                 "@p0 red.shared.or.b32 [%0], %1;\n\t@p1 red.shared.or.b32 [%0+4], %2;\n\t@p2 red.shared.or.b32 [%0+8], %3;\n\t"
+                 "@p3 red.shared.or.b32 [%0+12], %4;\n\t@p4 red.shared.or.b32 [%0+16], %5;\n\t}"
+                 :: "r"(base), "r"(w0), "r"(w1), "r"(w2), "r"(w3), "r"(w4) : "memory");
+}
+#endif
+__device__ __forceinline__ void put16_or(uint32_t pos, const uint4 x) {
     const uint32_t h = pos & 3u, s8 = 8 * h, base = pos - h;
-    // zero what lies beyond nb
+    const uint32_t w0 = x.x << s8, w1 = __funnelshift_l(x.x, x.y, s8), w2 = __funnelshift_l(x.y, x.z, s8);
+    const uint32_t w3 = __funnelshift_l(x.z, x.w, s8), w4 = __funnelshift_l(x.w, 0u, s8);
+    sts_or5(base, w0, w1, w2, w3, w4);
+}
+// zero the bytes of x from byte nb (0..16) on
+__device__ __forceinline__ uint4 keep_bytes(uint4 x, uint32_t nb) {
     x.x &= nb >= 4 ? 0xFFFFFFFFu : (1u << (8 * nb)) - 1;
     x.y &= nb >= 8 ? 0xFFFFFFFFu : nb > 4 ? (1u << (8 * (nb - 4))) - 1 : 0u;
     x.z &= nb >= 12 ? 0xFFFFFFFFu : nb > 8 ? (1u << (8 * (nb - 8))) - 1 : 0u;
     x.w &= nb >= 16 ? 0xFFFFFFFFu : nb > 12 ? (1u << (8 * (nb - 12))) - 1 : 0u;
-    const uint32_t w0 = x.x << s8, w1 = __funnelshift_l(x.x, x.y, s8), w2 = __funnelshift_l(x.y, x.z, s8);
-    const uint32_t w3 = __funnelshift_l(x.z, x.w, s8), w4 = __funnelshift_l(x.w, 0u, s8);
-    const uint32_t a0 = base, a1 = base + 4, a2 = base + 8, a3 = base + 12, a4 = base + 16;
-    if (w0) sts_or(a0 ^ ((a0 >> 3) & 0x70u), w0);
-    if (w1) sts_or(a1 ^ ((a1 >> 3) & 0x70u), w1);
-    if (w2) sts_or(a2 ^ ((a2 >> 3) & 0x70u), w2);
-    if (w3) sts_or(a3 ^ ((a3 >> 3) & 0x70u), w3);
-    if (w4) sts_or(a4 ^ ((a4 >> 3) & 0x70u), w4);
+    return x;
 }
-// Run the copy jobs of one list and one emit round into the staging buffer, a thread per 16-BYTE CHUNK of a job (a list holds
-// jobs of at most 16 << NCL bytes, so chunk v of the list is chunk v % (1 << NCL) of job v >> NCL): every thread does the same
-// small thing — one 16-byte load, one realigned write — four chunks per pass with all four loads issued first.  Tile byte
-// x lives at shared address delta + x (delta includes the buffer's address; the buffer is 1024-byte aligned).
-template <int NCL>
-__device__ void run_chunks(const Params& P, const Task* tl, uint32_t n, uint32_t k, uint32_t tid, uint32_t delta) {
-    const uint32_t nv = n << NCL;
+// Run the copy jobs [t0, t1) of one emit round into the staging buffer, a thread per job: up to four 16-byte loads, all
+// issued before the first write (one memory round trip per job, and every job of the tile's round is in flight at once:
+// the walk child by child that a thread per response would do is one dependent DRAM round trip after another), then the
+// realigned writes.  Tile byte x lives at shared address delta + x.
+__device__ __forceinline__ void run_tasks(const Params& P, const Task* tl, uint32_t t0, uint32_t t1, uint32_t tid, uint32_t delta) {
 #pragma unroll 1
-    for (uint32_t v0 = tid; v0 < nv; v0 += 4 * T) {
-        uint4 x[4]; uint32_t pos[4], nb[4];
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const uint32_t v = v0 + u * T;
-            nb[u] = 0; pos[u] = 0; x[u] = make_uint4(0, 0, 0, 0);
-            if (v < nv) {
-                const Task t = tl[v >> NCL];
-                const uint32_t off = 16u * (v & ((1u << NCL) - 1)), len = task_len(t);
-                if (task_round(t) == k && off < len) {
-                    nb[u] = min(16u, len - off); pos[u] = delta + task_dst(t) + off;
-                    if (task_smem(t)) { x[u].x = lds32(t.src + off); x[u].y = lds32(t.src + off + 4); x[u].z = lds32(t.src + off + 8); x[u].w = lds32(t.src + off + 12); }
-                    else x[u] = ldg_stream((const uint4*)(P.arena + t.src + off));
-                }
-            }
+    for (uint32_t i = t0 + tid; i < t1; i += T) {
+        const Task t = tl[i];
+        const uint32_t len = task_len(t), pos = delta + task_dst(t);
+        uint4 x0, x1 = make_uint4(0, 0, 0, 0), x2 = x1, x3 = x1;
+        if (task_smem(t)) {                                                   // the OPT: one chunk
+            x0.x = lds32(t.src); x0.y = lds32(t.src + 4); x0.z = lds32(t.src + 8); x0.w = lds32(t.src + 12);
+        } else {
+            const uint4* q = (const uint4*)(P.arena + t.src);
+            x0 = ldg_stream(q);
+            if (len > 16) x1 = ldg_stream(q + 1);
+            if (len > 32) x2 = ldg_stream(q + 2);
+            if (len > 48) x3 = ldg_stream(q + 3);
         }
-#pragma unroll
-        for (int u = 0; u < 4; u++) put16_or(pos[u], x[u], nb[u]);     // nb = 0: nothing but zeros to OR
+        if (task_exact(t)) {                                                  // rare: the source runs on past the piece
+            x0 = keep_bytes(x0, min(len, 16u)); x1 = keep_bytes(x1, len > 16 ? min(len - 16, 16u) : 0u);
+            x2 = keep_bytes(x2, len > 32 ? min(len - 32, 16u) : 0u); x3 = keep_bytes(x3, len > 48 ? len - 48 : 0u);
+        }
+        put16_or(pos, x0);
+        if (len > 16) put16_or(pos + 16, x1);
+        if (len > 32) put16_or(pos + 32, x2);
+        if (len > 48) put16_or(pos + 48, x3);
     }
 }
 

@@ -125,6 +125,11 @@ class Engine(object):
     def is_ready(self):
         return bool(lib().bb_engine_is_ready(self._h))
 
+    def set_kernel_profile(self, profile):
+        """Which variant of the resolve kernel batches run on (bb_engine_set_kernel_profile): 'auto' (0), 'small' (1:
+        thread per response), 'service' (2: long answers as copy jobs run by the whole tile).  Answers are identical."""
+        check(lib().bb_engine_set_kernel_profile(self._h, {'auto': 0, 'small': 1, 'service': 2}.get(profile, profile)))
+
     def launch_count(self):
         return int(lib().bb_engine_launch_count(self._h))
 

@@ -46,6 +46,9 @@ static inline uint32_t lds8(uint32_t a) { return bb_emu_smem[a]; }
 static inline void sts32(uint32_t a, uint32_t v) { memcpy(bb_emu_smem + a, &v, 4); }
 static inline void sts8(uint32_t a, uint32_t v) { bb_emu_smem[a] = (uint8_t)v; }
 static inline void sts_or(uint32_t a, uint32_t v) { uint32_t o; memcpy(&o, bb_emu_smem + a, 4); o |= v; memcpy(bb_emu_smem + a, &o, 4); }
+static inline void sts_or5(uint32_t base, uint32_t w0, uint32_t w1, uint32_t w2, uint32_t w3, uint32_t w4) {
+    if (w0) sts_or(base, w0); if (w1) sts_or(base + 4, w1); if (w2) sts_or(base + 8, w2); if (w3) sts_or(base + 12, w3); if (w4) sts_or(base + 16, w4);
+}
 static inline uint32_t shl_clamp(uint32_t v, uint32_t n) { return n > 31 ? 0u : v << n; }     // shl.b32 clamps its count
 static inline unsigned long long gtime() { return 0; }
 static inline unsigned long long gtime_early() { return 0; }

@@ -13,6 +13,10 @@ namespace bbk { unsigned long long bb_emu_lean_count = 0, bb_emu_general_count =
 #include <vector>
 
 uint8_t* bb_emu_smem = nullptr;
+// what the copy-job machinery saw so far: big tiles, job-mode responses, responses whose jobs did not fit the list, jobs
+// with a masked tail, emit rounds
+static unsigned long long g_job_stats[5];
+extern "C" void bb_emu_job_stats(unsigned long long* out, int reset) { for (int i = 0; i < 5; i++) { out[i] = g_job_stats[i]; if (reset) g_job_stats[i] = 0; } }
 extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
 
 namespace {
@@ -84,46 +88,55 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             }
         } else if (tile_bytes) {
             // the service variant's emit: one round when the tile fits the window; else rounds over the responses that START in
-            // each window, the job-mode service answers as copy jobs in four lists by length class (the kernel reserves list
-            // space with atomics, here in thread order) run by every "thread" in every round
+            // each window, the job-mode service answers as copy jobs in ONE list in tile-offset order (a thread's jobs at the
+            // exclusive prefix of the job counts), each round running its own contiguous run of the list
             const bool big = tile_bytes > (uint32_t)WIN;
-            const uint32_t cap[4] = { TASK_CAP0, TASK_CAP1, TASK_CAP2, TASK_CAP3 };
-            std::vector<Task> lists[4];
+            std::vector<Task> tl(TASKCAP);
             std::vector<uint8_t> jobs(nq, 0);
-            const uint32_t opt_words[3] = { 0x04290000u, 0x000000B0u, 0u };
-            memcpy(bb_emu_smem + OFF_OPT, opt_words, 12);
-            struct Fill { std::vector<Task>* l; uint32_t round; void put(uint32_t src, uint32_t dst, uint32_t len, uint32_t sm) { l[task_class(len)].push_back(Task{ src, task_word(dst, round, len, sm) }); } };
-            if (big) for (uint32_t t = 0; t < nq; t++) {
-                if (!r[t].rlen || !r[t].ntask) continue;
-                threadIdx.x = t;
-                TaskCount tc = { 0, 0, 0, 0, 0 };
-                plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, tc);
-                const uint32_t n[4] = { tc.n0, tc.n1, tc.n2, tc.n3 };
-                bool ok = !tc.toolong;
-                for (int c = 0; c < 4; c++) if (lists[c].size() + n[c] > cap[c]) ok = false;
-                if (ok) { Fill f{ lists, my_o[t] / WIN }; plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, f); jobs[t] = 1; }
+            std::vector<uint32_t> tbase(nq + 1, 0);
+            const uint32_t opt_words[4] = { 0x04290000u, 0x000000B0u, 0u, 0u };
+            memcpy(bb_emu_smem + OFF_OPT, opt_words, 16);
+            uint32_t tv = 0;
+            if (big) {
+                for (uint32_t t = 0; t < nq; t++) {
+                    uint32_t cnt = 0;
+                    if (r[t].rlen && r[t].ntask) { threadIdx.x = t; TaskCount tc = { 0 }; plan_service(P, r[t], qidx[t], 0, 0, tc); cnt = tc.n; }
+                    tbase[t + 1] = tbase[t] + cnt;
+                }
+                tv = std::min<uint32_t>(tbase[nq], TASKCAP);
+                g_job_stats[0]++;
+                for (uint32_t t = 0; t < nq; t++) {
+                    const uint32_t cnt = tbase[t + 1] - tbase[t];
+                    if (!cnt) continue;
+                    threadIdx.x = t;
+                    if (tbase[t] + cnt <= (uint32_t)TASKCAP) { TaskFill f = { tl.data() + tbase[t] }; plan_service(P, r[t], qidx[t], my_o[t], (uint32_t)OFF_OPT, f); jobs[t] = 1; g_job_stats[1]++;
+                        for (uint32_t i = tbase[t]; i < tbase[t] + cnt; i++) g_job_stats[3] += task_exact(tl[i]); }
+                    else { tv = std::min(tv, tbase[t]); g_job_stats[2]++; }
+                }
             }
             const uint32_t nr = big ? (tile_bytes + WIN - 1) / WIN : 1u;
             for (uint32_t k = 0; k < nr; k++) {
-                uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes;
-                for (uint32_t t = 0; t < nq; t++) if (r[t].rlen) { const uint32_t kr = big ? my_o[t] / WIN : 0u; if (kr == k) x0 = std::min(x0, my_o[t]); else if (kr > k) x1 = std::min(x1, my_o[t]); }
+                uint32_t x0 = 0xFFFFFFFFu, x1 = tile_bytes, t0 = 0xFFFFFFFFu, t1 = tv;
+                for (uint32_t t = 0; t < nq; t++) if (r[t].rlen) {
+                    const uint32_t kr = big ? my_o[t] / WIN : 0u;
+                    if (kr == k) { x0 = std::min(x0, my_o[t]); t0 = std::min(t0, tbase[t]); }
+                    else if (kr > k && my_o[t] < x1) { x1 = my_o[t]; t1 = std::min(tbase[t], tv); }
+                }
                 if (x0 == 0xFFFFFFFFu) continue;
+                g_job_stats[4] += big;
+                t0 = std::min(t0, tv);
                 const uint32_t shift = (uint32_t)((gbase + x0) & 15), delta = shift - x0;
                 if (shift + (x1 - x0) > (uint32_t)S_OUT) return BB_ERR_CAPACITY;                        // cannot happen: WIN + MAXRESP <= CAPW
                 if (big) memset(s_out, 0, S_OUT);                                                         // pieces are OR-ed into a zeroed buffer
                 for (uint32_t t = 0; t < nq; t++) {
                     if (!r[t].rlen || (big ? my_o[t] / WIN : 0u) != k) continue;
                     threadIdx.x = t;
-                    if (big) { WrT<3> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]); if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]); }
+                    if (big) { WrT<4> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]); if (jobs[t]) { emit_head_w(r[t], w); w.end(); } else emit_fast(P, r[t], w, qidx[t]); }
                     else { WrT<1> w; w.begin((uint32_t)OFF_OUT, delta + my_o[t]); emit_fast(P, r[t], w, qidx[t]); }
                 }
-                if (big) for (uint32_t t = 0; t < (uint32_t)T; t++) {
-                    run_chunks<0>(P, lists[0].data(), (uint32_t)lists[0].size(), k, t, (uint32_t)OFF_OUT + delta);
-                    run_chunks<1>(P, lists[1].data(), (uint32_t)lists[1].size(), k, t, (uint32_t)OFF_OUT + delta);
-                    run_chunks<2>(P, lists[2].data(), (uint32_t)lists[2].size(), k, t, (uint32_t)OFF_OUT + delta);
-                    run_chunks<5>(P, lists[3].data(), (uint32_t)lists[3].size(), k, t, (uint32_t)OFF_OUT + delta);
-                }
-                for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];              // the flush
+                if (big) for (uint32_t t = 0; t < (uint32_t)T; t++) run_tasks(P, tl.data(), t0, t1, t, (uint32_t)OFF_OUT + delta);
+                if (big) for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[delta + x];         // the flush (linear buffer)
+                else for (uint32_t x = x0; x < x1; x++) out[gbase + x] = s_out[swz(delta + x)];         // the flush (swizzled buffer)
             }
         }
         gbase += tile_bytes; mbase += tile_miss;

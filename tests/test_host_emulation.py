@@ -216,3 +216,54 @@ def test_fuzz_queries_mostly_lean(L):
     emu.resolve_batch(data, off, seed=1)
     lean, general = _path_counts(L)
     assert lean > general, (lean, general)
+
+
+def job_zone():
+    """Services whose answers exercise the copy-job machinery of big tiles: 3..14 children, some with several ports
+    (a truncated answer then cuts a run of SRV RRs short), a null-address child, a child with its own ttl."""
+    ent = [('/com/foo', None)]
+    for s in range(24):
+        ent.append(('/com/foo/svc%02d' % s, {'type': 'service', 'service': {'srvce': '_http', 'proto': '_tcp', 'port': 80 + s, 'ttl': 30 + s}}))
+        for k in range(3 + s % 12):
+            if (s + k) % 5 == 0:
+                rec = {'type': 'rr_host', 'rr_host': {'address': '10.%d.%d.1' % (s, k), 'ports': [8000 + k, 8100 + k, 8200 + k]}}
+            elif (s + k) % 7 == 3:
+                rec = {'type': 'load_balancer', 'load_balancer': {'address': None}}
+            elif (s + k) % 4 == 1:
+                rec = {'type': 'load_balancer', 'load_balancer': {'address': '10.%d.%d.2' % (s, k), 'ttl': 7 + k}}
+            else:
+                rec = {'type': 'load_balancer', 'load_balancer': {'address': '10.%d.%d.3' % (s, k)}}
+            ent.append(('/com/foo/svc%02d/%s%d' % (s, 'backend-number-' if k % 3 == 0 else 'lb', k), rec))
+    return H.snapshot(ent)
+
+
+@pytest.mark.parametrize('edns', [0, 1200, 700])
+def test_emulated_copy_jobs_edges(L, edns):
+    """Big tiles of service answers: more jobs than the list holds (the threads behind the first that does not fit write
+    their own answers), answers truncated in the middle of a multi-port child's SRV run (a job whose source does not
+    end in padding), the OPT as a job, several emit rounds per tile, upper-case names (not job mode) mixed in."""
+    snap = job_zone()
+    emu = EmuEngine(L, 'foo.com', snap)
+    orc = H.make_impl('oracle', 'foo.com', snap)
+    pk = []
+    for i in range(700):
+        s = (i * 7) % 24
+        name = 'svc%02d.foo.com' % s
+        if i % 11 == 0:
+            name = name.upper()[:5] + name[5:]
+        if i % 3 == 2:
+            pk.append(synth.make_query(name, 'A', i, edns=edns))
+        else:
+            pk.append(synth.make_query('_http._tcp.' + name, 'SRV', i, edns=edns))
+    data, off = synth.pack_batch(pk)
+    st = (ctypes.c_ulonglong * 5)()
+    L.bb_emu_job_stats(st, 1)
+    for seed in (1, 2):
+        assert_same(emu, orc, data, off, seed=seed)
+    L.bb_emu_job_stats(st, 1)
+    big, job_resp, unfit, masked, rounds = [int(x) for x in st]
+    assert big >= 10 and job_resp > 500 and rounds > 2 * big, list(st)
+    if edns == 1200:
+        assert unfit > 0, list(st)          # whole answers: more jobs than the list holds
+    else:
+        assert masked > 0, list(st)         # truncated answers: SRV runs cut short
