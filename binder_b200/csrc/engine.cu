@@ -40,6 +40,39 @@ __device__ __forceinline__ uint64_t warp_sum64(uint64_t v) {
     return v;
 }
 
+// ---- bulk asynchronous copies (the TMA unit's 1-D form) and the mbarrier they complete on ------------------------
+// A tile's packets are ONE contiguous, 16-byte aligned byte range of the batch: one thread hands the range to the
+// copy engine (cp.async.bulk global -> shared), the engine counts the bytes in on an mbarrier, everybody waits on the
+// barrier's phase.  No thread issues loads or stores for the staging and no register holds packet bytes in flight.
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");       // visible to the async proxy before the copy is issued
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {      // bytes: multiple of 16
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// wait for phase `parity` of the barrier; a bounded spin (a copy that never lands is a bug: trap instead of hanging the device)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0;; spin++) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        if (ok) return;
+        if (spin > (1u << 24)) __trap();
+    }
+}
+// shared -> global, issued by one thread after the writers' generic-proxy stores were fenced and the block synchronised
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_s2g(void* dst, uint32_t src, uint32_t bytes) {                            // bytes: multiple of 16
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(dst), "r"(src), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 #ifndef BB_MIN_BLOCKS
 #define BB_MIN_BLOCKS 8      /* 64 registers: 8 tiles (1024 threads) resident per SM */
 #endif
@@ -66,6 +99,7 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     __shared__ uint8_t s_perm[T];                              // which query of the tile each thread takes (grouped by question type)
     __shared__ uint32_t s_opt[4];                              // the OPT RR's 11 bytes, as a job source
     __shared__ unsigned long long s_prefix;
+    __shared__ __align__(8) unsigned long long s_bar;        // mbarrier of the input staging copy
     __shared__ __align__(16) uint8_t s_sfx[256];            // dnsDomain as wire labels, right-aligned (EngineConst::wire_tail)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const size_t ry = MULTI ? blockIdx.y : 0;
@@ -98,6 +132,18 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     const uint32_t nq = min((uint32_t)T, n - q0);
 
     // ---- stage this tile's packets ---------------------------------------------------------
+    // Thread 0 reads the tile's first and last offset and hands the byte range to the copy engine; meanwhile every thread
+    // loads its own packet's offset.  (The range is read again from s_off below: same memory, same values.)
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar);
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        const uint32_t f0 = r_pkt_off[q0], f1 = r_pkt_off[q0 + nq], fa = f0 & ~15u;
+        if (f1 >= f0 && f1 - fa <= (uint32_t)S_IN && f1 > fa) {
+            const uint32_t bytes = (f1 - fa + 15) & ~15u;
+            mbar_expect_tx(bar, bytes);
+            bulk_g2s((uint32_t)__cvta_generic_to_shared(s_in), r_pkts + fa, bytes, bar);
+        }
+    }
     if (tid < (int)nq) s_off[tid] = r_pkt_off[q0 + tid];
     if (tid == 0) s_off[nq] = r_pkt_off[q0 + nq];
     __syncthreads();
@@ -105,13 +151,7 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     const uint32_t b0 = s_off[0], b1 = s_off[nq];
     const uint32_t a0 = b0 & ~15u;
     const bool staged = b1 >= b0 && b1 - a0 <= S_IN;
-    if (staged) {
-        const uint4* src = (const uint4*)(r_pkts + a0);
-        uint4* dst = (uint4*)s_in;
-        const uint32_t nv = (b1 - a0 + 15) >> 4;
-        for (uint32_t i = tid; i < nv; i += T) dst[i] = __ldg(src + i);
-    }
-    __syncthreads();
+    if (staged && b1 > a0) mbar_wait(bar, 0);                 // the bytes have landed (and are visible to every waiting thread)
 
     STAMP(2);
     // ---- parse + lookup + size ----------------------------------------------------------------
@@ -157,7 +197,10 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
     const uint32_t my_miss = (qi < nq && r.status == ST_MISS) ? 1u : 0u;
     // service variant: how many copy jobs this response becomes (its jobs go to the exclusive prefix of these counts)
     uint32_t my_cnt = 0;
-    if (SVC && my_len && r.ntask) { TaskCount tc = { 0 }; plan_service(P, r, qidx, 0, 0, tc); my_cnt = tc.n; }
+    if (SVC && my_len && r.ntask) {
+        if (r.ntask >= 2) my_cnt = r.ntask - 2;          // whole answer: the count is a build-time sum
+        else { TaskCount tc = { 0 }; plan_service(P, r, qidx, 0, 0, tc); my_cnt = tc.n; }
+    }
 
     STAMP(6);
     // ---- CTA scan of (bytes, misses) ------------------------------------------------------------
@@ -314,14 +357,20 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
                 if (jobs) { emit_head_w(r, w); w.end(); } else emit_fast(P, r, w, qidx);
             }
             run_tasks(P, s_task, t0, t1, (uint32_t)tid, s_out_a + delta);
+            // The round's bytes leave as ONE bulk copy shared -> global (16-byte aligned on both sides: the buffer keeps the
+            // global address's phase), issued by one thread; the partial chunks at both ends go out as bytes.  Results
+            // in pinned host memory (zero-copy, P.bounce set) keep the 16-byte stores of all threads.
+            const bool bulk = r_bounce == nullptr;
+            if (bulk) fence_async_smem();                                     // this thread's writes, for the copy engine
             __syncthreads();
             if (tid < (int)head) g[x0 + tid] = s_out[delta + x0 + tid];
             x0 += head;
             const uint32_t nv = (x1 - x0) >> 4;
-            for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + delta + x0 + 16 * i);
+            if (bulk) { if (tid == 0 && nv) { bulk_s2g(g + x0, s_out_a + delta + x0, nv << 4); bulk_wait_read(); } }
+            else for (uint32_t i = tid; i < nv; i += T) *(uint4*)(g + x0 + 16 * i) = *(const uint4*)(s_out + delta + x0 + 16 * i);
             x0 += nv << 4;
             if (x0 + tid < x1) g[x0 + tid] = s_out[delta + x0 + tid];
-            if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round
+            if (k + 1 < nr) __syncthreads();                                  // the buffer is reused by the next round (thread 0 arrives once the engine has read it)
         }
         STAMP(9);
     } else if (!overflow && tile_bytes) {
@@ -362,7 +411,8 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
             if (lane == 0) {
                 const uint32_t tb = (uint32_t)(cur & ((1ull << D_MISS_SHIFT) - 1));
                 r_out_off[n] = tb; r_totals[0] = tb; r_totals[1] = (uint32_t)(cur >> D_MISS_SHIFT); r_totals[3] = P.epoch;
-                if (!MULTI && P.fb) { P.fb[0] = tb; P.fb[1] = n; __threadfence_system(); P.fb[3] = P.epoch; }
+                // one 16-byte store (one PCIe write, no fence, nothing waits for it): what the host picks the next batch's variant from
+                if (!MULTI && P.fb) *(uint4*)P.fb = make_uint4(tb, n, 0u, P.epoch);
                 if (MULTI) {                   // what a host reading only the totals needs to know about the region
                     r_totals[4] = n; r_totals[5] = r_n_dev ? r_n_dev[3] : 0u; r_totals[6] = P.err_in ? *(volatile const uint32_t*)P.err_in : 0u;
                 }
@@ -820,12 +870,10 @@ static int launch(bb_engine* e, unsigned long long* desc, const uint8_t* d_pkts,
             if (ep && f[1] && (best == 0 || (int32_t)(ep - best) > 0)) { best = ep; e->mean_resp = f[0] / f[1]; }
         }
     }
-    // (the service variant measured slower than thread-per-response direct emit on every workload so far — DESIGN.md §5 —
-    // so it runs only when asked for: bb_engine_set_kernel_profile(e, 2) / BB_PROFILE=service)
-    const bool svc = e->profile == 2;
-    // the feedback store costs the launch's tail a PCIe round trip: only when the variant is chosen automatically (profile 0
-    // is reserved for that; today's default is fixed)
-    P.fb = nullptr; (void)feedback;
+    // profile 0: the service variant when the latest known batch averaged >= 96 response bytes per query (its tiles are then
+    // "big": more than one staging window; measured on config 3/4: one launch 120 vs 150 us, config 2 prefers the small variant)
+    const bool svc = e->profile == 2 || (e->profile == 0 && e->mean_resp >= 96);
+    P.fb = (feedback && e->profile == 0) ? e->h_fb + 4 * (P.epoch % bb_engine::FB) : nullptr;
     // no memsets: the kernel leaves desc/counter zeroed for the next launch (self-cleaning)
     if (svc) {
         if (e->ordered) bbk::resolve_kernel<true, false, true><<<P.ntiles, bbk::T, 0, st>>>(P);

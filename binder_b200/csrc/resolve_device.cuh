@@ -71,7 +71,8 @@ struct Res {
     uint32_t keep_ans, keep_add, n_walk, nk;
     uint32_t status, rk, rcode, tc, opcode, rd, edns, trunc;
     uint32_t owner;          // route mode: rank that owns this query's lookup key
-    uint32_t ntask;          // 1: a service answer that can be assembled from copy jobs (plan_service): header + question by this thread, the RRs by anyone
+    uint32_t ntask;          // != 0: a service answer that can be assembled from copy jobs (plan_service): header + question by this thread, the
+                             // RRs by anyone.  1: count the jobs by walking the children; 2 + n: it is n jobs (whole answer: build-time sums)
 };
 
 __device__ __forceinline__ uint32_t lower8(uint32_t c) { return (c - 'A' < 26u) ? c + 32 : c; }
@@ -238,17 +239,22 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 // A service record in the arena (zone_image.h): 32-byte header, kid_info, fixed-stride child blocks.
 struct SvcView {
     const uint8_t* base; const uint8_t* arena;
-    uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports ; hflags,sp_len,dom_wl,sp[11],stride16
+    uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports,jobs_srv ; hflags,sp_len,dom_wl,sp[11],stride16
     __device__ void open(const uint8_t* arena_, uint32_t off) {
         arena = arena_; base = arena_ + off;
         h0 = ldg_stream((const uint4*)base); h1 = ldg_stream((const uint4*)base + 1);
+#ifndef BB_HOST_EMU
+        // kid_info follows the header: have its first sector (8 children) on the way while the header is still in flight
+        asm volatile("prefetch.global.L1 [%0];" :: "l"(base + sizeof(SvcHdr)));
+#endif
     }
     __device__ uint32_t ttl() const { return h0.x; }
     __device__ uint32_t nkids() const { return h0.y & 0xFFFF; }
     __device__ uint32_t n_valid() const { return h0.y >> 16; }
     __device__ uint32_t sum_ports() const { return h0.z & 0xFFFF; }
     __device__ uint32_t sum_wl() const { return h0.z >> 16; }
-    __device__ uint32_t sum_wl_ports() const { return h0.w; }
+    __device__ uint32_t sum_wl_ports() const { return h0.w & 0xFFFF; }
+    __device__ uint32_t jobs_srv() const { return h0.w >> 16; }
     __device__ uint32_t hflags() const { return h1.x & 0xFF; }
     __device__ uint32_t sp_len() const { return (h1.x >> 8) & 0xFF; }
     __device__ uint32_t dom_wl() const { return (h1.x >> 16) & 0xFF; }
@@ -326,6 +332,9 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
     if (fixed + ans_b + add_b <= r.maxsz) {
         r.keep_ans = n_ans; r.keep_add = n_add; r.rlen = fixed + ans_b + add_b;
         r.ntask = jobs_ok && (n_ans + n_add) && r.rlen <= (uint32_t)MAXRESP;
+        // a whole answer sized from the build-time sums: its job count is a build-time sum too (an A answer is one
+        // 16-byte RR per child), plus the OPT
+        if (r.ntask && sums) r.ntask = 2 + (srv ? sv.jobs_srv() : n_ans) + (r.edns ? 1u : 0u);
         return;
     }
     // truncation: keep the longest prefix of [answers..., additionals...] that fits

@@ -608,7 +608,7 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         }
         auto be16 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
         auto be32 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
-        uint64_t n_valid = 0, sum_ports = 0, sum_wl = 0, sum_wl_ports = 0;
+        uint64_t n_valid = 0, sum_ports = 0, sum_wl = 0, sum_wl_ports = 0, jobs_srv = 0;
         std::vector<std::vector<uint8_t>> blocks(kids.size());
         std::vector<uint32_t> info(kids.size(), 0);
         size_t stride = 16;
@@ -634,7 +634,11 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
             kr.wire_len = (uint8_t)kw.size(); kr.nports = (uint8_t)pl.size();
             if (kr.flags & KID_BAD_A) h.hflags |= SVC_BAD_A;
             if (kr.flags & KID_BAD_SRV) h.hflags |= SVC_BAD_SRV;
-            if (!(kr.flags & KID_ADDR_NULL)) { ++n_valid; sum_ports += pl.size(); sum_wl += kw.size(); sum_wl_ports += pl.size() * kw.size(); }
+            if (!(kr.flags & KID_ADDR_NULL)) {
+                ++n_valid; sum_ports += pl.size(); sum_wl += kw.size(); sum_wl_ports += pl.size() * kw.size();
+                // the pieces a whole SRV answer copies from this child: its run of SRV RRs and its additional RR, 64 bytes per job
+                jobs_srv += (pl.size() * kid_srv_len((uint32_t)kw.size(), (uint32_t)dom_wire.size() + 1) + 63) / 64 + (kid_add_len((uint32_t)kw.size()) + 63) / 64;
+            }
             info[ki] = (uint32_t)kr.flags | (uint32_t)kr.wire_len << 8 | (uint32_t)kr.nports << 16;
             // the block: KidRec | A answer | additional (pad 16) | SRV answers (pad 16)
             std::vector<uint8_t>& blk = blocks[ki];
@@ -656,8 +660,9 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         if (stride / 16 > 0xFFFF) return false;
         h.stride16 = (uint16_t)(stride / 16);
         // sums the kernel sizes an answer from without walking the children; a service too large for them is walked
-        if (n_valid > 0xFFFF || sum_ports > 0xFFFF || sum_wl > 0xFFFF) h.hflags |= SVC_BAD_A | SVC_BAD_SRV;
-        h.n_valid = (uint16_t)n_valid; h.sum_ports = (uint16_t)sum_ports; h.sum_wl = (uint16_t)sum_wl; h.sum_wl_ports = (uint32_t)sum_wl_ports;
+        if (n_valid > 0xFFFF || sum_ports > 0xFFFF || sum_wl > 0xFFFF || sum_wl_ports > 0xFFFF || jobs_srv > 0xFFFF) h.hflags |= SVC_BAD_A | SVC_BAD_SRV;
+        h.n_valid = (uint16_t)n_valid; h.sum_ports = (uint16_t)sum_ports; h.sum_wl = (uint16_t)sum_wl; h.sum_wl_ports = (uint16_t)sum_wl_ports;
+        h.jobs_srv = (uint16_t)jobs_srv;
         std::vector<uint8_t> rec(svc_blocks_off((uint32_t)kids.size()) + stride * kids.size(), 0);
         memcpy(rec.data(), &h, sizeof h);
         if (!info.empty()) memcpy(rec.data() + sizeof h, info.data(), 4 * info.size());

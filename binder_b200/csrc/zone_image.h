@@ -99,7 +99,8 @@ struct alignas(32) SvcHdr {
     uint16_t n_valid;        // of those, the ones with an address (not KID_ADDR_NULL): one A / one additional each
     uint16_t sum_ports;      // sum of nports over them: SRV answers
     uint16_t sum_wl;         // sum of wire_len over them
-    uint32_t sum_wl_ports;   // sum of nports * wire_len over them
+    uint16_t sum_wl_ports;   // sum of nports * wire_len over them
+    uint16_t jobs_srv;       // copy jobs of a whole SRV answer (resolve_device.cuh: a piece is ceil(len / 64) jobs), OPT not counted
     uint8_t  hflags;         // SVC_*
     uint8_t  sp_len;         // bytes of "_srvce._proto." on the wire = where the domain part of a matching SRV QNAME starts
     uint8_t  dom_wl;         // the service's fqdn as wire labels + terminator (what every SRV target ends with)

@@ -100,7 +100,10 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             if (big) {
                 for (uint32_t t = 0; t < nq; t++) {
                     uint32_t cnt = 0;
-                    if (r[t].rlen && r[t].ntask) { threadIdx.x = t; TaskCount tc = { 0 }; plan_service(P, r[t], qidx[t], 0, 0, tc); cnt = tc.n; }
+                    if (r[t].rlen && r[t].ntask) {
+                        threadIdx.x = t; TaskCount tc = { 0 }; plan_service(P, r[t], qidx[t], 0, 0, tc); cnt = tc.n;
+                        if (r[t].ntask >= 2 && r[t].ntask - 2 != cnt) return BB_ERR_ARG;          // the build-time job count must be the walk's
+                    }
                     tbase[t + 1] = tbase[t] + cnt;
                 }
                 tv = std::min<uint32_t>(tbase[nq], TASKCAP);
