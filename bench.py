@@ -149,6 +149,7 @@ class OracleLoader(object):
 
     def __init__(self, zone, recursion):
         self.zone, self.recursion, self.orc, self.err, self.secs = zone, recursion, None, None, 0.0
+        self.same, self.same_err, self.same_secs = None, None, 0.0
         self.th = threading.Thread(target=self._run, daemon=True)
         self.th.start()
 
@@ -161,6 +162,14 @@ class OracleLoader(object):
             self.secs = time.time() - t0
         except Exception as ex:          # reported by get()
             self.err = ex
+            return
+        try:                             # the second CPU arm: the same table image and algorithm on the host (oracle/same_table.py)
+            import same_table
+            t0 = time.time()
+            self.same = same_table.SameTable(self.zone.dns_domain, self.zone.jsonl, self.recursion)
+            self.same_secs = time.time() - t0
+        except Exception as ex:
+            self.same_err = repr(ex)
 
     def get(self):
         self.th.join()
@@ -183,6 +192,23 @@ def cpu_port(orc, data, off, budget_s=12.0):
                       '(single thread: %.0f queries/s on %d queries)' % (reps, n, cores, ns / min(t1), ns),
             'single_thread_value': ns / min(t1),
             'note': 'literal port: JSON-DOM walk + std::unordered_map<std::string> per query (oracle/oracle.cpp, -O2)'}
+
+
+def cpu_same_table(st, data, off, want_bytes, want_miss, per_q, seed=0, budget_s=8.0):
+    """SURVEY.md 8(d) "same open-addressed layout so the comparison isolates the processor": the word-wise device code
+    compiled for the host (-O3 -march=native) over the same zone image, all host threads; bounded sample."""
+    cores = os.cpu_count() or 1
+    n = len(off) - 1
+    ns = min(n, 65536)
+    s1, _, _ = st.timed_resolve(data[:int(off[ns]) + 16], off[:ns + 1], nthreads=1, repeat=1, resp_cap=per_q)
+    est = s1 * n / ns / max(cores * 0.5, 1)
+    reps = max(2, min(30, int(budget_s / max(est, 1e-3))))
+    sn, tb, tm = st.timed_resolve(data, off, seed=seed, nthreads=cores, repeat=reps, resp_cap=per_q)
+    return {'value': n / sn, 'unit': UNIT, 'cores': cores, 'kind': 'port (same table image, same word-wise algorithm: the device source compiled for the host)',
+            'sample': '%d x one %d-query batch of the same workload, best pass; all %d host threads (single thread: %.0f queries/s on %d queries)'
+                      % (reps, n, cores, ns / s1, ns),
+            'single_thread_value': ns / s1,
+            'parity': 'response bytes %d and misses %d %s the GPU result' % (tb, tm, 'equal' if (tb, tm) == (want_bytes, want_miss) else 'DIFFER from')}
 
 
 def workload_setup(args):
@@ -493,6 +519,14 @@ def run_single(args, local_rank):
             secondary[w]['parity'] = k2.check_oracle(orc, r2)
         cpu = cpu_port(orc, ring[0][0], ring[0][1])
         cpu['oracle_load_s'] = loader.secs
+        if loader.same is not None:
+            try:
+                cpu['same_table'] = cpu_same_table(loader.same, ring[0][0], ring[0][1], int(r0['tot'][0]), int(r0['tot'][1]), per_q, seed=SEED + 0)
+                cpu['same_table']['zone_build_s'] = loader.same_secs
+            except Exception as ex:
+                cpu['same_table'] = {'unavailable': repr(ex)}
+        else:
+            cpu['same_table'] = {'unavailable': loader.same_err}
 
     line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': 1, 'steps': K, 'warmup': args.warmup,
             'ms_per_step': ms_per_step, 'higher_is_better': True, 'scaling': 'strong' if wl == 'config4' else 'weak', 'vs_baseline': None,

@@ -847,7 +847,7 @@ __device__ __forceinline__ void res_init(Res& r) {
     r.ptr_tgt = NONE16; r.trunc = 0; r.perm = 0; r.ttl = r.val = 0; r.d_off = r.d_end = r.lastlen = 0;
 }
 #ifdef BB_HOST_EMU        /* the CPU emulation counts which front end settled each query (tests/test_host_emulation.py) */
-extern unsigned long long bb_emu_lean_count, bb_emu_general_count;
+extern thread_local unsigned long long bb_emu_lean_count, bb_emu_general_count;
 #define BB_EMU_COUNT(x) (++(x))
 #else
 #define BB_EMU_COUNT(x) ((void)0)

@@ -39,7 +39,7 @@ static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
 
 // emulated shared memory of the tile being processed
-extern uint8_t* bb_emu_smem;
+extern thread_local uint8_t* bb_emu_smem;
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)((const uint8_t*)p - bb_emu_smem); }
 static inline uint32_t lds32(uint32_t a) { uint32_t v; memcpy(&v, bb_emu_smem + a, 4); return v; }
 static inline uint32_t lds8(uint32_t a) { return bb_emu_smem[a]; }

@@ -7,15 +7,17 @@
 #include "cuda_shim.h"
 #include "../../binder_b200/csrc/zone_image.h"
 #include "../../include/binder_b200.h"
-namespace bbk { unsigned long long bb_emu_lean_count = 0, bb_emu_general_count = 0; }
+namespace bbk { thread_local unsigned long long bb_emu_lean_count = 0, bb_emu_general_count = 0; }
 #include "../../binder_b200/csrc/resolve_device.cuh"
 
 #include <vector>
+#include <cstdio>
+#include <cstdlib>
 
-uint8_t* bb_emu_smem = nullptr;
+thread_local uint8_t* bb_emu_smem = nullptr;
 // what the copy-job machinery saw so far: big tiles, job-mode responses, responses whose jobs did not fit the list, jobs
 // with a masked tail, emit rounds
-static unsigned long long g_job_stats[5];
+static thread_local unsigned long long g_job_stats[5];
 extern "C" void bb_emu_job_stats(unsigned long long* out, int reset) { for (int i = 0; i < 5; i++) { out[i] = g_job_stats[i]; if (reset) g_job_stats[i] = 0; } }
 extern "C" const bb::ZoneImage* bb_zone_image(const bb_zone* z);
 
@@ -29,17 +31,29 @@ constexpr size_t SMEM_BYTES = OFF_OPT + 16 + 64;
 static_assert(OFF_OUT >= OFF_IN + S_IN + 32 && OFF_OUT % 1024 == 0, "layout");
 }
 
+static int emu_resolve_image(const bb::ZoneImage* img, const bb::EngineConst& C,
+                             const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed, uint32_t qidx_base,
+                             int ordered, int tcp, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
+                             uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss, const uint32_t* qidx_map);
+
 extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain, int recursion,
                                     const char* rf_region, const char* const* rf_dcs, uint32_t rf_n, int rf_ptr,
                                     const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed, uint32_t qidx_base,
                                     int ordered, int tcp, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
                                     uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss, const uint32_t* qidx_map) {
-    static thread_local std::vector<uint8_t> smem(SMEM_BYTES + 1024);
-    bb_emu_smem = (uint8_t*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);     // offsets == emulated shared addresses
     bb::EngineConst C;
     if (!bb::make_engine_const(dns_domain, recursion != 0, C)) return BB_ERR_DOMAIN;
     if (rf_region && !bb::set_recursion_filter_const(C, rf_region, rf_dcs, rf_n, rf_ptr != 0)) return BB_ERR_ARG;
-    const bb::ZoneImage* img = zone ? bb_zone_image(zone) : nullptr;
+    return emu_resolve_image(zone ? bb_zone_image(zone) : nullptr, C, pkts, pkt_off, n, seed, qidx_base, ordered, tcp, out, out_cap, out_off, out_len,
+                             status, miss_idx, n_miss, qidx_map);
+}
+
+static int emu_resolve_image(const bb::ZoneImage* img, const bb::EngineConst& C,
+                             const uint8_t* pkts, const uint32_t* pkt_off, uint32_t n, uint64_t seed, uint32_t qidx_base,
+                             int ordered, int tcp, uint8_t* out, uint32_t out_cap, uint32_t* out_off, uint16_t* out_len,
+                             uint8_t* status, uint32_t* miss_idx, uint32_t* n_miss, const uint32_t* qidx_map) {
+    static thread_local std::vector<uint8_t> smem(SMEM_BYTES + 1024);
+    bb_emu_smem = (uint8_t*)(((uintptr_t)smem.data() + 1023) & ~(uintptr_t)1023);     // offsets == emulated shared addresses
     Params P; memset(&P, 0, sizeof P);
     P.pkts = pkts; P.pkt_off = pkt_off; P.n = n; P.seed = seed; P.qidx_base = qidx_base;
     P.out = out; P.out_cap = out_cap; P.out_off = out_off; P.out_len = out_len; P.status = status; P.miss_idx = miss_idx;
@@ -91,9 +105,8 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
             // each window, the job-mode service answers as copy jobs in ONE list in tile-offset order (a thread's jobs at the
             // exclusive prefix of the job counts), each round running its own contiguous run of the list
             const bool big = tile_bytes > (uint32_t)WIN;
-            std::vector<Task> tl(TASKCAP);
-            std::vector<uint8_t> jobs(nq, 0);
-            std::vector<uint32_t> tbase(nq + 1, 0);
+            static thread_local std::vector<Task> tl; static thread_local std::vector<uint8_t> jobs; static thread_local std::vector<uint32_t> tbase;
+            tl.resize(TASKCAP); jobs.assign(nq, 0); tbase.assign(nq + 1, 0);
             const uint32_t opt_words[4] = { 0x04290000u, 0x000000B0u, 0u, 0u };
             memcpy(bb_emu_smem + OFF_OPT, opt_words, 16);
             uint32_t tv = 0;
@@ -146,6 +159,66 @@ extern "C" int bb_emu_resolve_batch(const bb_zone* zone, const char* dns_domain,
     }
     out_off[n] = (uint32_t)gbase;
     *n_miss = mbase;
+    return BB_OK;
+}
+
+// ---- the CPU baseline "same table, same algorithm" (SURVEY.md section 8d): the word-wise device code over the SAME zone
+// image (the cuckoo table and the arena the GPU probes), on `nthreads` host threads, each taking a contiguous run of whole
+// tiles with its own output buffers.  `image` = the bb::ZoneImage of a built zone (bb_zone_image()).  Writes the best
+// wall-clock seconds of `repeat` passes; returns BB_OK, or the first error of any thread.
+#include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <thread>
+extern "C" int bb_emu_timed_resolve(const void* image, const char* dns_domain, int recursion, const uint8_t* pkts, const uint32_t* pkt_off,
+                                    uint32_t n, uint64_t seed, uint32_t nthreads, uint32_t repeat, uint32_t resp_cap_per_query,
+                                    double* best_secs, uint64_t* total_bytes, uint64_t* total_miss) {
+    bb::EngineConst C;
+    if (!image || !nthreads || !repeat || !bb::make_engine_const(dns_domain, recursion != 0, C)) return BB_ERR_ARG;
+    const bb::ZoneImage* img = (const bb::ZoneImage*)image;
+    const uint32_t ntiles = (n + T - 1) / T;
+    if (nthreads > ntiles) nthreads = ntiles ? ntiles : 1;
+    // `skew`: the slices' buffers are page-aligned allocations of equal size; started at the same offset the threads would
+    // walk them in lockstep on identical cache sets
+    struct Slice { uint32_t q0, q1; size_t skew; std::vector<uint8_t> out, status; std::vector<uint32_t> off, miss; std::vector<uint16_t> len; uint32_t nmiss = 0; int rc = 0; };
+    std::vector<Slice> sl(nthreads);
+    for (uint32_t t = 0; t < nthreads; t++) {
+        const uint32_t t0 = (uint32_t)((uint64_t)ntiles * t / nthreads), t1 = (uint32_t)((uint64_t)ntiles * (t + 1) / nthreads);
+        Slice& s = sl[t]; s.q0 = std::min(n, t0 * T); s.q1 = std::min(n, t1 * T);
+        const uint32_t m = s.q1 - s.q0;
+        s.skew = (size_t)t * 4160;
+        s.out.assign((size_t)m * resp_cap_per_query + 64 + s.skew, 0); s.status.assign(m + 1, 0); s.off.assign(m + 1, 0); s.miss.assign(m + 1, 0); s.len.assign(m + 1, 0);
+    }
+    // the workers live for the whole call and meet at a barrier per pass; pass 0 is a warm-up (their stacks, thread-local
+    // buffers and output pages are touched there), passes 1..repeat are timed from the main thread
+    struct Barrier {
+        std::mutex m; std::condition_variable cv; uint32_t n, waiting = 0, gen = 0;
+        void wait() { std::unique_lock<std::mutex> l(m); const uint32_t g = gen; if (++waiting == n) { waiting = 0; ++gen; cv.notify_all(); } else cv.wait(l, [&] { return gen != g; }); }
+    } bar; bar.n = nthreads + 1;
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < nthreads; t++) th.emplace_back([&, t] {
+        Slice& s = sl[t];
+        const uint32_t m = s.q1 - s.q0;
+        for (uint32_t rep = 0; rep <= repeat; rep++) {
+            bar.wait();
+            // the slice as a batch of its own: offsets are absolute in `pkts`, so the packets pointer stays and the offsets shift
+            if (m && !s.rc)
+                s.rc = emu_resolve_image(img, C, pkts, pkt_off + s.q0, m, seed, s.q0, 1, 0, s.out.data() + s.skew, (uint32_t)std::min<size_t>(s.out.size() - 64 - s.skew, 0xFFFFFF00u),
+                                         s.off.data(), s.len.data(), s.status.data(), s.miss.data(), &s.nmiss, nullptr);
+            bar.wait();
+        }
+    });
+    double best = 1e30;
+    for (uint32_t rep = 0; rep <= repeat; rep++) {
+        const auto a = std::chrono::steady_clock::now();
+        bar.wait(); bar.wait();
+        const double d = std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+        if (rep && d < best) best = d;
+    }
+    for (auto& x : th) x.join();
+    uint64_t tb = 0, tm = 0;
+    for (auto& s : sl) { if (s.rc) return s.rc; tb += s.off[s.q1 - s.q0]; tm += s.nmiss; }
+    *best_secs = best; *total_bytes = tb; *total_miss = tm;
     return BB_OK;
 }
 
