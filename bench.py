@@ -48,6 +48,7 @@ DEFAULTS = {   # workload: (zone records, batch, response bytes reserved per que
     'config3': (10000000, 262144, 512),
     'config4': (10000000, 1048576, 320),
     'config5': (10000000, 262144, 96),
+    'config5_rd0': (10000000, 262144, 96),
 }
 L2_BYTES = 126e6
 REGIONS = 15
@@ -233,7 +234,7 @@ def run_reference(args):
     if args.gpus > 1:
         batch = max(batch // args.gpus, 1)
     sample = min(batch, 65536)
-    data, off, _ = synth.gen_batch(zone, sample, 1000, mix, miss_frac)
+    data, off, _ = synth.gen_batch(zone, sample, 1000, mix, miss_frac, rd=synth.WORKLOAD_RD.get(args.workload, True))
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from oracle_lib import Oracle
     t0 = time.time()
@@ -270,7 +271,7 @@ class KernelPath(object):
         _, _, mix, miss_frac, _ = synth.WORKLOADS[workload]
         self.out_cap = B * per_q
         self.ring_n = int(min(24, max(3, np.ceil(1.5 * L2_BYTES / (B * (56 + per_q * 0.6))))))
-        self.ring = [synth.gen_batch(zone, B, seed0 + r, mix, miss_frac) for r in range(self.ring_n)]
+        self.ring = [synth.gen_batch(zone, B, seed0 + r, mix, miss_frac, rd=synth.WORKLOAD_RD.get(workload, True)) for r in range(self.ring_n)]
         self.d = []
         for data, off, _ in self.ring:
             self.d.append(dict(
@@ -286,15 +287,18 @@ class KernelPath(object):
         self.eng.resolve_device(b['pk'].data_ptr(), b['off'].data_ptr(), self.B, SEED, 0, b['out'].data_ptr(), self.out_cap,
                                 b['oo'].data_ptr(), b['ol'].data_ptr(), b['st'].data_ptr(), b['ms'].data_ptr(), b['tot'].data_ptr(), cs)
 
-    def timed_concurrent(self, k0, nsteps):
+    def timed_concurrent(self, k0, nsteps, depth=None):
+        """nsteps steps spread round-robin over `depth` side streams (= batches in flight), timed on the stream they fork
+        from and join into."""
         torch, stream = self.torch, self.stream
+        side = self.side[:depth or self.IN_FLIGHT]
         ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ea.record(stream)
-        for st in self.side:
+        for st in side:
             st.wait_event(ea)
         for k in range(nsteps):
-            self.step_on(k0 + k, self.side[k % self.IN_FLIGHT].cuda_stream)
-        for st in self.side:
+            self.step_on(k0 + k, side[k % len(side)].cuda_stream)
+        for st in side:
             ev = torch.cuda.Event()
             ev.record(st)
             stream.wait_event(ev)
@@ -314,6 +318,15 @@ class KernelPath(object):
             kk += K
         regions = [self.timed_concurrent(kk + r * K, K) for r in range(REGIONS)]
         ms_region = float(np.median(regions))
+        depth = self.IN_FLIGHT
+        # A kernel that already fills the GPU for several waves (a 262,144-query batch of long answers) gains nothing from a
+        # second batch in flight and can lose to the interleaving: the same regions with ONE batch in flight, and the
+        # better pipelining depth is the one reported (both are recorded)
+        regions1 = [self.timed_concurrent(kk + (REGIONS + r) * K, K, depth=1) for r in range(REGIONS)]
+        self.depth_ms = {self.IN_FLIGHT: ms_region / K, 1: float(np.median(regions1)) / K}
+        if float(np.median(regions1)) < ms_region:
+            regions, ms_region, depth = regions1, float(np.median(regions1)), 1
+        self.depth = depth
         # the same K steps strictly one after another on one stream: per-launch duration for the roofline
         serial = []
         for r in range(5):
@@ -412,6 +425,8 @@ def run_single(args, local_rank):
     zone, desc, mix, miss_frac, recursion, B, per_q = workload_setup(args)
     loader = None if args.no_cpu else OracleLoader(zone, recursion)
     # secondary workloads measured on the same engine (kernel path + roofline only): same-zone ones only
+    if args.also is None:
+        args.also = {'config3': 'config4', 'config5': 'config5_rd0'}.get(wl, 'none')
     also = [w for w in (args.also.split(',') if args.also and args.also != 'none' else [])
             if w in synth.WORKLOADS and w != wl and synth.WORKLOADS[w][1] == synth.WORKLOADS[wl][1] and synth.WORKLOADS[w][4] == recursion
             and not args.zone_records and not args.batch]
@@ -504,7 +519,7 @@ def run_single(args, local_rank):
         r2 = k2.result0()
         rf = k2.roofline(m2, r2)
         secondary[w] = {'workload': synth.WORKLOADS[w][0] + ' [single GPU]', 'batch': b2, 'value': m2['value'], 'ms_per_step': m2['ms_per_step'],
-                        'kernel_ms': m2['kern_ms'], 'roofline_frac': rf['frac'], 'in_flight_frac': rf['in_flight_frac'],
+                        'kernel_ms': m2['kern_ms'], 'roofline_frac': rf['frac'], 'in_flight_frac': rf['in_flight_frac'], 'batches_in_flight': k2.depth,
                         'bytes_per_query': rf['bytes_per_query'], 'answered': int((r2['st'] == 0).sum()), 'misses': int(r2['tot'][1])}
         launches += 0
         sec_kp.append((w, k2, r2))
@@ -534,7 +549,8 @@ def run_single(args, local_rank):
             'config': {'workload': desc, 'zone_records': zone.n_records, 'batch': B, 'table_mb': zstat['image_bytes'] / 1e6,
                        'l2_policy': 'inputs larger than L2: ring of %d distinct batches (%.0f MB in+out) over a %.0f MB table'
                                     % (ring_n, ring_n * (ring[0][0].size + int(tot[0]) + 11 * B) / 1e6, zstat['image_bytes'] / 1e6),
-                       'parallelism': 'single GPU', 'batches_in_flight': KernelPath.IN_FLIGHT,
+                       'parallelism': 'single GPU', 'batches_in_flight': kp.depth,
+                       'ms_per_step_by_batches_in_flight': {str(k): v for k, v in kp.depth_ms.items()},
                        'timing': 'median of %d regions of %d steps after %.0f ms of device warm-up (regions ms: min %.3f max %.3f)'
                                  % (REGIONS, K, warm_ms, min(regions), max(regions)),
                        'serial_ms_per_step': m['serial_ms'], 'graph_replay_ms_per_step': m['graph_ms'],
@@ -552,7 +568,7 @@ def main():
     ap.add_argument('--steps', type=int, default=50)
     ap.add_argument('--warmup', type=int, default=10)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--workload', default=None, choices=['config2', 'config3', 'config4', 'config5'],
+    ap.add_argument('--workload', default=None, choices=['config2', 'config3', 'config4', 'config5', 'config5_rd0'],
                     help='default: config3 on one GPU (largest single-GPU configuration), config4 on N>1')
     ap.add_argument('--zone-records', type=int, default=0, help='override the workload\'s zone size (recorded in config)')
     ap.add_argument('--batch', type=int, default=0, help='override the workload\'s batch (global batch for N>1)')
@@ -561,7 +577,7 @@ def main():
                          'holds the full zone, no exchange; nccl = sharded zone, routed records exchanged with an NCCL all-to-all')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg and the oracle parity check (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e leg (profiling runs)')
-    ap.add_argument('--also', default='config4', help='N=1: comma list of further workloads on the same zone measured (kernel path + '
+    ap.add_argument('--also', default=None, help='N=1: comma list of further workloads on the same zone measured (kernel path + '
                     'roofline) and reported under config.also_measured; "none" to skip')
     ap.add_argument('--ordered', action='store_true', help='query-order packing (look-back) instead of arrival packing')
     args = ap.parse_args()

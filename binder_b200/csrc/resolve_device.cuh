@@ -344,8 +344,9 @@ __device__ void size_service(const Params& P, Res& r, const SvcView& sv, uint32_
         const uint32_t inf = sv.info(perm_at(r, t, P.seed, qidx)), wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
         if (inf & KID_ADDR_NULL) continue;
         const uint32_t each = srv ? 18 + wl + dwl : dol + 14, cnt = srv ? np : 1;
-        const uint32_t fit = (r.maxsz - total) / each, take = min(cnt, fit);      // total <= maxsz throughout
-        total += take * each; ka += take;
+        uint32_t take = 0;                                                        // how many of this child's RRs still fit (cnt is 1..3 in practice:
+        while (take < cnt && total + each <= r.maxsz) { total += each; ++take; }  // a compare per RR beats an integer division per child)
+        ka += take;
         if (take < cnt) full = true;
     }
     if (!full && srv) for (uint32_t t = 0; t < n_walk; t++) {

@@ -300,7 +300,10 @@ WORKLOADS = {
                 {K_HOST_A: 0.6, K_SVC_SRV: 0.2, K_HOST_AAAA: 0.2}, 0.0, False),
     'config5': ('config5: 10M-record zone, A(host) lookups, 90% of names absent, RD=1, recursion on (misses -> compacted miss list)', 0.15,
                 {K_HOST_A: 1.0}, 0.9, True),
+    'config5_rd0': ('config5 with RD=0: the same 90%-absent names, recursion not desired -> every miss is answered REFUSED on the device', 0.15,
+                    {K_HOST_A: 1.0}, 0.9, True),
 }
+WORKLOAD_RD = {'config5_rd0': False}     # RD bit of a workload's queries (default set)
 
 
 def service_payload_bytes(zone):
