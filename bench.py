@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py — DNS queries/sec of the batched resolve path on N B200s (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload configX] [--mode shard|replicas|nccl]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload configX] [--mode auto|shard|replicas|nccl]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 A "step" = one pass of the hot path (parse -> zone lookup -> answer bytes) over one batch.
@@ -572,9 +572,10 @@ def main():
                     help='default: config3 on one GPU (largest single-GPU configuration), config4 on N>1')
     ap.add_argument('--zone-records', type=int, default=0, help='override the workload\'s zone size (recorded in config)')
     ap.add_argument('--batch', type=int, default=0, help='override the workload\'s batch (global batch for N>1)')
-    ap.add_argument('--mode', default='shard', choices=['shard', 'replicas', 'nccl'],
-                    help='N>1: shard = hash-sharded zone, route+push over NVLink peer memory (default); replicas = every GPU '
-                         'holds the full zone, no exchange; nccl = sharded zone, routed records exchanged with an NCCL all-to-all')
+    ap.add_argument('--mode', default='auto', choices=['auto', 'shard', 'replicas', 'nccl'],
+                    help='N>1: auto (default) = replicas while the zone image fits one GPU several times over (measured faster at every '
+                         'N: DESIGN.md section 8), else shard; shard = hash-sharded zone, route+push over NVLink peer memory; replicas = '
+                         'every GPU holds the full zone, no exchange; nccl = sharded zone, routed records exchanged with an NCCL all-to-all')
     ap.add_argument('--no-cpu', action='store_true', help='skip the cpu_baseline leg and the oracle parity check (profiling runs)')
     ap.add_argument('--no-e2e', action='store_true', help='skip the e2e leg (profiling runs)')
     ap.add_argument('--also', default=None, help='N=1: comma list of further workloads on the same zone measured (kernel path + '

@@ -85,7 +85,7 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 // SM instead of 8, which batches of 64-byte answers would feel, so the host picks per batch (engine: the previous batch's
 // mean response size).  Both variants answer every batch correctly.
 template <bool ORDERED, bool MULTI, bool SVC>
-__global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) resolve_kernel(const __grid_constant__ Params P) {
+__global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) resolve_kernel(const Params P) {
     // the packets start 16 bytes in: a staged packet's shared address is never 0 (Res::sp == 0 means "not staged")
     __shared__ __align__(16) uint8_t s_inbuf[16 + S_IN + 32];
     uint8_t* const s_in = s_inbuf + 16;
@@ -300,7 +300,10 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
         // so such tiles assemble in the device bounce buffer and then move their contiguous range with
         // coalesced 16-byte stores (the bytes are still in L2)
         uint8_t* const dst = r_bounce ? r_bounce : r_out;
-        if (my_len) { Res t = r; emit_direct(P, t, dst, gbase + my_o, qidx); }
+        if (my_len) {
+            if (!(r.sp && !r.trunc)) emit_response(P, r, dst + gbase + my_o, qidx);
+            else { WrT<2> w; w.begin_global(dst, (uint32_t)(gbase + my_o)); emit_fast(P, r, w, qidx); }
+        }
         STAMP(9);
         if (r_bounce && tile_bytes) {
             __syncthreads();
@@ -447,7 +450,7 @@ __host__ __device__ inline size_t region_qidx_array(uint32_t cap_q) { return 16 
 __host__ __device__ inline size_t region_bytes(uint32_t cap_q) { return (16 + 4 * ((size_t)cap_q + 1) + 4 * (size_t)cap_q + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t region_size(uint32_t cap_q, uint32_t cap_b) { return (region_bytes(cap_q) + cap_b + 64 + 255) & ~(size_t)255; }
 
-__global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const __grid_constant__ PushParams A) {
+__global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const PushParams A) {
     const Params& P = A.P;
     // the packets start 16 bytes in: a staged packet's shared address is never 0 (Res::sp == 0 means "not staged")
     __shared__ __align__(16) uint8_t s_inbuf[16 + S_IN + 32];

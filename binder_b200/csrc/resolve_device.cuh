@@ -853,11 +853,9 @@ extern thread_local unsigned long long bb_emu_lean_count, bb_emu_general_count;
 #else
 #define BB_EMU_COUNT(x) ((void)0)
 #endif
-// The complete decoder and the byte-serial resolve()/resolvePtr(): unusual packets only (long names, PTR, keys that live in the
-// arena, not-ready engines, packets that did not fit the staging buffer).  Out of line — the kernel's hot path stays a few
-// thousand contiguous instructions instead of being spread over this code — and called on a COPY of the per-query state, so
-// that the caller's copy never has its address taken and stays in registers.
-__device__ __noinline__ void general_query(const Params& P, Res& r, uint32_t len, uint32_t qidx) {
+__device__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
+    res_init(r);
+    if (r.sp && P.lean_ok && lean_query(P, r, len, qidx, s_sfx)) { BB_EMU_COUNT(bb_emu_lean_count); return; }
     BB_EMU_COUNT(bb_emu_general_count);
     res_init(r);
     if (!(r.sp ? decode_staged(r.sp, len, r) : decode(r.p, len, r))) { r.status = ST_DROPPED; return; }
@@ -874,13 +872,6 @@ __device__ __noinline__ void general_query(const Params& P, Res& r, uint32_t len
     }
     if (r.qtype == QT_PTR) resolve_ptr(P, r, fixed);
     else resolve_forward(P, r, qidx, fixed);
-}
-__device__ __forceinline__ void resolve_query(const Params& P, Res& r, uint32_t len, uint32_t qidx, uint32_t s_sfx) {
-    res_init(r);
-    if (r.sp && P.lean_ok && lean_query(P, r, len, qidx, s_sfx)) { BB_EMU_COUNT(bb_emu_lean_count); return; }
-    Res t = r;
-    general_query(P, t, len, qidx);
-    r = t;
 }
 
 // ---- mname encode (DESIGN.md "Wire spec: encode") ------------------------------------------
@@ -1245,14 +1236,21 @@ __device__ __forceinline__ void emit_head_w(const Res& r, W& w) {
     w.copy(p + 12, r.qn_len + 4);                                               // question, verbatim
 }
 
-// Everything emit_fast() writes after the header and the question except the two shapes it keeps inline.  Out of line, on
-// copies of the writer and of the per-query state (see general_query).
 template <class W>
-__device__ __noinline__ void emit_rest(const Params& P, const Res& r, W& w, uint32_t qidx) {
+__device__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
+    emit_head_w(r, w);
     bool opt_done = !r.edns;
-    if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310 — owner with labels in front of the pointer (upper case in the name)
-        put_dom_owner_w(w, r);
-        w.put4(0x01000100u); w.put4(bswap32(r.ttl)); w.put(0x0400u, 2); w.put4(bswap32(r.val));
+    if (r.rk == RK_A1 && r.keep_ans) {                                          // :299,310
+        const uint32_t bt = bswap32(r.ttl);
+        if (r.ptr_tgt == r.d_off) {              // owner is a bare pointer: the 16-byte RR as four whole words
+            w.put4(bswap16(0xC000u | (12u + r.ptr_tgt)) | 0x01000000u);        // ptr | TYPE A ...
+            w.put4(0x00000100u | (bt << 16));                                    // ... CLASS IN | ttl (high half)
+            w.put4((bt >> 16) | 0x04000000u);                                    // ttl (low half) | RDLENGTH 4
+            w.put4(bswap32(r.val));
+        } else {
+            put_dom_owner_w(w, r);
+            w.put4(0x01000100u); w.put4(bt); w.put(0x0400u, 2); w.put4(bswap32(r.val));
+        }
     } else if (r.rk == RK_PTR && r.keep_ans) {                                  // :130
         const uint32_t tl = P.arena[r.val];
         w.put(0x0CC0u, 2); w.put4(0x01000C00u); w.put4(bswap32(r.ttl)); w.put(bswap16(tl), 2);
@@ -1309,37 +1307,7 @@ __device__ __noinline__ void emit_rest(const Params& P, const Res& r, W& w, uint
         }
     }
     if (!opt_done) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }   // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-}
-
-// A whole response through the word-wise writer.  Inline: the header and the question, then the two shapes a batch of
-// host lookups is made of — one A record whose owner is the bare pointer to the QNAME, and no record at all (NOTIMP,
-// REFUSED, SERVFAIL ...), each with or without the OPT.  Everything else: emit_rest().
-template <class W>
-__device__ __forceinline__ void emit_fast(const Params& P, const Res& r, W& w, uint32_t qidx) {
-    emit_head_w(r, w);
-    const bool a1 = r.rk == RK_A1 && r.keep_ans && r.ptr_tgt == r.d_off;
-    if (a1 || r.rk == RK_HEADER || !r.keep_ans && (r.rk == RK_A1 || r.rk == RK_PTR || r.rk == RK_SOA)) {
-        if (a1) {                                // :299,310 — the 16-byte RR as four whole words
-            const uint32_t bt = bswap32(r.ttl);
-            w.put4(bswap16(0xC000u | (12u + r.ptr_tgt)) | 0x01000000u);        // ptr | TYPE A ...
-            w.put4(0x00000100u | (bt << 16));                                    // ... CLASS IN | ttl (high half)
-            w.put4((bt >> 16) | 0x04000000u);                                    // ttl (low half) | RDLENGTH 4
-            w.put4(bswap32(r.val));
-        }
-        if (r.edns) { w.put4(0x04290000u); w.put4(0x000000B0u); w.put(0, 3); }  // OPT: 00 | 00 29 | 04 B0 | ttl 0 | rdlen 0
-    } else {
-        Res tr = r; W tw = w;
-        emit_rest(P, tr, tw, qidx);
-        w = tw;
-    }
     w.end();
-}
-
-// A response written straight to its place in global memory (tiles that do not stage: answers larger than the window in the
-// small variant, a query on the generic path, TCP-sized answers): the byte emitter or the word-wise writer.  Out of line.
-__device__ __noinline__ void emit_direct(const Params& P, const Res& r, uint8_t* dst, uint64_t off, uint32_t qidx) {
-    if (!(r.sp && !r.trunc)) emit_response(P, r, dst + off, qidx);
-    else { WrT<2> w; w.begin_global(dst, (uint32_t)off); emit_fast(P, r, w, qidx); }
 }
 
 }  // namespace bbk

@@ -97,7 +97,8 @@ static int emu_resolve_image(const bb::ZoneImage* img, const bb::EngineConst& C,
             for (uint32_t t = 0; t < nq; t++) {
                 if (!r[t].rlen) continue;
                 threadIdx.x = t;
-                emit_direct(P, r[t], out, gbase + my_o[t], qidx[t]);
+                if (!(r[t].sp && !r[t].trunc)) emit_response(P, r[t], out + gbase + my_o[t], qidx[t]);
+                else { WrT<2> w; w.begin_global(out, (uint32_t)(gbase + my_o[t])); emit_fast(P, r[t], w, qidx[t]); }
             }
         } else if (tile_bytes) {
             // the service variant's emit: one round when the tile fits the window; else rounds over the responses that START in
