@@ -576,11 +576,11 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
         }
     }
     // The last block publishes the region headers (count, bytes, end-of-offsets sentinel) and then,
-    // after a system-scope fence, the epoch flag the owner's wait kernel spins on: the exchange
+    // with a system-scope release store, the epoch flag the owner's wait kernel acquires: the exchange
     // needs no collective, only this ordered pair of peer stores per (source, owner).
     // A block orders its peer stores before its done count with a device-scope fence only (the barrier
     // orders every thread's stores before thread 0's fence; fences are cumulative).  The system-scope
-    // fence is the last block's alone: it has observed every other block's count, so by causality
+    // release is the last block's alone: it has observed every other block's count, so by causality
     // order all their stores precede its flag store for whoever acquires the flag at system scope.
     __syncthreads();
     STAMP(9);
@@ -598,8 +598,9 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
             ((uint32_t*)(reg + region_off_array(A.cap_q)))[cnt] = nb;
             volatile uint32_t* hdr = (volatile uint32_t*)reg;
             hdr[0] = cnt; hdr[1] = nb; hdr[3] = *A.err;
-            __threadfence_system();
-            hdr[2] = A.epoch;                      // the flag: everything above is visible to whoever sees it
+            // the flag, released at system scope: everything above (and, by cumulativity, every other block's peer stores
+            // this thread has observed through the done counter) is visible to whoever acquires it
+            asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(reg + 8), "r"(A.epoch) : "memory");
             if (P.stage_log && lane == 0) P.stage_log[(size_t)gridDim.x * NSTAGE] = gtime();   // one extra row: flag published
             A.cursor[lane] = 0;
         }
@@ -611,14 +612,16 @@ __global__ void __launch_bounds__(T, BB_MIN_BLOCKS) route_push_kernel(const Push
 __global__ void wait_regions_kernel(const uint8_t* recv_set, size_t reg_size, uint32_t nranks, uint32_t epoch, uint32_t* err) {
     const uint32_t r = threadIdx.x;
     if (r < nranks) {
-        const volatile uint32_t* hdr = (const volatile uint32_t*)(recv_set + (size_t)r * reg_size);
+        const uint32_t* flag = (const uint32_t*)(recv_set + (size_t)r * reg_size) + 2;
         unsigned long long spins = 0;
-        while (hdr[2] != epoch) {
+        for (;;) {                                                // acquire at system scope: pairs with the sender's st.release.sys
+            uint32_t v;
+            asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v == epoch) break;
             if (++spins > (1ull << 28)) { *err = 2; break; }      // ~seconds: a peer died; fail instead of hanging
             __nanosleep(64);
         }
     }
-    __threadfence_system();
 }
 
 // Incremental zone update: overwrite the listed 32-byte slots (one thread per 16-byte chunk).  Runs with no
