@@ -360,7 +360,11 @@ __global__ void __launch_bounds__(T, SVC ? BB_MIN_BLOCKS - 1 : BB_MIN_BLOCKS) re
             // The round's bytes leave as ONE bulk copy shared -> global (16-byte aligned on both sides: the buffer keeps the
             // global address's phase), issued by one thread; the partial chunks at both ends go out as bytes.  Results
             // in pinned host memory (zero-copy, P.bounce set) keep the 16-byte stores of all threads.
+#ifdef BB_NO_BULK_FLUSH        /* experiment switch: every thread's 16-byte stores instead of the bulk copy */
+            const bool bulk = false;
+#else
             const bool bulk = r_bounce == nullptr;
+#endif
             if (bulk) fence_async_smem();                                     // this thread's writes, for the copy engine
             __syncthreads();
             if (tid < (int)head) g[x0 + tid] = s_out[delta + x0 + tid];

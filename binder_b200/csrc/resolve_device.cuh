@@ -9,7 +9,10 @@ using namespace bb;
 
 constexpr int T = 128;                    // queries (= threads) per tile
 constexpr int S_IN = 8192;                // staged input bytes per tile
-constexpr int CAPW = 12288;               // output staging window per flush round
+#ifndef BB_CAPW
+#define BB_CAPW 12288
+#endif
+constexpr int CAPW = BB_CAPW;             // output staging window per flush round
 constexpr int MAXRESP = 1232;             // >= the largest response (1200)
 constexpr int S_OUT = ((CAPW + 32 + 127) / 128 + 1) * 128;   // whole 128-byte rows (the staging buffer is swizzled per row)
 constexpr int WIN = CAPW - MAXRESP;        // output window of one emit round: a response STARTING in it ends inside the buffer
