@@ -1,7 +1,7 @@
 # A/B on one GPU: library variants x {config3 (automatic = service variant), config3 small variant, config2}, kernel path only
 mkdir -p gpurun_out
 cp binder_b200/libbinder_b200.so /tmp/lib_default.so
-for v in ${VARIANTS:-gq mono gq mono}; do
+for v in ${VARIANTS:-base noblk win16 base}; do
   cp binder_b200/variants/lib_$v.so binder_b200/libbinder_b200.so
   timeout 300 python bench.py --no-cpu --no-e2e --also none --zone-records 3000000 > gpurun_out/ab4_${v}_c3.json 2> gpurun_out/ab4_${v}.err
   BB_PROFILE=small timeout 300 python bench.py --no-cpu --no-e2e --also none --zone-records 3000000 > gpurun_out/ab4_${v}_c3small.json 2>> gpurun_out/ab4_${v}.err
