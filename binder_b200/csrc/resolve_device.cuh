@@ -239,7 +239,7 @@ __device__ __forceinline__ uint4 ldg_stream(const uint4* p) {
 }
 #endif
 
-// A service record in the arena (zone_image.h): 32-byte header, kid_info, fixed-stride child blocks.
+// A service record in the arena (zone_image.h): 32-byte header, kid_info, then one section per kind of piece.
 struct SvcView {
     const uint8_t* base; const uint8_t* arena;
     uint4 h0, h1;            // ttl | nkids,n_valid | sum_ports,sum_wl | sum_wl_ports,jobs_srv ; hflags,sp_len,dom_wl,sp[11],stride16
@@ -261,8 +261,12 @@ struct SvcView {
     __device__ uint32_t hflags() const { return h1.x & 0xFF; }
     __device__ uint32_t sp_len() const { return (h1.x >> 8) & 0xFF; }
     __device__ uint32_t dom_wl() const { return (h1.x >> 16) & 0xFF; }
-    __device__ uint32_t stride() const { return (h1.w >> 16) << 4; }
-    __device__ uint32_t blocks_off() const { return svc_blocks_off(nkids()); }
+    __device__ uint32_t srv_stride() const { return (h1.w >> 16) << 4; }
+    __device__ uint32_t add_stride() const { return ((h1.x & 0xFF) >> SVC_ADD_STRIDE_SHIFT) << 4; }
+    __device__ uint32_t a_off() const { return svc_a_off(nkids()); }
+    __device__ uint32_t rec_off() const { return svc_rec_off(nkids()); }
+    __device__ uint32_t add_off() const { return svc_add_off(nkids()); }
+    __device__ uint32_t srv_off() const { return svc_srv_off(nkids(), add_stride()); }
     // flags | wire_len << 8 | nports << 16 of child i
     __device__ uint32_t info(uint32_t i) const { return __ldg((const uint32_t*)(base + sizeof(SvcHdr)) + i); }
     // byte i of "_srvce._proto." as wire labels
@@ -273,14 +277,17 @@ struct SvcView {
         return (w >> (8 * (j & 3))) & 0xFF;
     }
 };
-// One child's block: KidRec | A answer | additional | SRV answers (the field-by-field paths read it through this).
+// One child's pieces: its KidRec and where its A answer, additional RR and SRV answers sit (the field-by-field paths read
+// them through this).
 struct KidView {
     uint4 a;                 // addr | rttl | flags,wire_len,nports,pad | -
-    const uint8_t* blk;
+    const uint8_t* a_; const uint8_t* add_; const uint8_t* srv_;
     uint32_t dwl;            // the service's dom_wl
     __device__ void load(const SvcView& sv, uint32_t i) {
-        blk = sv.base + sv.blocks_off() + (size_t)sv.stride() * i;
-        a = ldg_stream((const uint4*)blk);
+        a = ldg_stream((const uint4*)(sv.base + sv.rec_off() + 16 * (size_t)i));
+        a_ = sv.base + sv.a_off() + 16 * (size_t)i;
+        add_ = sv.base + sv.add_off() + (size_t)sv.add_stride() * i;
+        srv_ = sv.base + sv.srv_off() + (size_t)sv.srv_stride() * i;
         dwl = sv.dom_wl();
     }
     __device__ uint32_t addr() const { return a.x; }
@@ -288,9 +295,9 @@ struct KidView {
     __device__ uint32_t flags() const { return a.z & 0xFF; }
     __device__ uint32_t wire_len() const { return (a.z >> 8) & 0xFF; }
     __device__ uint32_t nports() const { return (a.z >> 16) & 0xFF; }
-    __device__ const uint8_t* a_rr() const { return blk + KID_A_OFF; }
-    __device__ const uint8_t* add_rr() const { return blk + KID_ADD_OFF; }                         // starts with the child's labels
-    __device__ const uint8_t* srv_rr() const { return blk + kid_srv_off(wire_len()); }
+    __device__ const uint8_t* a_rr() const { return a_; }
+    __device__ const uint8_t* add_rr() const { return add_; }                                      // starts with the child's labels
+    __device__ const uint8_t* srv_rr() const { return srv_; }
     __device__ uint32_t srv_len() const { return kid_srv_len(wire_len(), dwl); }
     __device__ uint32_t port(uint32_t c) const { const uint8_t* p = srv_rr() + c * srv_len() + 16; return (uint32_t)__ldg(p) << 8 | __ldg(p + 1); }
     __device__ uint32_t name_byte(uint32_t i) const { return __ldg(add_rr() + i); }
@@ -1121,13 +1128,14 @@ __device__ __forceinline__ bool task_exact(const Task& t) { return (t.w >> 26) &
 // The pieces of one job-mode response, given where the response starts in its tile: (a prefix of) the children's ready RRs
 // in shuffled child order (lib/server.js:361-416) — the same walk as emit_fast's, counters included — and, for EDNS, the
 // OPT (from `opt_sp`, a shared address holding its 11 bytes, zero padded to 16).  The header and the question are the
-// owning thread's.  Every arena piece ends in zero padding up to the next multiple of 16 (zone_build.cpp pads each part
-// of a child's block with zeros) unless it is a run of SRV answers cut short (`exact`).
+// owning thread's.  Every arena piece ends in zero padding up to the next multiple of 16 (zone_build.cpp pads each slot of
+// the additional and SRV sections with zeros up to its stride) unless it is a run of SRV answers cut short (`exact`).
 template <class Sink>
 __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint32_t my_o, uint32_t opt_sp, Sink& sink) {
     const bool srv = r.rk == RK_SVC_SRV;
     SvcView sv; sv.open(P.arena, r.val);
-    const uint32_t blocks = r.val + sv.blocks_off(), stride = sv.stride(), dwl = sv.dom_wl();
+    const uint32_t dwl = sv.dom_wl(), add_stride = sv.add_stride(), srv_stride = sv.srv_stride();
+    const uint32_t a0 = r.val + sv.a_off(), add0 = r.val + sv.add_off(), srv0 = r.val + sv.srv_off();
     uint32_t dst = my_o + 12 + r.qn_len + 4;
     uint32_t left = r.keep_ans;
     uint64_t pm = r.perm;                                                     // job mode implies nk <= 16: four bits per position
@@ -1137,9 +1145,9 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
         const uint32_t wl = (inf >> 8) & 0xFF, np = (inf >> 16) & 0xFF;
         if (srv) {
             const uint32_t n = min(np, left), len = n * kid_srv_len(wl, dwl);
-            if (len) sink.put(blocks + stride * k + kid_srv_off(wl), dst, len, 0, n < np);
+            if (len) sink.put(srv0 + srv_stride * k, dst, len, 0, n < np);
             dst += len; left -= n;
-        } else { sink.put(blocks + stride * k + KID_A_OFF, dst, 16, 0, 0); dst += 16; --left; }
+        } else { sink.put(a0 + 16 * k, dst, 16, 0, 0); dst += 16; --left; }
     }
     if (r.edns) { sink.put(opt_sp, dst, 11, 1, 0); dst += 11; }               // the OPT leads the additional section
     if (srv) {
@@ -1148,7 +1156,7 @@ __device__ void plan_service(const Params& P, const Res& r, uint32_t qidx, uint3
             const uint32_t k = (uint32_t)pm & 15u, inf = sv.info(k);
             if (inf & KID_ADDR_NULL) continue;
             const uint32_t wl = (inf >> 8) & 0xFF;
-            sink.put(blocks + stride * k + KID_ADD_OFF, dst, kid_add_len(wl), 0, 0); dst += kid_add_len(wl); --left;
+            sink.put(add0 + add_stride * k, dst, kid_add_len(wl), 0, 0); dst += kid_add_len(wl); --left;
         }
     }
 }

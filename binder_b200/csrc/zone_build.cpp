@@ -590,7 +590,7 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         for (uint32_t k = nd.first_kid; k; k = B.nodes[k].next_sib)
             if ((B.nodes[k].flags & (NF_KIDTYPE | NF_DEAD)) == NF_KIDTYPE) kids.push_back(k);
         if (kids.size() > 65535) return false;
-        // header | kid_info | one fixed-stride block per child with its RRs as ready wire bytes (zone_image.h)
+        // header | kid_info | A answers | KidRecs | additional RRs | SRV answers: ready wire bytes, one section per kind (zone_image.h)
         SvcHdr h; memset(&h, 0, sizeof h);
         h.ttl = si.ttl; h.nkids = (uint16_t)kids.size();
         h.dom_wl = (uint8_t)(dom_wire.size() + 1);
@@ -609,9 +609,10 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
         auto be16 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
         auto be32 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); };
         uint64_t n_valid = 0, sum_ports = 0, sum_wl = 0, sum_wl_ports = 0, jobs_srv = 0;
-        std::vector<std::vector<uint8_t>> blocks(kids.size());
+        std::vector<std::vector<uint8_t>> a_rr(kids.size()), add_rr(kids.size()), srv_rr(kids.size());
+        std::vector<KidRec> recs(kids.size());
         std::vector<uint32_t> info(kids.size(), 0);
-        size_t stride = 16;
+        size_t add_stride = 16, srv_stride = 16;
         for (size_t ki = 0; ki < kids.size(); ki++) {
             const Node& kn = B.nodes[kids[ki]];
             KidRec kr; memset(&kr, 0, sizeof kr);
@@ -640,33 +641,41 @@ bool emit_forward(bb_zone& zn, uint32_t id) {
                 jobs_srv += (pl.size() * kid_srv_len((uint32_t)kw.size(), (uint32_t)dom_wire.size() + 1) + 63) / 64 + (kid_add_len((uint32_t)kw.size()) + 63) / 64;
             }
             info[ki] = (uint32_t)kr.flags | (uint32_t)kr.wire_len << 8 | (uint32_t)kr.nports << 16;
-            // the block: KidRec | A answer | additional (pad 16) | SRV answers (pad 16)
-            std::vector<uint8_t>& blk = blocks[ki];
-            blk.insert(blk.end(), (uint8_t*)&kr, (uint8_t*)&kr + sizeof kr);
+            // the child's pieces: KidRec, A answer, additional RR, SRV answers
+            recs[ki] = kr;
             const uint32_t rttl = (kr.flags & KID_HAS_RTTL) ? kr.rttl : si.ttl;
-            be16(blk, 0xC00C); be16(blk, 1); be16(blk, 1); be32(blk, si.ttl < rttl ? si.ttl : rttl); be16(blk, 4); be32(blk, kr.addr);
-            blk.insert(blk.end(), kw.begin(), kw.end());
-            be16(blk, 0xC000u | (12u + h.sp_len)); be16(blk, 1); be16(blk, 1); be32(blk, rttl); be16(blk, 4); be32(blk, kr.addr);
-            while (blk.size() & 15) blk.push_back(0);
+            std::vector<uint8_t>& ar = a_rr[ki];
+            be16(ar, 0xC00C); be16(ar, 1); be16(ar, 1); be32(ar, si.ttl < rttl ? si.ttl : rttl); be16(ar, 4); be32(ar, kr.addr);
+            std::vector<uint8_t>& ad = add_rr[ki];
+            ad.insert(ad.end(), kw.begin(), kw.end());
+            be16(ad, 0xC000u | (12u + h.sp_len)); be16(ad, 1); be16(ad, 1); be32(ad, rttl); be16(ad, 4); be32(ad, kr.addr);
+            std::vector<uint8_t>& sr = srv_rr[ki];
             for (uint16_t port : pl) {
-                be16(blk, 0xC00C); be16(blk, 33); be16(blk, 1); be32(blk, si.ttl); be16(blk, (uint32_t)(6 + kw.size() + dom_wire.size() + 1));
-                be16(blk, 0); be16(blk, 10); be16(blk, port);
-                blk.insert(blk.end(), kw.begin(), kw.end());
-                blk.insert(blk.end(), dom_wire.begin(), dom_wire.end()); blk.push_back(0);
+                be16(sr, 0xC00C); be16(sr, 33); be16(sr, 1); be32(sr, si.ttl); be16(sr, (uint32_t)(6 + kw.size() + dom_wire.size() + 1));
+                be16(sr, 0); be16(sr, 10); be16(sr, port);
+                sr.insert(sr.end(), kw.begin(), kw.end());
+                sr.insert(sr.end(), dom_wire.begin(), dom_wire.end()); sr.push_back(0);
             }
-            while (blk.size() & 15) blk.push_back(0);
-            if (blk.size() > stride) stride = blk.size();
+            if (((ad.size() + 15) & ~(size_t)15) > add_stride) add_stride = (ad.size() + 15) & ~(size_t)15;
+            if (((sr.size() + 15) & ~(size_t)15) > srv_stride) srv_stride = (sr.size() + 15) & ~(size_t)15;
         }
-        if (stride / 16 > 0xFFFF) return false;
-        h.stride16 = (uint16_t)(stride / 16);
+        if (srv_stride / 16 > 0xFFFF || add_stride / 16 > 15) return false;
+        h.stride16 = (uint16_t)(srv_stride / 16);
+        h.hflags |= (uint8_t)((add_stride / 16) << SVC_ADD_STRIDE_SHIFT);
         // sums the kernel sizes an answer from without walking the children; a service too large for them is walked
         if (n_valid > 0xFFFF || sum_ports > 0xFFFF || sum_wl > 0xFFFF || sum_wl_ports > 0xFFFF || jobs_srv > 0xFFFF) h.hflags |= SVC_BAD_A | SVC_BAD_SRV;
         h.n_valid = (uint16_t)n_valid; h.sum_ports = (uint16_t)sum_ports; h.sum_wl = (uint16_t)sum_wl; h.sum_wl_ports = (uint16_t)sum_wl_ports;
         h.jobs_srv = (uint16_t)jobs_srv;
-        std::vector<uint8_t> rec(svc_blocks_off((uint32_t)kids.size()) + stride * kids.size(), 0);
+        const uint32_t nk = (uint32_t)kids.size();
+        std::vector<uint8_t> rec(svc_record_len(nk, (uint32_t)add_stride, (uint32_t)srv_stride), 0);     // zero padded throughout
         memcpy(rec.data(), &h, sizeof h);
         if (!info.empty()) memcpy(rec.data() + sizeof h, info.data(), 4 * info.size());
-        for (size_t ki = 0; ki < kids.size(); ki++) memcpy(rec.data() + svc_blocks_off((uint32_t)kids.size()) + stride * ki, blocks[ki].data(), blocks[ki].size());
+        for (size_t ki = 0; ki < kids.size(); ki++) {
+            memcpy(rec.data() + svc_a_off(nk) + 16 * ki, a_rr[ki].data(), 16);
+            memcpy(rec.data() + svc_rec_off(nk) + 16 * ki, &recs[ki], sizeof(KidRec));
+            memcpy(rec.data() + svc_add_off(nk) + add_stride * ki, add_rr[ki].data(), add_rr[ki].size());
+            memcpy(rec.data() + svc_srv_off(nk, (uint32_t)add_stride) + srv_stride * ki, srv_rr[ki].data(), srv_rr[ki].size());
+        }
         val = T.arena_put(rec.data(), rec.size(), 32);
     }
     uint32_t ttl = nd.kind == K_SERVICE ? B.svcs[nd.extra].ttl : nd.ttl;
@@ -1004,7 +1013,7 @@ extern "C" int bb_zone_probe(const bb_zone* z, uint32_t ns, const uint8_t* key, 
         std::string ext;
         if (h.hflags & bb::SVC_SP_EXT) { uint32_t off; memcpy(&off, h.sp, 4); ext.assign((const char*)A + off, h.sp_len); memset(h.sp, 0, 4); }
         out.append((const char*)&h, sizeof h); out += ext;                 // offsets are relative to the record: position independent
-        const size_t body = bb::svc_blocks_off(h.nkids) + (size_t)h.stride16 * 16 * h.nkids - sizeof h;
+        const size_t body = bb::svc_record_len(h.nkids, (uint32_t)(h.hflags >> bb::SVC_ADD_STRIDE_SHIFT) * 16, (uint32_t)h.stride16 * 16) - sizeof h;
         out.append((const char*)(A + s.val + sizeof h), body);
     } else if (s.kind == bb::K_PTR) {
         out.append((const char*)(A + s.val + 1), A[s.val]);

@@ -71,8 +71,8 @@ struct alignas(32) Slot {
 static_assert(sizeof(Slot) == 32, "slot must be one 32-byte sector");
 
 // ---- service record in the arena (32-byte aligned) ---------------------------------------------------------
-//   SvcHdr (32 B) | kid_info[nkids] (4 B each, padded to 16) | nkids blocks of `stride` bytes, child order:
-//   block = KidRec (16 B) | A answer (16 B) | additional RR (wire_len + 16, padded to 16) | SRV answers (padded to 16)
+//   SvcHdr (32 B) | kid_info[nkids] (4 B each, padded to 16) | A answers (16 B per child) | KidRec (16 B per child) |
+//   additional RRs (add_stride per child) | SRV answers (srv_stride per child) — every section in child order.
 // Sizing a service answer is one header read unless a child is malformed or the answer must be truncated:
 // the sums over the children that answer are taken at build time.  So are the resource records themselves:
 // everything in an answer RR except the bytes of the question is known when the zone is built (the SRV target is
@@ -82,17 +82,21 @@ static_assert(sizeof(Slot) == 32, "slot must be one 32-byte sector");
 //   A answer       C00C | A IN | min(ttl, rttl) | 4 | addr                                             (:411-414)
 //   additional     child labels | C0 ptr to the domain part of the QNAME | A IN | rttl | 4 | addr      (:401-402)
 //   SRV answers    per port: C00C | SRV IN | ttl | rdlen | 0 | 10 | port | child labels | fqdn | 0     (:396-400)
-// kid_info (flags | wire_len << 8 | nports << 16 per child) sits next to the header so that one memory round trip
-// tells where every child's bytes are and how long they are: the blocks have one stride, and the kernel turns an
-// answer into a list of independent copy jobs (engine.cu) instead of walking the children one load after another.
-// A query whose domain part carries upper-case letters (the owner pointers then land elsewhere), a truncated
+// SECTIONS, not per-child blocks: an A query on a service reads header + kid_info + its children's 16-byte A answers —
+// one or two 128-byte lines — instead of one sector out of every child's block; an SRV query reads the additional and the
+// SRV sections, both dense.  kid_info (flags | wire_len << 8 | nports << 16 per child) sits next to the header so that one
+// memory round trip tells how long every child's pieces are; their positions follow from the section strides, and the
+// kernel turns an answer into a list of independent copy jobs (engine.cu) instead of walking the children one load after
+// another.  A query whose domain part carries upper-case letters (the owner pointers then land elsewhere), a truncated
 // answer or a malformed child take the field-by-field writer instead, which reads names and ports out of the same bytes.
+// Every slot of the additional and SRV sections is padded with zeros up to its stride.
 enum : uint8_t {
     SVC_BAD_A = 1,       // some child is "bad zk info" for an A query (:366-376): the walk must find where
     SVC_BAD_SRV = 2,     // same for SRV
     SVC_SP_NEVER = 4,    // s.srvce / s.proto absent, not strings, or not spellable as labels: never equal (:334-335)
     SVC_SP_EXT = 8,      // the two labels do not fit `sp`: sp[0..3] = arena offset of the bytes
 };
+constexpr uint32_t SVC_ADD_STRIDE_SHIFT = 4;       // hflags >> 4: additional-section stride / 16 (1..5: a label is at most 63 bytes)
 struct alignas(32) SvcHdr {
     uint32_t ttl;            // after record.ttl / service.ttl / service.service.ttl (:270-274,331-332)
     uint16_t nkids;          // children that pass the type filter (:352-360), in child order
@@ -101,11 +105,11 @@ struct alignas(32) SvcHdr {
     uint16_t sum_wl;         // sum of wire_len over them
     uint16_t sum_wl_ports;   // sum of nports * wire_len over them
     uint16_t jobs_srv;       // copy jobs of a whole SRV answer (resolve_device.cuh: a piece is ceil(len / 64) jobs), OPT not counted
-    uint8_t  hflags;         // SVC_*
+    uint8_t  hflags;         // SVC_* | bytes per child of the additional section / 16 << 4 (SVC_ADD_STRIDE_SHIFT)
     uint8_t  sp_len;         // bytes of "_srvce._proto." on the wire = where the domain part of a matching SRV QNAME starts
     uint8_t  dom_wl;         // the service's fqdn as wire labels + terminator (what every SRV target ends with)
     uint8_t  sp[11];         // len, srvce bytes, len, proto bytes — as the query spells them
-    uint16_t stride16;       // bytes per child block / 16
+    uint16_t stride16;       // bytes per child of the SRV section / 16
 };
 static_assert(sizeof(SvcHdr) == 32, "service header is one sector");
 enum : uint8_t {
@@ -126,11 +130,12 @@ struct alignas(16) KidRec {
 static_assert(sizeof(KidRec) == 16, "child record is one 16-byte load");
 BB_HD uint32_t kid_add_len(uint32_t wire_len) { return wire_len + 16; }                            // additional RR
 BB_HD uint32_t kid_srv_len(uint32_t wire_len, uint32_t dom_wl) { return 18 + wire_len + dom_wl; }  // one SRV answer RR
-// offsets inside a record / a block (every part 16-byte aligned: they are streamed with 16-byte loads)
-BB_HD uint32_t svc_blocks_off(uint32_t nkids) { return 32 + ((4 * nkids + 15) & ~15u); }
-constexpr uint32_t KID_A_OFF = 16, KID_ADD_OFF = 32;
-BB_HD uint32_t kid_srv_off(uint32_t wire_len) { return KID_ADD_OFF + ((kid_add_len(wire_len) + 15) & ~15u); }
-BB_HD uint32_t kid_block_len(uint32_t wire_len, uint32_t nports, uint32_t dom_wl) { return kid_srv_off(wire_len) + ((nports * kid_srv_len(wire_len, dom_wl) + 15) & ~15u); }
+// offsets of the sections inside a record (every piece 16-byte aligned: they are streamed with 16-byte loads)
+BB_HD uint32_t svc_a_off(uint32_t nkids) { return 32 + ((4 * nkids + 15) & ~15u); }               // A answers
+BB_HD uint32_t svc_rec_off(uint32_t nkids) { return svc_a_off(nkids) + 16 * nkids; }                // KidRec
+BB_HD uint32_t svc_add_off(uint32_t nkids) { return svc_rec_off(nkids) + 16 * nkids; }              // additional RRs
+BB_HD uint32_t svc_srv_off(uint32_t nkids, uint32_t add_stride) { return svc_add_off(nkids) + add_stride * nkids; }      // SRV answers
+BB_HD uint32_t svc_record_len(uint32_t nkids, uint32_t add_stride, uint32_t srv_stride) { return svc_srv_off(nkids, add_stride) + srv_stride * nkids; }
 
 // ---- key hash: two independent multiply-fold accumulators over little-endian words, zero-padded tail -----
 // (one IMAD.WIDE + one LOP3 per accumulator per word on the device)
