@@ -197,7 +197,7 @@ def cpu_port(orc, data, off, budget_s=12.0):
 
 def cpu_same_table(st, data, off, want_bytes, want_miss, per_q, seed=0, budget_s=8.0):
     """SURVEY.md 8(d) "same open-addressed layout so the comparison isolates the processor": the word-wise device code
-    compiled for the host (-O3 -march=native) over the same zone image, all host threads; bounded sample."""
+    compiled for the host (-O3) over the same zone image, all host threads; bounded sample."""
     cores = os.cpu_count() or 1
     n = len(off) - 1
     ns = min(n, 65536)

@@ -3,7 +3,8 @@
 The per-query device source (binder_b200/csrc/resolve_device.cuh) compiled for the host through
 tests/native/cuda_shim.h and driven tile by tile by tests/native/emu_resolve.cpp — the word-wise parse, the
 multiply-fold hashes, the one-sector cuckoo probe, the ready-RR copy jobs — over the SAME zone image (table + arena)
-the GPU probes, on all host threads, -O3 -march=native.  It isolates the processor: same layout, same algorithm.
+the GPU probes, on all host threads, -O3 (x86-64-v2: the library is built where the repo is and runs on the GPU box, whose
+CPU may be another model — no -march=native).  It isolates the processor: same layout, same algorithm.
 Only tests/ and bench.py's cpu_baseline leg may import this; the product (binder_b200/) never does.
 """
 import ctypes
@@ -22,7 +23,7 @@ _DEPS = _SRCS + [os.path.join(_ROOT, 'binder_b200', 'csrc', f) for f in ('resolv
 
 def build(force=False):
     if force or not os.path.exists(_SO) or any(os.path.getmtime(_SO) < os.path.getmtime(d) for d in _DEPS):
-        subprocess.check_call(['g++', '-std=c++17', '-O3', '-march=native', '-fPIC', '-shared', '-pthread', '-ftls-model=initial-exec',
+        subprocess.check_call(['g++', '-std=c++17', '-O3', '-march=x86-64-v2', '-fPIC', '-shared', '-pthread', '-ftls-model=initial-exec',
                                '-Wno-unknown-pragmas', '-I', os.path.join(_ROOT, 'include'), '-I', os.path.join(_ROOT, 'binder_b200', 'csrc'),
                                '-o', _SO] + _SRCS)
     return _SO
