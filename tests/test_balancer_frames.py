@@ -50,6 +50,7 @@ def _run(kind):
             w = by_addr[a]
             assert w[:2] == p[:2] and w[2] & 0x80
     assert be.counters['answered'] + be.counters['missed'] + be.counters['dropped'] == len(pkts)
+    return by_addr, dict(be.counters)
 
 
 def test_balancer_frames_cpu_oracle():
@@ -58,7 +59,14 @@ def test_balancer_frames_cpu_oracle():
 
 @pytest.mark.gpu
 def test_balancer_frames_gpu_engine():
-    _run('gpu')
+    """The same frame stream through an engine-backed and an oracle-backed session: every OUTBOUND_UDP frame — destination
+    and payload bytes — and every counter must be identical (the chunking and the shuffle seed are the same on both sides)."""
+    g_frames, g_cnt = _run('gpu')
+    o_frames, o_cnt = _run('oracle')
+    assert g_cnt == o_cnt
+    assert g_frames.keys() == o_frames.keys()
+    for a in o_frames:
+        assert g_frames[a] == o_frames[a], (a, g_frames[a].hex(), o_frames[a].hex())
 
 
 def test_protocol_errors():
