@@ -13,7 +13,7 @@
 //   * a CTA owns a tile of 128 consecutive queries; their packed bytes are one contiguous
 //     range of the input, staged into shared memory with coalesced 16-byte loads;
 //   * each thread parses its packet from shared memory, hashes the normalised name and
-//     probes the zone table in HBM (one 64-byte slot = two sectors per host record);
+//     probes the zone table in HBM (one 32-byte slot = one sector per host record);
 //   * response sizes are scanned in the CTA, tile bases come from a single-pass decoupled
 //     look-back across CTAs (so output is packed, in query order, in ONE kernel);
 //   * responses are assembled in shared memory and flushed with 16-byte coalesced stores.
@@ -792,7 +792,7 @@ int bb_engine_swap_zone(bb_engine* e, const bb_zone* z) {
     return BB_OK;
 }
 
-// After bb_zone_apply: ship what changed — the touched 64-byte slots and the arena tail — instead of the
+// After bb_zone_apply: ship what changed — the touched 32-byte slots and the arena tail — instead of the
 // whole image.  Falls back to a full swap when the table was laid out again, the arena outgrew its
 // device allocation, or this engine is not the one that took the zone's previous changes.
 int bb_engine_apply_update(bb_engine* e, bb_zone* z) {

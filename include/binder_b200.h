@@ -123,7 +123,7 @@ void       bb_engine_destroy(bb_engine* e);
  * The engine keeps its own device copy; the caller may free `z` afterwards.
  */
 int bb_engine_swap_zone(bb_engine* e, const bb_zone* z);
-/* After bb_zone_apply: ship only what changed (the touched 64-byte slots, scattered by a small kernel, and the arena
+/* After bb_zone_apply: ship only what changed (the touched 32-byte slots, scattered by a small kernel, and the arena
  * tail) instead of the whole image; batches in flight finish on the old state first.  Falls back to a full swap when
  * the table had to be laid out again, the arena outgrew its device allocation, or another engine took the zone's
  * previous changes (a zone feeds ONE engine incrementally). */
