@@ -195,7 +195,7 @@ def cpu_port(orc, data, off, budget_s=12.0):
             'note': 'literal port: JSON-DOM walk + std::unordered_map<std::string> per query (oracle/oracle.cpp, -O2)'}
 
 
-def cpu_same_table(st, data, off, want_bytes, want_miss, per_q, seed=0, budget_s=8.0):
+def cpu_same_table(st, data, off, want_bytes, want_miss, per_q, seed=0, budget_s=8.0, against='the GPU result'):
     """SURVEY.md 8(d) "same open-addressed layout so the comparison isolates the processor": the word-wise device code
     compiled for the host (-O3) over the same zone image, all host threads; bounded sample."""
     cores = os.cpu_count() or 1
@@ -209,7 +209,7 @@ def cpu_same_table(st, data, off, want_bytes, want_miss, per_q, seed=0, budget_s
             'sample': '%d x one %d-query batch of the same workload, best pass; all %d host threads (single thread: %.0f queries/s on %d queries)'
                       % (reps, n, cores, ns / s1, ns),
             'single_thread_value': ns / s1,
-            'parity': 'response bytes %d and misses %d %s the GPU result' % (tb, tm, 'equal' if (tb, tm) == (want_bytes, want_miss) else 'DIFFER from')}
+            'parity': 'response bytes %d and misses %d %s %s' % (tb, tm, 'equal' if (tb, tm) == (want_bytes, want_miss) else 'DIFFER from', against)}
 
 
 def workload_setup(args):
@@ -228,12 +228,14 @@ def workload_setup(args):
 
 def run_reference(args):
     """--impl reference: the CPU port of the reference path (Node.js cannot run here), all host threads,
-    on the b200 arm's workload; each step = one bounded sample (65,536 queries) of that workload."""
+    on the b200 arm's workload; each step = one bounded sample (up to 262,144 queries: enough to amortise the thread start-up
+    of a step over 128+ threads) of that workload.  The line also carries the second CPU arm (same table image and algorithm
+    on the host) under cpu_baseline.same_table; `value` stays the literal port's."""
     from binder_b200 import synth
     zone, desc, mix, miss_frac, recursion, batch, _ = workload_setup(args)
     if args.gpus > 1:
         batch = max(batch // args.gpus, 1)
-    sample = min(batch, 65536)
+    sample = min(batch, 262144)
     data, off, _ = synth.gen_batch(zone, sample, 1000, mix, miss_frac, rd=synth.WORKLOAD_RD.get(args.workload, True))
     sys.path.insert(0, os.path.join(ROOT, 'oracle'))
     from oracle_lib import Oracle
@@ -245,6 +247,16 @@ def run_reference(args):
     ts = orc.timed_resolve(data, off, nthreads=cores, repeat=args.steps)
     total = sum(ts)
     v = sample * args.steps / total
+    same = None
+    try:
+        import same_table
+        t0 = time.time()
+        st = same_table.SameTable(zone.dns_domain, zone.jsonl, recursion)
+        o = orc.resolve_batch(data, off, seed=SEED, nthreads=cores)
+        same = cpu_same_table(st, data, off, len(o[0]), len(o[4]), 1232, seed=SEED, budget_s=5.0, against="the literal port's")
+        same['zone_build_s'] = time.time() - t0
+    except Exception as ex:
+        same = {'unavailable': repr(ex)}
     line = {'impl': 'reference', 'metric': METRIC, 'value': v, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': 1e3 * total / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if args.workload == 'config4' else 'weak', 'vs_baseline': None, 'dtype': 'u8', 'data': 'synthetic',
@@ -253,7 +265,8 @@ def run_reference(args):
                                'the Node.js reference is not runnable in this image; each step resolves a '
                                '%d-query sample of the workload on all host threads' % sample},
             'cpu_baseline': {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                             'sample': '%d steps x one %d-query sample of the workload, all %d host threads' % (args.steps, sample, cores)},
+                             'sample': '%d steps x one %d-query sample of the workload, all %d host threads' % (args.steps, sample, cores),
+                             'same_table': same},
             'e2e': {'value': v, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
             'gpu_launches': 0}
     emit(line)
